@@ -1,0 +1,161 @@
+/*
+ * kl_shell.h — C ABI of the B200-native Kirchhoff–Love shell assembly path.
+ *
+ * This is the drop-in boundary for the ONE hot path of gismo/gsStructuralAnalysis:
+ * the bodies of the Jacobian_t / Residual_t / ALResidual_t closures
+ * (reference: src/gsStructuralAnalysisTools/gsStructuralAnalysisTypes.h:58-93,
+ *  closure bodies tutorials/nonlinear_shell_static.cpp:120-136,
+ *  benchmarks/benchmark_Roof.cpp:324-344).  Every entry point below names the
+ * reference call it replaces.  Plain pointers and sizes only; no C++ / torch types.
+ *
+ * Conventions
+ *   - real_t = double, index_t = int32_t (G+Smo defaults).
+ *   - Control points are numbered tensor-style, first parametric direction fastest:
+ *       i = i1 + n1*i2,  n_d = n_knots[d] - degree[d] - 1.
+ *   - DoF numbering follows gsDofMapper (component-major; free first, coupled after the
+ *     plain free DoFs of their component, eliminated after ALL free DoFs).
+ *   - The sparse matrix is handed out as compressed arrays (outer/inner/values) that are
+ *     layout-compatible with Eigen::SparseMatrix<double,ColMajor,int> in compressed mode,
+ *     i.e. gsSparseMatrix<real_t>.  The pattern is structurally symmetric, so the same
+ *     arrays are a CSR of the transpose; values are written column-compressed (entry
+ *     (row i, col j) lives in outer[j]..outer[j+1]).
+ *   - All functions return 0 on success, a negative KL_E_* code on failure.  Nothing
+ *     throws across this boundary.  A non-zero return from kl_jacobian / kl_residual
+ *     maps to "closure returns false" => gsStatus::AssemblyError in the solvers
+ *     (reference: src/gsStaticSolvers/gsStaticNewton.hpp:196-212).
+ */
+#ifndef KL_SHELL_H
+#define KL_SHELL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes ---------------------------------------------------------------- */
+enum {
+    KL_OK            =  0,
+    KL_E_ARG         = -1,  /* bad argument / inconsistent sizes                      */
+    KL_E_CUDA        = -2,  /* CUDA runtime error (see kl_last_error)                  */
+    KL_E_NONFINITE   = -3,  /* a quadrature point produced a non-finite value          */
+    KL_E_JACOBIAN    = -4,  /* |a1 x a2| <= 0 at a quadrature point (inverted element) */
+    KL_E_C33         = -5,  /* plane-stress Newton on C33 did not converge             */
+    KL_E_NOGPU       = -6   /* no CUDA device: there is NO CPU fallback                */
+};
+
+/* ---- material selection (reference option strings:
+ *      tutorials/nonlinear_shell_static.cpp:103-104, unittests/gsStaticSolver_test.cpp:215-217) */
+enum {
+    KL_MAT_SVK = 0,   /* Material=0  St.Venant–Kirchhoff / gsMaterialMatrixLinear       */
+    KL_MAT_NH  = 1,   /* Material=1  Neo-Hookean                                          */
+    KL_MAT_MR  = 3    /* Material=3  Mooney–Rivlin (Ratio = c1/c2)                        */
+};
+
+/* boundary-condition kinds per side and component (gsBoundaryConditions condition_type) */
+enum { KL_BC_FREE = 0, KL_BC_DIRICHLET = 1, KL_BC_CLAMPED = 2, KL_BC_COLLAPSED = 3 };
+/* side order = G+Smo boxSide: west(u=0), east(u=1), south(v=0), north(v=1);
+ * corner order = southwest, southeast, northwest, northeast                              */
+enum { KL_WEST = 0, KL_EAST = 1, KL_SOUTH = 2, KL_NORTH = 3 };
+
+typedef struct kl_bc {
+    int32_t side[4][3];    /* KL_BC_* for [side][component]                              */
+    int32_t corner[4][3];  /* 1 = addCornerValue(corner, 0.0, patch, component)          */
+} kl_bc;
+
+/* ---- problem description: what the reference passes to
+ *      gsThinShellAssembler<3,real_t,true>(ori,bases,bc,force,materialMatrix)
+ *      (tutorials/nonlinear_shell_static.cpp:113) + setPointLoads/setPressure --------- */
+typedef struct kl_problem {
+    int32_t degree[2];          /* p1, p2 of the solution basis (= geometry basis)       */
+    int32_t n_knots[2];
+    const double* knots[2];     /* open knot vectors, possibly non-uniform                */
+    const double* cp;           /* [n_cp*3] undeformed control net, xyz interleaved       */
+    const double* weights;      /* [n_cp] NURBS weights of the GEOMETRY or NULL.  The     */
+                                /* displacement basis stays polynomial (gsMultiBasis(mp,true),*/
+                                /* benchmarks/benchmark_Balloon.cpp:122)                   */
+    const int32_t* dof_map;     /* [3*n_cp], dof_map[c*n_cp+i] = global index; an index    */
+                                /* >= n_free is eliminated; (index-n_free) addresses       */
+                                /* fixed_values (gsDofMapper::global_to_bindex)            */
+    int32_t n_free;
+    int32_t n_fixed;
+    const double* fixed_values; /* [n_fixed] Dirichlet displacement values or NULL (=0)    */
+
+    int32_t material;           /* KL_MAT_*                                               */
+    int32_t compressible;       /* option "Compressibility"                               */
+    int32_t num_gauss_thickness;/* option "NumGauss", default 4                           */
+    int32_t bending;            /* third template argument of gsThinShellAssembler        */
+    double  E, nu, thickness;   /* gsConstantFunction parameters                          */
+    double  mr_ratio;           /* Mooney–Rivlin c1/c2                                    */
+    int32_t metric_z2;          /* 1: add z^2 n,a.n,b to the through-thickness metric     */
+    int32_t quA, quB;           /* Gauss nodes per direction = quA*p+quB (solver_options.xml:11-12) */
+
+    double  body_force[3];      /* constant surface force (gsFunctionExpr force)          */
+    double  pressure;           /* follower pressure, setPressure (benchmark_Balloon.cpp:258) */
+    int32_t n_point_loads;
+    const double* point_load_uv;   /* [n_point_loads*2] parametric positions              */
+    const double* point_load_val;  /* [n_point_loads*3] load vectors                      */
+} kl_problem;
+
+typedef struct kl_ctx kl_ctx;
+
+/* Number the DoFs of one patch the way gsFeSpace::setupMapper + gsDofMapper::finalize do
+ * (SURVEY Appendix A.6).  Replaces: the mapper set-up inside the gsThinShellAssembler ctor.
+ * dof_map must hold 3*n1*n2 entries. */
+int kl_build_dofmap(int32_t n1, int32_t n2, const kl_bc* bc,
+                    int32_t* dof_map, int32_t* n_free, int32_t* n_fixed);
+
+/* Create a device context: uploads geometry, builds quadrature/basis tables, the symbolic
+ * pattern and the scatter tables ON THE GPU.  device < 0 selects the current device.
+ * Replaces: gsThinShellAssembler ctor + gsExprAssembler::initSystem. */
+int kl_create(const kl_problem* prob, int device, kl_ctx** out);
+void kl_destroy(kl_ctx* ctx);
+
+/* Sizes: numDofs() (tutorials/nonlinear_shell_static.cpp:153), nnz, elements, quadrature points */
+int kl_sizes(const kl_ctx* ctx, int32_t* n_dofs, int64_t* nnz, int64_t* n_elements, int64_t* n_qp);
+
+/* Copy the symbolic pattern to host arrays (outer[n_dofs+1], inner[nnz]). */
+int kl_pattern_host(const kl_ctx* ctx, int32_t* outer, int32_t* inner);
+/* Device-resident view (valid for the life of the context). */
+int kl_pattern_device(const kl_ctx* ctx, const int32_t** outer_dev, const int32_t** inner_dev);
+
+/* K(x): replaces constructSolution(x,def); assembleMatrix(def); m = matrix()
+ * (tutorials/nonlinear_shell_static.cpp:120-127).  x_host has n_dofs entries.
+ * values_host (nnz doubles) may be NULL: then the values stay on the device only. */
+int kl_jacobian(kl_ctx* ctx, const double* x_host, double* values_host);
+
+/* R(x) = F_ext - F_int(x): replaces constructSolution; assembleVector(def); v = rhs()
+ * (tutorials/nonlinear_shell_static.cpp:129-136). */
+int kl_residual(kl_ctx* ctx, const double* x_host, double* r_host);
+
+/* Arc-length form  F_int(x) - lam*F_ext  ==  Force - lam*Force - rhs()
+ * (benchmarks/benchmark_Roof.cpp:335-344). */
+int kl_al_residual(kl_ctx* ctx, const double* x_host, double lam, double* r_host);
+
+/* External force vector F (what assemble(); rhs() yields at u=0 for homogeneous BCs). */
+int kl_force(kl_ctx* ctx, double* f_host);
+
+/* Device-resident variants: x_dev / out pointers are device memory; work is enqueued on
+ * `stream` (a cudaStream_t passed as void*) and NOT synchronised — the error flag is
+ * fetched by kl_check().  These are what a device-resident solver (or bench.py's
+ * HBM-resident leg) calls. */
+int kl_jacobian_device(kl_ctx* ctx, const double* x_dev, void* stream);
+int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint,
+                       double* r_dev, void* stream);
+int kl_check(kl_ctx* ctx, void* stream);          /* sync stream, map device flag to KL_E_* */
+double* kl_values_device(kl_ctx* ctx);            /* device K values, length nnz            */
+
+/* Multi-GPU: restrict this context to the element rows [e2_begin, e2_end) of the second
+ * parametric direction (a strip).  The strip assembles its partial K / R; owners are
+ * completed by the halo reduce in the host layer. */
+int kl_set_strip(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end);
+
+/* Kernel-only timing of the last call in ms (CUDA events on the launch stream). */
+int kl_last_timing(const kl_ctx* ctx, float* ms_kernel, float* ms_h2d, float* ms_d2h);
+const char* kl_last_error(void);
+int kl_kernel_launches(const kl_ctx* ctx);        /* number of own kernels launched so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KL_SHELL_H */

@@ -1,0 +1,114 @@
+"""Pins the oracle (PARITY UNPINNED against G+Smo itself — see oracle/kl_oracle.c header):
+   (1) F_int == dW/du of an independently coded discrete energy,
+   (2) K == dF_int/du by central differences, K symmetric without follower pressure,
+   (3) rigid-body invariance.
+Tolerances are finite-difference tolerances, stated per test."""
+import numpy as np
+import pytest
+
+from gsstructuralanalysis_b200 import geometry as G
+from gsstructuralanalysis_b200.problem import (ShellProblem, BoundaryConditions, KL_MAT_SVK, KL_MAT_NH, KL_MAT_MR,
+                                                KL_BC_DIRICHLET, KL_BC_CLAMPED, WEST, EAST, SW, SE, NW, NE)
+from oracle.binding import Oracle
+from tests.energy_model import energy
+
+CASES = [
+    ("svk", KL_MAT_SVK, False, False), ("nh_inc", KL_MAT_NH, False, False), ("mr_inc", KL_MAT_MR, False, False),
+    ("nh_comp", KL_MAT_NH, True, False), ("mr_comp", KL_MAT_MR, True, False), ("nh_inc_z2", KL_MAT_NH, False, True),
+]
+
+
+def _problem(mat, comp, z2, surf=None, nu=0.3, **kw):
+    s = surf if surf is not None else G.paraboloid(0.15).degree_elevate(1).uniform_refine(1)
+    bc = BoundaryConditions()
+    for c in (SW, SE, NW, NE):
+        bc.add_corner_value(c)
+    return ShellProblem(s, bc, material=mat, compressible=comp, metric_z2=z2, E=1.0, nu=nu, thickness=0.05, **kw)
+
+
+@pytest.mark.parametrize("name,mat,comp,z2", CASES)
+def test_fint_is_energy_gradient(name, mat, comp, z2):
+    pr = _problem(mat, comp, z2)
+    o = Oracle(pr)
+    rng = np.random.default_rng(1)
+    x = 2e-2 * rng.uniform(-1, 1, o.n_dofs)
+    fint = -o.residual(x)            # no external load: R = -F_int
+    h = 1e-5
+    for k in rng.choice(o.n_dofs, 5, replace=False):
+        xp = x.copy(); xp[k] += h
+        xm = x.copy(); xm[k] -= h
+        g = (energy(pr, xp) - energy(pr, xm)) / (2 * h)
+        scale = np.abs(fint).max()
+        if z2:
+            # with the z^2 metric term the stress is still dpsi/dE of the exact metric, but the kinematic
+            # variation drops O(z^2): consistent only to O((t*kappa)^2)
+            assert abs(g - fint[k]) < 2e-2 * scale
+        else:
+            assert abs(g - fint[k]) < 1e-6 * scale, (name, k, g, fint[k])
+
+
+@pytest.mark.parametrize("name,mat,comp,z2", CASES[:5])
+def test_tangent_is_fd_of_residual_and_symmetric(name, mat, comp, z2):
+    pr = _problem(mat, comp, z2)
+    o = Oracle(pr)
+    rng = np.random.default_rng(2)
+    x = 2e-2 * rng.uniform(-1, 1, o.n_dofs)
+    K = o.jacobian(x)
+    assert abs(K - K.T).max() <= 1e-13 * abs(K).max()
+    h = 1e-6
+    for k in rng.choice(o.n_dofs, 6, replace=False):
+        xp = x.copy(); xp[k] += h
+        xm = x.copy(); xm[k] -= h
+        col = -(o.residual(xp) - o.residual(xm)) / (2 * h)
+        kc = K[:, k].toarray().ravel()
+        assert np.abs(col - kc).max() < 1e-7 * np.abs(kc).max()
+
+
+def test_follower_pressure_tangent_unsymmetric_but_consistent():
+    pr = _problem(KL_MAT_NH, False, False, pressure=0.02)
+    o = Oracle(pr)
+    rng = np.random.default_rng(3)
+    x = 1e-2 * rng.uniform(-1, 1, o.n_dofs)
+    K = o.jacobian(x)
+    assert abs(K - K.T).max() > 1e-8 * abs(K).max()
+    h = 1e-6
+    for k in rng.choice(o.n_dofs, 4, replace=False):
+        xp = x.copy(); xp[k] += h
+        xm = x.copy(); xm[k] -= h
+        col = -(o.residual(xp) - o.residual(xm)) / (2 * h)
+        assert np.abs(col - K[:, k].toarray().ravel()).max() < 1e-7 * abs(K).max()
+
+
+def test_nurbs_geometry_energy_gradient():
+    s = G.frustrum().degree_elevate(1).uniform_refine(1)
+    pr = _problem(KL_MAT_MR, False, False, surf=s)
+    o = Oracle(pr)
+    rng = np.random.default_rng(4)
+    x = 1e-2 * rng.uniform(-1, 1, o.n_dofs)
+    fint = -o.residual(x)
+    h = 1e-5
+    for k in rng.choice(o.n_dofs, 4, replace=False):
+        xp = x.copy(); xp[k] += h
+        xm = x.copy(); xm[k] -= h
+        g = (energy(pr, xp) - energy(pr, xm)) / (2 * h)
+        assert abs(g - fint[k]) < 1e-6 * np.abs(fint).max()
+
+
+def test_rigid_body_motion_gives_zero_internal_force():
+    s = G.paraboloid(0.2).degree_elevate(1).uniform_refine(1)
+    pr = ShellProblem(s, BoundaryConditions(), material=KL_MAT_NH, E=1.0, nu=0.3, thickness=0.05)
+    o = Oracle(pr)
+    th = 0.3
+    Rm = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    disp = s.cp @ Rm.T + np.array([0.1, -0.2, 0.3]) - s.cp
+    ncp = len(s.cp)
+    x = np.zeros(o.n_dofs)
+    for c in range(3):
+        x[pr.dof_map[c * ncp:(c + 1) * ncp]] = disp[:, c]
+    r = o.residual(x)
+    K = o.jacobian(np.zeros(o.n_dofs))
+    assert np.abs(r).max() < 1e-12
+    # translations are in the null space of K(0)
+    for c in range(3):
+        t = np.zeros(o.n_dofs); t[pr.dof_map[c * ncp:(c + 1) * ncp]] = 1.0
+        assert np.abs(K @ t).max() < 1e-12 * abs(K).max()
