@@ -1,0 +1,67 @@
+"""ctypes binding of the product library libkl_shell.so (C ABI: include/kl_shell.h).
+
+The library is built in-tree by build.py / __graft_entry__.build().  There is NO fallback: if the
+shared object is missing, or no CUDA device is present, every compute call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .problem import kl_problem, kl_bc, c_double_p, c_int_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkl_shell.so")
+
+KL_ERRORS = {0: "KL_OK", -1: "KL_E_ARG", -2: "KL_E_CUDA", -3: "KL_E_NONFINITE", -4: "KL_E_JACOBIAN", -5: "KL_E_C33",
+             -6: "KL_E_NOGPU"}
+
+# every symbol include/kl_shell.h declares
+SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern_host", "kl_pattern_device",
+           "kl_jacobian", "kl_residual", "kl_al_residual", "kl_force", "kl_jacobian_device", "kl_residual_device",
+           "kl_check", "kl_values_device", "kl_set_strip", "kl_last_timing", "kl_last_error", "kl_kernel_launches"]
+
+_LIB = None
+
+
+class KLError(RuntimeError):
+    def __init__(self, rc, msg):
+        super().__init__(f"{KL_ERRORS.get(rc, rc)}: {msg}")
+        self.rc = rc
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m gsstructuralanalysis_b200.build` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.kl_build_dofmap.argtypes = [C.c_int32, C.c_int32, C.POINTER(kl_bc), c_int_p, c_int_p, c_int_p]
+    L.kl_create.argtypes = [C.POINTER(kl_problem), C.c_int, C.POINTER(vp)]
+    L.kl_destroy.argtypes = [vp]
+    L.kl_destroy.restype = None
+    L.kl_sizes.argtypes = [vp, c_int_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.kl_pattern_host.argtypes = [vp, c_int_p, c_int_p]
+    L.kl_pattern_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.kl_jacobian.argtypes = [vp, c_double_p, c_double_p]
+    L.kl_residual.argtypes = [vp, c_double_p, c_double_p]
+    L.kl_al_residual.argtypes = [vp, c_double_p, C.c_double, c_double_p]
+    L.kl_force.argtypes = [vp, c_double_p]
+    L.kl_jacobian_device.argtypes = [vp, vp, vp]
+    L.kl_residual_device.argtypes = [vp, vp, C.c_double, C.c_double, vp, vp]
+    L.kl_check.argtypes = [vp, vp]
+    L.kl_values_device.argtypes = [vp]
+    L.kl_values_device.restype = vp
+    L.kl_set_strip.argtypes = [vp, C.c_int32, C.c_int32]
+    L.kl_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.kl_last_error.restype = C.c_char_p
+    L.kl_kernel_launches.argtypes = [vp]
+    _LIB = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise KLError(rc, lib().kl_last_error().decode())

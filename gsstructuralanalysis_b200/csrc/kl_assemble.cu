@@ -1,0 +1,441 @@
+// kl_assemble.cu — hand-written sm_100a FP64 kernels of the hot path:
+//   construct_solution   (gsThinShellAssembler::constructSolution, tutorials/nonlinear_shell_static.cpp:123)
+//   residual             (assembleVector,  tutorials/nonlinear_shell_static.cpp:133)
+//   jacobian             (assembleMatrix,  tutorials/nonlinear_shell_static.cpp:124)
+// Formulation: SURVEY Appendix A.3/A.4; in-reference restatement benchmarks/benchmark_cylinder_DC.cpp:536-555.
+//
+// Jacobian kernel structure (one CTA works on a group of EPG consecutive elements):
+//   phase 1  one thread per quadrature point: geometry, metric, material -> PointData in smem
+//   phase 2  one thread per (basis function j, point): Z_j = T(point) . d_j   (5 x 3x3 coefficients)
+//   phase 3  one thread per tile (row of P+1 functions i, function j), upper triangle only:
+//            K_ij^{cd} += sum_p d_i[p] Z_j^{p,cd}, sum-factorised over the tensor-product basis
+//   scatter  FP64 RED (atomicAdd, no return) into the compressed values through the position table,
+//            both (i,j) and the transposed (j,i) entry.
+#include "kl_device.cuh"
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_construct_solution(KLDev d, const double* __restrict__ x) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 3 * d.ncp) return;
+    const int c = k / d.ncp, i = k - c * d.ncp;
+    const int g = d.map[k];
+    double v;
+    if (g < d.nfree) v = x ? x[g] : 0.0;
+    else v = d.fixed ? d.fixed[g - d.nfree] : 0.0;
+    d.disp[3 * i + c] = v;
+}
+
+__global__ void k_axpby(double* __restrict__ r, const double* __restrict__ f, double a, double b, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) r[k] = a * r[k] + b * f[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual: F_int - F_pressure accumulated into r (atomic)
+template <int P>
+struct ResidualCfg {
+    static constexpr int NQ2 = (P + 1) * (P + 1);
+    static constexpr int NLOC = (P + 1) * (P + 1);
+    static constexpr int EPG = (P == 2) ? 14 : (P == 3 ? 8 : 5);   // elements per CTA
+    static constexpr int NT = EPG * NQ2;
+};
+struct ResPoint {   // what the force integrand needs per point
+    double q1[3], q2[3], nM[3][3], pn[3];
+};
+
+template <int P>
+__global__ void __launch_bounds__(ResidualCfg<P>::NT) k_residual(KLDev d, double* __restrict__ r, int e2_begin, int e2_end, int body, double bfx, double bfy, double bfz) {
+    using Cfg = ResidualCfg<P>;
+    constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, NLOC = Cfg::NLOC, EPG = Cfg::EPG;
+    __shared__ ElemStage<P> stage[EPG];
+    __shared__ ResPoint rp[EPG][NQ2];
+    const int tid = threadIdx.x;
+    const int le = tid / NQ2, lq = tid - le * NQ2;
+    const int nel = d.nel1 * (e2_end - e2_begin);
+    const int e = blockIdx.x * EPG + le;
+    const bool active = e < nel;
+    const int e1 = active ? e % d.nel1 : 0, e2 = active ? e2_begin + e / d.nel1 : e2_begin;
+    stage_element<P>(d, e1, e2, stage[le], lq, NQ2);
+    __syncthreads();
+    {
+        const int q1 = lq % NQ, q2 = lq / NQ;
+        ResPoint& o = rp[le][lq];
+        if (body) {
+            // external body force: only weight * meas(ori) is needed
+            double fo[6][3];
+            eval_field3<P, true>(stage[le].X, stage[le].b1[q1], stage[le].b2[q2], fo);
+            double A1[3], A2[3], Nn[3];
+            if (d.rational) {
+                double fw[6];
+                eval_field1<P>(stage[le].Wt, stage[le].b1[q1], stage[le].b2[q2], fw);
+                const double iw = 1.0 / fw[0];
+                for (int c = 0; c < 3; ++c) {
+                    const double X = fo[0][c] * iw;
+                    A1[c] = (fo[1][c] - fw[1] * X) * iw;
+                    A2[c] = (fo[2][c] - fw[2] * X) * iw;
+                }
+            } else {
+                for (int c = 0; c < 3; ++c) { A1[c] = fo[1][c]; A2[c] = fo[2][c]; }
+            }
+            cross3(A1, A2, Nn);
+            const double wJ = stage[le].w1[q1] * stage[le].w2[q2] * sqrt(dot3(Nn, Nn));
+            o.pn[0] = wJ * bfx; o.pn[1] = wJ * bfy; o.pn[2] = wJ * bfz;
+            for (int c = 0; c < 3; ++c) { o.q1[c] = 0; o.q2[c] = 0; o.nM[0][c] = o.nM[1][c] = o.nM[2][c] = 0; }
+        } else {
+            PointData pd;
+            const int flag = eval_point<P>(d, stage[le], q1, q2, pd);
+            if (flag && active) atomicOr(d.flag, flag);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                // coefficient of N_a,1 and N_a,2:  N:dEm  +  n_c * (H . a^gamma)   (the Christoffel part of M:dEf)
+                o.q1[c] = pd.N[0] * pd.a1[c] + pd.N[2] * pd.a2[c] + pd.n[c] * pd.Ha1;
+                o.q2[c] = pd.N[1] * pd.a2[c] + pd.N[2] * pd.a1[c] + pd.n[c] * pd.Ha2;
+                o.nM[0][c] = -pd.n[c] * pd.Mt[0];
+                o.nM[1][c] = -pd.n[c] * pd.Mt[1];
+                o.nM[2][c] = -pd.n[c] * pd.Mt[2];
+                o.pn[c] = -d.mat.pressure * pd.wJ * pd.n[c];
+            }
+        }
+    }
+    __syncthreads();
+    // one thread per local basis function: integrate over the element's points
+    if (lq < NLOC && active) {
+        const int a = lq % (P + 1), b = lq / (P + 1);
+        double f[3] = {0, 0, 0};
+        const ElemStage<P>& E = stage[le];
+#pragma unroll
+        for (int q2 = 0; q2 < NQ; ++q2)
+#pragma unroll
+            for (int q1 = 0; q1 < NQ; ++q1) {
+                const ResPoint& o = rp[le][q1 + NQ * q2];
+                const double x0 = E.b1[q1][0][a], x1 = E.b1[q1][1][a], x2 = E.b1[q1][2][a];
+                const double y0 = E.b2[q2][0][b], y1 = E.b2[q2][1][b], y2 = E.b2[q2][2][b];
+                const double R = x0 * y0, R1 = x1 * y0, R2 = x0 * y1, R11 = x2 * y0, R22 = x0 * y2, R12 = x1 * y1;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    f[c] += R1 * o.q1[c] + R2 * o.q2[c] + R11 * o.nM[0][c] + R22 * o.nM[1][c] + R12 * o.nM[2][c] + R * o.pn[c];
+            }
+        const int cpi = (d.span1[e1] - P + a) + d.n1 * (d.span2[e2] - P + b);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int g = d.map[c * d.ncp + cpi];
+            if (g < d.nfree) atomicAdd(&r[g], f[c]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Jacobian
+template <int P>
+struct JacCfg {
+    static constexpr int NQ = P + 1;
+    static constexpr int NQ2 = NQ * NQ;
+    static constexpr int NLOC = (P + 1) * (P + 1);
+    static constexpr int TILES = (P + 1) * (P + 1) * (P + 2) / 2;      // (i2, j) with i2 <= j2
+    static constexpr int EPG = (P == 4) ? 2 : 4;                        // elements per CTA
+    static constexpr int NT = TILES * EPG;                              // 72 / 160 / 150
+    static constexpr int QCH = (P == 3) ? 2 : NQ;                       // points per chunk (divides NQ2)
+    static constexpr int NZ = 45;
+};
+
+template <int P>
+struct JacShared {
+    using Cfg = JacCfg<P>;
+    ElemStage<P> stage[Cfg::EPG];
+    PointData pd[Cfg::EPG][Cfg::NQ2];
+    double Z[Cfg::EPG][Cfg::QCH][Cfg::NZ][Cfg::NLOC];
+};
+
+template <int P>
+__global__ void __launch_bounds__(JacCfg<P>::NT) k_jacobian(KLDev d, int e2_begin, int e2_end) {
+    using Cfg = JacCfg<P>;
+    constexpr int NQ = Cfg::NQ, NQ2 = Cfg::NQ2, NLOC = Cfg::NLOC, TILES = Cfg::TILES, EPG = Cfg::EPG, NT = Cfg::NT, QCH = Cfg::QCH;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    JacShared<P>& S = *reinterpret_cast<JacShared<P>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int nel = d.nel1 * (e2_end - e2_begin);
+    const int ebase = blockIdx.x * EPG;
+
+    // ---- stage the EPG elements
+    for (int le = 0; le < EPG; ++le) {
+        int e = ebase + le;
+        if (e >= nel) e = nel - 1;
+        stage_element<P>(d, e % d.nel1, e2_begin + e / d.nel1, S.stage[le], tid, NT);
+    }
+    __syncthreads();
+    // ---- phase 1: one thread per quadrature point
+    for (int k = tid; k < EPG * NQ2; k += NT) {
+        const int le = k / NQ2, lq = k - le * NQ2;
+        const int flag = eval_point<P>(d, S.stage[le], lq % NQ, lq / NQ, S.pd[le][lq]);
+        if (flag && (ebase + le) < nel) atomicOr(d.flag, flag);
+    }
+    // tile of this thread
+    const int le_t = tid / TILES, tt = tid - le_t * TILES;
+    // tiles enumerated by j ascending, i2 = 0..j2:  offset(j) = (P+1) * j2 (j2+1)/2 + (j - (P+1) j2) * (j2+1)
+    int tj = 0, ti2 = 0;
+    {
+        int rem = tt;
+        for (int j2 = 0; j2 <= P; ++j2) {
+            const int cnt = (P + 1) * (j2 + 1);
+            if (rem < cnt) { tj = (P + 1) * j2 + rem / (j2 + 1); ti2 = rem % (j2 + 1); break; }
+            rem -= cnt;
+        }
+    }
+    double acc[P + 1][9];
+#pragma unroll
+    for (int a = 0; a <= P; ++a)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[a][k] = 0.0;
+
+    for (int ch = 0; ch < NQ2 / QCH; ++ch) {
+        __syncthreads();   // phase-1 data ready / previous chunk's Z consumed
+        // ---- phase 2: Z_j for the points of this chunk
+        for (int k = tid; k < EPG * QCH * NLOC; k += NT) {
+            const int j = k % NLOC;
+            const int qc = (k / NLOC) % QCH;
+            const int le = k / (NLOC * QCH);
+            const int lq = ch * QCH + qc;
+            const int q1 = lq % NQ, q2 = lq / NQ;
+            const PointData& pd = S.pd[le][lq];
+            const ElemStage<P>& E = S.stage[le];
+            const int ja = j % (P + 1), jb = j / (P + 1);
+            const double x0 = E.b1[q1][0][ja], x1 = E.b1[q1][1][ja], x2 = E.b1[q1][2][ja];
+            const double y0 = E.b2[q2][0][jb], y1 = E.b2[q2][1][jb], y2 = E.b2[q2][2][jb];
+            const double N1 = x1 * y0, N2 = x0 * y1, N11 = x2 * y0, N22 = x0 * y2, N12 = x1 * y1;
+            double g[3], hh[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g[c] = N1 * pd.c1[c] + N2 * pd.c2[c];
+            hh[0] = N11 - pd.G1[0] * N1 - pd.G2[0] * N2;
+            hh[1] = N22 - pd.G1[1] * N1 - pd.G2[1] * N2;
+            hh[2] = 2.0 * (N12 - pd.G1[2] * N1 - pd.G2[2] * N2);
+            double AE1[3], AE2[3], BE1[3], BE2[3], Bh[3], Dh[3];
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                AE1[v] = N1 * pd.A[sidx(v, 0)] + N2 * pd.A[sidx(v, 2)];
+                AE2[v] = N2 * pd.A[sidx(v, 1)] + N1 * pd.A[sidx(v, 2)];
+                BE1[v] = N1 * pd.B[sidx(v, 0)] + N2 * pd.B[sidx(v, 2)];
+                BE2[v] = N2 * pd.B[sidx(v, 1)] + N1 * pd.B[sidx(v, 2)];
+                Bh[v] = pd.B[sidx(v, 0)] * hh[0] + pd.B[sidx(v, 1)] * hh[1] + pd.B[sidx(v, 2)] * hh[2];
+                Dh[v] = pd.D[sidx(v, 0)] * hh[0] + pd.D[sidx(v, 1)] * hh[1] + pd.D[sidx(v, 2)] * hh[2];
+            }
+            const double Nhat = pd.Mt[0] * N11 + pd.Mt[1] * N22 + pd.Mt[2] * N12;
+            const double eta = pd.Ha1 * N1 + pd.Ha2 * N2;
+            const double p1 = pd.N[0] * N1 + pd.N[2] * N2, p2 = pd.N[1] * N2 + pd.N[2] * N1;
+            const double ga1 = pd.acon[0] * N1 + pd.acon[2] * N2, ga2 = pd.acon[2] * N1 + pd.acon[1] * N2;
+            double sig[3][3], mu[3][3], s1[3], s2[3];
+#pragma unroll
+            for (int dd = 0; dd < 3; ++dd) {
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    sig[dd][v] = AE1[v] * pd.a1[dd] + AE2[v] * pd.a2[dd] - pd.n[dd] * Bh[v];
+                    mu[dd][v] = BE1[v] * pd.a1[dd] + BE2[v] * pd.a2[dd] - pd.n[dd] * Dh[v];
+                }
+                s1[dd] = pd.G1[0] * mu[dd][0] + pd.G1[1] * mu[dd][1] + 2.0 * pd.G1[2] * mu[dd][2] + Nhat * pd.c1[dd] - pd.Ha1 * g[dd]
+                         + pd.Hn * pd.n[dd] * ga1;
+                s2[dd] = pd.G2[0] * mu[dd][0] + pd.G2[1] * mu[dd][1] + 2.0 * pd.G2[2] * mu[dd][2] + Nhat * pd.c2[dd] - pd.Ha2 * g[dd]
+                         + pd.Hn * pd.n[dd] * ga2;
+            }
+            double (*Zo)[NLOC] = S.Z[le][qc];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dd = 0; dd < 3; ++dd) {
+                    // epsilon_{c dd k} q_k
+                    double eq = 0.0;
+                    if ((c + 1) % 3 == dd) eq = pd.q[(c + 2) % 3];
+                    else if ((dd + 1) % 3 == c) eq = -pd.q[(dd + 2) % 3];
+                    const double dl = (c == dd) ? 1.0 : 0.0;
+                    const int cd = c * 3 + dd;
+                    Zo[0 * 9 + cd][j] = pd.a1[c] * sig[dd][0] + pd.a2[c] * sig[dd][2] + pd.n[c] * s1[dd] - eta * pd.n[dd] * pd.c1[c] + dl * p1 - N2 * eq;
+                    Zo[1 * 9 + cd][j] = pd.a2[c] * sig[dd][1] + pd.a1[c] * sig[dd][2] + pd.n[c] * s2[dd] - eta * pd.n[dd] * pd.c2[c] + dl * p2 + N1 * eq;
+                    Zo[2 * 9 + cd][j] = -pd.n[c] * mu[dd][0] + pd.Mt[0] * pd.n[dd] * g[c];
+                    Zo[3 * 9 + cd][j] = -pd.n[c] * mu[dd][1] + pd.Mt[1] * pd.n[dd] * g[c];
+                    Zo[4 * 9 + cd][j] = -2.0 * pd.n[c] * mu[dd][2] + pd.Mt[2] * pd.n[dd] * g[c];
+                }
+        }
+        __syncthreads();
+        // ---- phase 3: tile (ti2, tj): K_{(i1,ti2), tj} += sum_p d_i[p] Z_j^p
+        {
+            const ElemStage<P>& E = S.stage[le_t];
+#pragma unroll 1
+            for (int qc = 0; qc < QCH; ++qc) {
+                const int lq = ch * QCH + qc;
+                const int q1 = lq % NQ, q2 = lq / NQ;
+                const double y0 = E.b2[q2][0][ti2], y1 = E.b2[q2][1][ti2], y2 = E.b2[q2][2][ti2];
+                double X0[P + 1], X1[P + 1], X2[P + 1];
+#pragma unroll
+                for (int a = 0; a <= P; ++a) { X0[a] = E.b1[q1][0][a]; X1[a] = E.b1[q1][1][a]; X2[a] = E.b1[q1][2][a]; }
+                const double (*Zi)[NLOC] = S.Z[le_t][qc];
+#pragma unroll
+                for (int cd = 0; cd < 9; ++cd) {
+                    const double z1 = Zi[0 * 9 + cd][tj], z2 = Zi[1 * 9 + cd][tj], z11 = Zi[2 * 9 + cd][tj], z22 = Zi[3 * 9 + cd][tj],
+                                 z12 = Zi[4 * 9 + cd][tj];
+                    const double W0 = y1 * z2 + y2 * z22;     // multiplies N_{i1}(q1)
+                    const double W1 = y0 * z1 + y1 * z12;     // multiplies N'_{i1}(q1)
+                    const double W2 = y0 * z11;               // multiplies N''_{i1}(q1)
+#pragma unroll
+                    for (int a = 0; a <= P; ++a) acc[a][cd] += X0[a] * W0 + X1[a] * W1 + X2[a] * W2;
+                }
+            }
+        }
+    }
+    // ---- scatter (upper triangle i <= j plus the transposed entries)
+    const int e = ebase + le_t;
+    if (e < nel) {
+        const int e1 = e % d.nel1, e2 = e2_begin + e / d.nel1;
+        const int i0 = d.span1[e1] - P, j0 = d.span2[e2] - P;
+        const int ja = tj % (P + 1), jb = tj / (P + 1);
+        const int J1 = i0 + ja, J2 = j0 + jb, Jc = J1 + d.n1 * J2;
+        const int S3 = d.nst * 3, W = 2 * P + 1;
+        double* __restrict__ val = d.values;
+#pragma unroll
+        for (int a = 0; a <= P; ++a) {
+            const int i = a + (P + 1) * ti2;
+            if (i > tj) continue;
+            const int I1 = i0 + a, I2 = j0 + ti2, Ic = I1 + d.n1 * I2;
+            const int st_ij = (I1 - J1 + P) + W * (I2 - J2 + P);   // position of row-function I in the stencil of column-function J
+            const int st_ji = (J1 - I1 + P) + W * (J2 - I2 + P);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dd = 0; dd < 3; ++dd) {
+                    const double v = acc[a][c * 3 + dd];
+                    // entry (row (I,c), col (J,dd))
+                    const int p1 = d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c];
+                    if (p1 >= 0) atomicAdd(&val[p1], v);
+                    if (i != tj) {
+                        const int p2 = d.pos[(size_t)(Ic * 3 + c) * S3 + st_ji * 3 + dd];
+                        if (p2 >= 0) atomicAdd(&val[p2], v);
+                    }
+                }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// follower-pressure tangent  -p R_i dn_jd[c] = +p R_i n_d g_j[c]  (unsymmetric, full i x j loop; cheap)
+template <int P>
+__global__ void __launch_bounds__(256) k_pressure_tangent(KLDev d, int e2_begin, int e2_end) {
+    constexpr int NQ = P + 1, NQ2 = NQ * NQ, NLOC = (P + 1) * (P + 1);
+    __shared__ ElemStage<P> stage;
+    __shared__ double pn[NQ2][3], pc1[NQ2][3], pc2[NQ2][3], pw[NQ2];
+    const int tid = threadIdx.x;
+    const int e = blockIdx.x;
+    const int e1 = e % d.nel1, e2 = e2_begin + e / d.nel1;
+    stage_element<P>(d, e1, e2, stage, tid, blockDim.x);
+    __syncthreads();
+    if (tid < NQ2) {
+        PointData pd;
+        eval_point<P>(d, stage, tid % NQ, tid / NQ, pd);
+        for (int c = 0; c < 3; ++c) { pn[tid][c] = pd.n[c]; pc1[tid][c] = pd.c1[c]; pc2[tid][c] = pd.c2[c]; }
+        pw[tid] = pd.wJ * d.mat.pressure;
+    }
+    __syncthreads();
+    const int i0 = d.span1[e1] - P, j0 = d.span2[e2] - P;
+    const int S3 = d.nst * 3, W = 2 * P + 1;
+    for (int pr = tid; pr < NLOC * NLOC; pr += blockDim.x) {
+        const int i = pr / NLOC, j = pr - i * NLOC;
+        const int ia = i % (P + 1), ib = i / (P + 1), ja = j % (P + 1), jb = j / (P + 1);
+        double k[3][3] = {{0}};
+        for (int lq = 0; lq < NQ2; ++lq) {
+            const int q1 = lq % NQ, q2 = lq / NQ;
+            const double Ri = stage.b1[q1][0][ia] * stage.b2[q2][0][ib];
+            const double N1 = stage.b1[q1][1][ja] * stage.b2[q2][0][jb], N2 = stage.b1[q1][0][ja] * stage.b2[q2][1][jb];
+            for (int c = 0; c < 3; ++c) {
+                const double gc = N1 * pc1[lq][c] + N2 * pc2[lq][c];
+                for (int dd = 0; dd < 3; ++dd) k[c][dd] += pw[lq] * Ri * pn[lq][dd] * gc;
+            }
+        }
+        const int I1 = i0 + ia, I2 = j0 + ib, J1 = i0 + ja, J2 = j0 + jb;
+        const int Jc = J1 + d.n1 * J2;
+        const int st_ij = (I1 - J1 + P) + W * (I2 - J2 + P);
+        for (int c = 0; c < 3; ++c)
+            for (int dd = 0; dd < 3; ++dd) {
+                const int p1 = d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c];
+                if (p1 >= 0) atomicAdd(&d.values[p1], k[c][dd]);
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+int kl_launch_construct(kl_ctx* ctx, const double* x_dev, cudaStream_t s) {
+    const int n = 3 * ctx->d.ncp;
+    k_construct_solution<<<(n + 255) / 256, 256, 0, s>>>(ctx->d, x_dev);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int kl_launch_axpby(kl_ctx* ctx, double* r, const double* fext, double a_r, double b_f, int n, cudaStream_t s) {
+    if (n <= 0) return 0;
+    k_axpby<<<(n + 255) / 256, 256, 0, s>>>(r, fext, a_r, b_f, n);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int P>
+static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
+    using Cfg = JacCfg<P>;
+    const int nel = ctx->d.nel1 * (e2e - e2b);
+    if (nel <= 0) return 0;
+    const size_t smem = sizeof(JacShared<P>);
+    static bool attr_set = false;
+    if (!attr_set) {
+        KL_CUDA(cudaFuncSetAttribute(k_jacobian<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
+    k_jacobian<P><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    if (ctx->d.mat.pressure != 0.0) {
+        k_pressure_tangent<P><<<nel, 256, 0, s>>>(ctx->d, e2b, e2e);
+        ctx->launches++;
+        KL_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int kl_launch_jacobian(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s) {
+    switch (ctx->d.p) {
+        case 2: return launch_jac<2>(ctx, e2_begin, e2_end, s);
+        case 3: return launch_jac<3>(ctx, e2_begin, e2_end, s);
+        case 4: return launch_jac<4>(ctx, e2_begin, e2_end, s);
+    }
+    kl_set_error("unsupported degree");
+    return KL_E_ARG;
+}
+
+template <int P>
+static int launch_res(kl_ctx* ctx, double* r, int body, const double* bf, cudaStream_t s) {
+    using Cfg = ResidualCfg<P>;
+    const int nel = ctx->d.nel1 * (ctx->e2_end - ctx->e2_begin);
+    if (nel <= 0) return 0;
+    const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
+    k_residual<P><<<grid, Cfg::NT, 0, s>>>(ctx->d, r, ctx->e2_begin, ctx->e2_end, body, bf ? bf[0] : 0.0, bf ? bf[1] : 0.0, bf ? bf[2] : 0.0);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s) {
+    switch (ctx->d.p) {
+        case 2: return launch_res<2>(ctx, r_dev, 0, nullptr, s);
+        case 3: return launch_res<3>(ctx, r_dev, 0, nullptr, s);
+        case 4: return launch_res<4>(ctx, r_dev, 0, nullptr, s);
+    }
+    kl_set_error("unsupported degree");
+    return KL_E_ARG;
+}
+
+// f_dev += integral(N_i * bf * meas(ori))
+int kl_launch_bodyforce(kl_ctx* ctx, double* f_dev, const double bf[3], cudaStream_t s) {
+    switch (ctx->d.p) {
+        case 2: return launch_res<2>(ctx, f_dev, 1, bf, s);
+        case 3: return launch_res<3>(ctx, f_dev, 1, bf, s);
+        case 4: return launch_res<4>(ctx, f_dev, 1, bf, s);
+    }
+    kl_set_error("unsupported degree");
+    return KL_E_ARG;
+}

@@ -1,0 +1,484 @@
+// kl_capi.cu — the C ABI (include/kl_shell.h) and the host-side set-up of the device context:
+// DoF numbering, knot-span / quadrature / 1-D basis tables, external force vector, streams.
+// There is NO CPU fallback: every compute entry point fails with KL_E_NOGPU / KL_E_CUDA when no
+// device is present.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include "kl_internal.h"
+
+static thread_local std::string g_err;
+void kl_set_error(const std::string& s) { g_err = s; }
+extern "C" const char* kl_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------------------------------------
+// DoF numbering (gsFeSpace::setupMapper + gsDofMapper::finalize)
+//   dirichlet side  -> eliminate the boundary DoFs of that component
+//   clamped side    -> match each boundary DoF with its neighbour in the second row
+//   collapsed side  -> match all boundary DoFs of the side with the first one
+//   corner value    -> eliminate that DoF
+// A matched group is eliminated as a whole when any member is.  Numbering is component-major:
+// plain free DoFs in tensor order, then matched groups by first appearance; eliminated DoFs follow
+// after ALL free ones (global_to_bindex = index - freeSize).
+extern "C" int kl_build_dofmap(int32_t n1, int32_t n2, const kl_bc* bc, int32_t* dof_map, int32_t* n_free, int32_t* n_fixed) {
+    if (n1 < 2 || n2 < 2 || !bc || !dof_map || !n_free || !n_fixed) { kl_set_error("kl_build_dofmap: bad argument"); return KL_E_ARG; }
+    const int ncp = n1 * n2;
+    std::vector<int> label(ncp), state(ncp);   // state: 0 plain, 1 matched, 2 eliminated
+    std::vector<std::pair<int, int>> pairs;
+    std::vector<std::vector<int>> elim_slot(3, std::vector<int>(ncp, -1));
+    int free_total = 0, elim_total = 0;
+    auto side_dof = [&](int s, int k, int layer) {
+        switch (s) {
+            case KL_WEST: return layer + n1 * k;
+            case KL_EAST: return (n1 - 1 - layer) + n1 * k;
+            case KL_SOUTH: return k + n1 * layer;
+            default: return k + n1 * (n2 - 1 - layer);
+        }
+    };
+    for (int c = 0; c < 3; ++c) {
+        pairs.clear();
+        for (int i = 0; i < ncp; ++i) { label[i] = i; state[i] = 0; }
+        for (int s = 0; s < 4; ++s) {
+            const int kind = bc->side[s][c];
+            const int len = (s == KL_WEST || s == KL_EAST) ? n2 : n1;
+            for (int k = 0; k < len; ++k) {
+                const int b0 = side_dof(s, k, 0);
+                if (kind == KL_BC_DIRICHLET) state[b0] = 2;
+                else if (kind == KL_BC_CLAMPED) pairs.emplace_back(b0, side_dof(s, k, 1));
+                else if (kind == KL_BC_COLLAPSED && k > 0) pairs.emplace_back(side_dof(s, 0, 0), b0);
+            }
+        }
+        const int corners[4] = {0, n1 - 1, n1 * (n2 - 1), n1 * n2 - 1};
+        for (int k = 0; k < 4; ++k) if (bc->corner[k][c]) state[corners[k]] = 2;
+        // min-label propagation over the match pairs
+        for (auto& pr : pairs) { if (state[pr.first] != 2) state[pr.first] = 1; if (state[pr.second] != 2) state[pr.second] = 1; }
+        bool changed = !pairs.empty();
+        while (changed) {
+            changed = false;
+            for (auto& pr : pairs) {
+                const int m = std::min(label[pr.first], label[pr.second]);
+                if (label[pr.first] != m) { label[pr.first] = m; changed = true; }
+                if (label[pr.second] != m) { label[pr.second] = m; changed = true; }
+            }
+        }
+        // elimination spreads over matched groups
+        std::vector<char> group_elim(ncp, 0);
+        for (auto& pr : pairs) if (state[pr.first] == 2 || state[pr.second] == 2) group_elim[label[pr.first]] = 1;
+        bool again = true;
+        while (again) {
+            again = false;
+            for (auto& pr : pairs) {
+                const int g = label[pr.first];
+                if (group_elim[g]) {
+                    if (state[pr.first] != 2) { state[pr.first] = 2; again = true; }
+                    if (state[pr.second] != 2) { state[pr.second] = 2; again = true; }
+                }
+            }
+        }
+        int cnt = 0;
+        for (int i = 0; i < ncp; ++i) if (state[i] == 0) dof_map[c * ncp + i] = free_total + cnt++;
+        std::vector<int> gid(ncp, -1);
+        for (int i = 0; i < ncp; ++i) if (state[i] == 1) {
+            int& g = gid[label[i]];
+            if (g < 0) g = free_total + cnt++;
+            dof_map[c * ncp + i] = g;
+        }
+        free_total += cnt;
+        std::fill(gid.begin(), gid.end(), -1);
+        for (int i = 0; i < ncp; ++i) if (state[i] == 2) {
+            int& g = gid[label[i]];
+            if (g < 0) g = elim_total++;
+            elim_slot[c][i] = g;
+        }
+    }
+    for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < ncp; ++i) if (elim_slot[c][i] >= 0) dof_map[c * ncp + i] = free_total + elim_slot[c][i];
+    *n_free = free_total;
+    *n_fixed = elim_total;
+    return KL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1-D B-spline values and derivatives on a knot span by the Cox–de Boor triangle
+// (gsBSplineBasis::evalAllDers_into):  T[m][q][j] = m-th derivative of N_{k-q+j, q}(u)
+static void bspline_span_ders(const std::vector<double>& U, int p, int k, double u, double out[3][KL_MAXP + 1]) {
+    double T[3][KL_MAXP + 1][KL_MAXP + 1];
+    std::memset(T, 0, sizeof(T));
+    T[0][0][0] = 1.0;
+    for (int q = 1; q <= p; ++q)
+        for (int j = 0; j <= q; ++j) {
+            const int i = k - q + j;
+            for (int m = 0; m <= 2; ++m) {
+                double v = 0.0;
+                if (m == 0) {
+                    if (j >= 1) v += (u - U[i]) / (U[i + q] - U[i]) * T[0][q - 1][j - 1];
+                    if (j <= q - 1) v += (U[i + q + 1] - u) / (U[i + q + 1] - U[i + 1]) * T[0][q - 1][j];
+                } else {
+                    if (j >= 1) v += T[m - 1][q - 1][j - 1] / (U[i + q] - U[i]);
+                    if (j <= q - 1) v -= T[m - 1][q - 1][j] / (U[i + q + 1] - U[i + 1]);
+                    v *= q;
+                }
+                T[m][q][j] = v;
+            }
+        }
+    for (int m = 0; m < 3; ++m)
+        for (int j = 0; j <= p; ++j) out[m][j] = T[m][p][j];
+}
+
+// Gauss–Legendre nodes/weights on [-1,1] (quRule = 1), Newton iteration in extended precision
+static void gauss_rule(int n, double* x, double* w) {
+    for (int i = 0; i < (n + 1) / 2; ++i) {
+        long double z = cosl(3.141592653589793238462643383279502884L * (i + 0.75L) / (n + 0.5L)), pp = 0;
+        for (int it = 0; it < 60; ++it) {
+            long double p1 = 1, p2 = 0;
+            for (int j = 1; j <= n; ++j) { long double p3 = p2; p2 = p1; p1 = ((2 * j - 1) * z * p2 - (j - 1) * p3) / j; }
+            pp = n * (z * p1 - p2) / (z * z - 1);
+            z -= p1 / pp;
+        }
+        {
+            long double p1 = 1, p2 = 0;
+            for (int j = 1; j <= n; ++j) { long double p3 = p2; p2 = p1; p1 = ((2 * j - 1) * z * p2 - (j - 1) * p3) / j; }
+            pp = n * (z * p1 - p2) / (z * z - 1);
+        }
+        x[i] = (double)(-z); x[n - 1 - i] = (double)z;
+        w[i] = w[n - 1 - i] = (double)(2 / ((1 - z * z) * pp * pp));
+    }
+}
+
+template <class T>
+static int upload(kl_ctx* ctx, const T** dst, const T* src, size_t n) {
+    T* p = nullptr;
+    KL_CUDA(cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)));
+    ctx->owned.push_back((void*)p);
+    if (n) KL_CUDA(cudaMemcpy(p, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+    *dst = p;
+    return 0;
+}
+
+static int build_tables(kl_ctx* ctx) {
+    KLDev& d = ctx->d;
+    const int p = d.p, nq = d.nq;
+    double xg[16], wg[16];
+    gauss_rule(nq, xg, wg);
+    for (int dir = 0; dir < 2; ++dir) {
+        const std::vector<double>& U = ctx->U[dir];
+        const int n = (int)U.size() - p - 1;
+        std::vector<int>& span = ctx->span[dir];
+        span.clear();
+        for (int k = p; k < n; ++k) if (U[k + 1] > U[k]) span.push_back(k);
+        const int nel = (int)span.size();
+        ctx->flo[dir].assign(n, 1 << 30);
+        ctx->fhi[dir].assign(n, -1);
+        std::vector<double> bas((size_t)nel * nq * 3 * (p + 1)), wq((size_t)nel * nq);
+        for (int e = 0; e < nel; ++e) {
+            const int k = span[e];
+            for (int a = 0; a <= p; ++a) {
+                ctx->flo[dir][k - p + a] = std::min(ctx->flo[dir][k - p + a], e);
+                ctx->fhi[dir][k - p + a] = std::max(ctx->fhi[dir][k - p + a], e);
+            }
+            const double ua = U[k], ub = U[k + 1];
+            for (int q = 0; q < nq; ++q) {
+                const double u = 0.5 * (ua + ub) + 0.5 * (ub - ua) * xg[q];
+                double ders[3][KL_MAXP + 1];
+                bspline_span_ders(U, p, k, u, ders);
+                for (int m = 0; m < 3; ++m)
+                    for (int a = 0; a <= p; ++a) bas[(((size_t)e * nq + q) * 3 + m) * (p + 1) + a] = ders[m][a];
+                wq[(size_t)e * nq + q] = 0.5 * (ub - ua) * wg[q];
+            }
+        }
+        const int* dspan; const double *dbas, *dwq;
+        if (int rc = upload(ctx, &dspan, span.data(), span.size())) return rc;
+        if (int rc = upload(ctx, &dbas, bas.data(), bas.size())) return rc;
+        if (int rc = upload(ctx, &dwq, wq.data(), wq.size())) return rc;
+        if (dir == 0) { d.span1 = dspan; d.bas1 = dbas; d.wq1 = dwq; d.nel1 = nel; }
+        else { d.span2 = dspan; d.bas2 = dbas; d.wq2 = dwq; d.nel2 = nel; }
+    }
+    return 0;
+}
+
+static int build_fext(kl_ctx* ctx, const kl_problem* P) {
+    KLDev& d = ctx->d;
+    KL_CUDA(cudaMalloc((void**)&ctx->d_fext, sizeof(double) * std::max(d.nfree, 1)));
+    ctx->owned.push_back(ctx->d_fext);
+    KL_CUDA(cudaMemset(ctx->d_fext, 0, sizeof(double) * std::max(d.nfree, 1)));
+    const double* bf = P->body_force;
+    if (bf[0] != 0.0 || bf[1] != 0.0 || bf[2] != 0.0) {
+        // needs the displacement net only formally (zero): reuse disp buffer zeroed
+        KL_CUDA(cudaMemset(d.disp, 0, sizeof(double) * 3 * d.ncp));
+        if (int rc = kl_launch_bodyforce(ctx, ctx->d_fext, bf, 0)) return rc;
+        KL_CUDA(cudaDeviceSynchronize());
+    }
+    if (P->n_point_loads > 0) {
+        // point loads: F[i,c] += N_i(u,v) * load[c]   (gsThinShellAssembler::setPointLoads)
+        std::vector<double> f(std::max(d.nfree, 1), 0.0), fdev(std::max(d.nfree, 1));
+        const int p = d.p;
+        for (int k = 0; k < P->n_point_loads; ++k) {
+            const double uv[2] = {P->point_load_uv[2 * k], P->point_load_uv[2 * k + 1]};
+            int sp[2];
+            double val[2][KL_MAXP + 1];
+            for (int dir = 0; dir < 2; ++dir) {
+                const std::vector<double>& U = ctx->U[dir];
+                const std::vector<int>& span = ctx->span[dir];
+                int s = span.back();
+                for (size_t e = 0; e < span.size(); ++e) if (uv[dir] >= U[span[e]] && uv[dir] < U[span[e] + 1]) { s = span[e]; break; }
+                sp[dir] = s;
+                double ders[3][KL_MAXP + 1];
+                bspline_span_ders(U, p, s, uv[dir], ders);
+                for (int a = 0; a <= p; ++a) val[dir][a] = ders[0][a];
+            }
+            for (int b = 0; b <= p; ++b)
+                for (int a = 0; a <= p; ++a) {
+                    const int cpi = (sp[0] - p + a) + d.n1 * (sp[1] - p + b);
+                    for (int c = 0; c < 3; ++c) {
+                        const int g = P->dof_map[c * d.ncp + cpi];
+                        if (g < d.nfree) f[g] += val[0][a] * val[1][b] * P->point_load_val[3 * k + c];
+                    }
+                }
+        }
+        KL_CUDA(cudaMemcpy(fdev.data(), ctx->d_fext, sizeof(double) * d.nfree, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < d.nfree; ++i) fdev[i] += f[i];
+        KL_CUDA(cudaMemcpy(ctx->d_fext, fdev.data(), sizeof(double) * d.nfree, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
+    if (!P || !out) { kl_set_error("kl_create: null argument"); return KL_E_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        kl_set_error("no CUDA device: libkl_shell has no CPU fallback");
+        return KL_E_NOGPU;
+    }
+    if (device >= 0) KL_CUDA(cudaSetDevice(device));
+    if (P->degree[0] != P->degree[1] || P->degree[0] < 2 || P->degree[0] > KL_MAXP) {
+        kl_set_error("kl_create: degrees must be equal and in [2,4]");
+        return KL_E_ARG;
+    }
+    const int p = P->degree[0];
+    const int quA = (P->quA == 0 && P->quB == 0) ? 1 : P->quA, quB = (P->quA == 0 && P->quB == 0) ? 1 : P->quB;
+    if (quA * p + quB != p + 1) { kl_set_error("kl_create: only quA*p+quB == p+1 Gauss nodes are supported on the device"); return KL_E_ARG; }
+    if (P->material != KL_MAT_SVK && P->material != KL_MAT_NH && P->material != KL_MAT_MR) { kl_set_error("kl_create: unsupported material"); return KL_E_ARG; }
+    if (!P->knots[0] || !P->knots[1] || !P->cp || !P->dof_map) { kl_set_error("kl_create: null array"); return KL_E_ARG; }
+    kl_ctx* ctx = new kl_ctx();
+    KL_CUDA(cudaGetDevice(&ctx->device));
+    ctx->prob = *P;
+    KLDev& d = ctx->d;
+    d.p = p; d.nq = p + 1;
+    for (int dir = 0; dir < 2; ++dir) ctx->U[dir].assign(P->knots[dir], P->knots[dir] + P->n_knots[dir]);
+    d.n1 = P->n_knots[0] - p - 1; d.n2 = P->n_knots[1] - p - 1; d.ncp = d.n1 * d.n2;
+    d.nfree = P->n_free; ctx->nfixed = P->n_fixed;
+    d.nst = (2 * p + 1) * (2 * p + 1);
+    d.rational = P->weights != nullptr;
+    int rc;
+    if ((rc = build_tables(ctx))) { kl_destroy(ctx); return rc; }
+    if ((rc = upload(ctx, &d.cp, P->cp, (size_t)3 * d.ncp))) { kl_destroy(ctx); return rc; }
+    d.w = nullptr;
+    if (P->weights && (rc = upload(ctx, &d.w, P->weights, (size_t)d.ncp))) { kl_destroy(ctx); return rc; }
+    if ((rc = upload(ctx, &d.map, P->dof_map, (size_t)3 * d.ncp))) { kl_destroy(ctx); return rc; }
+    d.fixed = nullptr;
+    if (P->fixed_values && P->n_fixed > 0 && (rc = upload(ctx, &d.fixed, P->fixed_values, (size_t)P->n_fixed))) { kl_destroy(ctx); return rc; }
+    KL_CUDA(cudaMalloc((void**)&d.disp, sizeof(double) * 3 * d.ncp)); ctx->owned.push_back(d.disp);
+    KL_CUDA(cudaMemset(d.disp, 0, sizeof(double) * 3 * d.ncp));
+    KL_CUDA(cudaMalloc((void**)&d.flag, sizeof(int))); ctx->owned.push_back(d.flag);
+    KL_CUDA(cudaMemset(d.flag, 0, sizeof(int)));
+    KL_CUDA(cudaMalloc((void**)&ctx->d_x, sizeof(double) * std::max(d.nfree, 1))); ctx->owned.push_back(ctx->d_x);
+    KL_CUDA(cudaMalloc((void**)&ctx->d_r, sizeof(double) * std::max(d.nfree, 1))); ctx->owned.push_back(ctx->d_r);
+    KL_CUDA(cudaMallocHost((void**)&ctx->h_pinned_x, sizeof(double) * std::max(d.nfree, 1)));
+    KL_CUDA(cudaMallocHost((void**)&ctx->h_pinned_r, sizeof(double) * std::max(d.nfree, 1)));
+    // material constants
+    KLMaterial& m = d.mat;
+    m.material = P->material; m.compressible = P->compressible; m.bending = P->bending; m.metric_z2 = P->metric_z2;
+    m.ngauss = P->num_gauss_thickness > 0 ? P->num_gauss_thickness : 4;
+    if (m.ngauss > 12) { kl_set_error("kl_create: NumGauss > 12"); kl_destroy(ctx); return KL_E_ARG; }
+    m.E = P->E; m.nu = P->nu; m.t = P->thickness;
+    m.mu = P->E / (2.0 * (1.0 + P->nu));
+    {
+        const double lam = P->E * P->nu / ((1.0 + P->nu) * (1.0 - 2.0 * P->nu));
+        m.lam_ps = 2.0 * lam * m.mu / (lam + 2.0 * m.mu);
+    }
+    m.bulk = 2.0 * m.mu * (1.0 + P->nu) / (3.0 - 6.0 * P->nu);
+    m.c1 = m.mu; m.c2 = 0.0;
+    if (P->material == KL_MAT_MR) { m.c2 = m.mu / (P->mr_ratio + 1.0); m.c1 = P->mr_ratio * m.c2; }
+    gauss_rule(m.ngauss, m.zg, m.wg);
+    m.pressure = P->pressure;
+    ctx->e2_begin = 0; ctx->e2_end = d.nel2;
+    if ((rc = kl_build_pattern(ctx))) { kl_destroy(ctx); return rc; }
+    if ((rc = build_fext(ctx, P))) { kl_destroy(ctx); return rc; }
+    KL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    KL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->ev) KL_CUDA(cudaEventCreate(&e));
+    *out = ctx;
+    return KL_OK;
+}
+
+extern "C" void kl_destroy(kl_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->registered) cudaHostUnregister(ctx->registered);
+    for (void* p : ctx->owned) cudaFree(p);
+    if (ctx->h_pinned_x) cudaFreeHost(ctx->h_pinned_x);
+    if (ctx->h_pinned_r) cudaFreeHost(ctx->h_pinned_r);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    delete ctx;
+}
+
+extern "C" int kl_sizes(const kl_ctx* ctx, int32_t* n_dofs, int64_t* nnz, int64_t* n_elements, int64_t* n_qp) {
+    if (!ctx) return KL_E_ARG;
+    if (n_dofs) *n_dofs = ctx->d.nfree;
+    if (nnz) *nnz = ctx->nnz;
+    const int64_t ne = (int64_t)ctx->d.nel1 * ctx->d.nel2;
+    if (n_elements) *n_elements = ne;
+    if (n_qp) *n_qp = ne * ctx->d.nq * ctx->d.nq;
+    return KL_OK;
+}
+
+extern "C" int kl_pattern_host(const kl_ctx* ctx, int32_t* outer, int32_t* inner) {
+    if (!ctx || !outer || !inner) return KL_E_ARG;
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KL_CUDA(cudaMemcpy(outer, ctx->d.outer, sizeof(int) * ((size_t)ctx->d.nfree + 1), cudaMemcpyDeviceToHost));
+    KL_CUDA(cudaMemcpy(inner, ctx->d.inner, sizeof(int) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost));
+    return KL_OK;
+}
+extern "C" int kl_pattern_device(const kl_ctx* ctx, const int32_t** outer_dev, const int32_t** inner_dev) {
+    if (!ctx) return KL_E_ARG;
+    if (outer_dev) *outer_dev = ctx->d.outer;
+    if (inner_dev) *inner_dev = ctx->d.inner;
+    return KL_OK;
+}
+extern "C" double* kl_values_device(kl_ctx* ctx) { return ctx ? ctx->d.values : nullptr; }
+extern "C" int kl_kernel_launches(const kl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int kl_set_strip(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end) {
+    if (!ctx || e2_begin < 0 || e2_end > ctx->d.nel2 || e2_begin > e2_end) { kl_set_error("kl_set_strip: bad range"); return KL_E_ARG; }
+    ctx->e2_begin = e2_begin; ctx->e2_end = e2_end;
+    return KL_OK;
+}
+
+extern "C" int kl_check(kl_ctx* ctx, void* stream) {
+    if (!ctx) return KL_E_ARG;
+    int flag = 0;
+    KL_CUDA(cudaMemcpyAsync(&flag, ctx->d.flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    KL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flag) {
+        KL_CUDA(cudaMemsetAsync(ctx->d.flag, 0, sizeof(int), (cudaStream_t)stream));
+        if (flag & KLF_JACOBIAN) { kl_set_error("inverted element: |a1 x a2| <= 0 or det(metric) <= 0"); return KL_E_JACOBIAN; }
+        if (flag & KLF_C33) { kl_set_error("plane-stress iteration on C33 did not converge"); return KL_E_C33; }
+        kl_set_error("non-finite value at a quadrature point");
+        return KL_E_NONFINITE;
+    }
+    return KL_OK;
+}
+
+// ---- device-resident entry points -----------------------------------------------------------------
+extern "C" int kl_jacobian_device(kl_ctx* ctx, const double* x_dev, void* stream) {
+    if (!ctx) return KL_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
+    KL_CUDA(cudaMemsetAsync(ctx->d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
+    return kl_launch_jacobian(ctx, ctx->e2_begin, ctx->e2_end, s);
+}
+
+extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, void* stream) {
+    if (!ctx || !r_dev) return KL_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
+    KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, s));
+    if ((rc = kl_launch_residual(ctx, r_dev, s))) return rc;
+    return kl_launch_axpby(ctx, r_dev, ctx->d_fext, sign_fint, lam_fext, ctx->d.nfree, s);
+}
+
+// ---- host-pointer entry points (what the Jacobian_t / Residual_t closures call) -------------------
+static int ensure_registered(kl_ctx* ctx, void* p, size_t bytes) {
+    if (ctx->registered == p && ctx->registered_bytes >= bytes) return 1;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return 1;   // already pinned
+    cudaGetLastError();
+    if (ctx->registered) { cudaHostUnregister(ctx->registered); ctx->registered = nullptr; }
+    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+        ctx->registered = p; ctx->registered_bytes = bytes;
+        return 1;
+    }
+    cudaGetLastError();
+    return 0;
+}
+
+static int run_residual(kl_ctx* ctx, const double* x_host, double lam_fext, double sign_fint, double* r_host) {
+    if (!ctx || !r_host) { kl_set_error("null argument"); return KL_E_ARG; }
+    KL_CUDA(cudaSetDevice(ctx->device));
+    const int n = ctx->d.nfree;
+    cudaStream_t s = ctx->stream;
+    KL_CUDA(cudaEventRecord(ctx->ev[0], s));
+    const double* xd = nullptr;
+    if (x_host) {
+        std::memcpy(ctx->h_pinned_x, x_host, sizeof(double) * n);
+        KL_CUDA(cudaMemcpyAsync(ctx->d_x, ctx->h_pinned_x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        xd = ctx->d_x;
+    }
+    KL_CUDA(cudaEventRecord(ctx->ev[1], s));
+    int rc = kl_residual_device(ctx, xd, lam_fext, sign_fint, ctx->d_r, s);
+    if (rc) return rc;
+    KL_CUDA(cudaEventRecord(ctx->ev[2], s));
+    KL_CUDA(cudaMemcpyAsync(ctx->h_pinned_r, ctx->d_r, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    KL_CUDA(cudaEventRecord(ctx->ev[3], s));
+    rc = kl_check(ctx, s);
+    std::memcpy(r_host, ctx->h_pinned_r, sizeof(double) * n);
+    cudaEventElapsedTime(&ctx->ms_h2d, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->ms_kernel, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->ms_d2h, ctx->ev[2], ctx->ev[3]);
+    return rc;
+}
+
+extern "C" int kl_residual(kl_ctx* ctx, const double* x_host, double* r_host) { return run_residual(ctx, x_host, 1.0, -1.0, r_host); }
+extern "C" int kl_al_residual(kl_ctx* ctx, const double* x_host, double lam, double* r_host) { return run_residual(ctx, x_host, -lam, 1.0, r_host); }
+
+extern "C" int kl_force(kl_ctx* ctx, double* f_host) {
+    if (!ctx || !f_host) return KL_E_ARG;
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KL_CUDA(cudaMemcpy(f_host, ctx->d_fext, sizeof(double) * ctx->d.nfree, cudaMemcpyDeviceToHost));
+    return KL_OK;
+}
+
+extern "C" int kl_jacobian(kl_ctx* ctx, const double* x_host, double* values_host) {
+    if (!ctx) { kl_set_error("null context"); return KL_E_ARG; }
+    KL_CUDA(cudaSetDevice(ctx->device));
+    const int n = ctx->d.nfree;
+    cudaStream_t s = ctx->stream;
+    KL_CUDA(cudaEventRecord(ctx->ev[0], s));
+    const double* xd = nullptr;
+    if (x_host) {
+        std::memcpy(ctx->h_pinned_x, x_host, sizeof(double) * n);
+        KL_CUDA(cudaMemcpyAsync(ctx->d_x, ctx->h_pinned_x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        xd = ctx->d_x;
+    }
+    KL_CUDA(cudaEventRecord(ctx->ev[1], s));
+    int rc = kl_jacobian_device(ctx, xd, s);
+    if (rc) return rc;
+    KL_CUDA(cudaEventRecord(ctx->ev[2], s));
+    if (values_host) {
+        const size_t bytes = sizeof(double) * (size_t)ctx->nnz;
+        ensure_registered(ctx, values_host, bytes);   // pageable memory still works, only slower
+        KL_CUDA(cudaMemcpyAsync(values_host, ctx->d.values, bytes, cudaMemcpyDeviceToHost, s));
+    }
+    KL_CUDA(cudaEventRecord(ctx->ev[3], s));
+    rc = kl_check(ctx, s);
+    cudaEventElapsedTime(&ctx->ms_h2d, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->ms_kernel, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->ms_d2h, ctx->ev[2], ctx->ev[3]);
+    return rc;
+}
+
+extern "C" int kl_last_timing(const kl_ctx* ctx, float* ms_kernel, float* ms_h2d, float* ms_d2h) {
+    if (!ctx) return KL_E_ARG;
+    if (ms_kernel) *ms_kernel = ctx->ms_kernel;
+    if (ms_h2d) *ms_h2d = ctx->ms_h2d;
+    if (ms_d2h) *ms_d2h = ctx->ms_d2h;
+    return KL_OK;
+}

@@ -1,0 +1,96 @@
+// kl_internal.h — context and device-side views shared by the translation units of libkl_shell.so
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/kl_shell.h"
+
+#define KL_MAXP 4
+
+// device error flag bits (mapped to KL_E_* by kl_check)
+#define KLF_NONFINITE 1
+#define KLF_JACOBIAN 2
+#define KLF_C33 4
+
+struct KLMaterial {
+    int material, compressible, ngauss, bending, metric_z2;
+    double E, nu, t, mu, lam_ps, bulk, c1, c2;
+    double zg[12], wg[12];   // thickness Gauss rule on [-1,1]
+    double pressure;
+};
+
+// Everything a kernel needs (passed by value as a __grid_constant__-friendly POD)
+struct KLDev {
+    int p;                 // degree (both directions)
+    int nq;                // Gauss nodes per direction
+    int n1, n2, ncp;       // control points
+    int nel1, nel2;        // non-empty elements per direction
+    int nfree;
+    int rational;
+    const int* span1;      // [nel1] knot span index per element
+    const int* span2;
+    const double* bas1;    // [nel1][nq][3][p+1] values / 1st / 2nd derivative of the p+1 active functions
+    const double* bas2;
+    const double* wq1;     // [nel1][nq] quadrature weight * half element length
+    const double* wq2;
+    const double* cp;      // [ncp*3] undeformed control net
+    const double* w;       // [ncp] weights or nullptr
+    const int* map;        // [3*ncp]
+    const double* fixed;   // [nfixed]
+    double* disp;          // [ncp*3] displacement control net (constructSolution)
+    // sparse matrix
+    const int* outer;      // [nfree+1]
+    const int* inner;      // [nnz]
+    double* values;        // [nnz]
+    const int* pos;        // [ncp*3][nst*3] scatter table (-1: eliminated / not coupled)
+    int nst;               // (2p+1)^2
+    int* flag;             // device error flag
+    KLMaterial mat;
+};
+
+struct kl_ctx {
+    int device = 0;
+    KLDev d{};
+    kl_problem prob{};               // scalar copy
+    std::vector<double> U[2];
+    std::vector<int> span[2];
+    std::vector<int> flo[2], fhi[2]; // element range of each 1-D function
+    int nfixed = 0;
+    int64_t nnz = 0;
+    int e2_begin = 0, e2_end = 0;    // strip of element rows assembled by this context
+    // owned device buffers
+    std::vector<void*> owned;
+    double* d_x = nullptr;           // [nfree]
+    double* d_r = nullptr;           // [nfree]
+    double* d_fext = nullptr;        // [nfree]
+    double* h_pinned_x = nullptr;    // pinned staging for x / r
+    double* h_pinned_r = nullptr;
+    void* registered = nullptr;      // user value buffer currently cudaHostRegister'ed
+    size_t registered_bytes = 0;
+    cudaStream_t stream = nullptr;   // own stream for the host-pointer entry points
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[6]{};
+    float ms_kernel = 0, ms_h2d = 0, ms_d2h = 0;
+    int launches = 0;
+    int n_strips_d2h = 8;            // pipelined D2H granularity
+};
+
+void kl_set_error(const std::string& s);
+#define KL_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            kl_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+            return KL_E_CUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+// kl_pattern.cu
+int kl_build_pattern(kl_ctx* ctx);
+// kl_assemble.cu
+int kl_launch_construct(kl_ctx* ctx, const double* x_dev, cudaStream_t s);
+int kl_launch_jacobian(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s);
+int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s);   // r += F_int - F_pressure (atomic)
+int kl_launch_bodyforce(kl_ctx* ctx, double* f_dev, const double bf[3], cudaStream_t s);
+int kl_launch_axpby(kl_ctx* ctx, double* r, const double* fext, double a_r, double b_f, int n, cudaStream_t s);

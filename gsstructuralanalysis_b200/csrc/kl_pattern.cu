@@ -1,0 +1,168 @@
+// kl_pattern.cu — one-time symbolic build ON THE GPU of
+//   (1) the compressed pattern (outer/inner) of the structurally symmetric stiffness matrix,
+//       bit-exact with what gsExprAssembler::initSystem + coeffRef + makeCompressed leave behind
+//       when no local entry is an exact zero, including eliminated and
+//       matched (clamped / collapsed) DoFs of gsDofMapper (Appendix A.6);
+//   (2) the scatter table  pos[(J,d)][stencil(I-J)][c] -> index into the value array.
+// Replaces: gsExprAssembler::initSystem / gsSparseMatrix::reservePerColumn + makeCompressed
+// (reference consumers: gsSparseMatrix in src/gsStructuralAnalysisTools/gsStructuralAnalysisTypes.h:88).
+#include <cub/cub.cuh>
+#include "kl_internal.h"
+
+struct PatArgs {
+    int p, n1, n2, ncp, nfree, nst;
+    const int* map;
+    const int *lo1, *hi1, *lo2, *hi2;   // element range of every 1-D basis function
+};
+
+__device__ __forceinline__ bool coupled(const PatArgs& a, int I1, int I2, int J1, int J2) {
+    if (J1 < 0 || J1 >= a.n1 || J2 < 0 || J2 >= a.n2) return false;
+    return !(a.hi1[J1] < a.lo1[I1] || a.lo1[J1] > a.hi1[I1] || a.hi2[J2] < a.lo2[I2] || a.lo2[J2] > a.hi2[I2]);
+}
+
+// one key per (column control point J, stencil slot, d, c); invalid slots get the sentinel
+__global__ void k_gen_keys(PatArgs a, unsigned long long* __restrict__ keys, long long total) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const int c = (int)(k % 3);
+    const int d = (int)((k / 3) % 3);
+    const int st = (int)((k / 9) % a.nst);
+    const int J = (int)(k / (9LL * a.nst));
+    const int W = 2 * a.p + 1;
+    const int J1 = J % a.n1, J2 = J / a.n1;
+    const int I1 = J1 + (st % W) - a.p, I2 = J2 + (st / W) - a.p;
+    unsigned long long key = ~0ULL;
+    if (coupled(a, J1, J2, I1, I2)) {
+        const int col = a.map[d * a.ncp + J];
+        const int row = a.map[c * a.ncp + (I1 + a.n1 * I2)];
+        if (col < a.nfree && row < a.nfree) key = ((unsigned long long)col << 32) | (unsigned int)row;
+    }
+    keys[k] = key;
+}
+
+__global__ void k_outer_inner(const unsigned long long* __restrict__ ukeys, long long nnz, int nfree, int* __restrict__ outer,
+                              int* __restrict__ inner) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nnz) inner[k] = (int)(ukeys[k] & 0xffffffffULL);
+    if (k <= nfree) {
+        // lower_bound of (k << 32)
+        const unsigned long long target = (unsigned long long)k << 32;
+        long long lo = 0, hi = nnz;
+        while (lo < hi) {
+            const long long mid = (lo + hi) >> 1;
+            if (ukeys[mid] < target) lo = mid + 1; else hi = mid;
+        }
+        outer[k] = (int)lo;
+    }
+}
+
+__global__ void k_pos_table(PatArgs a, const int* __restrict__ outer, const int* __restrict__ inner, int* __restrict__ pos, long long total) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    // layout: pos[(J*3 + d) * (nst*3) + st*3 + c]
+    const int c = (int)(k % 3);
+    const int st = (int)((k / 3) % a.nst);
+    const int d = (int)((k / (3LL * a.nst)) % 3);
+    const int J = (int)(k / (9LL * a.nst));
+    const int W = 2 * a.p + 1;
+    const int J1 = J % a.n1, J2 = J / a.n1;
+    const int I1 = J1 + (st % W) - a.p, I2 = J2 + (st / W) - a.p;
+    int res = -1;
+    if (coupled(a, J1, J2, I1, I2)) {
+        const int col = a.map[d * a.ncp + J];
+        const int row = a.map[c * a.ncp + (I1 + a.n1 * I2)];
+        if (col < a.nfree && row < a.nfree) {
+            int lo = outer[col], hi = outer[col + 1] - 1;
+            while (lo <= hi) {
+                const int mid = (lo + hi) >> 1;
+                const int v = inner[mid];
+                if (v == row) { res = mid; break; }
+                if (v < row) lo = mid + 1; else hi = mid - 1;
+            }
+        }
+    }
+    pos[k] = res;
+}
+
+template <class T>
+static int dev_alloc(kl_ctx* ctx, T** p, size_t n) {
+    KL_CUDA(cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)));
+    ctx->owned.push_back((void*)*p);
+    return 0;
+}
+
+int kl_build_pattern(kl_ctx* ctx) {
+    KLDev& d = ctx->d;
+    PatArgs a{};
+    a.p = d.p; a.n1 = d.n1; a.n2 = d.n2; a.ncp = d.ncp; a.nfree = d.nfree; a.nst = d.nst;
+    a.map = d.map;
+    int *lo1, *hi1, *lo2, *hi2;
+    if (int rc = dev_alloc(ctx, &lo1, d.n1)) return rc;
+    if (int rc = dev_alloc(ctx, &hi1, d.n1)) return rc;
+    if (int rc = dev_alloc(ctx, &lo2, d.n2)) return rc;
+    if (int rc = dev_alloc(ctx, &hi2, d.n2)) return rc;
+    KL_CUDA(cudaMemcpy(lo1, ctx->flo[0].data(), sizeof(int) * d.n1, cudaMemcpyHostToDevice));
+    KL_CUDA(cudaMemcpy(hi1, ctx->fhi[0].data(), sizeof(int) * d.n1, cudaMemcpyHostToDevice));
+    KL_CUDA(cudaMemcpy(lo2, ctx->flo[1].data(), sizeof(int) * d.n2, cudaMemcpyHostToDevice));
+    KL_CUDA(cudaMemcpy(hi2, ctx->fhi[1].data(), sizeof(int) * d.n2, cudaMemcpyHostToDevice));
+    a.lo1 = lo1; a.hi1 = hi1; a.lo2 = lo2; a.hi2 = hi2;
+
+    const long long total = 9LL * d.nst * d.ncp;
+    unsigned long long *keys = nullptr, *keys_alt = nullptr, *ukeys = nullptr;
+    long long* d_num = nullptr;
+    KL_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * total));
+    KL_CUDA(cudaMalloc(&keys_alt, sizeof(unsigned long long) * total));
+    KL_CUDA(cudaMalloc(&d_num, sizeof(long long)));
+    const int T = 256;
+    k_gen_keys<<<(unsigned)((total + T - 1) / T), T>>>(a, keys, total);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    // radix sort (all 64 bits: the sentinel must end up last)
+    cub::DoubleBuffer<unsigned long long> db(keys, keys_alt);
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    KL_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, (int)total));
+    KL_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    KL_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, (int)total));
+    KL_CUDA(cudaFree(tmp));
+    unsigned long long* sorted = db.Current();
+    ukeys = (sorted == keys) ? keys_alt : keys;
+    tmp = nullptr; tmp_bytes = 0;
+    KL_CUDA(cub::DeviceSelect::Unique(tmp, tmp_bytes, sorted, ukeys, d_num, (int)total));
+    KL_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    KL_CUDA(cub::DeviceSelect::Unique(tmp, tmp_bytes, sorted, ukeys, d_num, (int)total));
+    KL_CUDA(cudaFree(tmp));
+    long long nuniq = 0;
+    KL_CUDA(cudaMemcpy(&nuniq, d_num, sizeof(long long), cudaMemcpyDeviceToHost));
+    // drop the sentinel if present (it is the largest key)
+    if (nuniq > 0) {
+        unsigned long long last = 0;
+        KL_CUDA(cudaMemcpy(&last, ukeys + (nuniq - 1), sizeof(last), cudaMemcpyDeviceToHost));
+        if (last == ~0ULL) --nuniq;
+    }
+    ctx->nnz = nuniq;
+    if (nuniq >= (1LL << 31)) { kl_set_error("nnz exceeds int32 (index_t)"); return KL_E_ARG; }
+    int *outer, *inner, *pos;
+    if (int rc = dev_alloc(ctx, &outer, (size_t)d.nfree + 1)) return rc;
+    if (int rc = dev_alloc(ctx, &inner, (size_t)nuniq)) return rc;
+    {
+        const long long n = std::max<long long>(nuniq, (long long)d.nfree + 1);
+        k_outer_inner<<<(unsigned)((n + T - 1) / T), T>>>(ukeys, nuniq, d.nfree, outer, inner);
+        ctx->launches++;
+        KL_CUDA(cudaGetLastError());
+    }
+    KL_CUDA(cudaDeviceSynchronize());
+    KL_CUDA(cudaFree(keys));
+    KL_CUDA(cudaFree(keys_alt));
+    KL_CUDA(cudaFree(d_num));
+    if (int rc = dev_alloc(ctx, &pos, (size_t)total)) return rc;
+    k_pos_table<<<(unsigned)((total + T - 1) / T), T>>>(a, outer, inner, pos, total);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    double* values;
+    if (int rc = dev_alloc(ctx, &values, (size_t)nuniq)) return rc;
+    KL_CUDA(cudaMemset(values, 0, sizeof(double) * (nuniq ? nuniq : 1)));
+    KL_CUDA(cudaDeviceSynchronize());
+    d.outer = outer; d.inner = inner; d.pos = pos; d.values = values;
+    return 0;
+}

@@ -1,0 +1,146 @@
+"""Host-side mirror of the reference's operator interface for the hot path.
+
+`ShellAssembler` plays the role of gsThinShellAssembler<3,real_t,true> behind the closures of
+tutorials/nonlinear_shell_static.cpp:120-136, and `operators()` returns callables with the shapes of
+gsStructuralAnalysisOps<T>::{Jacobian_t, Residual_t, ALResidual_t}
+(src/gsStructuralAnalysisTools/gsStructuralAnalysisTypes.h:70-88): they return (ok, result) where the
+reference returns bool and fills an out-parameter.  All arithmetic happens in libkl_shell.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import capi
+from .problem import ShellProblem, c_double_p, c_int_p
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+class SparseView:
+    """Compressed column storage (outer/inner/values), layout-compatible with
+    Eigen::SparseMatrix<double, ColMajor, int> = gsSparseMatrix<real_t>."""
+
+    def __init__(self, n, outer, inner, values):
+        self.n, self.outer, self.inner, self.values = n, outer, inner, values
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.values, self.inner, self.outer), shape=(self.n, self.n))
+
+
+class ShellAssembler:
+    def __init__(self, prob: ShellProblem, device: int = -1):
+        self.L = capi.lib()
+        if prob.dof_map is None:
+            prob.number_dofs(self.L.kl_build_dofmap)
+        self.prob = prob
+        P, self._keep = prob.to_c()
+        h = C.c_void_p()
+        capi.check(self.L.kl_create(C.byref(P), device, C.byref(h)))
+        self.h = h
+        nd, nnz, ne, nq = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64()
+        capi.check(self.L.kl_sizes(self.h, C.byref(nd), C.byref(nnz), C.byref(ne), C.byref(nq)))
+        self.n_dofs, self.nnz, self.n_elements, self.n_qp = nd.value, nnz.value, ne.value, nq.value
+        self._pattern = None
+        self._values = None
+
+    # -- numDofs(), pattern -------------------------------------------------------------------
+    def numDofs(self):
+        return self.n_dofs
+
+    def pattern(self):
+        if self._pattern is None:
+            outer = np.zeros(self.n_dofs + 1, dtype=np.int32)
+            inner = np.zeros(max(self.nnz, 1), dtype=np.int32)
+            capi.check(self.L.kl_pattern_host(self.h, outer.ctypes.data_as(c_int_p), inner.ctypes.data_as(c_int_p)))
+            self._pattern = (outer, inner[:self.nnz])
+        return self._pattern
+
+    def values_buffer(self):
+        """Host value array that the matrix view aliases (pinned on first use by the library)."""
+        if self._values is None:
+            self._values = np.zeros(max(self.nnz, 1))
+        return self._values
+
+    # -- the closure bodies -------------------------------------------------------------------
+    def jacobian(self, x, fetch=True):
+        """constructSolution(x,def); assembleMatrix(def); m = matrix()."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == (self.n_dofs,)
+        v = self.values_buffer() if fetch else None
+        rc = self.L.kl_jacobian(self.h, _dp(x), _dp(v) if fetch else None)
+        if rc != 0:
+            self.last_error = self.L.kl_last_error().decode()
+            return False, None
+        if not fetch:
+            return True, None
+        outer, inner = self.pattern()
+        return True, SparseView(self.n_dofs, outer, inner, v[:self.nnz])
+
+    def residual(self, x):
+        """constructSolution; assembleVector(def); v = rhs()   (= F_ext - F_int)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r = np.zeros(self.n_dofs)
+        rc = self.L.kl_residual(self.h, _dp(x), _dp(r))
+        if rc != 0:
+            self.last_error = self.L.kl_last_error().decode()
+            return False, None
+        return True, r
+
+    def al_residual(self, x, lam):
+        """Force - lam*Force - rhs()  (benchmarks/benchmark_Roof.cpp:335-344)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r = np.zeros(self.n_dofs)
+        rc = self.L.kl_al_residual(self.h, _dp(x), float(lam), _dp(r))
+        if rc != 0:
+            self.last_error = self.L.kl_last_error().decode()
+            return False, None
+        return True, r
+
+    def force(self):
+        f = np.zeros(self.n_dofs)
+        capi.check(self.L.kl_force(self.h, _dp(f)))
+        return f
+
+    def operators(self):
+        """(Jacobian_t, Residual_t, ALResidual_t) — cheap-to-copy handles like the reference's lambdas."""
+        return (lambda x: self.jacobian(x)), (lambda x: self.residual(x)), (lambda x, lam: self.al_residual(x, lam))
+
+    # -- device-resident leg ------------------------------------------------------------------
+    def jacobian_device(self, x_dev_ptr, stream=0):
+        capi.check(self.L.kl_jacobian_device(self.h, C.c_void_p(x_dev_ptr), C.c_void_p(stream)))
+
+    def residual_device(self, x_dev_ptr, r_dev_ptr, lam_fext=1.0, sign_fint=-1.0, stream=0):
+        capi.check(self.L.kl_residual_device(self.h, C.c_void_p(x_dev_ptr), lam_fext, sign_fint, C.c_void_p(r_dev_ptr),
+                                             C.c_void_p(stream)))
+
+    def check(self, stream=0):
+        return self.L.kl_check(self.h, C.c_void_p(stream))
+
+    def values_device_ptr(self):
+        return self.L.kl_values_device(self.h)
+
+    def set_strip(self, e2_begin, e2_end):
+        capi.check(self.L.kl_set_strip(self.h, e2_begin, e2_end))
+
+    def last_timing(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self.L.kl_last_timing(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return {"kernel_ms": a.value, "h2d_ms": b.value, "d2h_ms": c.value}
+
+    def kernel_launches(self):
+        return self.L.kl_kernel_launches(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,95 @@
+"""Named workloads = BASELINE.json configs / SURVEY §8(d) synthetic inputs S1..S5, as ShellProblem builders.
+Only problem *definitions* live here (geometry, BCs, material, loads); no arithmetic of the hot path."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import geometry as G
+from .problem import (ShellProblem, BoundaryConditions, KL_MAT_SVK, KL_MAT_NH, KL_MAT_MR, KL_BC_DIRICHLET,
+                      KL_BC_CLAMPED, KL_BC_COLLAPSED, WEST, EAST, SOUTH, NORTH, SW, SE, NW, NE)
+
+
+def _uniform(surface, degree, nel):
+    s = surface.degree_elevate(degree - surface.p[0]) if surface.p[0] == surface.p[1] else surface
+    if s.p != (degree, degree):
+        s = surface.respace((degree, degree), (G.elevate_knots(surface.p[0], surface.U[0], degree - surface.p[0]),
+                                              G.elevate_knots(surface.p[1], surface.U[1], degree - surface.p[1])))
+    return s.refine_to(nel)
+
+
+def tutorial_paraboloid(nel=4, degree=3, material=KL_MAT_NH, compressible=False):
+    """configs[0]: tutorials/nonlinear_shell_static.cpp — corner-pinned paraboloid, E=1e9, nu=0.45, t=1e-2,
+    point load (0,0,-1e4) at (0.5,0.5), Material=1 (NH), Implementation=1 (:71-80,92-105)."""
+    s = _uniform(G.paraboloid(), degree, nel)
+    bc = BoundaryConditions()
+    for c in (SW, SE, NW, NE):
+        bc.add_corner_value(c)
+    return ShellProblem(s, bc, material=material, compressible=compressible, E=1e9, nu=0.45, thickness=1e-2,
+                        point_loads=[((0.5, 0.5), (0.0, 0.0, -1e4))])
+
+
+def roof(nel=8, degree=3, thickness=6.35):
+    """configs[1]: benchmarks/benchmark_Roof.cpp — shallow Scordelis-Lo roof, E=3102.75, nu=0.3, SvK,
+    north/south edges fixed in all components, point load at (0.5,0.5) (:128-144,201-232)."""
+    s = _uniform(G.scordelis_lo_roof_shallow(), degree, nel)
+    bc = BoundaryConditions()
+    bc.add_condition(NORTH, KL_BC_DIRICHLET).add_condition(SOUTH, KL_BC_DIRICHLET)
+    return ShellProblem(s, bc, material=KL_MAT_SVK, E=3102.75, nu=0.3, thickness=thickness,
+                        point_loads=[((0.5, 0.5), (0.0, 0.0, -1e1))])
+
+
+def balloon(nel=8, degree=3, material=KL_MAT_NH, pressure=1e3):
+    """configs[2]: benchmarks/benchmark_Balloon.cpp — NURBS eighth sphere, incompressible NH, mu=4.225e5,
+    t=0.1, follower pressure, symmetry BCs (:50-51,93-110,149,258)."""
+    s = _uniform(G.eighth_sphere(10.0), degree, nel)
+    mu = 4.225e5
+    bc = BoundaryConditions()
+    # symmetry planes: x=0 on the east edge (u=1), y=0 on the west edge (u=0), z=0 on the south edge (v=0)
+    bc.add_condition(WEST, KL_BC_DIRICHLET, 1).add_condition(WEST, KL_BC_CLAMPED, 0).add_condition(WEST, KL_BC_CLAMPED, 2)
+    bc.add_condition(EAST, KL_BC_DIRICHLET, 0).add_condition(EAST, KL_BC_CLAMPED, 1).add_condition(EAST, KL_BC_CLAMPED, 2)
+    bc.add_condition(SOUTH, KL_BC_DIRICHLET, 2).add_condition(SOUTH, KL_BC_CLAMPED, 0).add_condition(SOUTH, KL_BC_CLAMPED, 1)
+    bc.add_condition(NORTH, KL_BC_COLLAPSED, 2).add_condition(NORTH, KL_BC_DIRICHLET, 0).add_condition(NORTH, KL_BC_DIRICHLET, 1)
+    return ShellProblem(s, bc, material=material, compressible=False, E=2 * mu * 1.5, nu=0.5, thickness=0.1, pressure=pressure)
+
+
+def tension_sheet(nel=8, degree=3):
+    """configs[3]: benchmarks/benchmark_TensionWrinkling.cpp — Rectangle(0.14,0.07) with clamping knots, MR
+    C10=6.21485502e4, C01=15.8114570e4, t=0.14e-3 (:160-205,229-234)."""
+    s = G.rectangle_with_clamping(0.14, 0.07, degree, nel, nel, 1e-2)
+    C10, C01 = 6.21485502e4, 15.8114570e4
+    mu = 2 * (C10 + C01)
+    nu = 0.5
+    bc = BoundaryConditions()
+    bc.add_condition(WEST, KL_BC_DIRICHLET)
+    bc.add_condition(EAST, KL_BC_COLLAPSED, 0).add_condition(EAST, KL_BC_DIRICHLET, 1).add_condition(EAST, KL_BC_DIRICHLET, 2)
+    bc.add_condition(WEST, KL_BC_CLAMPED, 2).add_condition(EAST, KL_BC_CLAMPED, 2)
+    bc.add_condition(WEST, KL_BC_DIRICHLET)
+    return ShellProblem(s, bc, material=KL_MAT_MR, compressible=False, E=2 * mu * (1 + nu), nu=nu, thickness=0.14e-3,
+                        mr_ratio=C10 / C01, point_loads=[((1.0, 0.5), (1.0, 0.0, 0.0))])
+
+
+def frustrum(nel=8, degree=3):
+    """configs[4]: benchmarks/benchmark_Frustrum_APALM.cpp — quarter frustrum R1=2,R2=1,h=1, MR mu=4.225,
+    ratio 7, t=0.1, bottom fixed, top collapsed in z, symmetry on the sides (:207-259,751-810)."""
+    s = _uniform(G.frustrum(), degree, nel)
+    mu = 4.225
+    bc = BoundaryConditions()
+    bc.add_condition(SOUTH, KL_BC_DIRICHLET)
+    bc.add_condition(NORTH, KL_BC_COLLAPSED, 2)
+    bc.add_condition(WEST, KL_BC_DIRICHLET, 1).add_condition(WEST, KL_BC_CLAMPED, 0).add_condition(WEST, KL_BC_CLAMPED, 2)
+    bc.add_condition(EAST, KL_BC_DIRICHLET, 0).add_condition(EAST, KL_BC_CLAMPED, 1).add_condition(EAST, KL_BC_CLAMPED, 2)
+    return ShellProblem(s, bc, material=KL_MAT_MR, compressible=False, E=2 * mu * 1.5, nu=0.5, thickness=0.1, mr_ratio=7.0,
+                        point_loads=[((0.0, 1.0), (0.0, 0.0, -1.0))])
+
+
+def plate_1m(nel=576, degree=3, material=KL_MAT_SVK, compressible=False):
+    """SURVEY §8 canonical 1M-DOF case: single patch, degree 3, 576x576 elements, corner-pinned shallow
+    paraboloid with the tutorial's material constants."""
+    return tutorial_paraboloid(nel, degree, material, compressible)
+
+
+def displacement_state(n_dofs, scale, seed=20240607):
+    """x = scale * U(-1,1) per DoF, seed 20240607.  numpy's PCG64 stands in for mt19937_64:
+    the same generator feeds the oracle and the GPU path, so parity does not depend on it."""
+    rng = np.random.default_rng(seed)
+    return scale * rng.uniform(-1.0, 1.0, n_dofs)
