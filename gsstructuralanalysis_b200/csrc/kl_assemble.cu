@@ -386,7 +386,9 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
         attr_set = true;
     }
     const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
+    KL_CUDA(cudaEventRecord(ctx->ev[4], s));
     k_jacobian<P><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
+    KL_CUDA(cudaEventRecord(ctx->ev[5], s));
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
     if (ctx->d.mat.pressure != 0.0) {
@@ -438,4 +440,55 @@ int kl_launch_bodyforce(kl_ctx* ctx, double* f_dev, const double bf[3], cudaStre
     }
     kl_set_error("unsupported degree");
     return KL_E_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 peak microbenchmark: 8 independent DFMA chains per thread, register resident
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+extern "C" int kl_measure_fp64_peak(int device, double* tflops, float* ms_out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { kl_set_error("no CUDA device"); return KL_E_NOGPU; }
+    if (device >= 0) KL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    int dev;
+    KL_CUDA(cudaGetDevice(&dev));
+    KL_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double* out;
+    KL_CUDA(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    KL_CUDA(cudaEventCreate(&e0)); KL_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        KL_CUDA(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+        KL_CUDA(cudaEventRecord(e1));
+        KL_CUDA(cudaEventSynchronize(e1));
+        float ms;
+        KL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return KL_OK;
+}
+
+extern "C" int kl_jacobian_kernel_ms(kl_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return KL_E_ARG;
+    KL_CUDA(cudaEventSynchronize(ctx->ev[5]));
+    KL_CUDA(cudaEventElapsedTime(ms, ctx->ev[4], ctx->ev[5]));
+    return KL_OK;
 }
