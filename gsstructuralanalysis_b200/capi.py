@@ -19,7 +19,7 @@ KL_ERRORS = {0: "KL_OK", -1: "KL_E_ARG", -2: "KL_E_CUDA", -3: "KL_E_NONFINITE", 
 SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern_host", "kl_pattern_device",
            "kl_jacobian", "kl_residual", "kl_al_residual", "kl_force", "kl_jacobian_device", "kl_residual_device",
            "kl_check", "kl_values_device", "kl_set_strip", "kl_last_timing", "kl_last_error", "kl_kernel_launches",
-           "kl_jacobian_kernel_ms", "kl_measure_fp64_peak"]
+           "kl_jacobian_kernel_ms", "kl_points_kernel_ms", "kl_measure_fp64_peak"]
 
 _LIB = None
 
@@ -60,6 +60,7 @@ def lib():
     L.kl_last_error.restype = C.c_char_p
     L.kl_kernel_launches.argtypes = [vp]
     L.kl_jacobian_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.kl_points_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.kl_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     _LIB = L
     return L

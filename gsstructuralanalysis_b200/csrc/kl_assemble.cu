@@ -1,17 +1,19 @@
 // kl_assemble.cu — hand-written sm_100a FP64 kernels of the hot path:
-//   construct_solution   (gsThinShellAssembler::constructSolution, tutorials/nonlinear_shell_static.cpp:123)
-//   residual             (assembleVector,  tutorials/nonlinear_shell_static.cpp:133)
-//   jacobian             (assembleMatrix,  tutorials/nonlinear_shell_static.cpp:124)
+//   k_construct_solution (gsThinShellAssembler::constructSolution, tutorials/nonlinear_shell_static.cpp:123)
+//   k_points             geometry + metric + material at every quadrature point  -> PointData (HBM)
+//   k_residual           (assembleVector,  tutorials/nonlinear_shell_static.cpp:133)
+//   k_jacobian           (assembleMatrix,  tutorials/nonlinear_shell_static.cpp:124)
 // Formulation: SURVEY Appendix A.3/A.4; in-reference restatement benchmarks/benchmark_cylinder_DC.cpp:536-555.
 //
 // Jacobian kernel structure (one CTA works on a group of EPG consecutive elements):
-//   phase 1  one thread per quadrature point: geometry, metric, material -> PointData in smem
-//   phase 2  one thread per (basis function j, point): Z_j = T(point) . d_j   (5 x 3x3 coefficients)
+//   phase 2  one thread per (basis function j, point): Z_j = T(point) . d_j   (9 x 5 coefficients) -> smem
 //   phase 3  one thread per tile (row of P+1 functions i, function j), upper triangle only:
 //            K_ij^{cd} += sum_p d_i[p] Z_j^{p,cd}, sum-factorised over the tensor-product basis
 //   scatter  FP64 RED (atomicAdd, no return) into the compressed values through the position table,
 //            both (i,j) and the transposed (j,i) entry.
 #include "kl_device.cuh"
+
+size_t kl_pointdata_bytes(void) { return sizeof(PointData); }
 
 // ------------------------------------------------------------------------------------------------
 __global__ void k_construct_solution(KLDev d, const double* __restrict__ x) {
@@ -31,24 +33,19 @@ __global__ void k_axpby(double* __restrict__ r, const double* __restrict__ f, do
 }
 
 // ------------------------------------------------------------------------------------------------
-// residual: F_int - F_pressure accumulated into r (atomic)
 template <int P>
-struct ResidualCfg {
+struct PointCfg {
     static constexpr int NQ2 = (P + 1) * (P + 1);
-    static constexpr int NLOC = (P + 1) * (P + 1);
     static constexpr int EPG = (P == 2) ? 14 : (P == 3 ? 8 : 5);   // elements per CTA
     static constexpr int NT = EPG * NQ2;
 };
-struct ResPoint {   // what the force integrand needs per point
-    double q1[3], q2[3], nM[3][3], pn[3];
-};
 
+// phase 1: one thread per quadrature point
 template <int P>
-__global__ void __launch_bounds__(ResidualCfg<P>::NT) k_residual(KLDev d, double* __restrict__ r, int e2_begin, int e2_end, int body, double bfx, double bfy, double bfz) {
-    using Cfg = ResidualCfg<P>;
-    constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, NLOC = Cfg::NLOC, EPG = Cfg::EPG;
+__global__ void __launch_bounds__(PointCfg<P>::NT) k_points(KLDev d, int e2_begin, int e2_end) {
+    using Cfg = PointCfg<P>;
+    constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;
     __shared__ ElemStage<P> stage[EPG];
-    __shared__ ResPoint rp[EPG][NQ2];
     const int tid = threadIdx.x;
     const int le = tid / NQ2, lq = tid - le * NQ2;
     const int nel = d.nel1 * (e2_end - e2_begin);
@@ -57,52 +54,68 @@ __global__ void __launch_bounds__(ResidualCfg<P>::NT) k_residual(KLDev d, double
     const int e1 = active ? e % d.nel1 : 0, e2 = active ? e2_begin + e / d.nel1 : e2_begin;
     stage_element<P>(d, e1, e2, stage[le], lq, NQ2);
     __syncthreads();
+    PointData pd;
+    const int flag = eval_point<P>(d, stage[le], lq % NQ, lq / NQ, pd);
+    if (active) {
+        if (flag) atomicOr(d.flag, flag);
+        d.pd[(size_t)(e1 + d.nel1 * e2) * NQ2 + lq] = pd;
+    }
+}
+
+// residual: F_int - F_pressure accumulated into r (atomic); reads PointData
+struct ResPoint {   // what the force integrand needs per point
+    double q1[3], q2[3], nM[3][3], pn[3];
+};
+template <int P>
+struct BasisStage {
+    static constexpr int NQ = P + 1;
+    double b1[NQ][3][P + 1];
+    double b2[NQ][3][P + 1];
+};
+template <int P>
+__device__ __forceinline__ void stage_basis(const KLDev& d, int e1, int e2, BasisStage<P>& E, int t, int nthr) {
+    constexpr int NB = (P + 1) * 3 * (P + 1);
+    const double* g1 = d.bas1 + (size_t)e1 * NB;
+    const double* g2 = d.bas2 + (size_t)e2 * NB;
+    double* s1 = &E.b1[0][0][0];
+    double* s2 = &E.b2[0][0][0];
+    for (int k = t; k < NB; k += nthr) { s1[k] = g1[k]; s2[k] = g2[k]; }
+}
+
+template <int P>
+__global__ void __launch_bounds__(PointCfg<P>::NT) k_residual(KLDev d, double* __restrict__ r, int e2_begin, int e2_end) {
+    using Cfg = PointCfg<P>;
+    constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;
+    __shared__ BasisStage<P> stage[EPG];
+    __shared__ ResPoint rp[EPG][NQ2];
+    const int tid = threadIdx.x;
+    const int le = tid / NQ2, lq = tid - le * NQ2;
+    const int nel = d.nel1 * (e2_end - e2_begin);
+    const int e = blockIdx.x * EPG + le;
+    const bool active = e < nel;
+    const int e1 = active ? e % d.nel1 : 0, e2 = active ? e2_begin + e / d.nel1 : e2_begin;
+    stage_basis<P>(d, e1, e2, stage[le], lq, NQ2);
     {
-        const int q1 = lq % NQ, q2 = lq / NQ;
+        const PointData& pd = d.pd[(size_t)(e1 + d.nel1 * e2) * NQ2 + lq];
         ResPoint& o = rp[le][lq];
-        if (body) {
-            // external body force: only weight * meas(ori) is needed
-            double fo[6][3];
-            eval_field3<P, true>(stage[le].X, stage[le].b1[q1], stage[le].b2[q2], fo);
-            double A1[3], A2[3], Nn[3];
-            if (d.rational) {
-                double fw[6];
-                eval_field1<P>(stage[le].Wt, stage[le].b1[q1], stage[le].b2[q2], fw);
-                const double iw = 1.0 / fw[0];
-                for (int c = 0; c < 3; ++c) {
-                    const double X = fo[0][c] * iw;
-                    A1[c] = (fo[1][c] - fw[1] * X) * iw;
-                    A2[c] = (fo[2][c] - fw[2] * X) * iw;
-                }
-            } else {
-                for (int c = 0; c < 3; ++c) { A1[c] = fo[1][c]; A2[c] = fo[2][c]; }
-            }
-            cross3(A1, A2, Nn);
-            const double wJ = stage[le].w1[q1] * stage[le].w2[q2] * sqrt(dot3(Nn, Nn));
-            o.pn[0] = wJ * bfx; o.pn[1] = wJ * bfy; o.pn[2] = wJ * bfz;
-            for (int c = 0; c < 3; ++c) { o.q1[c] = 0; o.q2[c] = 0; o.nM[0][c] = o.nM[1][c] = o.nM[2][c] = 0; }
-        } else {
-            PointData pd;
-            const int flag = eval_point<P>(d, stage[le], q1, q2, pd);
-            if (flag && active) atomicOr(d.flag, flag);
+        const double pw = d.mat.pressure * pd.wJ;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                // coefficient of N_a,1 and N_a,2:  N:dEm  +  n_c * (H . a^gamma)   (the Christoffel part of M:dEf)
-                o.q1[c] = pd.N[0] * pd.a1[c] + pd.N[2] * pd.a2[c] + pd.n[c] * pd.Ha1;
-                o.q2[c] = pd.N[1] * pd.a2[c] + pd.N[2] * pd.a1[c] + pd.n[c] * pd.Ha2;
-                o.nM[0][c] = -pd.n[c] * pd.Mt[0];
-                o.nM[1][c] = -pd.n[c] * pd.Mt[1];
-                o.nM[2][c] = -pd.n[c] * pd.Mt[2];
-                o.pn[c] = -d.mat.pressure * pd.wJ * pd.n[c];
-            }
+        for (int c = 0; c < 3; ++c) {
+            // coefficient of N_a,1 and N_a,2:  N:dEm  +  n_c * (H . a^gamma)   (the Christoffel part of M:dEf)
+            o.q1[c] = pd.N[0] * pd.a1[c] + pd.N[2] * pd.a2[c] + pd.n[c] * pd.Ha1;
+            o.q2[c] = pd.N[1] * pd.a2[c] + pd.N[2] * pd.a1[c] + pd.n[c] * pd.Ha2;
+            o.nM[0][c] = -pd.n[c] * pd.Mt[0];
+            o.nM[1][c] = -pd.n[c] * pd.Mt[1];
+            o.nM[2][c] = -pd.n[c] * pd.Mt[2];
+            o.pn[c] = -pw * pd.n[c];
         }
     }
     __syncthreads();
     // one thread per local basis function: integrate over the element's points
-    if (lq < NLOC && active) {
+    if (active) {
         const int a = lq % (P + 1), b = lq / (P + 1);
         double f[3] = {0, 0, 0};
-        const ElemStage<P>& E = stage[le];
+        const BasisStage<P>& E = stage[le];
 #pragma unroll
         for (int q2 = 0; q2 < NQ; ++q2)
 #pragma unroll
@@ -124,6 +137,56 @@ __global__ void __launch_bounds__(ResidualCfg<P>::NT) k_residual(KLDev d, double
     }
 }
 
+// external body force (set-up only): f += integral N_a * bf * meas(ori)
+template <int P>
+__global__ void __launch_bounds__(PointCfg<P>::NT) k_bodyforce(KLDev d, double* __restrict__ f_out, double bfx, double bfy, double bfz) {
+    using Cfg = PointCfg<P>;
+    constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;
+    __shared__ ElemStage<P> stage[EPG];
+    __shared__ double wj[EPG][NQ2];
+    const int tid = threadIdx.x;
+    const int le = tid / NQ2, lq = tid - le * NQ2;
+    const int nel = d.nel1 * d.nel2;
+    const int e = blockIdx.x * EPG + le;
+    const bool active = e < nel;
+    const int e1 = active ? e % d.nel1 : 0, e2 = active ? e / d.nel1 : 0;
+    stage_element<P>(d, e1, e2, stage[le], lq, NQ2);
+    __syncthreads();
+    {
+        const int q1 = lq % NQ, q2 = lq / NQ;
+        double fo[6][3];
+        eval_field3<P, true>(stage[le].X, stage[le].b1[q1], stage[le].b2[q2], fo);
+        double A1[3], A2[3], Nn[3];
+        if (d.rational) {
+            double fw[6];
+            eval_field1<P>(stage[le].Wt, stage[le].b1[q1], stage[le].b2[q2], fw);
+            const double iw = 1.0 / fw[0];
+            for (int c = 0; c < 3; ++c) {
+                const double X = fo[0][c] * iw;
+                A1[c] = (fo[1][c] - fw[1] * X) * iw;
+                A2[c] = (fo[2][c] - fw[2] * X) * iw;
+            }
+        } else {
+            for (int c = 0; c < 3; ++c) { A1[c] = fo[1][c]; A2[c] = fo[2][c]; }
+        }
+        cross3(A1, A2, Nn);
+        wj[le][lq] = stage[le].w1[q1] * stage[le].w2[q2] * sqrt(dot3(Nn, Nn));
+    }
+    __syncthreads();
+    if (active) {
+        const int a = lq % (P + 1), b = lq / (P + 1);
+        double s = 0.0;
+        for (int q2 = 0; q2 < NQ; ++q2)
+            for (int q1 = 0; q1 < NQ; ++q1) s += stage[le].b1[q1][0][a] * stage[le].b2[q2][0][b] * wj[le][q1 + NQ * q2];
+        const int cpi = (d.span1[e1] - P + a) + d.n1 * (d.span2[e2] - P + b);
+        const double bf[3] = {bfx, bfy, bfz};
+        for (int c = 0; c < 3; ++c) {
+            const int g = d.map[c * d.ncp + cpi];
+            if (g < d.nfree && bf[c] != 0.0) atomicAdd(&f_out[g], s * bf[c]);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Jacobian
 template <int P>
@@ -134,20 +197,20 @@ struct JacCfg {
     static constexpr int TILES = (P + 1) * (P + 1) * (P + 2) / 2;      // (i2, j) with i2 <= j2
     static constexpr int EPG = (P == 4) ? 2 : 4;                        // elements per CTA
     static constexpr int NT = TILES * EPG;                              // 72 / 160 / 150
-    static constexpr int QCH = (P == 3) ? 2 : NQ;                       // points per chunk (divides NQ2)
-    static constexpr int NZ = 45;
+    static constexpr int QCH = NQ;                                      // points per chunk: fixed q1, all q2
+    static constexpr int ZS = 46;                                       // 45 coefficients [cd][p] + 1 pad: stride = 28 banks mod 32
 };
 
 template <int P>
 struct JacShared {
     using Cfg = JacCfg<P>;
-    ElemStage<P> stage[Cfg::EPG];
-    PointData pd[Cfg::EPG][Cfg::NQ2];
-    double Z[Cfg::EPG][Cfg::QCH][Cfg::NZ][Cfg::NLOC];
+    BasisStage<P> stage[Cfg::EPG];
+    double Z[Cfg::EPG][Cfg::QCH][Cfg::NLOC][Cfg::ZS];
+    int4 cb[Cfg::EPG][Cfg::NLOC];     // colbase of the element's control points (scatter addressing)
 };
 
 template <int P>
-__global__ void __launch_bounds__(JacCfg<P>::NT) k_jacobian(KLDev d, int e2_begin, int e2_end) {
+__global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_begin, int e2_end) {
     using Cfg = JacCfg<P>;
     constexpr int NQ = Cfg::NQ, NQ2 = Cfg::NQ2, NLOC = Cfg::NLOC, TILES = Cfg::TILES, EPG = Cfg::EPG, NT = Cfg::NT, QCH = Cfg::QCH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -156,22 +219,27 @@ __global__ void __launch_bounds__(JacCfg<P>::NT) k_jacobian(KLDev d, int e2_begi
     const int nel = d.nel1 * (e2_end - e2_begin);
     const int ebase = blockIdx.x * EPG;
 
-    // ---- stage the EPG elements
+    if (tid == 0) {
+        // the group's per-point records are contiguous: pull them into L2 while the basis tables are staged
+        const int ne = min(EPG, nel - ebase);
+        const PointData* src = d.pd + (size_t)((ebase % d.nel1) + d.nel1 * (e2_begin + ebase / d.nel1)) * NQ2;
+        const unsigned bytes = (unsigned)(ne * NQ2 * sizeof(PointData));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+    }
     for (int le = 0; le < EPG; ++le) {
         int e = ebase + le;
         if (e >= nel) e = nel - 1;
-        stage_element<P>(d, e % d.nel1, e2_begin + e / d.nel1, S.stage[le], tid, NT);
+        stage_basis<P>(d, e % d.nel1, e2_begin + e / d.nel1, S.stage[le], tid, NT);
     }
-    __syncthreads();
-    // ---- phase 1: one thread per quadrature point
-    for (int k = tid; k < EPG * NQ2; k += NT) {
-        const int le = k / NQ2, lq = k - le * NQ2;
-        const int flag = eval_point<P>(d, S.stage[le], lq % NQ, lq / NQ, S.pd[le][lq]);
-        if (flag && (ebase + le) < nel) atomicOr(d.flag, flag);
+    for (int k = tid; k < EPG * NLOC; k += NT) {
+        const int le = k / NLOC, l = k - le * NLOC;
+        int e = ebase + le;
+        if (e >= nel) e = nel - 1;
+        const int cpi = (d.span1[e % d.nel1] - P + l % (P + 1)) + d.n1 * (d.span2[e2_begin + e / d.nel1] - P + l / (P + 1));
+        S.cb[le][l] = reinterpret_cast<const int4*>(d.colbase)[cpi];
     }
-    // tile of this thread
+    // tile of this thread: tiles enumerated by j ascending, i2 = 0..j2
     const int le_t = tid / TILES, tt = tid - le_t * TILES;
-    // tiles enumerated by j ascending, i2 = 0..j2:  offset(j) = (P+1) * j2 (j2+1)/2 + (j - (P+1) j2) * (j2+1)
     int tj = 0, ti2 = 0;
     {
         int rem = tt;
@@ -188,26 +256,33 @@ __global__ void __launch_bounds__(JacCfg<P>::NT) k_jacobian(KLDev d, int e2_begi
         for (int k = 0; k < 9; ++k) acc[a][k] = 0.0;
 
     for (int ch = 0; ch < NQ2 / QCH; ++ch) {
-        __syncthreads();   // phase-1 data ready / previous chunk's Z consumed
+        __syncthreads();   // basis staged / previous chunk's Z consumed
         // ---- phase 2: Z_j for the points of this chunk
         for (int k = tid; k < EPG * QCH * NLOC; k += NT) {
             const int j = k % NLOC;
             const int qc = (k / NLOC) % QCH;
             const int le = k / (NLOC * QCH);
-            const int lq = ch * QCH + qc;
-            const int q1 = lq % NQ, q2 = lq / NQ;
-            const PointData& pd = S.pd[le][lq];
-            const ElemStage<P>& E = S.stage[le];
+            const int q1 = ch, q2 = qc;
+            const int lq = q1 + NQ * q2;
+            int e = ebase + le;
+            if (e >= nel) e = nel - 1;
+            const int ge = (e % d.nel1) + d.nel1 * (e2_begin + e / d.nel1);
+            const PointData& pd = d.pd[(size_t)ge * NQ2 + lq];
+            const BasisStage<P>& E = S.stage[le];
             const int ja = j % (P + 1), jb = j / (P + 1);
             const double x0 = E.b1[q1][0][ja], x1 = E.b1[q1][1][ja], x2 = E.b1[q1][2][ja];
             const double y0 = E.b2[q2][0][jb], y1 = E.b2[q2][1][jb], y2 = E.b2[q2][2][jb];
             const double N1 = x1 * y0, N2 = x0 * y1, N11 = x2 * y0, N22 = x0 * y2, N12 = x1 * y1;
+            double n[3], a1[3], a2[3], c1[3], c2[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { n[c] = pd.n[c]; a1[c] = pd.a1[c]; a2[c] = pd.a2[c]; c1[c] = pd.c1[c]; c2[c] = pd.c2[c]; }
             double g[3], hh[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) g[c] = N1 * pd.c1[c] + N2 * pd.c2[c];
-            hh[0] = N11 - pd.G1[0] * N1 - pd.G2[0] * N2;
-            hh[1] = N22 - pd.G1[1] * N1 - pd.G2[1] * N2;
-            hh[2] = 2.0 * (N12 - pd.G1[2] * N1 - pd.G2[2] * N2);
+            for (int c = 0; c < 3; ++c) g[c] = N1 * c1[c] + N2 * c2[c];
+            const double G1[3] = {pd.G1[0], pd.G1[1], pd.G1[2]}, G2[3] = {pd.G2[0], pd.G2[1], pd.G2[2]};
+            hh[0] = N11 - G1[0] * N1 - G2[0] * N2;
+            hh[1] = N22 - G1[1] * N1 - G2[1] * N2;
+            hh[2] = 2.0 * (N12 - G1[2] * N1 - G2[2] * N2);
             double AE1[3], AE2[3], BE1[3], BE2[3], Bh[3], Dh[3];
 #pragma unroll
             for (int v = 0; v < 3; ++v) {
@@ -218,96 +293,133 @@ __global__ void __launch_bounds__(JacCfg<P>::NT) k_jacobian(KLDev d, int e2_begi
                 Bh[v] = pd.B[sidx(v, 0)] * hh[0] + pd.B[sidx(v, 1)] * hh[1] + pd.B[sidx(v, 2)] * hh[2];
                 Dh[v] = pd.D[sidx(v, 0)] * hh[0] + pd.D[sidx(v, 1)] * hh[1] + pd.D[sidx(v, 2)] * hh[2];
             }
-            const double Nhat = pd.Mt[0] * N11 + pd.Mt[1] * N22 + pd.Mt[2] * N12;
-            const double eta = pd.Ha1 * N1 + pd.Ha2 * N2;
+            const double Mt0 = pd.Mt[0], Mt1 = pd.Mt[1], Mt2 = pd.Mt[2];
+            const double Nhat = Mt0 * N11 + Mt1 * N22 + Mt2 * N12;
+            const double Ha1 = pd.Ha1, Ha2 = pd.Ha2, Hn = pd.Hn;
+            const double eta = Ha1 * N1 + Ha2 * N2;
             const double p1 = pd.N[0] * N1 + pd.N[2] * N2, p2 = pd.N[1] * N2 + pd.N[2] * N1;
             const double ga1 = pd.acon[0] * N1 + pd.acon[2] * N2, ga2 = pd.acon[2] * N1 + pd.acon[1] * N2;
-            double sig[3][3], mu[3][3], s1[3], s2[3];
+            const double q[3] = {pd.q[0], pd.q[1], pd.q[2]};
+            double* Zo = S.Z[le][qc][j];
 #pragma unroll
             for (int dd = 0; dd < 3; ++dd) {
+                double sig[3], mu[3];
 #pragma unroll
                 for (int v = 0; v < 3; ++v) {
-                    sig[dd][v] = AE1[v] * pd.a1[dd] + AE2[v] * pd.a2[dd] - pd.n[dd] * Bh[v];
-                    mu[dd][v] = BE1[v] * pd.a1[dd] + BE2[v] * pd.a2[dd] - pd.n[dd] * Dh[v];
+                    sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd] - n[dd] * Bh[v];
+                    mu[v] = BE1[v] * a1[dd] + BE2[v] * a2[dd] - n[dd] * Dh[v];
                 }
-                s1[dd] = pd.G1[0] * mu[dd][0] + pd.G1[1] * mu[dd][1] + 2.0 * pd.G1[2] * mu[dd][2] + Nhat * pd.c1[dd] - pd.Ha1 * g[dd]
-                         + pd.Hn * pd.n[dd] * ga1;
-                s2[dd] = pd.G2[0] * mu[dd][0] + pd.G2[1] * mu[dd][1] + 2.0 * pd.G2[2] * mu[dd][2] + Nhat * pd.c2[dd] - pd.Ha2 * g[dd]
-                         + pd.Hn * pd.n[dd] * ga2;
-            }
-            double (*Zo)[NLOC] = S.Z[le][qc];
+                const double s1 = G1[0] * mu[0] + G1[1] * mu[1] + 2.0 * G1[2] * mu[2] + Nhat * c1[dd] - Ha1 * g[dd] + Hn * n[dd] * ga1;
+                const double s2 = G2[0] * mu[0] + G2[1] * mu[1] + 2.0 * G2[2] * mu[2] + Nhat * c2[dd] - Ha2 * g[dd] + Hn * n[dd] * ga2;
+                const double en = eta * n[dd];
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int dd = 0; dd < 3; ++dd) {
-                    // epsilon_{c dd k} q_k
-                    double eq = 0.0;
-                    if ((c + 1) % 3 == dd) eq = pd.q[(c + 2) % 3];
-                    else if ((dd + 1) % 3 == c) eq = -pd.q[(dd + 2) % 3];
+                for (int c = 0; c < 3; ++c) {
+                    double eq = 0.0;   // epsilon_{c dd k} q_k
+                    if ((c + 1) % 3 == dd) eq = q[(c + 2) % 3];
+                    else if ((dd + 1) % 3 == c) eq = -q[(dd + 2) % 3];
                     const double dl = (c == dd) ? 1.0 : 0.0;
-                    const int cd = c * 3 + dd;
-                    Zo[0 * 9 + cd][j] = pd.a1[c] * sig[dd][0] + pd.a2[c] * sig[dd][2] + pd.n[c] * s1[dd] - eta * pd.n[dd] * pd.c1[c] + dl * p1 - N2 * eq;
-                    Zo[1 * 9 + cd][j] = pd.a2[c] * sig[dd][1] + pd.a1[c] * sig[dd][2] + pd.n[c] * s2[dd] - eta * pd.n[dd] * pd.c2[c] + dl * p2 + N1 * eq;
-                    Zo[2 * 9 + cd][j] = -pd.n[c] * mu[dd][0] + pd.Mt[0] * pd.n[dd] * g[c];
-                    Zo[3 * 9 + cd][j] = -pd.n[c] * mu[dd][1] + pd.Mt[1] * pd.n[dd] * g[c];
-                    Zo[4 * 9 + cd][j] = -2.0 * pd.n[c] * mu[dd][2] + pd.Mt[2] * pd.n[dd] * g[c];
+                    double* z = Zo + (c * 3 + dd) * 5;
+                    z[0] = a1[c] * sig[0] + a2[c] * sig[2] + n[c] * s1 - en * c1[c] + dl * p1 - N2 * eq;
+                    z[1] = a2[c] * sig[1] + a1[c] * sig[2] + n[c] * s2 - en * c2[c] + dl * p2 + N1 * eq;
+                    const double ng = n[dd] * g[c];
+                    z[2] = -n[c] * mu[0] + Mt0 * ng;
+                    z[3] = -n[c] * mu[1] + Mt1 * ng;
+                    z[4] = -2.0 * n[c] * mu[2] + Mt2 * ng;
                 }
+            }
         }
         __syncthreads();
-        // ---- phase 3: tile (ti2, tj): K_{(i1,ti2), tj} += sum_p d_i[p] Z_j^p
+        // ---- phase 3: tile (ti2, tj).  The first-direction factors X(q1) are constant over the chunk, so
+        //      V_m^{cd} = sum_{q2} W_m^{cd}(q1,q2) is formed first and applied once per chunk (sum factorisation).
         {
-            const ElemStage<P>& E = S.stage[le_t];
+            const BasisStage<P>& E = S.stage[le_t];
+            double V0[9], V1[9], V2[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { V0[k] = 0.0; V1[k] = 0.0; V2[k] = 0.0; }
 #pragma unroll 1
             for (int qc = 0; qc < QCH; ++qc) {
-                const int lq = ch * QCH + qc;
-                const int q1 = lq % NQ, q2 = lq / NQ;
-                const double y0 = E.b2[q2][0][ti2], y1 = E.b2[q2][1][ti2], y2 = E.b2[q2][2][ti2];
-                double X0[P + 1], X1[P + 1], X2[P + 1];
+                const double y0 = E.b2[qc][0][ti2], y1 = E.b2[qc][1][ti2], y2 = E.b2[qc][2][ti2];
+                const double2* Zi = reinterpret_cast<const double2*>(S.Z[le_t][qc][tj]);
 #pragma unroll
-                for (int a = 0; a <= P; ++a) { X0[a] = E.b1[q1][0][a]; X1[a] = E.b1[q1][1][a]; X2[a] = E.b1[q1][2][a]; }
-                const double (*Zi)[NLOC] = S.Z[le_t][qc];
+                for (int m = 0; m < 5; ++m) {
+                    // coefficients of two (c,d) entries: 10 contiguous doubles (the last pair has 5 + pad)
+                    double zz[10];
 #pragma unroll
-                for (int cd = 0; cd < 9; ++cd) {
-                    const double z1 = Zi[0 * 9 + cd][tj], z2 = Zi[1 * 9 + cd][tj], z11 = Zi[2 * 9 + cd][tj], z22 = Zi[3 * 9 + cd][tj],
-                                 z12 = Zi[4 * 9 + cd][tj];
-                    const double W0 = y1 * z2 + y2 * z22;     // multiplies N_{i1}(q1)
-                    const double W1 = y0 * z1 + y1 * z12;     // multiplies N'_{i1}(q1)
-                    const double W2 = y0 * z11;               // multiplies N''_{i1}(q1)
+                    for (int k = 0; k < (m < 4 ? 5 : 3); ++k) { const double2 t = Zi[m * 5 + k]; zz[2 * k] = t.x; zz[2 * k + 1] = t.y; }
 #pragma unroll
-                    for (int a = 0; a <= P; ++a) acc[a][cd] += X0[a] * W0 + X1[a] * W1 + X2[a] * W2;
+                    for (int h = 0; h < (m < 4 ? 2 : 1); ++h) {
+                        const int cd = 2 * m + h;
+                        const double z1 = zz[5 * h], z2 = zz[5 * h + 1], z11 = zz[5 * h + 2], z22 = zz[5 * h + 3], z12 = zz[5 * h + 4];
+                        V0[cd] += y1 * z2 + y2 * z22;     // multiplies N_{i1}(q1)
+                        V1[cd] += y0 * z1 + y1 * z12;     // multiplies N'_{i1}(q1)
+                        V2[cd] += y0 * z11;               // multiplies N''_{i1}(q1)
+                    }
                 }
+            }
+#pragma unroll
+            for (int a = 0; a <= P; ++a) {
+                const double X0 = E.b1[ch][0][a], X1 = E.b1[ch][1][a], X2 = E.b1[ch][2][a];
+#pragma unroll
+                for (int cd = 0; cd < 9; ++cd) acc[a][cd] += X0 * V0[cd] + X1 * V1[cd] + X2 * V2[cd];
             }
         }
     }
-    // ---- scatter (upper triangle i <= j plus the transposed entries)
+    // ---- scatter (upper triangle i <= j plus the transposed entries).  Regular columns are addressed
+    //      arithmetically (outer[col] + c*nst + stencil slot); irregular ones (boundary, eliminated or matched
+    //      DoFs in the stencil) go through the position table.
     const int e = ebase + le_t;
     if (e < nel) {
         const int e1 = e % d.nel1, e2 = e2_begin + e / d.nel1;
         const int i0 = d.span1[e1] - P, j0 = d.span2[e2] - P;
         const int ja = tj % (P + 1), jb = tj / (P + 1);
         const int J1 = i0 + ja, J2 = j0 + jb, Jc = J1 + d.n1 * J2;
-        const int S3 = d.nst * 3, W = 2 * P + 1;
+        const int NST = d.nst, S3 = NST * 3, W = 2 * P + 1;
         double* __restrict__ val = d.values;
+        const int4 cbJ = S.cb[le_t][tj];
+        const int baseJ[3] = {cbJ.x, cbJ.y, cbJ.z};
 #pragma unroll
         for (int a = 0; a <= P; ++a) {
             const int i = a + (P + 1) * ti2;
             if (i > tj) continue;
             const int I1 = i0 + a, I2 = j0 + ti2, Ic = I1 + d.n1 * I2;
-            const int st_ij = (I1 - J1 + P) + W * (I2 - J2 + P);   // position of row-function I in the stencil of column-function J
+            const int st_ij = (I1 - J1 + P) + W * (I2 - J2 + P);   // slot of row-function I in the stencil of column-function J
             const int st_ji = (J1 - I1 + P) + W * (J2 - I2 + P);
+            const int4 cbI = S.cb[le_t][i];
+            const int baseI[3] = {cbI.x, cbI.y, cbI.z};
+            int p1[9], p2[9];
+            if (cbJ.w) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+                for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int dd = 0; dd < 3; ++dd) {
-                    const double v = acc[a][c * 3 + dd];
-                    // entry (row (I,c), col (J,dd))
-                    const int p1 = d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c];
-                    if (p1 >= 0) atomicAdd(&val[p1], v);
-                    if (i != tj) {
-                        const int p2 = d.pos[(size_t)(Ic * 3 + c) * S3 + st_ji * 3 + dd];
-                        if (p2 >= 0) atomicAdd(&val[p2], v);
-                    }
+                    for (int dd = 0; dd < 3; ++dd) p1[c * 3 + dd] = baseJ[dd] + c * NST + st_ij;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int dd = 0; dd < 3; ++dd) p1[c * 3 + dd] = __ldg(&d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c]);
+            }
+            if (i != tj) {
+                if (cbI.w) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int dd = 0; dd < 3; ++dd) p2[c * 3 + dd] = baseI[c] + dd * NST + st_ji;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int dd = 0; dd < 3; ++dd) p2[c * 3 + dd] = __ldg(&d.pos[(size_t)(Ic * 3 + c) * S3 + st_ji * 3 + dd]);
                 }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) p2[k] = -1;
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                const double v = acc[a][k];
+                if (p1[k] >= 0) atomicAdd(&val[p1[k]], v);   // entry (row (I,c), col (J,dd))
+                if (p2[k] >= 0) atomicAdd(&val[p2[k]], v);   // entry (row (J,dd), col (I,c))
+            }
         }
     }
 }
@@ -317,16 +429,14 @@ __global__ void __launch_bounds__(JacCfg<P>::NT) k_jacobian(KLDev d, int e2_begi
 template <int P>
 __global__ void __launch_bounds__(256) k_pressure_tangent(KLDev d, int e2_begin, int e2_end) {
     constexpr int NQ = P + 1, NQ2 = NQ * NQ, NLOC = (P + 1) * (P + 1);
-    __shared__ ElemStage<P> stage;
+    __shared__ BasisStage<P> stage;
     __shared__ double pn[NQ2][3], pc1[NQ2][3], pc2[NQ2][3], pw[NQ2];
     const int tid = threadIdx.x;
     const int e = blockIdx.x;
     const int e1 = e % d.nel1, e2 = e2_begin + e / d.nel1;
-    stage_element<P>(d, e1, e2, stage, tid, blockDim.x);
-    __syncthreads();
+    stage_basis<P>(d, e1, e2, stage, tid, blockDim.x);
     if (tid < NQ2) {
-        PointData pd;
-        eval_point<P>(d, stage, tid % NQ, tid / NQ, pd);
+        const PointData& pd = d.pd[(size_t)(e1 + d.nel1 * e2) * NQ2 + tid];
         for (int c = 0; c < 3; ++c) { pn[tid][c] = pd.n[c]; pc1[tid][c] = pd.c1[c]; pc2[tid][c] = pd.c2[c]; }
         pw[tid] = pd.wJ * d.mat.pressure;
     }
@@ -375,6 +485,26 @@ int kl_launch_axpby(kl_ctx* ctx, double* r, const double* fext, double a_r, doub
 }
 
 template <int P>
+static int launch_points(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
+    using Cfg = PointCfg<P>;
+    const int nel = ctx->d.nel1 * (e2e - e2b);
+    if (nel <= 0) return 0;
+    k_points<P><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, 0, s>>>(ctx->d, e2b, e2e);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    return 0;
+}
+int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s) {
+    switch (ctx->d.p) {
+        case 2: return launch_points<2>(ctx, e2_begin, e2_end, s);
+        case 3: return launch_points<3>(ctx, e2_begin, e2_end, s);
+        case 4: return launch_points<4>(ctx, e2_begin, e2_end, s);
+    }
+    kl_set_error("unsupported degree");
+    return KL_E_ARG;
+}
+
+template <int P>
 static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     using Cfg = JacCfg<P>;
     const int nel = ctx->d.nel1 * (e2e - e2b);
@@ -383,6 +513,7 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         KL_CUDA(cudaFuncSetAttribute(k_jacobian<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KL_CUDA(cudaFuncSetAttribute(k_jacobian<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
@@ -410,12 +541,12 @@ int kl_launch_jacobian(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s) {
 }
 
 template <int P>
-static int launch_res(kl_ctx* ctx, double* r, int body, const double* bf, cudaStream_t s) {
-    using Cfg = ResidualCfg<P>;
+static int launch_res(kl_ctx* ctx, double* r, cudaStream_t s) {
+    using Cfg = PointCfg<P>;
     const int nel = ctx->d.nel1 * (ctx->e2_end - ctx->e2_begin);
     if (nel <= 0) return 0;
     const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
-    k_residual<P><<<grid, Cfg::NT, 0, s>>>(ctx->d, r, ctx->e2_begin, ctx->e2_end, body, bf ? bf[0] : 0.0, bf ? bf[1] : 0.0, bf ? bf[2] : 0.0);
+    k_residual<P><<<grid, Cfg::NT, 0, s>>>(ctx->d, r, ctx->e2_begin, ctx->e2_end);
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
     return 0;
@@ -423,20 +554,29 @@ static int launch_res(kl_ctx* ctx, double* r, int body, const double* bf, cudaSt
 
 int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s) {
     switch (ctx->d.p) {
-        case 2: return launch_res<2>(ctx, r_dev, 0, nullptr, s);
-        case 3: return launch_res<3>(ctx, r_dev, 0, nullptr, s);
-        case 4: return launch_res<4>(ctx, r_dev, 0, nullptr, s);
+        case 2: return launch_res<2>(ctx, r_dev, s);
+        case 3: return launch_res<3>(ctx, r_dev, s);
+        case 4: return launch_res<4>(ctx, r_dev, s);
     }
     kl_set_error("unsupported degree");
     return KL_E_ARG;
 }
 
+template <int P>
+static int launch_body(kl_ctx* ctx, double* f, const double* bf, cudaStream_t s) {
+    using Cfg = PointCfg<P>;
+    const int nel = ctx->d.nel1 * ctx->d.nel2;
+    k_bodyforce<P><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, 0, s>>>(ctx->d, f, bf[0], bf[1], bf[2]);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    return 0;
+}
 // f_dev += integral(N_i * bf * meas(ori))
 int kl_launch_bodyforce(kl_ctx* ctx, double* f_dev, const double bf[3], cudaStream_t s) {
     switch (ctx->d.p) {
-        case 2: return launch_res<2>(ctx, f_dev, 1, bf, s);
-        case 3: return launch_res<3>(ctx, f_dev, 1, bf, s);
-        case 4: return launch_res<4>(ctx, f_dev, 1, bf, s);
+        case 2: return launch_body<2>(ctx, f_dev, bf, s);
+        case 3: return launch_body<3>(ctx, f_dev, bf, s);
+        case 4: return launch_body<4>(ctx, f_dev, bf, s);
     }
     kl_set_error("unsupported degree");
     return KL_E_ARG;
@@ -483,6 +623,13 @@ extern "C" int kl_measure_fp64_peak(int device, double* tflops, float* ms_out) {
     if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
     cudaFree(out); cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return KL_OK;
+}
+
+extern "C" int kl_points_kernel_ms(kl_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return KL_E_ARG;
+    KL_CUDA(cudaEventSynchronize(ctx->ev[7]));
+    KL_CUDA(cudaEventElapsedTime(ms, ctx->ev[6], ctx->ev[7]));
     return KL_OK;
 }
 

@@ -204,8 +204,6 @@ static int build_fext(kl_ctx* ctx, const kl_problem* P) {
     KL_CUDA(cudaMemset(ctx->d_fext, 0, sizeof(double) * std::max(d.nfree, 1)));
     const double* bf = P->body_force;
     if (bf[0] != 0.0 || bf[1] != 0.0 || bf[2] != 0.0) {
-        // needs the displacement net only formally (zero): reuse disp buffer zeroed
-        KL_CUDA(cudaMemset(d.disp, 0, sizeof(double) * 3 * d.ncp));
         if (int rc = kl_launch_bodyforce(ctx, ctx->d_fext, bf, 0)) return rc;
         KL_CUDA(cudaDeviceSynchronize());
     }
@@ -282,6 +280,13 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     if (P->fixed_values && P->n_fixed > 0 && (rc = upload(ctx, &d.fixed, P->fixed_values, (size_t)P->n_fixed))) { kl_destroy(ctx); return rc; }
     KL_CUDA(cudaMalloc((void**)&d.disp, sizeof(double) * 3 * d.ncp)); ctx->owned.push_back(d.disp);
     KL_CUDA(cudaMemset(d.disp, 0, sizeof(double) * 3 * d.ncp));
+    {
+        const size_t npts = (size_t)d.nel1 * d.nel2 * d.nq * d.nq;
+        void* pdbuf = nullptr;
+        KL_CUDA(cudaMalloc(&pdbuf, kl_pointdata_bytes() * (npts ? npts : 1)));
+        ctx->owned.push_back(pdbuf);
+        d.pd = (PointData*)pdbuf;
+    }
     KL_CUDA(cudaMalloc((void**)&d.flag, sizeof(int))); ctx->owned.push_back(d.flag);
     KL_CUDA(cudaMemset(d.flag, 0, sizeof(int)));
     KL_CUDA(cudaMalloc((void**)&ctx->d_x, sizeof(double) * std::max(d.nfree, 1))); ctx->owned.push_back(ctx->d_x);
@@ -381,6 +386,9 @@ extern "C" int kl_jacobian_device(kl_ctx* ctx, const double* x_dev, void* stream
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
+    KL_CUDA(cudaEventRecord(ctx->ev[6], s));
+    if ((rc = kl_launch_points(ctx, ctx->e2_begin, ctx->e2_end, s))) return rc;
+    KL_CUDA(cudaEventRecord(ctx->ev[7], s));
     KL_CUDA(cudaMemsetAsync(ctx->d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
     return kl_launch_jacobian(ctx, ctx->e2_begin, ctx->e2_end, s);
 }
@@ -390,6 +398,7 @@ extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_f
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
+    if ((rc = kl_launch_points(ctx, ctx->e2_begin, ctx->e2_end, s))) return rc;
     KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, s));
     if ((rc = kl_launch_residual(ctx, r_dev, s))) return rc;
     return kl_launch_axpby(ctx, r_dev, ctx->d_fext, sign_fint, lam_fext, ctx->d.nfree, s);

@@ -13,6 +13,8 @@
 #define KLF_JACOBIAN 2
 #define KLF_C33 4
 
+struct PointData;
+
 struct KLMaterial {
     int material, compressible, ngauss, bending, metric_z2;
     double E, nu, t, mu, lam_ps, bulk, c1, c2;
@@ -45,7 +47,9 @@ struct KLDev {
     double* values;        // [nnz]
     const int* pos;        // [ncp*3][nst*3] scatter table (-1: eliminated / not coupled)
     int nst;               // (2p+1)^2
+    const int* colbase;    // [ncp][4]: outer[map[d][J]] for d=0..2 (-1 if eliminated), [3] = 1 if the column block of J is regular
     int* flag;             // device error flag
+    PointData* pd;         // [elements][nq*nq] per-point records written by k_points
     KLMaterial mat;
 };
 
@@ -70,7 +74,7 @@ struct kl_ctx {
     size_t registered_bytes = 0;
     cudaStream_t stream = nullptr;   // own stream for the host-pointer entry points
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev[6]{};
+    cudaEvent_t ev[8]{};
     float ms_kernel = 0, ms_h2d = 0, ms_d2h = 0;
     int launches = 0;
     int n_strips_d2h = 8;            // pipelined D2H granularity
@@ -91,6 +95,8 @@ int kl_build_pattern(kl_ctx* ctx);
 // kl_assemble.cu
 int kl_launch_construct(kl_ctx* ctx, const double* x_dev, cudaStream_t s);
 int kl_launch_jacobian(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s);
+int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s);
 int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s);   // r += F_int - F_pressure (atomic)
+size_t kl_pointdata_bytes(void);
 int kl_launch_bodyforce(kl_ctx* ctx, double* f_dev, const double bf[3], cudaStream_t s);
 int kl_launch_axpby(kl_ctx* ctx, double* r, const double* fext, double a_r, double b_f, int n, cudaStream_t s);

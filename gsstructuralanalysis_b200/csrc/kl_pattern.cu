@@ -84,6 +84,25 @@ __global__ void k_pos_table(PatArgs a, const int* __restrict__ outer, const int*
     pos[k] = res;
 }
 
+// colbase[J][d] = outer[map[d][J]] (or -1), colbase[J][3] = 1 when every column (J,d) holds exactly the full
+// (2p+1)^2 x 3 stencil in canonical order, i.e. pos[(J,d)][st][c] == outer[col] + c*nst + st for all st,c,d.
+__global__ void k_colbase(PatArgs a, const int* __restrict__ outer, const int* __restrict__ pos, int* __restrict__ colbase) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x;
+    if (J >= a.ncp) return;
+    int regular = 1;
+    for (int d = 0; d < 3; ++d) {
+        const int col = a.map[d * a.ncp + J];
+        const int base = col < a.nfree ? outer[col] : -1;
+        colbase[4 * J + d] = base;
+        if (base < 0) { regular = 0; continue; }
+        const int* pp = pos + (size_t)(J * 3 + d) * (a.nst * 3);
+        for (int st = 0; st < a.nst && regular; ++st)
+            for (int c = 0; c < 3; ++c)
+                if (pp[st * 3 + c] != base + c * a.nst + st) { regular = 0; break; }
+    }
+    colbase[4 * J + 3] = regular;
+}
+
 template <class T>
 static int dev_alloc(kl_ctx* ctx, T** p, size_t n) {
     KL_CUDA(cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)));
@@ -159,6 +178,12 @@ int kl_build_pattern(kl_ctx* ctx) {
     k_pos_table<<<(unsigned)((total + T - 1) / T), T>>>(a, outer, inner, pos, total);
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
+    int* colbase;
+    if (int rc = dev_alloc(ctx, &colbase, (size_t)4 * d.ncp)) return rc;
+    k_colbase<<<(d.ncp + T - 1) / T, T>>>(a, outer, pos, colbase);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    d.colbase = colbase;
     double* values;
     if (int rc = dev_alloc(ctx, &values, (size_t)nuniq)) return rc;
     KL_CUDA(cudaMemset(values, 0, sizeof(double) * (nuniq ? nuniq : 1)));

@@ -154,6 +154,8 @@ int kl_set_strip(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end);
 int kl_last_timing(const kl_ctx* ctx, float* ms_kernel, float* ms_h2d, float* ms_d2h);
 /* Duration in ms of the last Jacobian kernel launch itself (CUDA events on its stream; syncs). */
 int kl_jacobian_kernel_ms(kl_ctx* ctx, float* ms);
+/* Same for the per-quadrature-point kernel (geometry + material) that precedes it. */
+int kl_points_kernel_ms(kl_ctx* ctx, float* ms);
 /* FP64 FMA peak of the current device measured with a register-resident DFMA chain kernel
  * (MEASURED_PEAKS.json has no FP64 figure).  Returns TFLOP/s in *tflops. */
 int kl_measure_fp64_peak(int device, double* tflops, float* ms);
