@@ -40,25 +40,38 @@ struct PointCfg {
     static constexpr int NT = EPG * NQ2;
 };
 
-// phase 1: one thread per quadrature point
+// phase 1: one thread per quadrature point.  The CTA's records are contiguous in HBM, so they are staged in
+// shared memory (q1-major per element) and written back with ONE TMA bulk store instead of 56 strided stores
+// per thread.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
 template <int P>
 __global__ void __launch_bounds__(PointCfg<P>::NT) k_points(KLDev d, int e2_begin, int e2_end) {
     using Cfg = PointCfg<P>;
     constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;
-    __shared__ ElemStage<P> stage[EPG];
+    extern __shared__ __align__(16) unsigned char smem_pts[];
+    ElemStage<P>* stage = reinterpret_cast<ElemStage<P>*>(smem_pts);
+    PointData* out = reinterpret_cast<PointData*>(smem_pts + ((sizeof(ElemStage<P>) * EPG + 15) / 16) * 16);
     const int tid = threadIdx.x;
     const int le = tid / NQ2, lq = tid - le * NQ2;
     const int nel = d.nel1 * (e2_end - e2_begin);
-    const int e = blockIdx.x * EPG + le;
+    const int ebase = blockIdx.x * EPG;
+    const int e = ebase + le;
     const bool active = e < nel;
     const int e1 = active ? e % d.nel1 : 0, e2 = active ? e2_begin + e / d.nel1 : e2_begin;
     stage_element<P>(d, e1, e2, stage[le], lq, NQ2);
     __syncthreads();
-    PointData pd;
-    const int flag = eval_point<P>(d, stage[le], lq % NQ, lq / NQ, pd);
-    if (active) {
-        if (flag) atomicOr(d.flag, flag);
-        d.pd[(size_t)(e1 + d.nel1 * e2) * NQ2 + lq] = pd;
+    const int flag = eval_point<P>(d, stage[le], lq % NQ, lq / NQ, out[le * NQ2 + (lq / NQ) + NQ * (lq % NQ)]);   // [q1][q2]
+    if (flag && active) atomicOr(d.flag, flag);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // make the generic-proxy writes visible to the TMA engine
+    __syncthreads();
+    if (tid == 0) {
+        const int ne = min(EPG, nel - ebase);
+        PointData* dst = d.pd + (size_t)((ebase % d.nel1) + d.nel1 * (e2_begin + ebase / d.nel1)) * NQ2;
+        const unsigned bytes = (unsigned)(ne * NQ2 * sizeof(PointData));
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(out)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay valid until the engine has read it
     }
 }
 
@@ -86,7 +99,7 @@ template <int P>
 __global__ void __launch_bounds__(PointCfg<P>::NT) k_residual(KLDev d, double* __restrict__ r, int e2_begin, int e2_end) {
     using Cfg = PointCfg<P>;
     constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;
-    __shared__ BasisStage<P> stage[EPG];
+    __shared__ ElemStage<P> stage[EPG];
     __shared__ ResPoint rp[EPG][NQ2];
     const int tid = threadIdx.x;
     const int le = tid / NQ2, lq = tid - le * NQ2;
@@ -94,9 +107,12 @@ __global__ void __launch_bounds__(PointCfg<P>::NT) k_residual(KLDev d, double* _
     const int e = blockIdx.x * EPG + le;
     const bool active = e < nel;
     const int e1 = active ? e % d.nel1 : 0, e2 = active ? e2_begin + e / d.nel1 : e2_begin;
-    stage_basis<P>(d, e1, e2, stage[le], lq, NQ2);
+    stage_element<P>(d, e1, e2, stage[le], lq, NQ2);
+    __syncthreads();
     {
-        const PointData& pd = d.pd[(size_t)(e1 + d.nel1 * e2) * NQ2 + lq];
+        PointData pd;
+        const int flag = eval_point<P>(d, stage[le], lq % NQ, lq / NQ, pd);
+        if (flag && active) atomicOr(d.flag, flag);
         ResPoint& o = rp[le][lq];
         const double pw = d.mat.pressure * pd.wJ;
 #pragma unroll
@@ -115,7 +131,7 @@ __global__ void __launch_bounds__(PointCfg<P>::NT) k_residual(KLDev d, double* _
     if (active) {
         const int a = lq % (P + 1), b = lq / (P + 1);
         double f[3] = {0, 0, 0};
-        const BasisStage<P>& E = stage[le];
+        const ElemStage<P>& E = stage[le];
 #pragma unroll
         for (int q2 = 0; q2 < NQ; ++q2)
 #pragma unroll
@@ -207,9 +223,37 @@ struct JacShared {
     BasisStage<P> stage[Cfg::EPG];
     double Z[Cfg::EPG][Cfg::QCH][Cfg::NLOC][Cfg::ZS];
     int4 cb[Cfg::EPG][Cfg::NLOC];     // colbase of the element's control points (scatter addressing)
+    PointData pd[Cfg::EPG][Cfg::QCH]; // per-point records of the current chunk (TMA bulk copy)
+    unsigned long long bar;           // mbarrier of the bulk copies
 };
 
-template <int P>
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int P, bool HASB>
 __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_begin, int e2_end) {
     using Cfg = JacCfg<P>;
     constexpr int NQ = Cfg::NQ, NQ2 = Cfg::NQ2, NLOC = Cfg::NLOC, TILES = Cfg::TILES, EPG = Cfg::EPG, NT = Cfg::NT, QCH = Cfg::QCH;
@@ -219,13 +263,19 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
     const int nel = d.nel1 * (e2_end - e2_begin);
     const int ebase = blockIdx.x * EPG;
 
-    if (tid == 0) {
-        // the group's per-point records are contiguous: pull them into L2 while the basis tables are staged
-        const int ne = min(EPG, nel - ebase);
-        const PointData* src = d.pd + (size_t)((ebase % d.nel1) + d.nel1 * (e2_begin + ebase / d.nel1)) * NQ2;
-        const unsigned bytes = (unsigned)(ne * NQ2 * sizeof(PointData));
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-    }
+    // per-point records of element le, chunk ch (= fixed q1) are QCH contiguous records: one TMA bulk copy each
+    auto issue_pd = [&](int ch) {
+        mbar_expect_tx(&S.bar, (unsigned)(EPG * QCH * sizeof(PointData)));
+        for (int le = 0; le < EPG; ++le) {
+            int e = ebase + le;
+            if (e >= nel) e = nel - 1;
+            const size_t ge = (size_t)(e % d.nel1) + (size_t)d.nel1 * (e2_begin + e / d.nel1);
+            tma_bulk_g2s(&S.pd[le][0], d.pd + ge * NQ2 + (size_t)ch * QCH, (unsigned)(QCH * sizeof(PointData)), &S.bar);
+        }
+    };
+    if (tid == 0) mbar_init(&S.bar, 1);
+    __syncthreads();
+    if (tid == 0) issue_pd(0);
     for (int le = 0; le < EPG; ++le) {
         int e = ebase + le;
         if (e >= nel) e = nel - 1;
@@ -257,17 +307,14 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
 
     for (int ch = 0; ch < NQ2 / QCH; ++ch) {
         __syncthreads();   // basis staged / previous chunk's Z consumed
+        mbar_wait(&S.bar, ch & 1);   // this chunk's per-point records have landed in shared memory
         // ---- phase 2: Z_j for the points of this chunk
         for (int k = tid; k < EPG * QCH * NLOC; k += NT) {
             const int j = k % NLOC;
             const int qc = (k / NLOC) % QCH;
             const int le = k / (NLOC * QCH);
             const int q1 = ch, q2 = qc;
-            const int lq = q1 + NQ * q2;
-            int e = ebase + le;
-            if (e >= nel) e = nel - 1;
-            const int ge = (e % d.nel1) + d.nel1 * (e2_begin + e / d.nel1);
-            const PointData& pd = d.pd[(size_t)ge * NQ2 + lq];
+            const PointData& pd = S.pd[le][qc];
             const BasisStage<P>& E = S.stage[le];
             const int ja = j % (P + 1), jb = j / (P + 1);
             const double x0 = E.b1[q1][0][ja], x1 = E.b1[q1][1][ja], x2 = E.b1[q1][2][ja];
@@ -288,9 +335,11 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
             for (int v = 0; v < 3; ++v) {
                 AE1[v] = N1 * pd.A[sidx(v, 0)] + N2 * pd.A[sidx(v, 2)];
                 AE2[v] = N2 * pd.A[sidx(v, 1)] + N1 * pd.A[sidx(v, 2)];
-                BE1[v] = N1 * pd.B[sidx(v, 0)] + N2 * pd.B[sidx(v, 2)];
-                BE2[v] = N2 * pd.B[sidx(v, 1)] + N1 * pd.B[sidx(v, 2)];
-                Bh[v] = pd.B[sidx(v, 0)] * hh[0] + pd.B[sidx(v, 1)] * hh[1] + pd.B[sidx(v, 2)] * hh[2];
+                if (HASB) {
+                    BE1[v] = N1 * pd.B[sidx(v, 0)] + N2 * pd.B[sidx(v, 2)];
+                    BE2[v] = N2 * pd.B[sidx(v, 1)] + N1 * pd.B[sidx(v, 2)];
+                    Bh[v] = pd.B[sidx(v, 0)] * hh[0] + pd.B[sidx(v, 1)] * hh[1] + pd.B[sidx(v, 2)] * hh[2];
+                } else { BE1[v] = 0.0; BE2[v] = 0.0; Bh[v] = 0.0; }
                 Dh[v] = pd.D[sidx(v, 0)] * hh[0] + pd.D[sidx(v, 1)] * hh[1] + pd.D[sidx(v, 2)] * hh[2];
             }
             const double Mt0 = pd.Mt[0], Mt1 = pd.Mt[1], Mt2 = pd.Mt[2];
@@ -306,8 +355,13 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
                 double sig[3], mu[3];
 #pragma unroll
                 for (int v = 0; v < 3; ++v) {
-                    sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd] - n[dd] * Bh[v];
-                    mu[v] = BE1[v] * a1[dd] + BE2[v] * a2[dd] - n[dd] * Dh[v];
+                    if (HASB) {
+                        sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd] - n[dd] * Bh[v];
+                        mu[v] = BE1[v] * a1[dd] + BE2[v] * a2[dd] - n[dd] * Dh[v];
+                    } else {
+                        sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd];
+                        mu[v] = -n[dd] * Dh[v];
+                    }
                 }
                 const double s1 = G1[0] * mu[0] + G1[1] * mu[1] + 2.0 * G1[2] * mu[2] + Nhat * c1[dd] - Ha1 * g[dd] + Hn * n[dd] * ga1;
                 const double s2 = G2[0] * mu[0] + G2[1] * mu[1] + 2.0 * G2[2] * mu[2] + Nhat * c2[dd] - Ha2 * g[dd] + Hn * n[dd] * ga2;
@@ -329,6 +383,10 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
             }
         }
         __syncthreads();
+        if (tid == 0 && ch + 1 < NQ2 / QCH) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of S.pd are done; async proxy may overwrite
+            issue_pd(ch + 1);
+        }
         // ---- phase 3: tile (ti2, tj).  The first-direction factors X(q1) are constant over the chunk, so
         //      V_m^{cd} = sum_{q2} W_m^{cd}(q1,q2) is formed first and applied once per chunk (sum factorisation).
         {
@@ -336,7 +394,7 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
             double V0[9], V1[9], V2[9];
 #pragma unroll
             for (int k = 0; k < 9; ++k) { V0[k] = 0.0; V1[k] = 0.0; V2[k] = 0.0; }
-#pragma unroll 1
+#pragma unroll 2
             for (int qc = 0; qc < QCH; ++qc) {
                 const double y0 = E.b2[qc][0][ti2], y1 = E.b2[qc][1][ti2], y2 = E.b2[qc][2][ti2];
                 const double2* Zi = reinterpret_cast<const double2*>(S.Z[le_t][qc][tj]);
@@ -350,9 +408,9 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
                     for (int h = 0; h < (m < 4 ? 2 : 1); ++h) {
                         const int cd = 2 * m + h;
                         const double z1 = zz[5 * h], z2 = zz[5 * h + 1], z11 = zz[5 * h + 2], z22 = zz[5 * h + 3], z12 = zz[5 * h + 4];
-                        V0[cd] += y1 * z2 + y2 * z22;     // multiplies N_{i1}(q1)
-                        V1[cd] += y0 * z1 + y1 * z12;     // multiplies N'_{i1}(q1)
-                        V2[cd] += y0 * z11;               // multiplies N''_{i1}(q1)
+                        V0[cd] = fma(y2, z22, fma(y1, z2, V0[cd]));    // multiplies N_{i1}(q1)
+                        V1[cd] = fma(y1, z12, fma(y0, z1, V1[cd]));    // multiplies N'_{i1}(q1)
+                        V2[cd] = fma(y0, z11, V2[cd]);                 // multiplies N''_{i1}(q1)
                     }
                 }
             }
@@ -360,7 +418,7 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
             for (int a = 0; a <= P; ++a) {
                 const double X0 = E.b1[ch][0][a], X1 = E.b1[ch][1][a], X2 = E.b1[ch][2][a];
 #pragma unroll
-                for (int cd = 0; cd < 9; ++cd) acc[a][cd] += X0 * V0[cd] + X1 * V1[cd] + X2 * V2[cd];
+                for (int cd = 0; cd < 9; ++cd) acc[a][cd] = fma(X2, V2[cd], fma(X1, V1[cd], fma(X0, V0[cd], acc[a][cd])));
             }
         }
     }
@@ -437,8 +495,9 @@ __global__ void __launch_bounds__(256) k_pressure_tangent(KLDev d, int e2_begin,
     stage_basis<P>(d, e1, e2, stage, tid, blockDim.x);
     if (tid < NQ2) {
         const PointData& pd = d.pd[(size_t)(e1 + d.nel1 * e2) * NQ2 + tid];
-        for (int c = 0; c < 3; ++c) { pn[tid][c] = pd.n[c]; pc1[tid][c] = pd.c1[c]; pc2[tid][c] = pd.c2[c]; }
-        pw[tid] = pd.wJ * d.mat.pressure;
+        const int lq = (tid / NQ) + NQ * (tid % NQ);
+        for (int c = 0; c < 3; ++c) { pn[lq][c] = pd.n[c]; pc1[lq][c] = pd.c1[c]; pc2[lq][c] = pd.c2[c]; }
+        pw[lq] = pd.wJ * d.mat.pressure;
     }
     __syncthreads();
     const int i0 = d.span1[e1] - P, j0 = d.span2[e2] - P;
@@ -489,7 +548,13 @@ static int launch_points(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     using Cfg = PointCfg<P>;
     const int nel = ctx->d.nel1 * (e2e - e2b);
     if (nel <= 0) return 0;
-    k_points<P><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, 0, s>>>(ctx->d, e2b, e2e);
+    const size_t smem = ((sizeof(ElemStage<P>) * Cfg::EPG + 15) / 16) * 16 + sizeof(PointData) * Cfg::EPG * Cfg::NQ2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        KL_CUDA(cudaFuncSetAttribute(k_points<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    k_points<P><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
     return 0;
@@ -512,13 +577,18 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     const size_t smem = sizeof(JacShared<P>);
     static bool attr_set = false;
     if (!attr_set) {
-        KL_CUDA(cudaFuncSetAttribute(k_jacobian<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        KL_CUDA(cudaFuncSetAttribute(k_jacobian<P>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        KL_CUDA(cudaFuncSetAttribute(k_jacobian<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KL_CUDA(cudaFuncSetAttribute(k_jacobian<P, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        KL_CUDA(cudaFuncSetAttribute(k_jacobian<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KL_CUDA(cudaFuncSetAttribute(k_jacobian<P, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_set = true;
     }
     const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
+    // the membrane-bending coupling block B vanishes identically for the linear (SvK) law and for membranes
+    const bool hasB = ctx->d.mat.material != KL_MAT_SVK && ctx->d.mat.bending;
     KL_CUDA(cudaEventRecord(ctx->ev[4], s));
-    k_jacobian<P><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
+    if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
+    else k_jacobian<P, false><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     KL_CUDA(cudaEventRecord(ctx->ev[5], s));
     ctx->launches++;
     KL_CUDA(cudaGetLastError());

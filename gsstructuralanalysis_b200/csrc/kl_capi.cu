@@ -398,7 +398,6 @@ extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_f
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
-    if ((rc = kl_launch_points(ctx, ctx->e2_begin, ctx->e2_end, s))) return rc;
     KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, s));
     if ((rc = kl_launch_residual(ctx, r_dev, s))) return rc;
     return kl_launch_axpby(ctx, r_dev, ctx->d_fext, sign_fint, lam_fext, ctx->d.nfree, s);
