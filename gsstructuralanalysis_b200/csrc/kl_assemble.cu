@@ -11,6 +11,7 @@
 //            K_ij^{cd} += sum_p d_i[p] Z_j^{p,cd}, sum-factorised over the tensor-product basis
 //   scatter  FP64 RED (atomicAdd, no return) into the compressed values through the position table,
 //            both (i,j) and the transposed (j,i) entry.
+#include <cstdlib>
 #include "kl_device.cuh"
 
 size_t kl_pointdata_bytes(void) { return sizeof(PointData); }
@@ -253,6 +254,173 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
+// ---- Z_j = T(point) . d_j : the 45 coefficients [cd][p] of one basis function at one quadrature point
+template <int P, bool HASB>
+__device__ __forceinline__ void compute_Z(const PointData& pd, const BasisStage<P>& E, int q1, int q2, int j, double* Zo) {
+    const int ja = j % (P + 1), jb = j / (P + 1);
+    const double x0 = E.b1[q1][0][ja], x1 = E.b1[q1][1][ja], x2 = E.b1[q1][2][ja];
+    const double y0 = E.b2[q2][0][jb], y1 = E.b2[q2][1][jb], y2 = E.b2[q2][2][jb];
+    const double N1 = x1 * y0, N2 = x0 * y1, N11 = x2 * y0, N22 = x0 * y2, N12 = x1 * y1;
+    double n[3], a1[3], a2[3], c1[3], c2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { n[c] = pd.n[c]; a1[c] = pd.a1[c]; a2[c] = pd.a2[c]; c1[c] = pd.c1[c]; c2[c] = pd.c2[c]; }
+    double g[3], hh[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = N1 * c1[c] + N2 * c2[c];
+    const double G1[3] = {pd.G1[0], pd.G1[1], pd.G1[2]}, G2[3] = {pd.G2[0], pd.G2[1], pd.G2[2]};
+    hh[0] = N11 - G1[0] * N1 - G2[0] * N2;
+    hh[1] = N22 - G1[1] * N1 - G2[1] * N2;
+    hh[2] = 2.0 * (N12 - G1[2] * N1 - G2[2] * N2);
+    double AE1[3], AE2[3], BE1[3], BE2[3], Bh[3], Dh[3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        AE1[v] = N1 * pd.A[sidx(v, 0)] + N2 * pd.A[sidx(v, 2)];
+        AE2[v] = N2 * pd.A[sidx(v, 1)] + N1 * pd.A[sidx(v, 2)];
+        if (HASB) {
+            BE1[v] = N1 * pd.B[sidx(v, 0)] + N2 * pd.B[sidx(v, 2)];
+            BE2[v] = N2 * pd.B[sidx(v, 1)] + N1 * pd.B[sidx(v, 2)];
+            Bh[v] = pd.B[sidx(v, 0)] * hh[0] + pd.B[sidx(v, 1)] * hh[1] + pd.B[sidx(v, 2)] * hh[2];
+        } else { BE1[v] = 0.0; BE2[v] = 0.0; Bh[v] = 0.0; }
+        Dh[v] = pd.D[sidx(v, 0)] * hh[0] + pd.D[sidx(v, 1)] * hh[1] + pd.D[sidx(v, 2)] * hh[2];
+    }
+    const double Mt0 = pd.Mt[0], Mt1 = pd.Mt[1], Mt2 = pd.Mt[2];
+    const double Nhat = Mt0 * N11 + Mt1 * N22 + Mt2 * N12;
+    const double Ha1 = pd.Ha1, Ha2 = pd.Ha2, Hn = pd.Hn;
+    const double eta = Ha1 * N1 + Ha2 * N2;
+    const double p1 = pd.N[0] * N1 + pd.N[2] * N2, p2 = pd.N[1] * N2 + pd.N[2] * N1;
+    const double ga1 = pd.acon[0] * N1 + pd.acon[2] * N2, ga2 = pd.acon[2] * N1 + pd.acon[1] * N2;
+    const double q[3] = {pd.q[0], pd.q[1], pd.q[2]};
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {
+        double sig[3], mu[3];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            if (HASB) {
+                sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd] - n[dd] * Bh[v];
+                mu[v] = BE1[v] * a1[dd] + BE2[v] * a2[dd] - n[dd] * Dh[v];
+            } else {
+                sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd];
+                mu[v] = -n[dd] * Dh[v];
+            }
+        }
+        const double s1 = G1[0] * mu[0] + G1[1] * mu[1] + 2.0 * G1[2] * mu[2] + Nhat * c1[dd] - Ha1 * g[dd] + Hn * n[dd] * ga1;
+        const double s2 = G2[0] * mu[0] + G2[1] * mu[1] + 2.0 * G2[2] * mu[2] + Nhat * c2[dd] - Ha2 * g[dd] + Hn * n[dd] * ga2;
+        const double en = eta * n[dd];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double eq = 0.0;   // epsilon_{c dd k} q_k
+            if ((c + 1) % 3 == dd) eq = q[(c + 2) % 3];
+            else if ((dd + 1) % 3 == c) eq = -q[(dd + 2) % 3];
+            const double dl = (c == dd) ? 1.0 : 0.0;
+            double* z = Zo + (c * 3 + dd) * 5;
+            z[0] = a1[c] * sig[0] + a2[c] * sig[2] + n[c] * s1 - en * c1[c] + dl * p1 - N2 * eq;
+            z[1] = a2[c] * sig[1] + a1[c] * sig[2] + n[c] * s2 - en * c2[c] + dl * p2 + N1 * eq;
+            const double ng = n[dd] * g[c];
+            z[2] = -n[c] * mu[0] + Mt0 * ng;
+            z[3] = -n[c] * mu[1] + Mt1 * ng;
+            z[4] = -2.0 * n[c] * mu[2] + Mt2 * ng;
+        }
+    }
+}
+
+// ---- tile (ti2, tj) over one chunk (fixed q1): V_m^{cd} = sum_{q2} W_m^{cd}(q1,q2) first, then applied once with the
+//      first-direction factors X(q1) (sum factorisation).  Zc = Z[element][q2][j][ZS]
+template <int P>
+__device__ __forceinline__ void tile_chunk(const BasisStage<P>& E, const double (*Zc)[JacCfg<P>::NLOC][JacCfg<P>::ZS], int ch, int ti2, int tj,
+                                           double (&acc)[P + 1][9]) {
+    constexpr int QCH = JacCfg<P>::QCH;
+    double X0[P + 1], X1[P + 1], X2[P + 1];
+#pragma unroll
+    for (int a = 0; a <= P; ++a) { X0[a] = E.b1[ch][0][a]; X1[a] = E.b1[ch][1][a]; X2[a] = E.b1[ch][2][a]; }
+    // (c,d) entries in groups of 4, 4, 1: 20 / 20 / 5(+pad) contiguous coefficients per point; few live registers so that
+    // the loads of the next point can be issued ahead of the FMAs of the current one
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        constexpr int NG[3] = {4, 4, 1};
+        const int ng = NG[g];
+        double V0[4], V1[4], V2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { V0[k] = 0.0; V1[k] = 0.0; V2[k] = 0.0; }
+#pragma unroll
+        for (int qc = 0; qc < QCH; ++qc) {
+            const double y0 = E.b2[qc][0][ti2], y1 = E.b2[qc][1][ti2], y2 = E.b2[qc][2][ti2];
+            const double2* Zi = reinterpret_cast<const double2*>(Zc[qc][tj]) + g * 10;
+            double zz[20];
+#pragma unroll
+            for (int k = 0; k < (ng == 4 ? 10 : 3); ++k) { const double2 t = Zi[k]; zz[2 * k] = t.x; zz[2 * k + 1] = t.y; }
+#pragma unroll
+            for (int h = 0; h < ng; ++h) {
+                const double z1 = zz[5 * h], z2 = zz[5 * h + 1], z11 = zz[5 * h + 2], z22 = zz[5 * h + 3], z12 = zz[5 * h + 4];
+                V0[h] = fma(y2, z22, fma(y1, z2, V0[h]));    // multiplies N_{i1}(q1)
+                V1[h] = fma(y1, z12, fma(y0, z1, V1[h]));    // multiplies N'_{i1}(q1)
+                V2[h] = fma(y0, z11, V2[h]);                 // multiplies N''_{i1}(q1)
+            }
+        }
+#pragma unroll
+        for (int a = 0; a <= P; ++a)
+#pragma unroll
+            for (int h = 0; h < ng; ++h) acc[a][4 * g + h] = fma(X2[a], V2[h], fma(X1[a], V1[h], fma(X0[a], V0[h], acc[a][4 * g + h])));
+    }
+}
+
+// ---- scatter of one tile (upper triangle i <= j plus the transposed entries).  Regular columns are addressed
+//      arithmetically (outer[col] + c*nst + stencil slot); irregular ones (boundary, eliminated or matched DoFs in
+//      the stencil) go through the position table.  cb = colbase of the element's control points.
+template <int P>
+__device__ __forceinline__ void tile_scatter(const KLDev& d, const int4* cb, int e1, int e2, int ti2, int tj, const double (&acc)[P + 1][9]) {
+    const int i0 = d.span1[e1] - P, j0 = d.span2[e2] - P;
+    const int ja = tj % (P + 1), jb = tj / (P + 1);
+    const int J1 = i0 + ja, J2 = j0 + jb, Jc = J1 + d.n1 * J2;
+    const int NST = d.nst, S3 = NST * 3, W = 2 * P + 1;
+    double* __restrict__ val = d.values;
+    const int4 cbJ = cb[tj];
+    const int baseJ[3] = {cbJ.x, cbJ.y, cbJ.z};
+#pragma unroll
+    for (int a = 0; a <= P; ++a) {
+        const int i = a + (P + 1) * ti2;
+        if (i > tj) continue;
+        const int I1 = i0 + a, I2 = j0 + ti2, Ic = I1 + d.n1 * I2;
+        const int st_ij = (I1 - J1 + P) + W * (I2 - J2 + P);   // slot of row-function I in the stencil of column-function J
+        const int st_ji = (J1 - I1 + P) + W * (J2 - I2 + P);
+        const int4 cbI = cb[i];
+        const int baseI[3] = {cbI.x, cbI.y, cbI.z};
+        int p1[9], p2[9];
+        if (cbJ.w) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dd = 0; dd < 3; ++dd) p1[c * 3 + dd] = baseJ[dd] + c * NST + st_ij;
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int dd = 0; dd < 3; ++dd) p1[c * 3 + dd] = __ldg(&d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c]);
+        }
+        if (i != tj) {
+            if (cbI.w) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int dd = 0; dd < 3; ++dd) p2[c * 3 + dd] = baseI[c] + dd * NST + st_ji;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int dd = 0; dd < 3; ++dd) p2[c * 3 + dd] = __ldg(&d.pos[(size_t)(Ic * 3 + c) * S3 + st_ji * 3 + dd]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) p2[k] = -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            const double v = acc[a][k];
+            if (p1[k] >= 0) atomicAdd(&val[p1[k]], v);   // entry (row (I,c), col (J,dd))
+            if (p2[k] >= 0) atomicAdd(&val[p2[k]], v);   // entry (row (J,dd), col (I,c))
+        }
+    }
+}
+
 template <int P, bool HASB>
 __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_begin, int e2_end) {
     using Cfg = JacCfg<P>;
@@ -313,74 +481,7 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
             const int j = k % NLOC;
             const int qc = (k / NLOC) % QCH;
             const int le = k / (NLOC * QCH);
-            const int q1 = ch, q2 = qc;
-            const PointData& pd = S.pd[le][qc];
-            const BasisStage<P>& E = S.stage[le];
-            const int ja = j % (P + 1), jb = j / (P + 1);
-            const double x0 = E.b1[q1][0][ja], x1 = E.b1[q1][1][ja], x2 = E.b1[q1][2][ja];
-            const double y0 = E.b2[q2][0][jb], y1 = E.b2[q2][1][jb], y2 = E.b2[q2][2][jb];
-            const double N1 = x1 * y0, N2 = x0 * y1, N11 = x2 * y0, N22 = x0 * y2, N12 = x1 * y1;
-            double n[3], a1[3], a2[3], c1[3], c2[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) { n[c] = pd.n[c]; a1[c] = pd.a1[c]; a2[c] = pd.a2[c]; c1[c] = pd.c1[c]; c2[c] = pd.c2[c]; }
-            double g[3], hh[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) g[c] = N1 * c1[c] + N2 * c2[c];
-            const double G1[3] = {pd.G1[0], pd.G1[1], pd.G1[2]}, G2[3] = {pd.G2[0], pd.G2[1], pd.G2[2]};
-            hh[0] = N11 - G1[0] * N1 - G2[0] * N2;
-            hh[1] = N22 - G1[1] * N1 - G2[1] * N2;
-            hh[2] = 2.0 * (N12 - G1[2] * N1 - G2[2] * N2);
-            double AE1[3], AE2[3], BE1[3], BE2[3], Bh[3], Dh[3];
-#pragma unroll
-            for (int v = 0; v < 3; ++v) {
-                AE1[v] = N1 * pd.A[sidx(v, 0)] + N2 * pd.A[sidx(v, 2)];
-                AE2[v] = N2 * pd.A[sidx(v, 1)] + N1 * pd.A[sidx(v, 2)];
-                if (HASB) {
-                    BE1[v] = N1 * pd.B[sidx(v, 0)] + N2 * pd.B[sidx(v, 2)];
-                    BE2[v] = N2 * pd.B[sidx(v, 1)] + N1 * pd.B[sidx(v, 2)];
-                    Bh[v] = pd.B[sidx(v, 0)] * hh[0] + pd.B[sidx(v, 1)] * hh[1] + pd.B[sidx(v, 2)] * hh[2];
-                } else { BE1[v] = 0.0; BE2[v] = 0.0; Bh[v] = 0.0; }
-                Dh[v] = pd.D[sidx(v, 0)] * hh[0] + pd.D[sidx(v, 1)] * hh[1] + pd.D[sidx(v, 2)] * hh[2];
-            }
-            const double Mt0 = pd.Mt[0], Mt1 = pd.Mt[1], Mt2 = pd.Mt[2];
-            const double Nhat = Mt0 * N11 + Mt1 * N22 + Mt2 * N12;
-            const double Ha1 = pd.Ha1, Ha2 = pd.Ha2, Hn = pd.Hn;
-            const double eta = Ha1 * N1 + Ha2 * N2;
-            const double p1 = pd.N[0] * N1 + pd.N[2] * N2, p2 = pd.N[1] * N2 + pd.N[2] * N1;
-            const double ga1 = pd.acon[0] * N1 + pd.acon[2] * N2, ga2 = pd.acon[2] * N1 + pd.acon[1] * N2;
-            const double q[3] = {pd.q[0], pd.q[1], pd.q[2]};
-            double* Zo = S.Z[le][qc][j];
-#pragma unroll
-            for (int dd = 0; dd < 3; ++dd) {
-                double sig[3], mu[3];
-#pragma unroll
-                for (int v = 0; v < 3; ++v) {
-                    if (HASB) {
-                        sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd] - n[dd] * Bh[v];
-                        mu[v] = BE1[v] * a1[dd] + BE2[v] * a2[dd] - n[dd] * Dh[v];
-                    } else {
-                        sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd];
-                        mu[v] = -n[dd] * Dh[v];
-                    }
-                }
-                const double s1 = G1[0] * mu[0] + G1[1] * mu[1] + 2.0 * G1[2] * mu[2] + Nhat * c1[dd] - Ha1 * g[dd] + Hn * n[dd] * ga1;
-                const double s2 = G2[0] * mu[0] + G2[1] * mu[1] + 2.0 * G2[2] * mu[2] + Nhat * c2[dd] - Ha2 * g[dd] + Hn * n[dd] * ga2;
-                const double en = eta * n[dd];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    double eq = 0.0;   // epsilon_{c dd k} q_k
-                    if ((c + 1) % 3 == dd) eq = q[(c + 2) % 3];
-                    else if ((dd + 1) % 3 == c) eq = -q[(dd + 2) % 3];
-                    const double dl = (c == dd) ? 1.0 : 0.0;
-                    double* z = Zo + (c * 3 + dd) * 5;
-                    z[0] = a1[c] * sig[0] + a2[c] * sig[2] + n[c] * s1 - en * c1[c] + dl * p1 - N2 * eq;
-                    z[1] = a2[c] * sig[1] + a1[c] * sig[2] + n[c] * s2 - en * c2[c] + dl * p2 + N1 * eq;
-                    const double ng = n[dd] * g[c];
-                    z[2] = -n[c] * mu[0] + Mt0 * ng;
-                    z[3] = -n[c] * mu[1] + Mt1 * ng;
-                    z[4] = -2.0 * n[c] * mu[2] + Mt2 * ng;
-                }
-            }
+            compute_Z<P, HASB>(S.pd[le][qc], S.stage[le], ch, qc, j, S.Z[le][qc][j]);
         }
         __syncthreads();
         if (tid == 0 && ch + 1 < NQ2 / QCH) {
@@ -389,95 +490,121 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
         }
         // ---- phase 3: tile (ti2, tj).  The first-direction factors X(q1) are constant over the chunk, so
         //      V_m^{cd} = sum_{q2} W_m^{cd}(q1,q2) is formed first and applied once per chunk (sum factorisation).
-        {
-            const BasisStage<P>& E = S.stage[le_t];
-            double V0[9], V1[9], V2[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) { V0[k] = 0.0; V1[k] = 0.0; V2[k] = 0.0; }
-#pragma unroll 2
-            for (int qc = 0; qc < QCH; ++qc) {
-                const double y0 = E.b2[qc][0][ti2], y1 = E.b2[qc][1][ti2], y2 = E.b2[qc][2][ti2];
-                const double2* Zi = reinterpret_cast<const double2*>(S.Z[le_t][qc][tj]);
-#pragma unroll
-                for (int m = 0; m < 5; ++m) {
-                    // coefficients of two (c,d) entries: 10 contiguous doubles (the last pair has 5 + pad)
-                    double zz[10];
-#pragma unroll
-                    for (int k = 0; k < (m < 4 ? 5 : 3); ++k) { const double2 t = Zi[m * 5 + k]; zz[2 * k] = t.x; zz[2 * k + 1] = t.y; }
-#pragma unroll
-                    for (int h = 0; h < (m < 4 ? 2 : 1); ++h) {
-                        const int cd = 2 * m + h;
-                        const double z1 = zz[5 * h], z2 = zz[5 * h + 1], z11 = zz[5 * h + 2], z22 = zz[5 * h + 3], z12 = zz[5 * h + 4];
-                        V0[cd] = fma(y2, z22, fma(y1, z2, V0[cd]));    // multiplies N_{i1}(q1)
-                        V1[cd] = fma(y1, z12, fma(y0, z1, V1[cd]));    // multiplies N'_{i1}(q1)
-                        V2[cd] = fma(y0, z11, V2[cd]);                 // multiplies N''_{i1}(q1)
-                    }
-                }
+        tile_chunk<P>(S.stage[le_t], S.Z[le_t], ch, ti2, tj, acc);
+    }
+    const int e = ebase + le_t;
+    if (e < nel) tile_scatter<P>(d, S.cb[le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Warp-specialised persistent Jacobian kernel (degree 3): one CTA per SM, 13 warps.
+//   warps 0..4   consumers: 160 tile threads (4 elements x 40 upper-triangle tiles) keep the 3x3 blocks in registers
+//   warps 5..12  producers: 256 threads, one (element, q2, basis function) Z task each per chunk
+// Z is double-buffered in shared memory and handed over with mbarriers (full/empty), so the two phases of the
+// non-specialised kernel overlap instead of alternating behind CTA-wide barriers; the per-point records arrive
+// by TMA bulk copies two chunks ahead.
+struct JacWSShared {
+    static constexpr int EPG = 4, QCH = 4, NLOC = 16, ZS = 46;
+    double Z[2][EPG][QCH][NLOC][ZS];
+    PointData pd[2][EPG][QCH];
+    BasisStage<3> stage[2][EPG];
+    int4 cb[2][EPG][NLOC];
+    unsigned long long zfull[2], zempty[2], pdfull[2];
+};
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <bool HASB>
+__global__ void __launch_bounds__(416, 1) k_jacobian_ws(KLDev d, int e2_begin, int e2_end) {
+    constexpr int P = 3, NQ = 4, NQ2 = 16, NLOC = 16, TILES = 40, EPG = 4, QCH = 4, NCONS = 160, NPROD = 256;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    JacWSShared& S = *reinterpret_cast<JacWSShared*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int nel = d.nel1 * (e2_end - e2_begin);
+    const int ngroups = (nel + EPG - 1) / EPG;
+    const int my_groups = ((int)blockIdx.x < ngroups) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nchunks = my_groups * (NQ2 / QCH);
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) { mbar_init(&S.zfull[b], NPROD); mbar_init(&S.zempty[b], NCONS); mbar_init(&S.pdfull[b], 1); }
+    }
+    __syncthreads();
+    if (nchunks == 0) return;
+
+    if (tid >= NCONS) {
+        // ================================ producers ================================
+        const int pt = tid - NCONS;
+        const int j = pt % NLOC, qc = (pt / NLOC) % QCH, le = pt / (NLOC * QCH);
+        auto issue_pd = [&](int n) {   // chunk n of this CTA -> buffer n&1
+            const int b = n & 1, it = n / (NQ2 / QCH), ch = n % (NQ2 / QCH);
+            const int ebase = ((int)blockIdx.x + it * (int)gridDim.x) * EPG;
+            mbar_expect_tx(&S.pdfull[b], (unsigned)(EPG * QCH * sizeof(PointData)));
+            for (int l = 0; l < EPG; ++l) {
+                int e = ebase + l;
+                if (e >= nel) e = nel - 1;
+                const size_t ge = (size_t)(e % d.nel1) + (size_t)d.nel1 * (e2_begin + e / d.nel1);
+                tma_bulk_g2s(&S.pd[b][l][0], d.pd + ge * NQ2 + (size_t)ch * QCH, (unsigned)(QCH * sizeof(PointData)), &S.pdfull[b]);
             }
-#pragma unroll
-            for (int a = 0; a <= P; ++a) {
-                const double X0 = E.b1[ch][0][a], X1 = E.b1[ch][1][a], X2 = E.b1[ch][2][a];
-#pragma unroll
-                for (int cd = 0; cd < 9; ++cd) acc[a][cd] = fma(X2, V2[cd], fma(X1, V1[cd], fma(X0, V0[cd], acc[a][cd])));
+        };
+        if (pt == 0) { issue_pd(0); if (nchunks > 1) issue_pd(1); }
+        for (int n = 0; n < nchunks; ++n) {
+            const int b = n & 1, k = n >> 1, it = n / (NQ2 / QCH), ch = n % (NQ2 / QCH), gb = it & 1;
+            mbar_wait(&S.zempty[b], (k & 1) ^ 1);      // consumers have released Z[b] (passes at once the first time)
+            if (ch == 0) {
+                // basis tables and scatter bases of this group (consumers are past group it-2, see zempty wait above)
+                const int ebase = ((int)blockIdx.x + it * (int)gridDim.x) * EPG;
+                for (int l = 0; l < EPG; ++l) {
+                    int e = ebase + l;
+                    if (e >= nel) e = nel - 1;
+                    stage_basis<P>(d, e % d.nel1, e2_begin + e / d.nel1, S.stage[gb][l], pt, NPROD);
+                }
+                if (pt < EPG * NLOC) {
+                    const int l = pt / NLOC, f = pt - l * NLOC;
+                    int e = ebase + l;
+                    if (e >= nel) e = nel - 1;
+                    const int cpi = (d.span1[e % d.nel1] - P + f % (P + 1)) + d.n1 * (d.span2[e2_begin + e / d.nel1] - P + f / (P + 1));
+                    S.cb[gb][l][f] = reinterpret_cast<const int4*>(d.colbase)[cpi];
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            mbar_wait(&S.pdfull[b], k & 1);            // per-point records of this chunk have landed
+            compute_Z<P, HASB>(S.pd[b][le][qc], S.stage[gb][le], ch, qc, j, S.Z[b][le][qc][j]);
+            mbar_arrive(&S.zfull[b]);                  // release: Z[b] (and, for ch==0, stage/cb) visible to the consumers
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // every producer is done reading pd[b]
+            if (pt == 0 && n + 2 < nchunks) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_pd(n + 2);
             }
         }
-    }
-    // ---- scatter (upper triangle i <= j plus the transposed entries).  Regular columns are addressed
-    //      arithmetically (outer[col] + c*nst + stencil slot); irregular ones (boundary, eliminated or matched
-    //      DoFs in the stencil) go through the position table.
-    const int e = ebase + le_t;
-    if (e < nel) {
-        const int e1 = e % d.nel1, e2 = e2_begin + e / d.nel1;
-        const int i0 = d.span1[e1] - P, j0 = d.span2[e2] - P;
-        const int ja = tj % (P + 1), jb = tj / (P + 1);
-        const int J1 = i0 + ja, J2 = j0 + jb, Jc = J1 + d.n1 * J2;
-        const int NST = d.nst, S3 = NST * 3, W = 2 * P + 1;
-        double* __restrict__ val = d.values;
-        const int4 cbJ = S.cb[le_t][tj];
-        const int baseJ[3] = {cbJ.x, cbJ.y, cbJ.z};
-#pragma unroll
-        for (int a = 0; a <= P; ++a) {
-            const int i = a + (P + 1) * ti2;
-            if (i > tj) continue;
-            const int I1 = i0 + a, I2 = j0 + ti2, Ic = I1 + d.n1 * I2;
-            const int st_ij = (I1 - J1 + P) + W * (I2 - J2 + P);   // slot of row-function I in the stencil of column-function J
-            const int st_ji = (J1 - I1 + P) + W * (J2 - I2 + P);
-            const int4 cbI = S.cb[le_t][i];
-            const int baseI[3] = {cbI.x, cbI.y, cbI.z};
-            int p1[9], p2[9];
-            if (cbJ.w) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int dd = 0; dd < 3; ++dd) p1[c * 3 + dd] = baseJ[dd] + c * NST + st_ij;
-            } else {
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int dd = 0; dd < 3; ++dd) p1[c * 3 + dd] = __ldg(&d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c]);
+    } else {
+        // ================================ consumers ================================
+        const int le_t = tid / TILES, tt = tid - le_t * TILES;
+        int tj = 0, ti2 = 0;
+        {
+            int rem = tt;
+            for (int j2 = 0; j2 <= P; ++j2) {
+                const int cnt = (P + 1) * (j2 + 1);
+                if (rem < cnt) { tj = (P + 1) * j2 + rem / (j2 + 1); ti2 = rem % (j2 + 1); break; }
+                rem -= cnt;
             }
-            if (i != tj) {
-                if (cbI.w) {
+        }
+        for (int it = 0; it < my_groups; ++it) {
+            const int gb = it & 1;
+            double acc[P + 1][9];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c)
+            for (int a = 0; a <= P; ++a)
 #pragma unroll
-                        for (int dd = 0; dd < 3; ++dd) p2[c * 3 + dd] = baseI[c] + dd * NST + st_ji;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-#pragma unroll
-                        for (int dd = 0; dd < 3; ++dd) p2[c * 3 + dd] = __ldg(&d.pos[(size_t)(Ic * 3 + c) * S3 + st_ji * 3 + dd]);
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 9; ++k) p2[k] = -1;
+                for (int q = 0; q < 9; ++q) acc[a][q] = 0.0;
+#pragma unroll 1
+            for (int ch = 0; ch < NQ2 / QCH; ++ch) {
+                const int n = it * (NQ2 / QCH) + ch, b = n & 1, k = n >> 1;
+                mbar_wait(&S.zfull[b], k & 1);
+                tile_chunk<P>(S.stage[gb][le_t], S.Z[b][le_t], ch, ti2, tj, acc);
+                mbar_arrive(&S.zempty[b]);
             }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const double v = acc[a][k];
-                if (p1[k] >= 0) atomicAdd(&val[p1[k]], v);   // entry (row (I,c), col (J,dd))
-                if (p2[k] >= 0) atomicAdd(&val[p2[k]], v);   // entry (row (J,dd), col (I,c))
-            }
+            const int e = ((int)blockIdx.x + it * (int)gridDim.x) * EPG + le_t;
+            if (e < nel) tile_scatter<P>(d, S.cb[gb][le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
         }
     }
 }
@@ -586,8 +713,23 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
     // the membrane-bending coupling block B vanishes identically for the linear (SvK) law and for membranes
     const bool hasB = ctx->d.mat.material != KL_MAT_SVK && ctx->d.mat.bending;
+    static const bool use_ws = getenv("KL_JAC_WS") != nullptr;   // experimental warp-specialised variant (slower so far: profiles/)
     KL_CUDA(cudaEventRecord(ctx->ev[4], s));
-    if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
+    if (P == 3 && use_ws) {
+        static bool ws_attr = false;
+        static int n_sm = 0;
+        if (!ws_attr) {
+            KL_CUDA(cudaFuncSetAttribute(k_jacobian_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacWSShared)));
+            KL_CUDA(cudaFuncSetAttribute(k_jacobian_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacWSShared)));
+            int dev = 0;
+            KL_CUDA(cudaGetDevice(&dev));
+            KL_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+            ws_attr = true;
+        }
+        const int g = grid < n_sm ? grid : n_sm;
+        if (hasB) k_jacobian_ws<true><<<g, 416, sizeof(JacWSShared), s>>>(ctx->d, e2b, e2e);
+        else k_jacobian_ws<false><<<g, 416, sizeof(JacWSShared), s>>>(ctx->d, e2b, e2e);
+    } else if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     else k_jacobian<P, false><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     KL_CUDA(cudaEventRecord(ctx->ev[5], s));
     ctx->launches++;
