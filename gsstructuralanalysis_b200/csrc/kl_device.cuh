@@ -155,7 +155,7 @@ __device__ __forceinline__ bool hyper_comp(const KLMaterial& m, const double Gi[
     const double trs = t00 + t11;
     const double tr2s = Cup[0] * gc[0] + Cup[1] * gc[1] + 2.0 * Cup[2] * gc[2];
     const double K = m.bulk, c1 = m.c1, c2 = m.c2;
-    double c33 = 1.0, I1, I2, Jsq, j23, j43, ci;
+    double c33 = 1.0 / J0sq, I1, I2, Jsq, j23, j43, ci;   // start from the incompressible solution C33 = J0^-2
     bool conv = false;
     for (int it = 0; it < 100; ++it) {
         I1 = trs + c33;

@@ -137,3 +137,30 @@ def material(prob: ShellProblem, Ac, Bc, ac, bc):
     A, B, D, N, M = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((3, 3)), np.zeros(3), np.zeros(3)
     rc = L.klo_material(C.byref(P), *[_dp(a) for a in arrs], _dp(A), _dp(B), _dp(D), _dp(N), _dp(M))
     return rc, A, B, D, N, M
+
+
+class OracleOps:
+    """The oracle in the closure shapes of gsStructuralAnalysisOps (returns (ok, value)), so that the same test
+    drivers run on the oracle and on the GPU path."""
+
+    def __init__(self, prob, threads=None):
+        self.o = Oracle(prob, threads)
+        self.n_dofs, self.nnz = self.o.n_dofs, self.o.nnz
+
+    def jacobian(self, x):
+        try:
+            return True, self.o.jacobian(x)
+        except RuntimeError:
+            return False, None
+
+    def residual(self, x):
+        try:
+            return True, self.o.residual(x)
+        except RuntimeError:
+            return False, None
+
+    def force(self):
+        return self.o.force()
+
+    def close(self):
+        self.o.close()

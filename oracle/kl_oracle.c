@@ -205,7 +205,7 @@ static int hyper_point(const kl_problem* P, const double Gc[3], const double gc[
     double G3[3][3] = {{0}}, Cc[3][3] = {{0}}, Ci[3][3] = {{0}}, Cup[3][3];
     for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { G3[a][b] = s2(Gi, a, b); Cc[a][b] = s2(gc, a, b); Ci[a][b] = s2(gi, a, b); }
     G3[2][2] = 1.0;
-    double c33 = 1.0;
+    double c33 = 1.0 / J0sq;   /* start from the incompressible solution C33 = J0^-2 */
     double S3[3][3], C4[3][3][3][3];
     int converged = 0;
     for (int it = 0; it < 100; ++it) {

@@ -111,3 +111,28 @@ def test_nonfinite_state_returns_false(gpu):
     assert not ok and not ok2
     ok, _ = asm.residual(np.zeros(asm.n_dofs))     # flag is cleared: next call succeeds
     assert ok
+
+
+# ---- the reference's own known answers, solved with the GPU closures (same drivers as tests/test_oracle_kat.py)
+@pytest.mark.parametrize("material,compressible", [(KL_MAT_NH, False), (KL_MAT_MR, False), (KL_MAT_NH, True), (KL_MAT_MR, True)])
+def test_gpu_uniaxial_tension_known_answer(gpu, material, compressible):
+    from tests import kat_problems as kp
+    from gsstructuralanalysis_b200 import capi
+    pr, _ = kp.uat_problem(material, compressible, capi.lib().kl_build_dofmap)
+    asm, x = kp.newton(lambda p: gpu(p), pr, load_steps=np.linspace(0.25, 1.0, 4), scale_fixed=1.0)
+    lam2 = kp.uat_lateral_stretch(pr, x)
+    expect = np.sqrt(kp.UAT_J[(material, compressible)] / 2.0)
+    assert abs(lam2 - expect) / expect < 1e-7      # unittests/gsStaticSolver_test.cpp:415
+
+
+def test_gpu_scordelis_lo_known_answer(gpu):
+    import scipy.sparse.linalg as spla
+    from tests import kat_problems as kp
+    from gsstructuralanalysis_b200 import capi
+    pr = kp.scordelis_lo_problem(12, capi.lib().kl_build_dofmap)
+    asm = gpu(pr)
+    ok, K = asm.jacobian(np.zeros(asm.n_dofs))
+    assert ok
+    u = spla.spsolve(K.to_scipy(), asm.force())
+    uz = kp.scordelis_lo_deflection(pr, u)
+    assert abs(-uz - 0.3006) / 0.3006 < 5e-3       # filedata/pde/kirchhoff_shell_scordelis.xml:104-107 gives 0.30024
