@@ -1,0 +1,103 @@
+/** examples/newton_shell.cpp — the reference's tutorial driver shape (tutorials/nonlinear_shell_static.cpp:115-160)
+    on top of the B200 operators: define Jacobian / Residual closures, solve K du = R with a Newton loop
+    (src/gsStaticSolvers/gsStaticNewton.hpp:142-193) and the reference's default "CGDiagonal" linear solver
+    (Jacobi-preconditioned CG, gsStaticNewton.hpp:23).  The linear solve stays on the host, as in the reference.
+
+    usage: newton_shell problem.klp [max_iterations]        (problem.klp written by ShellProblem.save)
+    exit code 0 = converged (or no GPU present: prints the reason and exits 0 so that CPU-only CI can build/run it). */
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+
+#include "../include/gsStructuralAnalysisOps_b200.h"
+
+using namespace gismo;
+
+struct ProblemFile {
+    kl_problem P{};
+    std::vector<double> U1, U2, cp, w, fixed, pl_uv, pl_val;
+    std::vector<int32_t> map;
+    bool load(const char* path) {
+        std::ifstream f(path, std::ios::binary);
+        char magic[4];
+        int32_t h[16];
+        double d[8];
+        if (!f.read(magic, 4) || std::string(magic, 4) != "KLP1") return false;
+        f.read((char*)h, sizeof(h));
+        f.read((char*)d, sizeof(d));
+        const int ncp = h[4], has_w = h[5], npl = h[15];
+        auto rd = [&](std::vector<double>& v, size_t n) { v.resize(n); f.read((char*)v.data(), sizeof(double) * n); };
+        rd(U1, h[2]); rd(U2, h[3]); rd(cp, 3 * (size_t)ncp);
+        if (has_w) rd(w, ncp);
+        map.resize(3 * (size_t)ncp);
+        f.read((char*)map.data(), sizeof(int32_t) * map.size());
+        rd(fixed, h[7]);
+        if (npl) { rd(pl_uv, 2 * (size_t)npl); rd(pl_val, 3 * (size_t)npl); }
+        P.degree[0] = h[0]; P.degree[1] = h[1]; P.n_knots[0] = h[2]; P.n_knots[1] = h[3];
+        P.knots[0] = U1.data(); P.knots[1] = U2.data(); P.cp = cp.data(); P.weights = has_w ? w.data() : nullptr;
+        P.dof_map = map.data(); P.n_free = h[6]; P.n_fixed = h[7]; P.fixed_values = h[7] ? fixed.data() : nullptr;
+        P.material = h[8]; P.compressible = h[9]; P.num_gauss_thickness = h[10]; P.bending = h[11]; P.metric_z2 = h[12];
+        P.quA = h[13]; P.quB = h[14]; P.n_point_loads = npl;
+        P.E = d[0]; P.nu = d[1]; P.thickness = d[2]; P.mr_ratio = d[3];
+        P.body_force[0] = d[4]; P.body_force[1] = d[5]; P.body_force[2] = d[6]; P.pressure = d[7];
+        P.point_load_uv = npl ? pl_uv.data() : nullptr; P.point_load_val = npl ? pl_val.data() : nullptr;
+        return (bool)f;
+    }
+};
+
+// Jacobi-preconditioned CG ("CGDiagonal")
+static int pcg(const gsSparseMatrix<>& A, const gsVector<>& b, gsVector<>& x, double tol, int maxit) {
+    const index_t n = b.size();
+    gsVector<> r(n), z(n), p(n), Ap(n), dinv(n);
+    x.setZero(n);
+    for (index_t i = 0; i < n; ++i) { dinv[i] = 1.0 / A.diagonal(i); r[i] = b[i]; z[i] = dinv[i] * r[i]; p[i] = z[i]; }
+    double rz = 0; for (index_t i = 0; i < n; ++i) rz += r[i] * z[i];
+    const double bn = b.norm();
+    for (int it = 0; it < maxit; ++it) {
+        A.apply(p, Ap);
+        double pAp = 0; for (index_t i = 0; i < n; ++i) pAp += p[i] * Ap[i];
+        const double alpha = rz / pAp;
+        for (index_t i = 0; i < n; ++i) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; }
+        if (r.norm() <= tol * bn) return it + 1;
+        double rz2 = 0; for (index_t i = 0; i < n; ++i) { z[i] = dinv[i] * r[i]; rz2 += r[i] * z[i]; }
+        const double beta = rz2 / rz; rz = rz2;
+        for (index_t i = 0; i < n; ++i) p[i] = z[i] + beta * p[i];
+    }
+    return -1;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) { std::fprintf(stderr, "usage: %s problem.klp [maxit]\n", argv[0]); return 2; }
+    ProblemFile pf;
+    if (!pf.load(argv[1])) { std::fprintf(stderr, "cannot read %s\n", argv[1]); return 2; }
+    const int maxIt = argc > 2 ? std::atoi(argv[2]) : 25;
+    std::unique_ptr<gsThinShellAssemblerB200> assembler;
+    try {
+        assembler.reset(new gsThinShellAssemblerB200(pf.P));
+    } catch (const std::exception& e) {
+        std::printf("NO_GPU %s\n", e.what());     // libkl_shell has no CPU fallback
+        return 0;
+    }
+    gsStructuralAnalysisOps<real_t>::Jacobian_t Jacobian = assembler->jacobian();
+    gsStructuralAnalysisOps<real_t>::Residual_t Residual = assembler->residual();
+    const index_t n = assembler->numDofs();
+    std::printf("Solving system with %d DoFs, %lld non-zeros\n", n, (long long)assembler->nonZeros());
+    gsVector<> U(n), dU(n), R(n);
+    gsSparseMatrix<> K;
+    U.setZero(n);
+    if (!Residual(U, R)) return 1;
+    const double R0 = R.norm();
+    gsStatus status = gsStatus::NotConverged;
+    for (int it = 0; it < maxIt; ++it) {
+        if (!Jacobian(U, K)) { status = gsStatus::AssemblyError; break; }
+        const int cg = pcg(K, R, dU, 1e-12, 20 * n);
+        if (cg < 0) { status = gsStatus::SolverError; break; }
+        U += dU;
+        if (!Residual(U, R)) { status = gsStatus::AssemblyError; break; }
+        std::printf("it %2d  |dU|/|U| = %.3e  |R|/|R0| = %.3e  (cg %d)\n", it, dU.norm() / U.norm(), R.norm() / R0, cg);
+        if (dU.norm() / U.norm() < 1e-6 && R.norm() / R0 < 1e-9) { status = gsStatus::Success; break; }   // tolU, tolF
+    }
+    std::printf("STATUS %s |U| = %.12e\n", status == gsStatus::Success ? "Success" : "NotConverged", U.norm());
+    return status == gsStatus::Success ? 0 : 1;
+}

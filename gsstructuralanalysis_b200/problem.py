@@ -152,3 +152,28 @@ class ShellProblem:
             P.point_load_uv = dp(np.array([pl[0] for pl in self.point_loads]).reshape(-1))
             P.point_load_val = dp(np.array([pl[1] for pl in self.point_loads]).reshape(-1))
         return P, keep
+
+    def save(self, path):
+        """Binary dump read by examples/newton_shell.cpp (little endian):
+        'KLP1', 16 int32 header, 8 doubles, then the arrays in the order of kl_problem."""
+        import struct
+        s = self.surface
+        assert self.dof_map is not None
+        n1, n2 = s.n
+        ncp = n1 * n2
+        with open(path, "wb") as f:
+            f.write(b"KLP1")
+            f.write(struct.pack("<16i", s.p[0], s.p[1], len(s.U[0]), len(s.U[1]), ncp, int(s.w is not None), self.n_free,
+                                self.n_fixed, int(self.material), int(self.compressible), int(self.num_gauss_thickness),
+                                int(self.bending), int(self.metric_z2), self.quA, self.quB, len(self.point_loads)))
+            f.write(struct.pack("<8d", self.E, self.nu, self.thickness, self.mr_ratio, *[float(v) for v in self.body_force],
+                                float(self.pressure)))
+            for a in (s.U[0], s.U[1], s.cp.reshape(-1)):
+                f.write(np.ascontiguousarray(a, dtype="<f8").tobytes())
+            if s.w is not None:
+                f.write(np.ascontiguousarray(s.w, dtype="<f8").tobytes())
+            f.write(np.ascontiguousarray(self.dof_map, dtype="<i4").tobytes())
+            f.write(np.ascontiguousarray(self.fixed_values if self.n_fixed else np.zeros(0), dtype="<f8").tobytes())
+            if self.point_loads:
+                f.write(np.array([pl[0] for pl in self.point_loads], dtype="<f8").tobytes())
+                f.write(np.array([pl[1] for pl in self.point_loads], dtype="<f8").tobytes())

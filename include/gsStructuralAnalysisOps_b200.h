@@ -1,0 +1,222 @@
+/** @file gsStructuralAnalysisOps_b200.h
+
+    Header-only C++ adapter: turns a kl_ctx (include/kl_shell.h, libkl_shell.so) into the std::function operators
+    every gsStructuralAnalysis solver consumes.
+
+    Mirrors, name for name, the reference interface
+        gismo::gsStatus                               src/gsStructuralAnalysisTools/gsStructuralAnalysisTypes.h:22-30
+        gismo::gsStructuralAnalysisOps<T>::*_t        src/gsStructuralAnalysisTools/gsStructuralAnalysisTypes.h:58-93
+    and replaces the closure bodies of the drivers
+        Jacobian / Residual                           tutorials/nonlinear_shell_static.cpp:120-136
+        ALResidual                                    benchmarks/benchmark_Roof.cpp:335-344
+
+    With G+Smo on the include path (__has_include(<gismo.h>)) the real gsVector / gsSparseMatrix are used and the
+    reference's solvers (gsStaticNewton, gsALMCrisfield, gsAPALM, ...) take these callables unchanged.  Without it a
+    minimal stand-in with the same storage layout (Eigen compressed column-major: outerIndexPtr / innerIndexPtr /
+    valuePtr) is provided so that the adapter, its tests and the examples build on their own.
+*/
+#pragma once
+
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kl_shell.h"
+
+#if defined(__has_include)
+#if __has_include(<gismo.h>)
+#include <gismo.h>
+#define KL_HAVE_GISMO 1
+#endif
+#endif
+
+#ifndef KL_HAVE_GISMO
+namespace gismo {
+
+typedef int index_t;
+typedef double real_t;
+
+/// Dense column vector (stand-in for gsVector<T> = Eigen::Matrix<T,Dynamic,1>)
+template <class T = real_t>
+class gsVector {
+public:
+    gsVector() {}
+    explicit gsVector(index_t n) : m_v(n, T(0)) {}
+    void resize(index_t n) { m_v.resize(n); }
+    void setZero() { std::fill(m_v.begin(), m_v.end(), T(0)); }
+    void setZero(index_t n) { m_v.assign(n, T(0)); }
+    index_t size() const { return (index_t)m_v.size(); }
+    index_t rows() const { return size(); }
+    T* data() { return m_v.data(); }
+    const T* data() const { return m_v.data(); }
+    T& operator[](index_t i) { return m_v[i]; }
+    const T& operator[](index_t i) const { return m_v[i]; }
+    T& at(index_t i) { return m_v[i]; }
+    T norm() const { T s = 0; for (T v : m_v) s += v * v; return std::sqrt(s); }
+    gsVector& operator+=(const gsVector& o) { for (index_t i = 0; i < size(); ++i) m_v[i] += o[i]; return *this; }
+private:
+    std::vector<T> m_v;
+};
+
+/// Compressed column-major sparse matrix (stand-in for gsSparseMatrix<T> = Eigen::SparseMatrix<T,ColMajor,index_t>)
+template <class T = real_t>
+class gsSparseMatrix {
+public:
+    gsSparseMatrix() : m_rows(0), m_cols(0) {}
+    index_t rows() const { return m_rows; }
+    index_t cols() const { return m_cols; }
+    index_t nonZeros() const { return (index_t)m_val.size(); }
+    bool isCompressed() const { return true; }
+    const index_t* outerIndexPtr() const { return m_outer.data(); }
+    const index_t* innerIndexPtr() const { return m_inner.data(); }
+    index_t* outerIndexPtr() { return m_outer.data(); }
+    index_t* innerIndexPtr() { return m_inner.data(); }
+    const T* valuePtr() const { return m_val.data(); }
+    T* valuePtr() { return m_val.data(); }
+    /// adopt a compressed pattern (what `m = assembler.matrix()` leaves behind)
+    void setPattern(index_t n, const index_t* outer, const index_t* inner) {
+        m_rows = m_cols = n;
+        m_outer.assign(outer, outer + n + 1);
+        m_inner.assign(inner, inner + outer[n]);
+        m_val.assign((size_t)outer[n], T(0));
+    }
+    /// y = A x
+    void apply(const gsVector<T>& x, gsVector<T>& y) const {
+        y.setZero(m_rows);
+        for (index_t j = 0; j < m_cols; ++j) {
+            const T xj = x[j];
+            for (index_t k = m_outer[j]; k < m_outer[j + 1]; ++k) y[m_inner[k]] += m_val[k] * xj;
+        }
+    }
+    T diagonal(index_t j) const {
+        for (index_t k = m_outer[j]; k < m_outer[j + 1]; ++k) if (m_inner[k] == j) return m_val[k];
+        return T(0);
+    }
+private:
+    index_t m_rows, m_cols;
+    std::vector<index_t> m_outer, m_inner;
+    std::vector<T> m_val;
+};
+
+/// src/gsStructuralAnalysisTools/gsStructuralAnalysisTypes.h:22-30
+enum struct gsStatus { Success, NotConverged, AssemblyError, SolverError, NotStarted, OtherError };
+
+/// src/gsStructuralAnalysisTools/gsStructuralAnalysisTypes.h:58-93
+template <class T>
+struct gsStructuralAnalysisOps {
+    typedef std::function<bool(gsVector<T> const&, T&)> Energy_t;
+    typedef std::function<bool(gsVector<T>&)> Force_t;
+    typedef std::function<bool(const T, gsVector<T>&)> TForce_t;
+    typedef std::function<bool(gsVector<T> const&, gsVector<T>&)> Residual_t;
+    typedef std::function<bool(gsVector<T> const&, const T, gsVector<T>&)> ALResidual_t;
+    typedef std::function<bool(gsVector<T> const&, const T, gsVector<T>&)> TResidual_t;
+    typedef std::function<bool(gsSparseMatrix<T>&)> Mass_t;
+    typedef std::function<bool(const T, gsSparseMatrix<T>&)> TMass_t;
+    typedef std::function<bool(gsVector<T> const&, gsSparseMatrix<T>&)> Damping_t;
+    typedef std::function<bool(gsVector<T> const&, const T, gsSparseMatrix<T>&)> TDamping_t;
+    typedef std::function<bool(gsSparseMatrix<T>&)> Stiffness_t;
+    typedef std::function<bool(gsVector<T> const&, gsSparseMatrix<T>&)> Jacobian_t;
+    typedef std::function<bool(gsVector<T> const&, const T, gsSparseMatrix<T>&)> TJacobian_t;
+    typedef std::function<bool(gsVector<T> const&, gsVector<T> const&, gsSparseMatrix<T>&)> dJacobian_t;
+};
+
+}  // namespace gismo
+#endif  // !KL_HAVE_GISMO
+
+namespace gismo {
+
+/** Owns one device context and hands out cheap-to-copy operator handles (the reference stores its closures by
+    value inside the solvers: src/gsStaticSolvers/gsStaticNewton.h:232-235), so the handles share the context through
+    a shared_ptr.  One object per GPU / solver thread; calls on one object are serialised by the caller, as in the
+    reference (closures are not re-entrant, benchmarks/benchmark_Frustrum_APALM.cpp:403-412). */
+class gsThinShellAssemblerB200 {
+public:
+    typedef double T;
+    typedef gsStructuralAnalysisOps<T> Ops;
+
+    gsThinShellAssemblerB200(const kl_problem& prob, int device = -1) {
+        kl_ctx* c = nullptr;
+        const int rc = kl_create(&prob, device, &c);
+        if (rc != KL_OK) throw std::runtime_error(std::string("kl_create: ") + kl_last_error());
+        m_s = std::make_shared<Shared>();
+        m_s->ctx = c;
+        int64_t nnz = 0, ne = 0, nq = 0;
+        kl_sizes(c, &m_s->ndofs, &nnz, &ne, &nq);
+        m_s->nnz = nnz;
+        m_s->outer.resize((size_t)m_s->ndofs + 1);
+        m_s->inner.resize((size_t)nnz);
+        if (kl_pattern_host(c, m_s->outer.data(), m_s->inner.data()) != KL_OK)
+            throw std::runtime_error(std::string("kl_pattern_host: ") + kl_last_error());
+    }
+
+    index_t numDofs() const { return m_s->ndofs; }
+    int64_t nonZeros() const { return m_s->nnz; }
+    kl_ctx* context() const { return m_s->ctx; }
+
+    /// K(x): constructSolution(x,def); assembleMatrix(def); m = matrix()
+    Ops::Jacobian_t jacobian() const {
+        auto s = m_s;
+        return [s](gsVector<T> const& x, gsSparseMatrix<T>& m) {
+            adoptPattern(m, s->ndofs, s->nnz, s->outer.data(), s->inner.data());
+            return kl_jacobian(s->ctx, x.data(), m.valuePtr()) == KL_OK;
+        };
+    }
+    /// dJacobian_t ignores dx, like the wrappers in gsStaticNewton.h:79-82 / gsALMBase.h:57-60
+    Ops::dJacobian_t djacobian() const {
+        Ops::Jacobian_t J = jacobian();
+        return [J](gsVector<T> const& x, gsVector<T> const&, gsSparseMatrix<T>& m) { return J(x, m); };
+    }
+    /// R(x) = F_ext - F_int: constructSolution; assembleVector(def); v = rhs()
+    Ops::Residual_t residual() const {
+        auto s = m_s;
+        return [s](gsVector<T> const& x, gsVector<T>& r) {
+            r.resize(s->ndofs);
+            return kl_residual(s->ctx, x.data(), r.data()) == KL_OK;
+        };
+    }
+    /// F_int - lam F_ext = Force - lam*Force - rhs()
+    Ops::ALResidual_t alResidual() const {
+        auto s = m_s;
+        return [s](gsVector<T> const& x, const T lam, gsVector<T>& r) {
+            r.resize(s->ndofs);
+            return kl_al_residual(s->ctx, x.data(), lam, r.data()) == KL_OK;
+        };
+    }
+    /// F (what assemble(); rhs() gives at u = 0)
+    Ops::Force_t force() const {
+        auto s = m_s;
+        return [s](gsVector<T>& f) {
+            f.resize(s->ndofs);
+            return kl_force(s->ctx, f.data()) == KL_OK;
+        };
+    }
+
+private:
+    static void adoptPattern(gsSparseMatrix<T>& m, index_t n, int64_t nnz, const int32_t* outer, const int32_t* inner) {
+        if (m.rows() == n && m.cols() == n && (int64_t)m.nonZeros() == nnz && m.isCompressed()) return;   // values only
+#ifdef KL_HAVE_GISMO
+        // one-time deep copy of the symbolic pattern into the solver's matrix; afterwards only valuePtr() is refreshed
+        typedef gsEigen::Map<const gsEigen::SparseMatrix<T, gsEigen::ColMajor, index_t> > MapT;
+        std::vector<T> zeros((size_t)nnz, T(0));
+        m = MapT(n, n, (index_t)nnz, outer, inner, zeros.data());
+        m.makeCompressed();
+#else
+        m.setPattern(n, outer, inner);
+#endif
+    }
+
+    struct Shared {
+        kl_ctx* ctx = nullptr;
+        int32_t ndofs = 0;
+        int64_t nnz = 0;
+        std::vector<int32_t> outer, inner;
+        ~Shared() { if (ctx) kl_destroy(ctx); }
+    };
+    std::shared_ptr<Shared> m_s;   // shared by every handle handed out, so handles may outlive this object
+};
+
+}  // namespace gismo

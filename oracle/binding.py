@@ -31,6 +31,7 @@ def lib():
         L.klo_create.argtypes = [C.POINTER(kl_problem)]
         L.klo_destroy.argtypes = [C.c_void_p]
         L.klo_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.klo_set_strip.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.klo_get_threads.argtypes = [C.c_void_p]
         L.klo_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long)]
         L.klo_pattern.argtypes = [C.c_void_p, c_int_p, c_int_p]
@@ -68,6 +69,9 @@ class Oracle:
         self.inner = np.zeros(max(self.nnz, 1), dtype=np.int32)
         self.L.klo_pattern(self.h, self.outer.ctypes.data_as(c_int_p), self.inner.ctypes.data_as(c_int_p))
         self.inner = self.inner[:self.nnz]
+
+    def set_strip(self, e2_begin, e2_end):
+        self.L.klo_set_strip(self.h, e2_begin, e2_end)
 
     @property
     def threads(self):

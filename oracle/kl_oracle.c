@@ -60,6 +60,7 @@ typedef struct klo {
     long nnz;
     double* fext;         /* [nfree] */
     int nthreads;
+    int e2_begin, e2_end;  /* element rows assembled (strip partition tests) */
 } klo;
 
 /* ------------------------------------------------------------------------------------ */
@@ -559,6 +560,7 @@ static int assemble(const klo* o, const double* x, double* Kval, double* fint) {
     for (int e = 0; e < nel; ++e) {
         if (err) continue;
         int e1 = e % o->nel[0], e2 = e / o->nel[0];
+        if (e2 < o->e2_begin || e2 >= o->e2_end) continue;
         double ua = o->U[0][o->span[0][e1]], ub = o->U[0][o->span[0][e1] + 1];
         double va = o->U[1][o->span[1][e2]], vb = o->U[1][o->span[1][e2] + 1];
         qpdata q;
@@ -744,6 +746,7 @@ klo* klo_create(const kl_problem* P) {
 #ifdef _OPENMP
     o->nthreads = omp_get_max_threads();
 #endif
+    o->e2_begin = 0; o->e2_end = o->nel[1];
     build_pattern(o);
     build_fext(o);
     return o;
@@ -756,6 +759,7 @@ void klo_destroy(klo* o) {
     free(o->outer); free(o->inner); free(o->fext); free(o);
 }
 
+void klo_set_strip(klo* o, int b, int e) { o->e2_begin = b; o->e2_end = e; }
 void klo_set_threads(klo* o, int n) { o->nthreads = n > 0 ? n : 1; }
 int klo_get_threads(const klo* o) { return o->nthreads; }
 

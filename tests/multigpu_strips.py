@@ -1,0 +1,63 @@
+"""torchrun entry (one process per GPU): strip-partitioned assembly of ONE matrix with the NCCL halo exchange,
+checked against the full oracle matrix.  Launched by tests/test_gpu_multigpu.py and usable by hand:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/multigpu_strips.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from gsstructuralanalysis_b200 import workloads as W
+    from gsstructuralanalysis_b200.ops import ShellAssembler
+    from gsstructuralanalysis_b200.parallel import plan_strips, exchange_halo, value_ranges, DevicePointerView
+    from oracle.binding import Oracle
+    nel = int(os.environ.get("KL_NEL", "24"))
+    pr = W.roof(nel)
+    asm = ShellAssembler(pr, device=local)
+    n1, n2 = pr.surface.n
+    plan = plan_strips(n1, n2, 3, n2 - 3, pr.dof_map, pr.n_free, world, rank)
+    asm.set_strip(plan.e2_begin, plan.e2_end)
+    x = W.displacement_state(asm.n_dofs, 0.05)
+    xd = torch.from_numpy(x).cuda()
+    rd = torch.zeros(asm.n_dofs, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    asm.jacobian_device(xd.data_ptr(), stream)
+    asm.residual_device(xd.data_ptr(), rd.data_ptr(), 0.0, 1.0, stream)     # partial F_int of the strip
+    assert asm.check(stream) == 0
+    vals = DevicePointerView(asm.values_device_ptr(), asm.nnz).tensor()
+    outer, _ = asm.pattern()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    moved = exchange_halo(plan, outer, vals, rd, dist)
+    e1.record()
+    torch.cuda.synchronize()
+    ok = True
+    if os.environ.get("KL_CHECK", "1") == "1":
+        orc = Oracle(pr)
+        Kf, Rf = orc.jacobian_values(x), orc.force() - orc.residual(x)
+        v, r = vals.cpu().numpy(), rd.cpu().numpy()
+        for (a, b) in value_ranges(plan.owned_cols, outer):
+            ok &= bool(np.abs(v[a:b] - Kf[a:b]).max() <= 1e-12 * np.abs(Kf).max())
+        for (c0, c1) in plan.owned_cols:
+            ok &= bool(np.abs(r[c0:c1] - Rf[c0:c1]).max() <= 1e-12 * np.abs(Rf).max())
+    t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"STRIPS world={world} n_dofs={asm.n_dofs} ok={bool(t.item())} halo_bytes={moved} exchange_ms={e0.elapsed_time(e1):.3f}")
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
