@@ -54,19 +54,17 @@ def make_problem(nel, material):
 
 
 def flops_per_qp(p, material):
-    """Mathematically necessary FP64 operations of the assembly algorithm per quadrature point:
-    phase 3 (upper-triangle pairs, sum-factorised):  tiles*63 + pairs*54
-    phase 2 (Z_j = T.d_j per basis function):        576 * nloc
-    phase 1 (geometry, metric, material):            4*(9*(p+1)^2 + 18*(p+1))*... counted below"""
+    """FP64 operations of the Jacobian kernel per quadrature point for the algorithm of DESIGN.md §5 (FMA = 2 flops):
+    phase 3 (upper-triangle tiles, sum-factorised): tiles * [ (p+1)*45 + 27*(p+1) ] FMA per fixed-q1 column
+    phase 2 (Z_j = T.d_j):  478 flops per (basis function, point) for the linear law (B = 0), 555 with the
+                             membrane-bending coupling block (hyperelastic laws)
+    p = 3 linear law: 5760 + 16*478 = 13408, which is what ncu counts as executed
+    (sm__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on, profiles/r1_r1i_summary.txt)."""
     nloc = (p + 1) ** 2
-    pairs = nloc * (nloc + 1) // 2
     tiles = (p + 1) * (p + 1) * (p + 2) // 2
-    ph3 = tiles * 63 + pairs * 54
-    ph2 = 576 * nloc
-    geom = 2 * 2 * (9 * nloc + 18 * (p + 1))            # two 3-component fields, sum-factorised, FMA = 2 flops
-    mat = {"svk": 150, "nh": 4 * 170, "mr": 4 * 190, "nh_c": 4 * 600, "mr_c": 4 * 700}[material]
-    ph1 = geom + 450 + mat
-    return ph1 + ph2 + ph3
+    ph3 = 2 * tiles * ((p + 1) * 45 + 27 * (p + 1)) / (p + 1)     # per point: one column has p+1 points
+    ph2 = (478 if material == "svk" else 555) * nloc
+    return int(ph3 + ph2)
 
 
 class ClockSampler:
