@@ -212,8 +212,11 @@ struct JacCfg {
     static constexpr int NQ2 = NQ * NQ;
     static constexpr int NLOC = (P + 1) * (P + 1);
     static constexpr int TILES = (P + 1) * (P + 1) * (P + 2) / 2;      // (i2, j) with i2 <= j2
-    static constexpr int EPG = (P == 4) ? 2 : 4;                        // elements per CTA
-    static constexpr int NT = TILES * EPG;                              // 72 / 160 / 150
+    static constexpr int EPG = (P == 2) ? 4 : 2;                        // elements per CTA
+    static constexpr int NTILE = TILES * EPG;                           // threads that own a tile
+    static constexpr int NTASK = EPG * NQ * NLOC;                       // phase-2 tasks per chunk
+    static constexpr int NT = NTILE;                                    // 72 / 80 / 150 (measured: more, smaller CTAs beat one task per thread)
+    static constexpr int MINB = (P == 3) ? 4 : 1;
     static constexpr int QCH = NQ;                                      // points per chunk: fixed q1, all q2
     static constexpr int ZS = 46;                                       // 45 coefficients [cd][p] + 1 pad: stride = 28 banks mod 32
 };
@@ -422,7 +425,7 @@ __device__ __forceinline__ void tile_scatter(const KLDev& d, const int4* cb, int
 }
 
 template <int P, bool HASB>
-__global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_begin, int e2_end) {
+__global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLDev d, int e2_begin, int e2_end) {
     using Cfg = JacCfg<P>;
     constexpr int NQ = Cfg::NQ, NQ2 = Cfg::NQ2, NLOC = Cfg::NLOC, TILES = Cfg::TILES, EPG = Cfg::EPG, NT = Cfg::NT, QCH = Cfg::QCH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -456,8 +459,9 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
         const int cpi = (d.span1[e % d.nel1] - P + l % (P + 1)) + d.n1 * (d.span2[e2_begin + e / d.nel1] - P + l / (P + 1));
         S.cb[le][l] = reinterpret_cast<const int4*>(d.colbase)[cpi];
     }
-    // tile of this thread: tiles enumerated by j ascending, i2 = 0..j2
-    const int le_t = tid / TILES, tt = tid - le_t * TILES;
+    // tile of this thread: tiles enumerated by j ascending, i2 = 0..j2 (threads beyond NTILE only help in phase 2)
+    const bool has_tile = tid < Cfg::NTILE;
+    const int le_t = has_tile ? tid / TILES : 0, tt = has_tile ? tid - le_t * TILES : 0;
     int tj = 0, ti2 = 0;
     {
         int rem = tt;
@@ -490,10 +494,10 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, 2) k_jacobian(KLDev d, int e2_b
         }
         // ---- phase 3: tile (ti2, tj).  The first-direction factors X(q1) are constant over the chunk, so
         //      V_m^{cd} = sum_{q2} W_m^{cd}(q1,q2) is formed first and applied once per chunk (sum factorisation).
-        tile_chunk<P>(S.stage[le_t], S.Z[le_t], ch, ti2, tj, acc);
+        if (has_tile) tile_chunk<P>(S.stage[le_t], S.Z[le_t], ch, ti2, tj, acc);
     }
     const int e = ebase + le_t;
-    if (e < nel) tile_scatter<P>(d, S.cb[le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
+    if (has_tile && e < nel) tile_scatter<P>(d, S.cb[le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
 }
 
 
