@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--nel", type=int, default=576)
     ap.add_argument("--ref-nel", type=int, default=96)
     ap.add_argument("--material", default="svk", choices=list(MATS))
-    ap.add_argument("--scale", type=float, default=0.02, help="displacement amplitude as a fraction of the element size")
+    ap.add_argument("--scale", type=float, default=0.002, help="displacement amplitude as a fraction of the element size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -4,6 +4,7 @@
 // device is present.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include "kl_internal.h"
@@ -241,6 +242,47 @@ static int build_fext(kl_ctx* ctx, const kl_problem* P) {
     return 0;
 }
 
+// Pipelined copy-out plan: the element rows are cut into strips; a column of K is final once every element in the
+// support of every control point mapped to it has been assembled, so after each strip a few contiguous value ranges
+// can already travel to the host while the next strip is being assembled.
+static int build_d2h_plan(kl_ctx* ctx, const kl_problem* P) {
+    const KLDev& d = ctx->d;
+    const int nel2 = d.nel2, n1 = d.n1, n2 = d.n2, nf = d.nfree;
+    int S = ctx->n_strips_d2h;
+    if (const char* e = getenv("KL_D2H_STRIPS")) S = atoi(e);
+    S = std::max(1, std::min(S, nel2 / std::max(1, 2 * d.p)));
+    std::vector<int> outer((size_t)nf + 1);
+    KL_CUDA(cudaMemcpy(outer.data(), d.outer, sizeof(int) * ((size_t)nf + 1), cudaMemcpyDeviceToHost));
+    std::vector<int> last_row(nf, -1);
+    for (int c = 0; c < 3; ++c)
+        for (int i = 0; i < n1 * n2; ++i) {
+            const int g = P->dof_map[c * d.ncp + i];
+            if (g < nf) last_row[g] = std::max(last_row[g], i / n1);
+        }
+    ctx->d2h_plan.clear();
+    int prev_done = 0;
+    std::vector<int> strip_of_row(n2, S - 1);
+    for (int s = 0; s < S; ++s) {
+        kl_ctx::D2HStrip st;
+        st.e2_begin = (int)((long long)nel2 * s / S);
+        st.e2_end = (int)((long long)nel2 * (s + 1) / S);
+        int done = prev_done;
+        while (done < n2 && ctx->fhi[1][done] < st.e2_end) ++done;   // rows whose support ends inside the assembled part
+        for (int r = prev_done; r < done; ++r) strip_of_row[r] = s;
+        prev_done = done;
+        ctx->d2h_plan.push_back(st);
+    }
+    for (int g = 0; g < nf; ++g) {
+        const int s = last_row[g] >= 0 ? strip_of_row[last_row[g]] : S - 1;
+        auto& r = ctx->d2h_plan[s].ranges;
+        const size_t a = (size_t)outer[g], b = (size_t)outer[g + 1];
+        if (!r.empty() && r.back().second == a) r.back().second = b; else r.emplace_back(a, b);
+    }
+    ctx->strip_ev.resize(S);
+    for (auto& e : ctx->strip_ev) KL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     if (!P || !out) { kl_set_error("kl_create: null argument"); return KL_E_ARG; }
@@ -312,6 +354,7 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     ctx->e2_begin = 0; ctx->e2_end = d.nel2;
     if ((rc = kl_build_pattern(ctx))) { kl_destroy(ctx); return rc; }
     if ((rc = build_fext(ctx, P))) { kl_destroy(ctx); return rc; }
+    if ((rc = build_d2h_plan(ctx, P))) { kl_destroy(ctx); return rc; }
     KL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     KL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->ev) KL_CUDA(cudaEventCreate(&e));
@@ -330,6 +373,7 @@ extern "C" void kl_destroy(kl_ctx* ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->strip_ev) if (e) cudaEventDestroy(e);
     delete ctx;
 }
 
@@ -372,7 +416,9 @@ extern "C" int kl_check(kl_ctx* ctx, void* stream) {
     KL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     if (flag) {
         KL_CUDA(cudaMemsetAsync(ctx->d.flag, 0, sizeof(int), (cudaStream_t)stream));
-        if (flag & KLF_JACOBIAN) { kl_set_error("inverted element: |a1 x a2| <= 0 or det(metric) <= 0"); return KL_E_JACOBIAN; }
+        const std::string bits = " (device flag " + std::to_string(flag) + ")";
+        if (flag & KLF_JACOBIAN) { kl_set_error("inverted element: |a1 x a2| <= 0" + bits); return KL_E_JACOBIAN; }
+        if (flag & KLF_METRIC) { kl_set_error("det of the (through-thickness) metric <= 0" + bits); return KL_E_JACOBIAN; }
         if (flag & KLF_C33) { kl_set_error("plane-stress iteration on C33 did not converge"); return KL_E_C33; }
         kl_set_error("non-finite value at a quadrature point");
         return KL_E_NONFINITE;
@@ -467,19 +513,41 @@ extern "C" int kl_jacobian(kl_ctx* ctx, const double* x_host, double* values_hos
         xd = ctx->d_x;
     }
     KL_CUDA(cudaEventRecord(ctx->ev[1], s));
-    int rc = kl_jacobian_device(ctx, xd, s);
-    if (rc) return rc;
-    KL_CUDA(cudaEventRecord(ctx->ev[2], s));
-    if (values_host) {
-        const size_t bytes = sizeof(double) * (size_t)ctx->nnz;
-        ensure_registered(ctx, values_host, bytes);   // pageable memory still works, only slower
-        KL_CUDA(cudaMemcpyAsync(values_host, ctx->d.values, bytes, cudaMemcpyDeviceToHost, s));
+    int rc;
+    const bool whole = ctx->e2_begin == 0 && ctx->e2_end == ctx->d.nel2;
+    if (!values_host || !whole || ctx->d2h_plan.size() < 2) {
+        if ((rc = kl_jacobian_device(ctx, xd, s))) return rc;
+        KL_CUDA(cudaEventRecord(ctx->ev[2], s));
+        if (values_host) {
+            const size_t bytes = sizeof(double) * (size_t)ctx->nnz;
+            ensure_registered(ctx, values_host, bytes);   // pageable memory still works, only slower
+            KL_CUDA(cudaMemcpyAsync(values_host, ctx->d.values, bytes, cudaMemcpyDeviceToHost, s));
+        }
+        KL_CUDA(cudaEventRecord(ctx->ev[3], s));
+    } else {
+        // strips of element rows on the compute stream; the value ranges a strip completes are copied out on the copy
+        // stream while the next strip is assembled (only `double` values ever cross PCIe)
+        ensure_registered(ctx, values_host, sizeof(double) * (size_t)ctx->nnz);
+        if ((rc = kl_launch_construct(ctx, xd, s))) return rc;
+        if ((rc = kl_launch_points(ctx, 0, ctx->d.nel2, s))) return rc;
+        KL_CUDA(cudaMemsetAsync(ctx->d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
+        for (size_t k = 0; k < ctx->d2h_plan.size(); ++k) {
+            const auto& st = ctx->d2h_plan[k];
+            if ((rc = kl_launch_jacobian(ctx, st.e2_begin, st.e2_end, s))) return rc;
+            KL_CUDA(cudaEventRecord(ctx->strip_ev[k], s));
+            KL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->strip_ev[k], 0));
+            for (const auto& r : st.ranges)
+                KL_CUDA(cudaMemcpyAsync(values_host + r.first, ctx->d.values + r.first, sizeof(double) * (r.second - r.first),
+                                        cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        KL_CUDA(cudaEventRecord(ctx->ev[2], s));
+        KL_CUDA(cudaEventRecord(ctx->ev[3], ctx->copy_stream));
+        KL_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     }
-    KL_CUDA(cudaEventRecord(ctx->ev[3], s));
     rc = kl_check(ctx, s);
     cudaEventElapsedTime(&ctx->ms_h2d, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->ms_kernel, ctx->ev[1], ctx->ev[2]);
-    cudaEventElapsedTime(&ctx->ms_d2h, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->ms_d2h, ctx->ev[2], ctx->ev[3]);   // copy-out time NOT hidden behind the assembly
     return rc;
 }
 

@@ -221,7 +221,7 @@ __device__ __forceinline__ int material_point(const KLMaterial& m, const double 
     double Ai[3], ai[3], dA, da;
     inv2s(Ac, Ai, dA);
     inv2s(ac, ai, da);
-    if (!(dA > 0.0) || !(da > 0.0)) return KLF_JACOBIAN;
+    if (!(dA > 0.0) || !(da > 0.0)) return KLF_METRIC;
     if (m.material == KL_MAT_SVK) {
         double sy[6], Cm[6];
         symprod(Ai, sy);
@@ -272,7 +272,7 @@ __device__ __forceinline__ int material_point(const KLMaterial& m, const double 
         }
         inv2s(Gc, Gi, dG);
         inv2s(gc, gi, dg);
-        if (!(dG > 0.0) || !(dg > 0.0)) { flag |= KLF_JACOBIAN; break; }
+        if (!(dG > 0.0) || !(dg > 0.0)) { flag |= KLF_METRIC; break; }
         const double J0sq = dg / dG;
         if (m.compressible) {
             if (!hyper_comp(m, Gi, gc, gi, J0sq, S, C)) { flag |= KLF_C33; break; }

@@ -12,6 +12,7 @@
 #define KLF_NONFINITE 1
 #define KLF_JACOBIAN 2
 #define KLF_C33 4
+#define KLF_METRIC 8      // det of a (through-thickness) metric <= 0 inside the material law
 
 struct PointData;
 
@@ -78,6 +79,9 @@ struct kl_ctx {
     float ms_kernel = 0, ms_h2d = 0, ms_d2h = 0;
     int launches = 0;
     int n_strips_d2h = 8;            // pipelined D2H granularity
+    struct D2HStrip { int e2_begin, e2_end; std::vector<std::pair<size_t, size_t>> ranges; };   // value ranges complete after the strip
+    std::vector<D2HStrip> d2h_plan;
+    std::vector<cudaEvent_t> strip_ev;
 };
 
 void kl_set_error(const std::string& s);

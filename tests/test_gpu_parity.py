@@ -136,3 +136,9 @@ def test_gpu_scordelis_lo_known_answer(gpu):
     u = spla.spsolve(K.to_scipy(), asm.force())
     uz = kp.scordelis_lo_deflection(pr, u)
     assert abs(-uz - 0.3006) / 0.3006 < 5e-3       # filedata/pde/kirchhoff_shell_scordelis.xml:104-107 gives 0.30024
+
+
+def test_pipelined_copy_out_path(gpu):
+    """nel >= 12 switches kl_jacobian to the strip-pipelined D2H path (kl_capi.cu: build_d2h_plan)."""
+    _compare(gpu, W.roof(16), 0.3, "roof16-pipelined")
+    _compare(gpu, W.balloon(14), 1e-4, "balloon14-pipelined")
