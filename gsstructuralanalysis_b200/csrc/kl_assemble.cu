@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(PointCfg<P>::NT) k_residual(KLDev d, double* _
     __syncthreads();
     {
         PointData pd;
-        const int flag = eval_point<P>(d, stage[le], lq % NQ, lq / NQ, pd);
+        const int flag = eval_point<P, false>(d, stage[le], lq % NQ, lq / NQ, pd);
         if (flag && active) atomicOr(d.flag, flag);
         ResPoint& o = rp[le][lq];
         const double pw = d.mat.pressure * pd.wJ;
@@ -257,73 +257,88 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
-// ---- Z_j = T(point) . d_j : the 45 coefficients [cd][p] of one basis function at one quadrature point
-template <int P, bool HASB>
-__device__ __forceinline__ void compute_Z(const PointData& pd, const BasisStage<P>& E, int q1, int q2, int j, double* Zo) {
-    const int ja = j % (P + 1), jb = j / (P + 1);
-    const double x0 = E.b1[q1][0][ja], x1 = E.b1[q1][1][ja], x2 = E.b1[q1][2][ja];
-    const double y0 = E.b2[q2][0][jb], y1 = E.b2[q2][1][jb], y2 = E.b2[q2][2][jb];
-    const double N1 = x1 * y0, N2 = x0 * y1, N11 = x2 * y0, N22 = x0 * y2, N12 = x1 * y1;
+// ---- Z = T(point) . d : the 45 coefficients [cd][p] for one input vector d = (N1,N2,N11,N22,N12) at one quadrature point.
+//      The F* flags say which inputs are present; absent ones are folded away at compile time (they are written as the
+//      additive identity -0.0 so that no multiplication by zero is ever emitted).  All flags true = a basis function.
+#define TZ(f, e) ((f) ? (e) : -0.0)
+template <bool HASB, bool F1, bool F2, bool F11, bool F22, bool F12>
+__device__ __forceinline__ void compute_Zc(const PointData& pd, double N1, double N2, double N11, double N22, double N12, double* Zo) {
+    constexpr bool FG = F1 || F2;              // first derivatives present
+    constexpr bool FS = F11 || F22 || F12;     // second derivatives present
+    constexpr bool H0 = F11 || FG, H1 = F22 || FG, H2 = F12 || FG;
+    constexpr bool FSIG = FG || HASB;
     double n[3], a1[3], a2[3], c1[3], c2[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) { n[c] = pd.n[c]; a1[c] = pd.a1[c]; a2[c] = pd.a2[c]; c1[c] = pd.c1[c]; c2[c] = pd.c2[c]; }
     double g[3], hh[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) g[c] = N1 * c1[c] + N2 * c2[c];
+    for (int c = 0; c < 3; ++c) g[c] = TZ(F1, N1 * c1[c]) + TZ(F2, N2 * c2[c]);
     const double G1[3] = {pd.G1[0], pd.G1[1], pd.G1[2]}, G2[3] = {pd.G2[0], pd.G2[1], pd.G2[2]};
-    hh[0] = N11 - G1[0] * N1 - G2[0] * N2;
-    hh[1] = N22 - G1[1] * N1 - G2[1] * N2;
-    hh[2] = 2.0 * (N12 - G1[2] * N1 - G2[2] * N2);
+    hh[0] = TZ(F11, N11) + TZ(F1, -(G1[0] * N1)) + TZ(F2, -(G2[0] * N2));
+    hh[1] = TZ(F22, N22) + TZ(F1, -(G1[1] * N1)) + TZ(F2, -(G2[1] * N2));
+    hh[2] = TZ(H2, 2.0 * (TZ(F12, N12) + TZ(F1, -(G1[2] * N1)) + TZ(F2, -(G2[2] * N2))));
     double AE1[3], AE2[3], BE1[3], BE2[3], Bh[3], Dh[3];
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
-        AE1[v] = N1 * pd.A[sidx(v, 0)] + N2 * pd.A[sidx(v, 2)];
-        AE2[v] = N2 * pd.A[sidx(v, 1)] + N1 * pd.A[sidx(v, 2)];
-        if (HASB) {
-            BE1[v] = N1 * pd.B[sidx(v, 0)] + N2 * pd.B[sidx(v, 2)];
-            BE2[v] = N2 * pd.B[sidx(v, 1)] + N1 * pd.B[sidx(v, 2)];
-            Bh[v] = pd.B[sidx(v, 0)] * hh[0] + pd.B[sidx(v, 1)] * hh[1] + pd.B[sidx(v, 2)] * hh[2];
-        } else { BE1[v] = 0.0; BE2[v] = 0.0; Bh[v] = 0.0; }
-        Dh[v] = pd.D[sidx(v, 0)] * hh[0] + pd.D[sidx(v, 1)] * hh[1] + pd.D[sidx(v, 2)] * hh[2];
+        AE1[v] = TZ(F1, N1 * pd.A[sidx(v, 0)]) + TZ(F2, N2 * pd.A[sidx(v, 2)]);
+        AE2[v] = TZ(F2, N2 * pd.A[sidx(v, 1)]) + TZ(F1, N1 * pd.A[sidx(v, 2)]);
+        BE1[v] = TZ(HASB && F1, N1 * pd.B[sidx(v, 0)]) + TZ(HASB && F2, N2 * pd.B[sidx(v, 2)]);
+        BE2[v] = TZ(HASB && F2, N2 * pd.B[sidx(v, 1)]) + TZ(HASB && F1, N1 * pd.B[sidx(v, 2)]);
+        Bh[v] = TZ(HASB && H0, pd.B[sidx(v, 0)] * hh[0]) + TZ(HASB && H1, pd.B[sidx(v, 1)] * hh[1]) + TZ(HASB && H2, pd.B[sidx(v, 2)] * hh[2]);
+        Dh[v] = TZ(H0, pd.D[sidx(v, 0)] * hh[0]) + TZ(H1, pd.D[sidx(v, 1)] * hh[1]) + TZ(H2, pd.D[sidx(v, 2)] * hh[2]);
     }
     const double Mt0 = pd.Mt[0], Mt1 = pd.Mt[1], Mt2 = pd.Mt[2];
-    const double Nhat = Mt0 * N11 + Mt1 * N22 + Mt2 * N12;
+    const double Nhat = TZ(F11, Mt0 * N11) + TZ(F22, Mt1 * N22) + TZ(F12, Mt2 * N12);
     const double Ha1 = pd.Ha1, Ha2 = pd.Ha2, Hn = pd.Hn;
-    const double eta = Ha1 * N1 + Ha2 * N2;
-    const double p1 = pd.N[0] * N1 + pd.N[2] * N2, p2 = pd.N[1] * N2 + pd.N[2] * N1;
-    const double ga1 = pd.acon[0] * N1 + pd.acon[2] * N2, ga2 = pd.acon[2] * N1 + pd.acon[1] * N2;
+    const double eta = TZ(F1, Ha1 * N1) + TZ(F2, Ha2 * N2);
+    const double p1 = TZ(F1, pd.N[0] * N1) + TZ(F2, pd.N[2] * N2), p2 = TZ(F2, pd.N[1] * N2) + TZ(F1, pd.N[2] * N1);
+    const double ga1 = TZ(F1, pd.acon[0] * N1) + TZ(F2, pd.acon[2] * N2), ga2 = TZ(F1, pd.acon[2] * N1) + TZ(F2, pd.acon[1] * N2);
     const double q[3] = {pd.q[0], pd.q[1], pd.q[2]};
 #pragma unroll
     for (int dd = 0; dd < 3; ++dd) {
         double sig[3], mu[3];
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
-            if (HASB) {
-                sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd] - n[dd] * Bh[v];
-                mu[v] = BE1[v] * a1[dd] + BE2[v] * a2[dd] - n[dd] * Dh[v];
-            } else {
-                sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd];
-                mu[v] = -n[dd] * Dh[v];
-            }
+            sig[v] = TZ(FG, AE1[v] * a1[dd] + AE2[v] * a2[dd]) + TZ(HASB, -(n[dd] * Bh[v]));
+            mu[v] = TZ(HASB && FG, BE1[v] * a1[dd] + BE2[v] * a2[dd]) + (-(n[dd] * Dh[v]));
         }
-        const double s1 = G1[0] * mu[0] + G1[1] * mu[1] + 2.0 * G1[2] * mu[2] + Nhat * c1[dd] - Ha1 * g[dd] + Hn * n[dd] * ga1;
-        const double s2 = G2[0] * mu[0] + G2[1] * mu[1] + 2.0 * G2[2] * mu[2] + Nhat * c2[dd] - Ha2 * g[dd] + Hn * n[dd] * ga2;
-        const double en = eta * n[dd];
+        const double s1 = G1[0] * mu[0] + G1[1] * mu[1] + 2.0 * G1[2] * mu[2] + TZ(FS, Nhat * c1[dd]) + TZ(FG, -(Ha1 * g[dd]))
+                          + TZ(FG, Hn * n[dd] * ga1);
+        const double s2 = G2[0] * mu[0] + G2[1] * mu[1] + 2.0 * G2[2] * mu[2] + TZ(FS, Nhat * c2[dd]) + TZ(FG, -(Ha2 * g[dd]))
+                          + TZ(FG, Hn * n[dd] * ga2);
+        const double en = TZ(FG, eta * n[dd]);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            double eq = 0.0;   // epsilon_{c dd k} q_k
-            if ((c + 1) % 3 == dd) eq = q[(c + 2) % 3];
-            else if ((dd + 1) % 3 == c) eq = -q[(dd + 2) % 3];
-            const double dl = (c == dd) ? 1.0 : 0.0;
             double* z = Zo + (c * 3 + dd) * 5;
-            z[0] = a1[c] * sig[0] + a2[c] * sig[2] + n[c] * s1 - en * c1[c] + dl * p1 - N2 * eq;
-            z[1] = a2[c] * sig[1] + a1[c] * sig[2] + n[c] * s2 - en * c2[c] + dl * p2 + N1 * eq;
-            const double ng = n[dd] * g[c];
-            z[2] = -n[c] * mu[0] + Mt0 * ng;
-            z[3] = -n[c] * mu[1] + Mt1 * ng;
-            z[4] = -2.0 * n[c] * mu[2] + Mt2 * ng;
+            double z0 = TZ(FSIG, a1[c] * sig[0] + a2[c] * sig[2]) + n[c] * s1 + TZ(FG, -(en * c1[c]));
+            double z1 = TZ(FSIG, a2[c] * sig[1] + a1[c] * sig[2]) + n[c] * s2 + TZ(FG, -(en * c2[c]));
+            if (c == dd) {
+                z0 += TZ(FG, p1);
+                z1 += TZ(FG, p2);
+            } else {
+                // epsilon_{c dd k} q_k
+                const double eq = ((c + 1) % 3 == dd) ? q[(c + 2) % 3] : -q[(dd + 2) % 3];
+                z0 += TZ(F2, -(N2 * eq));
+                z1 += TZ(F1, N1 * eq);
+            }
+            z[0] = z0;
+            z[1] = z1;
+            const double ng = TZ(FG, n[dd] * g[c]);
+            z[2] = -(n[c] * mu[0]) + TZ(FG, Mt0 * ng);
+            z[3] = -(n[c] * mu[1]) + TZ(FG, Mt1 * ng);
+            z[4] = -(2.0 * n[c] * mu[2]) + TZ(FG, Mt2 * ng);
         }
     }
+}
+#undef TZ
+
+// Z_j of basis function j at point (q1,q2)
+template <int P, bool HASB>
+__device__ __forceinline__ void compute_Z(const PointData& pd, const BasisStage<P>& E, int q1, int q2, int j, double* Zo) {
+    const int ja = j % (P + 1), jb = j / (P + 1);
+    const double x0 = E.b1[q1][0][ja], x1 = E.b1[q1][1][ja], x2 = E.b1[q1][2][ja];
+    const double y0 = E.b2[q2][0][jb], y1 = E.b2[q2][1][jb], y2 = E.b2[q2][2][jb];
+    compute_Zc<HASB, true, true, true, true, true>(pd, x1 * y0, x0 * y1, x2 * y0, x0 * y2, x1 * y1, Zo);
 }
 
 // ---- tile (ti2, tj) over one chunk (fixed q1): V_m^{cd} = sum_{q2} W_m^{cd}(q1,q2) first, then applied once with the
@@ -500,6 +515,202 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLD
     if (has_tile && e < nel) tile_scatter<P>(d, S.cb[le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Jacobian kernel, sum-factorised in BOTH index directions of the column function j = (j1,j2).
+//   Z_j(q1,q2) = x0(j1,q1) U0 + x1(j1,q1) U1 + x2(j1,q1) U2   with  U_a(q1,q2,j2) = T.(pseudo input built from Y_{j2}(q2) only)
+//   => phase A  U_a for (q2, j2, a): 12 evaluations per point instead of 16, and with mostly-zero inputs (folded at compile time)
+//      phase B  W_{m,a}(i2,j2) = sum_{q2} Y_{i2}(q2) . U_a(q2,j2)        (30 tasks per element and column; depends on (i2,j2) only)
+//      phase C  tile (i2, j):  V_m = sum_a x_a(j1) W_{m,a}(i2,j2),  acc += X_m(i1) V_m       (36 accumulators per thread as before)
+// One CTA = EPG elements; per fixed-q1 column: B | barrier | C + A(next column) | barrier.
+template <int P>
+struct Jac3Cfg {
+    static constexpr int NQ = P + 1, NQ2 = NQ * NQ, NLOC = (P + 1) * (P + 1);
+    static constexpr int TILES = (P + 1) * (P + 1) * (P + 2) / 2;
+    static constexpr int NPAIR = (P + 1) * (P + 2) / 2;                 // (i2 <= j2)
+    static constexpr int EPG = (P == 4) ? 1 : 2;
+    static constexpr int NT = TILES * EPG;                              // 36 / 80 / 75
+    static constexpr int NL = EPG * NQ * (P + 1);                       // (element, q2, j2) combinations
+    static constexpr int NW = EPG * NPAIR * 3;                          // phase-B tasks
+    static constexpr int ZS = 46, WS = 30;                              // row strides (doubles): conflict-free LDS.128
+    static constexpr int MINB = (P == 3) ? 4 : 1;
+};
+template <int P>
+struct Jac3Shared {
+    using Cfg = Jac3Cfg<P>;
+    BasisStage<P> stage[Cfg::EPG];
+    double U[Cfg::EPG][Cfg::NQ][P + 1][3][Cfg::ZS];
+    double Wm[Cfg::EPG][Cfg::NPAIR][3][Cfg::WS];      // [a][m*10 + cd]
+    int4 cb[Cfg::EPG][Cfg::NLOC];
+    PointData pd[Cfg::EPG][Cfg::NQ];
+    unsigned long long bar;
+};
+
+template <int P, bool HASB>
+__global__ void __launch_bounds__(Jac3Cfg<P>::NT, Jac3Cfg<P>::MINB) k_jacobian3(KLDev d, int e2_begin, int e2_end) {
+    using Cfg = Jac3Cfg<P>;
+    constexpr int NQ = Cfg::NQ, NQ2 = Cfg::NQ2, NLOC = Cfg::NLOC, TILES = Cfg::TILES, NPAIR = Cfg::NPAIR, EPG = Cfg::EPG, NT = Cfg::NT,
+                  NL = Cfg::NL, NW = Cfg::NW;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Jac3Shared<P>& S = *reinterpret_cast<Jac3Shared<P>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int nel = d.nel1 * (e2_end - e2_begin);
+    const int ebase = blockIdx.x * EPG;
+
+    auto issue_pd = [&](int ch) {
+        mbar_expect_tx(&S.bar, (unsigned)(EPG * NQ * sizeof(PointData)));
+        for (int le = 0; le < EPG; ++le) {
+            int e = ebase + le;
+            if (e >= nel) e = nel - 1;
+            const size_t ge = (size_t)(e % d.nel1) + (size_t)d.nel1 * (e2_begin + e / d.nel1);
+            tma_bulk_g2s(&S.pd[le][0], d.pd + ge * NQ2 + (size_t)ch * NQ, (unsigned)(NQ * sizeof(PointData)), &S.bar);
+        }
+    };
+    // phase A: one (element, q2, j2, a) evaluation
+    auto phaseA_task = [&](int a, int idx) {
+        const int j2 = idx % (P + 1), q2 = (idx / (P + 1)) % NQ, le = idx / ((P + 1) * NQ);
+        const BasisStage<P>& E = S.stage[le];
+        const double y0 = E.b2[q2][0][j2], y1 = E.b2[q2][1][j2], y2 = E.b2[q2][2][j2];
+        double* out = S.U[le][q2][j2][a];
+        if (a == 0) compute_Zc<HASB, false, true, false, true, false>(S.pd[le][q2], -0.0, y1, -0.0, y2, -0.0, out);        // multiplies N_{j1}
+        else if (a == 1) compute_Zc<HASB, true, false, false, false, true>(S.pd[le][q2], y0, -0.0, -0.0, -0.0, y1, out);   // multiplies N'_{j1}
+        else compute_Zc<HASB, false, false, true, false, false>(S.pd[le][q2], -0.0, -0.0, y0, -0.0, -0.0, out);            // multiplies N''_{j1}
+    };
+    auto phaseA = [&]() {
+        if (NT > 2 * NL) {
+            // the two heavy variants first (uniform per group of NL threads), the cheap a = 2 variant shared by the remaining threads
+            if (tid < 2 * NL) phaseA_task(tid / NL, tid % NL);
+            else for (int idx = tid - 2 * NL; idx < NL; idx += NT - 2 * NL) phaseA_task(2, idx);
+        } else {
+            for (int k = tid; k < 3 * NL; k += NT) phaseA_task(k / NL, k % NL);
+        }
+    };
+
+    if (tid == 0) mbar_init(&S.bar, 1);
+    __syncthreads();
+    if (tid == 0) issue_pd(0);
+    for (int le = 0; le < EPG; ++le) {
+        int e = ebase + le;
+        if (e >= nel) e = nel - 1;
+        stage_basis<P>(d, e % d.nel1, e2_begin + e / d.nel1, S.stage[le], tid, NT);
+    }
+    for (int k = tid; k < EPG * NLOC; k += NT) {
+        const int le = k / NLOC, l = k - le * NLOC;
+        int e = ebase + le;
+        if (e >= nel) e = nel - 1;
+        const int cpi = (d.span1[e % d.nel1] - P + l % (P + 1)) + d.n1 * (d.span2[e2_begin + e / d.nel1] - P + l / (P + 1));
+        S.cb[le][l] = reinterpret_cast<const int4*>(d.colbase)[cpi];
+    }
+    // tile of this thread
+    const int le_t = tid / TILES, tt = tid - le_t * TILES;
+    int tj = 0, ti2 = 0;
+    {
+        int rem = tt;
+        for (int j2 = 0; j2 <= P; ++j2) {
+            const int cnt = (P + 1) * (j2 + 1);
+            if (rem < cnt) { tj = (P + 1) * j2 + rem / (j2 + 1); ti2 = rem % (j2 + 1); break; }
+            rem -= cnt;
+        }
+    }
+    const int tj1 = tj % (P + 1), tj2 = tj / (P + 1);
+    const int tpi = tj2 * (tj2 + 1) / 2 + ti2;
+    double acc[P + 1][9];
+#pragma unroll
+    for (int a = 0; a <= P; ++a)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[a][k] = 0.0;
+
+    __syncthreads();             // basis tables staged
+    mbar_wait(&S.bar, 0);
+    phaseA();                    // column 0
+    __syncthreads();
+
+    for (int ch = 0; ch < NQ; ++ch) {
+        if (tid == 0 && ch + 1 < NQ) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_pd(ch + 1);    // S.pd is free: phase A of this column is complete
+        }
+        // ---- phase B: W_{m,a}(i2,j2) = sum_{q2} Y_{i2}(q2) . U_a(q2, j2)
+        for (int t = tid; t < NW; t += NT) {
+            const int a = t % 3, pi = (t / 3) % NPAIR, le = t / (3 * NPAIR);
+            int j2 = 0;
+            while ((j2 + 1) * (j2 + 2) / 2 <= pi) ++j2;
+            const int i2 = pi - j2 * (j2 + 1) / 2;
+            const BasisStage<P>& E = S.stage[le];
+            double V0[9], V1[9], V2[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { V0[k] = 0.0; V1[k] = 0.0; V2[k] = 0.0; }
+#pragma unroll
+            for (int q2 = 0; q2 < NQ; ++q2) {
+                const double y0 = E.b2[q2][0][i2], y1 = E.b2[q2][1][i2], y2 = E.b2[q2][2][i2];
+                const double2* Zi = reinterpret_cast<const double2*>(S.U[le][q2][j2][a]);
+#pragma unroll
+                for (int m = 0; m < 5; ++m) {
+                    double zz[10];
+#pragma unroll
+                    for (int k = 0; k < (m < 4 ? 5 : 3); ++k) { const double2 v = Zi[m * 5 + k]; zz[2 * k] = v.x; zz[2 * k + 1] = v.y; }
+#pragma unroll
+                    for (int h = 0; h < (m < 4 ? 2 : 1); ++h) {
+                        const int cd = 2 * m + h;
+                        const double z1 = zz[5 * h], z2 = zz[5 * h + 1], z11 = zz[5 * h + 2], z22 = zz[5 * h + 3], z12 = zz[5 * h + 4];
+                        V0[cd] = fma(y2, z22, fma(y1, z2, V0[cd]));
+                        V1[cd] = fma(y1, z12, fma(y0, z1, V1[cd]));
+                        V2[cd] = fma(y0, z11, V2[cd]);
+                    }
+                }
+            }
+            double* w = S.Wm[le][pi][a];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { w[k] = V0[k]; w[10 + k] = V1[k]; w[20 + k] = V2[k]; }
+        }
+        __syncthreads();
+        // ---- phase C: tile (ti2, tj): V_m = sum_a x_a(j1,q1) W_{m,a};  acc += X_m(i1,q1) V_m
+        {
+            const BasisStage<P>& E = S.stage[le_t];
+            const double xa0 = E.b1[ch][0][tj1], xa1 = E.b1[ch][1][tj1], xa2 = E.b1[ch][2][tj1];
+            double X0[P + 1], X1[P + 1], X2[P + 1];
+#pragma unroll
+            for (int a = 0; a <= P; ++a) { X0[a] = E.b1[ch][0][a]; X1[a] = E.b1[ch][1][a]; X2[a] = E.b1[ch][2][a]; }
+            const double* w0 = S.Wm[le_t][tpi][0];
+            const double* w1 = S.Wm[le_t][tpi][1];
+            const double* w2 = S.Wm[le_t][tpi][2];
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                constexpr int NG[3] = {4, 4, 1};
+                const int ng = NG[g];
+                double V[3][4];
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    double r0[4], r1[4], r2[4];
+                    if (ng == 4) {
+                        const double2 a0 = *reinterpret_cast<const double2*>(w0 + m * 10 + 4 * g), a1 = *reinterpret_cast<const double2*>(w0 + m * 10 + 4 * g + 2);
+                        const double2 b0 = *reinterpret_cast<const double2*>(w1 + m * 10 + 4 * g), b1 = *reinterpret_cast<const double2*>(w1 + m * 10 + 4 * g + 2);
+                        const double2 c0 = *reinterpret_cast<const double2*>(w2 + m * 10 + 4 * g), c1 = *reinterpret_cast<const double2*>(w2 + m * 10 + 4 * g + 2);
+                        r0[0] = a0.x; r0[1] = a0.y; r0[2] = a1.x; r0[3] = a1.y;
+                        r1[0] = b0.x; r1[1] = b0.y; r1[2] = b1.x; r1[3] = b1.y;
+                        r2[0] = c0.x; r2[1] = c0.y; r2[2] = c1.x; r2[3] = c1.y;
+                    } else {
+                        r0[0] = w0[m * 10 + 8]; r1[0] = w1[m * 10 + 8]; r2[0] = w2[m * 10 + 8];
+                    }
+#pragma unroll
+                    for (int h = 0; h < ng; ++h) V[m][h] = fma(xa2, r2[h], fma(xa1, r1[h], xa0 * r0[h]));
+                }
+#pragma unroll
+                for (int a = 0; a <= P; ++a)
+#pragma unroll
+                    for (int h = 0; h < ng; ++h) acc[a][4 * g + h] = fma(X2[a], V[2][h], fma(X1[a], V[1][h], fma(X0[a], V[0][h], acc[a][4 * g + h])));
+            }
+        }
+        // ---- phase A of the next column (U is free since the barrier above)
+        if (ch + 1 < NQ) {
+            mbar_wait(&S.bar, (ch + 1) & 1);
+            phaseA();
+        }
+        __syncthreads();
+    }
+    const int e = ebase + le_t;
+    if (e < nel) tile_scatter<P>(d, S.cb[le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Warp-specialised persistent Jacobian kernel (degree 3): one CTA per SM, 13 warps.
@@ -717,7 +928,32 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
     // the membrane-bending coupling block B vanishes identically for the linear (SvK) law and for membranes
     const bool hasB = ctx->d.mat.material != KL_MAT_SVK && ctx->d.mat.bending;
-    static const bool use_ws = getenv("KL_JAC_WS") != nullptr;   // experimental warp-specialised variant (slower so far: profiles/)
+    static const bool use_ws = getenv("KL_JAC_WS") != nullptr;
+    static const bool use_k3 = getenv("KL_JAC") != nullptr && atoi(getenv("KL_JAC")) == 3;
+    if (use_k3) {
+        using C3 = Jac3Cfg<P>;
+        static bool a3 = false;
+        if (!a3) {
+            KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jac3Shared<P>)));
+            KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jac3Shared<P>)));
+            KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            a3 = true;
+        }
+        const int g3 = (nel + C3::EPG - 1) / C3::EPG;
+        KL_CUDA(cudaEventRecord(ctx->ev[4], s));
+        if (hasB) k_jacobian3<P, true><<<g3, C3::NT, sizeof(Jac3Shared<P>), s>>>(ctx->d, e2b, e2e);
+        else k_jacobian3<P, false><<<g3, C3::NT, sizeof(Jac3Shared<P>), s>>>(ctx->d, e2b, e2e);
+        KL_CUDA(cudaEventRecord(ctx->ev[5], s));
+        ctx->launches++;
+        KL_CUDA(cudaGetLastError());
+        if (ctx->d.mat.pressure != 0.0) {
+            k_pressure_tangent<P><<<nel, 256, 0, s>>>(ctx->d, e2b, e2e);
+            ctx->launches++;
+            KL_CUDA(cudaGetLastError());
+        }
+        return 0;
+    }   // experimental warp-specialised variant (slower so far: profiles/)
     KL_CUDA(cudaEventRecord(ctx->ev[4], s));
     if (P == 3 && use_ws) {
         static bool ws_attr = false;

@@ -124,6 +124,7 @@ __device__ __forceinline__ void outer_s(const double a[3], const double b[3], do
 }
 
 // incompressible NH / MR at one thickness point (Kiendl et al. 2015, static condensation C33 = J0^-2)
+template <bool TANGENT>
 __device__ __forceinline__ void hyper_incomp(const KLMaterial& m, const double Gi[3], const double gc[3], const double gi[3],
                                              double J0sq, double S[3], double C[6]) {
     const double c33 = 1.0 / J0sq;
@@ -132,6 +133,7 @@ __device__ __forceinline__ void hyper_incomp(const KLMaterial& m, const double G
     const double sa = m.c1 + m.c2 * c33, sb = m.c2 * J0sq - 2.0 * dpsi33 * c33;
 #pragma unroll
     for (int v = 0; v < 3; ++v) S[v] = sa * Gi[v] + sb * gi[v];
+    if (!TANGENT) return;
     double sy[6];
     symprod(gi, sy);
     const double k1 = 2.0 * m.c2 * J0sq + 4.0 * dpsi33 * c33, k2 = -m.c2 * J0sq + 2.0 * dpsi33 * c33, k3 = -2.0 * m.c2 * c33;
@@ -146,6 +148,7 @@ __device__ __forceinline__ void hyper_incomp(const KLMaterial& m, const double G
 
 // compressible NH / MR: psi = c1/2 (J^-2/3 I1 - 3) + c2/2 (J^-4/3 I2 - 3) + K/4 (J^2 - 1 - 2 ln J);
 // Newton on C33 until S33 = 0, then static condensation.  Returns false if not converged.
+template <bool TANGENT>
 __device__ __forceinline__ bool hyper_comp(const KLMaterial& m, const double Gi[3], const double gc[3], const double gi[3],
                                            double J0sq, double S[3], double C[6]) {
     // contravariant push of the in-plane C: Cup = Gi * gc * Gi  (2x2, symmetric)
@@ -182,11 +185,13 @@ __device__ __forceinline__ bool hyper_comp(const KLMaterial& m, const double Gi[
         dI2v[v] = I1 * Gi[v] - Cup[v];
         Sv[v] = c1 * j23 * (Gi[v] - I1 / 3.0 * gi[v]) + c2 * j43 * (dI2v[v] - 2.0 / 3.0 * I2 * gi[v]) + 0.5 * K * (Jsq - 1.0) * gi[v];
         S[v] = Sv[v];
+        if (!TANGENT) continue;
         // C^{ab33}: Ci^{33}=ci, G^{33}=1, Ic^{ab33}=0, dI2^{33}=I1-c33, d2I2^{ab33}=G^{ab}
         Cab33[v] = 2.0 * c1 * j23 * (-1.0 / 3.0 * ci * Gi[v] - 1.0 / 3.0 * gi[v] + I1 / 9.0 * gi[v] * ci)
                  + 2.0 * c2 * j43 * (-2.0 / 3.0 * ci * (dI2v[v] - 2.0 / 3.0 * I2 * gi[v]) + Gi[v] - 2.0 / 3.0 * (I1 - c33) * gi[v])
                  + K * Jsq * gi[v] * ci;
     }
+    if (!TANGENT) return true;
     const double dI2_33 = I1 - c33;
     const double C3333 = 2.0 * c1 * j23 * (-2.0 / 3.0 * ci + 4.0 / 9.0 * I1 * ci * ci)
                        + 2.0 * c2 * j43 * (-4.0 / 3.0 * dI2_33 * ci + 10.0 / 9.0 * I2 * ci * ci) + K * ci * ci;
@@ -211,6 +216,7 @@ __device__ __forceinline__ bool hyper_comp(const KLMaterial& m, const double Gi[
 
 // A,B,D (sym Voigt, 6 each), N, M (3 each) from the covariant metrics / curvatures [11,22,12].
 // Returns a KLF_* flag word (0 = ok).
+template <bool TANGENT>
 __device__ __forceinline__ int material_point(const KLMaterial& m, const double Ac[3], const double Bc[3], const double ac[3],
                                               const double bc[3], double A[6], double B[6], double D[6], double N[3], double M[3]) {
     int flag = 0;
@@ -275,15 +281,17 @@ __device__ __forceinline__ int material_point(const KLMaterial& m, const double 
         if (!(dG > 0.0) || !(dg > 0.0)) { flag |= KLF_METRIC; break; }
         const double J0sq = dg / dG;
         if (m.compressible) {
-            if (!hyper_comp(m, Gi, gc, gi, J0sq, S, C)) { flag |= KLF_C33; break; }
+            if (!hyper_comp<TANGENT>(m, Gi, gc, gi, J0sq, S, C)) { flag |= KLF_C33; break; }
         } else {
-            hyper_incomp(m, Gi, gc, gi, J0sq, S, C);
+            hyper_incomp<TANGENT>(m, Gi, gc, gi, J0sq, S, C);
         }
         const double wz1 = wz * z, wz2 = wz * z * z;
 #pragma unroll
         for (int v = 0; v < 3; ++v) { N[v] = fma(wz, S[v], N[v]); M[v] = fma(wz1, S[v], M[v]); }
 #pragma unroll
-        for (int s = 0; s < 6; ++s) { A[s] = fma(wz, C[s], A[s]); B[s] = fma(wz1, C[s], B[s]); D[s] = fma(wz2, C[s], D[s]); }
+        if (TANGENT)
+#pragma unroll
+            for (int s = 0; s < 6; ++s) { A[s] = fma(wz, C[s], A[s]); B[s] = fma(wz1, C[s], B[s]); D[s] = fma(wz2, C[s], D[s]); }
     }
     return flag;
 }
@@ -306,7 +314,8 @@ struct PointData {
 };
 static_assert(sizeof(PointData) % 8 == 0, "PointData must be a whole number of doubles");
 
-template <int P>
+// TANGENT = false skips the material tangent (A,B,D): all the residual needs are the stress resultants
+template <int P, bool TANGENT = true>
 __device__ __forceinline__ int eval_point(const KLDev& d, const ElemStage<P>& E, int q1, int q2, PointData& o) {
     double fo[6][3], fu[6][3];
     eval_field3<P, true>(E.X, E.b1[q1], E.b2[q2], fo);
@@ -358,7 +367,7 @@ __device__ __forceinline__ int eval_point(const KLDev& d, const ElemStage<P>& E,
         for (int k = 0; k < 3; ++k) { Bc[k] = 0; bc[k] = 0; }
     }
     double Mm[3];
-    flag |= material_point(d.mat, Ac, Bc, ac, bc, o.A, o.B, o.D, o.N, Mm);
+    flag |= material_point<TANGENT>(d.mat, Ac, Bc, ac, bc, o.A, o.B, o.D, o.N, Mm);
     const double wJ = E.w1[q1] * E.w2[q2] * JA;
     o.wJ = wJ;
 #pragma unroll

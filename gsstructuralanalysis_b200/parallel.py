@@ -88,28 +88,30 @@ def value_ranges(col_ranges, outer):
 
 
 def exchange_halo(plan: StripPlan, outer, values, residual, dist, device_tensor_fn=None):
-    """Send the partial sums of the interface columns to rank+1 and add what rank-1 sent.
-    `values` / `residual` are torch tensors (CPU for gloo, CUDA views for nccl).  After the call the entries of
-    plan.owned_cols are complete on this rank."""
+    """Send the partial sums of the interface columns to rank+1 and add what rank-1 sent (one batched group of
+    point-to-point operations).  `values` / `residual` are torch tensors (CPU for gloo, CUDA views for nccl).
+    After the call the entries of plan.owned_cols are complete on this rank.  Returns the bytes received."""
     import torch
-    reqs = []
-    bufs = []
+    ops, bufs = [], []
     if plan.rank + 1 < plan.world:
         for (a, b) in value_ranges(plan.send_cols, outer):
-            reqs.append(dist.isend(values[a:b].contiguous(), plan.rank + 1))
-        for (c0, c1) in plan.send_cols:
-            reqs.append(dist.isend(residual[c0:c1].contiguous(), plan.rank + 1))
+            ops.append(dist.P2POp(dist.isend, values[a:b], plan.rank + 1))
+        if residual is not None:
+            for (c0, c1) in plan.send_cols:
+                ops.append(dist.P2POp(dist.isend, residual[c0:c1], plan.rank + 1))
     if plan.rank > 0:
         for (a, b) in value_ranges(plan.recv_cols, outer):
             t = torch.empty(b - a, dtype=values.dtype, device=values.device)
-            reqs.append(dist.irecv(t, plan.rank - 1))
+            ops.append(dist.P2POp(dist.irecv, t, plan.rank - 1))
             bufs.append((values, a, b, t))
-        for (c0, c1) in plan.recv_cols:
-            t = torch.empty(c1 - c0, dtype=residual.dtype, device=residual.device)
-            reqs.append(dist.irecv(t, plan.rank - 1))
-            bufs.append((residual, c0, c1, t))
-    for r in reqs:
-        r.wait()
+        if residual is not None:
+            for (c0, c1) in plan.recv_cols:
+                t = torch.empty(c1 - c0, dtype=residual.dtype, device=residual.device)
+                ops.append(dist.P2POp(dist.irecv, t, plan.rank - 1))
+                bufs.append((residual, c0, c1, t))
+    if ops:
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
     for (dst, a, b, t) in bufs:
         dst[a:b] += t
     return sum(t.numel() for (_, _, _, t) in bufs) * 8
