@@ -43,3 +43,47 @@ def test_cpp_newton_converges_on_gpu(tmp_path):
     r = subprocess.run([EXE, _problem(str(tmp_path)), "25"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "STATUS Success" in r.stdout, r.stdout
+
+
+APALM = os.path.join(ROOT, "examples", "apalm_dispatch")
+
+
+def _build_apalm():
+    from gsstructuralanalysis_b200 import build as kbuild
+    kbuild.build()
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-o", APALM, os.path.join(ROOT, "examples", "apalm_dispatch.cpp"),
+                           "-L" + os.path.join(ROOT, "gsstructuralanalysis_b200"), "-l:libkl_shell.so",
+                           "-Wl,-rpath," + os.path.join(ROOT, "gsstructuralanalysis_b200")])
+
+
+def _parse(line):
+    return dict(tok.split("=") for tok in line.split() if "=" in tok and not tok.startswith("per_worker"))
+
+
+def test_apalm_queue_semantics_cpu():
+    """gsAPALMData pop/submit rules (src/gsALMSolvers/gsAPALMData.hpp:215-252,391-409) with fake workers: every level-1
+    interval is 25 % off and gets refined once into 2 children, deeper levels are exact."""
+    _build_apalm()
+    for workers in (1, 3, 8):
+        r = subprocess.run([APALM, "--fake", str(workers), "8"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        d = _parse(r.stdout.strip().splitlines()[-1])
+        assert int(d["jobs"]) == 8 + 16 and int(d["points"]) == 24 and int(d["maxLevel"]) == 2 and int(d["failed"]) == 0
+        per = [int(v) for v in r.stdout.strip().split("per_worker=")[1].split()]
+        assert len(per) == workers and sum(per) == 24 and min(per) >= 1
+
+
+@pytest.mark.gpu
+def test_apalm_intervals_one_per_gpu(tmp_path):
+    import torch
+    _build_apalm()
+    from gsstructuralanalysis_b200 import workloads as W, capi
+    pr = W.frustrum(24)
+    pr.number_dofs(capi.lib().kl_build_dofmap)
+    path = os.path.join(str(tmp_path), "f.klp")
+    pr.save(path)
+    n = torch.cuda.device_count()
+    r = subprocess.run([APALM, path, str(n), str(4 * n), "3"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    d = _parse(r.stdout.strip().splitlines()[-1])
+    assert int(d["jobs"]) == 4 * n and int(d["failed"]) == 0
