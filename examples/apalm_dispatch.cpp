@@ -101,7 +101,7 @@ int main(int argc, char** argv) {
                 gsAPALMJobResultB200 r;
                 const double lam = 0.5 * (iv.xilow + iv.xiupp);
                 for (int s = 0; s < steps; ++s) {      // corrector iterations of one arc-length step: 1 Jacobian + 1 residual each
-                    for (index_t i = 0; i < w.U.size(); ++i) w.U[i] = 1e-4 * lam * ((i * 2654435761u % 1000) / 500.0 - 1.0);
+                    for (index_t i = 0; i < w.U.size(); ++i) w.U[i] = 1e-7 * lam * ((i * 2654435761u % 1000) / 500.0 - 1.0);
                     r.ok = r.ok && w.Jacobian(w.U, w.K) && w.ALResidual(w.U, lam, w.R);
                 }
                 r.xi = {lam};

@@ -891,10 +891,9 @@ static int launch_points(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     const int nel = ctx->d.nel1 * (e2e - e2b);
     if (nel <= 0) return 0;
     const size_t smem = ((sizeof(ElemStage<P>) * Cfg::EPG + 15) / 16) * 16 + sizeof(PointData) * Cfg::EPG * Cfg::NQ2;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_done & 1u)) {      // function attributes are per device: tracked in the context, not in a static
         KL_CUDA(cudaFuncSetAttribute(k_points<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        ctx->attr_done |= 1u;
     }
     k_points<P><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     ctx->launches++;
@@ -917,13 +916,12 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     const int nel = ctx->d.nel1 * (e2e - e2b);
     if (nel <= 0) return 0;
     const size_t smem = sizeof(JacShared<P>);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_done & 2u)) {
         KL_CUDA(cudaFuncSetAttribute(k_jacobian<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KL_CUDA(cudaFuncSetAttribute(k_jacobian<P, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         KL_CUDA(cudaFuncSetAttribute(k_jacobian<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KL_CUDA(cudaFuncSetAttribute(k_jacobian<P, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        attr_set = true;
+        ctx->attr_done |= 2u;
     }
     const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
     // the membrane-bending coupling block B vanishes identically for the linear (SvK) law and for membranes
@@ -932,13 +930,12 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     static const bool use_k3 = getenv("KL_JAC") != nullptr && atoi(getenv("KL_JAC")) == 3;
     if (use_k3) {
         using C3 = Jac3Cfg<P>;
-        static bool a3 = false;
-        if (!a3) {
+        if (!(ctx->attr_done & 4u)) {
             KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jac3Shared<P>)));
             KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jac3Shared<P>)));
             KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            a3 = true;
+            ctx->attr_done |= 4u;
         }
         const int g3 = (nel + C3::EPG - 1) / C3::EPG;
         KL_CUDA(cudaEventRecord(ctx->ev[4], s));
@@ -956,17 +953,15 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     }   // experimental warp-specialised variant (slower so far: profiles/)
     KL_CUDA(cudaEventRecord(ctx->ev[4], s));
     if (P == 3 && use_ws) {
-        static bool ws_attr = false;
-        static int n_sm = 0;
-        if (!ws_attr) {
+        if (!(ctx->attr_done & 8u)) {
             KL_CUDA(cudaFuncSetAttribute(k_jacobian_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacWSShared)));
             KL_CUDA(cudaFuncSetAttribute(k_jacobian_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacWSShared)));
             int dev = 0;
             KL_CUDA(cudaGetDevice(&dev));
-            KL_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-            ws_attr = true;
+            KL_CUDA(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev));
+            ctx->attr_done |= 8u;
         }
-        const int g = grid < n_sm ? grid : n_sm;
+        const int g = grid < ctx->n_sm ? grid : ctx->n_sm;
         if (hasB) k_jacobian_ws<true><<<g, 416, sizeof(JacWSShared), s>>>(ctx->d, e2b, e2e);
         else k_jacobian_ws<false><<<g, 416, sizeof(JacWSShared), s>>>(ctx->d, e2b, e2e);
     } else if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);

@@ -78,6 +78,8 @@ struct kl_ctx {
     cudaEvent_t ev[8]{};
     float ms_kernel = 0, ms_h2d = 0, ms_d2h = 0;
     int launches = 0;
+    unsigned attr_done = 0;          // per-context (= per-device) cudaFuncSetAttribute bookkeeping, bit per kernel family
+    int n_sm = 0;
     int n_strips_d2h = 8;            // pipelined D2H granularity
     struct D2HStrip { int e2_begin, e2_end; std::vector<std::pair<size_t, size_t>> ranges; };   // value ranges complete after the strip
     std::vector<D2HStrip> d2h_plan;
