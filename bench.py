@@ -167,6 +167,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("KL_NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gsstructuralanalysis_b200 import build as kbuild, capi
     if rank == 0:
