@@ -113,7 +113,7 @@ def run_reference(args):
     from oracle.binding import Oracle
     nel = args.ref_nel
     pr = make_problem(nel, args.material)
-    orc = Oracle(pr)
+    orc = Oracle(pr, threads=os.cpu_count())     # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
     cores = orc.threads
     x = W.displacement_state(orc.n_dofs, args.scale * 508.0 / nel)
     vals, r = np.zeros(orc.nnz), np.zeros(orc.n_dofs)
@@ -289,7 +289,7 @@ def main():
         from oracle.binding import Oracle
         nel_s = args.ref_nel
         prs = make_problem(nel_s, args.material)
-        orc = Oracle(prs)
+        orc = Oracle(prs, threads=os.cpu_count())
         xs = W.displacement_state(orc.n_dofs, args.scale * 508.0 / nel_s)
         vals, rr = np.zeros(orc.nnz), np.zeros(orc.n_dofs)
         orc.jacobian_residual(xs, vals, rr)

@@ -142,3 +142,64 @@ def test_pipelined_copy_out_path(gpu):
     """nel >= 12 switches kl_jacobian to the strip-pipelined D2H path (kl_capi.cu: build_d2h_plan)."""
     _compare(gpu, W.roof(16), 0.3, "roof16-pipelined")
     _compare(gpu, W.balloon(14), 1e-4, "balloon14-pipelined")
+
+
+def test_ragged_mesh_and_unequal_element_counts(gpu):
+    """7 x 5 elements (odd counts, last CTA partially filled) and a single-element-row strip."""
+    from gsstructuralanalysis_b200 import geometry as G
+    from gsstructuralanalysis_b200.problem import ShellProblem, BoundaryConditions, KL_BC_DIRICHLET, WEST
+    s = G.paraboloid(0.2).degree_elevate(1).refine_to(7, 5)
+    pr = ShellProblem(s, BoundaryConditions().add_condition(WEST, KL_BC_DIRICHLET), material=KL_MAT_MR, E=2.0, nu=0.5, thickness=0.02,
+                      body_force=(0.0, 0.1, -0.3))
+    _compare(gpu, pr, 1e-3, "ragged-7x5")
+    s = G.paraboloid(0.2).degree_elevate(1).refine_to(13, 1)
+    pr = ShellProblem(s, BoundaryConditions().add_condition(WEST, KL_BC_DIRICHLET), material=KL_MAT_SVK, E=2.0, nu=0.3, thickness=0.02)
+    _compare(gpu, pr, 1e-3, "ragged-13x1")
+
+
+def test_full_size_properties_1m_dof(gpu):
+    """BASELINE.json size (576 x 576 elements, 1.0M DOFs): size-independent properties instead of an oracle run.
+       - K symmetric:  u.K v == v.K u                                       (no follower pressure)
+       - rigid translation in the null space of K, rigid motion gives zero internal force  (unconstrained shell)
+       - AL residual is affine in the load factor."""
+    import scipy.sparse as sp
+    from gsstructuralanalysis_b200 import geometry as G
+    from gsstructuralanalysis_b200.problem import ShellProblem, BoundaryConditions
+    s = G.scordelis_lo_roof_shallow().degree_elevate(1).refine_to(576)
+    pr = ShellProblem(s, BoundaryConditions(), material=KL_MAT_NH, E=3102.75, nu=0.5, thickness=6.35,
+                      point_loads=[((0.5, 0.5), (0.0, 0.0, -10.0))])
+    asm = gpu(pr)
+    n = asm.n_dofs
+    assert n == 3 * 579 * 579
+    rng = np.random.default_rng(5)
+    x = W.displacement_state(n, 0.002 * 508.0 / 576)
+    ok, K = asm.jacobian(x)
+    assert ok
+    Ks = sp.csc_matrix((K.values, K.inner, K.outer), shape=(n, n))
+    u, v = rng.standard_normal(n), rng.standard_normal(n)
+    a, b = u @ (Ks @ v), v @ (Ks @ u)
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+    # rigid body: translation + rotation about z of the undeformed control net
+    ncp = 579 * 579
+    th = 0.01
+    Rm = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    disp = s.cp @ Rm.T + np.array([0.3, -0.2, 0.1]) - s.cp
+    xr = np.zeros(n)
+    for c in range(3):
+        xr[pr.dof_map[c * ncp:(c + 1) * ncp]] = disp[:, c]
+    ok, rint = asm.al_residual(xr, 0.0)          # F_int at a rigid motion
+    assert ok
+    ok, K0 = asm.jacobian(np.zeros(n))
+    assert ok
+    K0s = sp.csc_matrix((K0.values, K0.inner, K0.outer), shape=(n, n))
+    scale = np.abs(K0.values).max()
+    assert np.abs(rint).max() <= 1e-9 * scale
+    for c in range(3):
+        t = np.zeros(n)
+        t[pr.dof_map[c * ncp:(c + 1) * ncp]] = 1.0
+        assert np.abs(K0s @ t).max() <= 1e-9 * scale
+    # affine in lambda
+    ok, r1 = asm.al_residual(x, 0.25)
+    ok, r2 = asm.al_residual(x, 1.75)
+    f = asm.force()
+    assert np.abs((r1 - r2) - 1.5 * f).max() <= 1e-12 * max(np.abs(f).max(), np.abs(r1).max())
