@@ -19,7 +19,7 @@ KL_ERRORS = {0: "KL_OK", -1: "KL_E_ARG", -2: "KL_E_CUDA", -3: "KL_E_NONFINITE", 
 SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern_host", "kl_pattern_device",
            "kl_jacobian", "kl_residual", "kl_al_residual", "kl_force", "kl_jacobian_device", "kl_residual_device",
            "kl_check", "kl_values_device", "kl_set_strip", "kl_last_timing", "kl_last_error", "kl_kernel_launches",
-           "kl_jacobian_kernel_ms", "kl_points_kernel_ms", "kl_measure_fp64_peak"]
+           "kl_jacobian_kernel_ms", "kl_points_kernel_ms", "kl_measure_fp64_peak", "kl_mass"]
 
 _LIB = None
 
@@ -50,6 +50,7 @@ def lib():
     L.kl_residual.argtypes = [vp, c_double_p, c_double_p]
     L.kl_al_residual.argtypes = [vp, c_double_p, C.c_double, c_double_p]
     L.kl_force.argtypes = [vp, c_double_p]
+    L.kl_mass.argtypes = [vp, C.c_double, c_double_p, c_double_p]
     L.kl_jacobian_device.argtypes = [vp, vp, vp]
     L.kl_residual_device.argtypes = [vp, vp, C.c_double, C.c_double, vp, vp]
     L.kl_check.argtypes = [vp, vp]

@@ -204,6 +204,89 @@ __global__ void __launch_bounds__(PointCfg<P>::NT) k_bodyforce(KLDev d, double* 
     }
 }
 
+// mass matrix / lumped mass (set-up path, not tuned): M_ab = rho*t * int N_a N_b meas(ori), identical for the 3 components
+template <int P>
+__global__ void __launch_bounds__(PointCfg<P>::NT) k_mass(KLDev d, double rho_t, double* __restrict__ values, double* __restrict__ lumped) {
+    using Cfg = PointCfg<P>;
+    constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG, NLOC = (P + 1) * (P + 1), W = 2 * P + 1, S3 = W * W * 3;
+    __shared__ ElemStage<P> stage[EPG];
+    __shared__ double wj[EPG][NQ2];
+    const int tid = threadIdx.x;
+    const int le = tid / NQ2, lq = tid - le * NQ2;
+    const int nel = d.nel1 * d.nel2;
+    const int e = blockIdx.x * EPG + le;
+    const bool active = e < nel;
+    const int e1 = active ? e % d.nel1 : 0, e2 = active ? e / d.nel1 : 0;
+    stage_element<P>(d, e1, e2, stage[le], lq, NQ2);
+    __syncthreads();
+    {
+        const int q1 = lq % NQ, q2 = lq / NQ;
+        double fo[6][3];
+        eval_field3<P, true>(stage[le].X, stage[le].b1[q1], stage[le].b2[q2], fo);
+        double A1[3], A2[3], Nn[3];
+        if (d.rational) {
+            double fw[6];
+            eval_field1<P>(stage[le].Wt, stage[le].b1[q1], stage[le].b2[q2], fw);
+            const double iw = 1.0 / fw[0];
+            for (int c = 0; c < 3; ++c) {
+                const double X = fo[0][c] * iw;
+                A1[c] = (fo[1][c] - fw[1] * X) * iw;
+                A2[c] = (fo[2][c] - fw[2] * X) * iw;
+            }
+        } else {
+            for (int c = 0; c < 3; ++c) { A1[c] = fo[1][c]; A2[c] = fo[2][c]; }
+        }
+        cross3(A1, A2, Nn);
+        wj[le][lq] = rho_t * stage[le].w1[q1] * stage[le].w2[q2] * sqrt(dot3(Nn, Nn));
+    }
+    __syncthreads();
+    if (!active) return;
+    const ElemStage<P>& E = stage[le];
+    const int a = lq, a1 = a % (P + 1), a2 = a / (P + 1);
+    const int i0 = d.span1[e1] - P, j0 = d.span2[e2] - P;
+    const int I1 = i0 + a1, I2 = j0 + a2, Ic = I1 + d.n1 * I2;
+    double rowsum = 0.0;
+    for (int b = 0; b < NLOC; ++b) {
+        const int b1 = b % (P + 1), b2 = b / (P + 1);
+        double m = 0.0;
+        for (int q2 = 0; q2 < NQ; ++q2)
+            for (int q1 = 0; q1 < NQ; ++q1) m += E.b1[q1][0][a1] * E.b2[q2][0][a2] * E.b1[q1][0][b1] * E.b2[q2][0][b2] * wj[le][q1 + NQ * q2];
+        rowsum += m;
+        if (values) {
+            const int J1 = i0 + b1, J2 = j0 + b2, Jc = J1 + d.n1 * J2;
+            const int st = (I1 - J1 + P) + W * (I2 - J2 + P);
+            for (int c = 0; c < 3; ++c) {
+                const int pp = d.pos[(size_t)(Jc * 3 + c) * S3 + st * 3 + c];      // (row (I,c), col (J,c))
+                if (pp >= 0) atomicAdd(&values[pp], m);
+            }
+        }
+    }
+    if (lumped)
+        for (int c = 0; c < 3; ++c) {
+            const int g = d.map[c * d.ncp + Ic];
+            if (g < d.nfree) atomicAdd(&lumped[g], rowsum);
+        }
+}
+
+template <int P>
+static int launch_mass(kl_ctx* ctx, double rho_t, double* values, double* lumped, cudaStream_t s) {
+    using Cfg = PointCfg<P>;
+    const int nel = ctx->d.nel1 * ctx->d.nel2;
+    k_mass<P><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, 0, s>>>(ctx->d, rho_t, values, lumped);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    return 0;
+}
+int kl_launch_mass(kl_ctx* ctx, double rho_t, double* values, double* lumped, cudaStream_t s) {
+    switch (ctx->d.p) {
+        case 2: return launch_mass<2>(ctx, rho_t, values, lumped, s);
+        case 3: return launch_mass<3>(ctx, rho_t, values, lumped, s);
+        case 4: return launch_mass<4>(ctx, rho_t, values, lumped, s);
+    }
+    kl_set_error("unsupported degree");
+    return KL_E_ARG;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Jacobian
 template <int P>

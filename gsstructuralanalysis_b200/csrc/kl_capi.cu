@@ -493,6 +493,21 @@ static int run_residual(kl_ctx* ctx, const double* x_host, double lam_fext, doub
 extern "C" int kl_residual(kl_ctx* ctx, const double* x_host, double* r_host) { return run_residual(ctx, x_host, 1.0, -1.0, r_host); }
 extern "C" int kl_al_residual(kl_ctx* ctx, const double* x_host, double lam, double* r_host) { return run_residual(ctx, x_host, -lam, 1.0, r_host); }
 
+extern "C" int kl_mass(kl_ctx* ctx, double density, double* values_host, double* lumped_host) {
+    if (!ctx || (!values_host && !lumped_host)) { kl_set_error("kl_mass: null argument"); return KL_E_ARG; }
+    KL_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    // the mass matrix shares the value array of K on the device (it is a set-up quantity; K is re-assembled every call)
+    if (values_host) KL_CUDA(cudaMemsetAsync(ctx->d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
+    if (lumped_host) KL_CUDA(cudaMemsetAsync(ctx->d_r, 0, sizeof(double) * ctx->d.nfree, s));
+    int rc = kl_launch_mass(ctx, density * ctx->d.mat.t, values_host ? ctx->d.values : nullptr, lumped_host ? ctx->d_r : nullptr, s);
+    if (rc) return rc;
+    if (values_host) KL_CUDA(cudaMemcpyAsync(values_host, ctx->d.values, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost, s));
+    if (lumped_host) KL_CUDA(cudaMemcpyAsync(lumped_host, ctx->d_r, sizeof(double) * ctx->d.nfree, cudaMemcpyDeviceToHost, s));
+    KL_CUDA(cudaStreamSynchronize(s));
+    return KL_OK;
+}
+
 extern "C" int kl_force(kl_ctx* ctx, double* f_host) {
     if (!ctx || !f_host) return KL_E_ARG;
     KL_CUDA(cudaSetDevice(ctx->device));

@@ -105,4 +105,5 @@ int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s);
 int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s);   // r += F_int - F_pressure (atomic)
 size_t kl_pointdata_bytes(void);
 int kl_launch_bodyforce(kl_ctx* ctx, double* f_dev, const double bf[3], cudaStream_t s);
+int kl_launch_mass(kl_ctx* ctx, double rho_t, double* values, double* lumped, cudaStream_t s);
 int kl_launch_axpby(kl_ctx* ctx, double* r, const double* fext, double a_r, double b_f, int n, cudaStream_t s);

@@ -105,6 +105,17 @@ class ShellAssembler:
         capi.check(self.L.kl_force(self.h, _dp(f)))
         return f
 
+    def mass(self, density, lumped=False):
+        """assembleMass(lumped): consistent mass matrix on the stiffness pattern, or the lumped mass vector."""
+        if lumped:
+            m = np.zeros(self.n_dofs)
+            capi.check(self.L.kl_mass(self.h, float(density), None, _dp(m)))
+            return m
+        v = np.zeros(max(self.nnz, 1))
+        capi.check(self.L.kl_mass(self.h, float(density), _dp(v), None))
+        outer, inner = self.pattern()
+        return SparseView(self.n_dofs, outer, inner, v[:self.nnz])
+
     def operators(self):
         """(Jacobian_t, Residual_t, ALResidual_t) — cheap-to-copy handles like the reference's lambdas."""
         return (lambda x: self.jacobian(x)), (lambda x: self.residual(x)), (lambda x, lam: self.al_residual(x, lam))

@@ -186,6 +186,22 @@ public:
             return kl_al_residual(s->ctx, x.data(), lam, r.data()) == KL_OK;
         };
     }
+    /// M: assembler.assembleMass(); m = matrix()  (Mass_t, gsStructuralAnalysisTypes.h:77)
+    Ops::Mass_t mass(T density) const {
+        auto s = m_s;
+        return [s, density](gsSparseMatrix<T>& m) {
+            adoptPattern(m, s->ndofs, s->nnz, s->outer.data(), s->inner.data());
+            return kl_mass(s->ctx, density, m.valuePtr(), nullptr) == KL_OK;
+        };
+    }
+    /// lumped mass vector: assembleMass(true); rhs()  (used by gsStaticDR, unittests/gsStaticSolver_test.cpp:252-253)
+    Ops::Force_t lumpedMass(T density) const {
+        auto s = m_s;
+        return [s, density](gsVector<T>& v) {
+            v.resize(s->ndofs);
+            return kl_mass(s->ctx, density, nullptr, v.data()) == KL_OK;
+        };
+    }
     /// F (what assemble(); rhs() gives at u = 0)
     Ops::Force_t force() const {
         auto s = m_s;

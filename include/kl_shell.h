@@ -132,6 +132,12 @@ int kl_residual(kl_ctx* ctx, const double* x_host, double* r_host);
  * (benchmarks/benchmark_Roof.cpp:335-344). */
 int kl_al_residual(kl_ctx* ctx, const double* x_host, double lam, double* r_host);
 
+/* Mass matrix M_ij^{cd} = delta_cd * density * thickness * int N_i N_j dA on the SAME pattern as K (values of the
+ * off-diagonal component blocks are zero) and/or the lumped mass vector (row sums over all basis functions):
+ * replaces assembler.assembleMass(); M = matrix()  /  assembleMass(true); rhs()
+ * (unittests/gsStaticSolver_test.cpp:249-253; Mass_t in gsStructuralAnalysisTypes.h:77).  Either output may be NULL. */
+int kl_mass(kl_ctx* ctx, double density, double* values_host, double* lumped_host);
+
 /* External force vector F (what assemble(); rhs() yields at u=0 for homogeneous BCs). */
 int kl_force(kl_ctx* ctx, double* f_host);
 

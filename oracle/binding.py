@@ -39,6 +39,7 @@ def lib():
         L.klo_residual.argtypes = [C.c_void_p, c_double_p, c_double_p]
         L.klo_al_residual.argtypes = [C.c_void_p, c_double_p, C.c_double, c_double_p]
         L.klo_force.argtypes = [C.c_void_p, c_double_p]
+        L.klo_mass.argtypes = [C.c_void_p, C.c_double, c_double_p, c_double_p]
         L.klo_jacobian_residual.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
         L.klo_build_dofmap.argtypes = [C.c_int, C.c_int, C.POINTER(kl_bc), c_int_p, c_int_p, c_int_p]
         L.klo_material.argtypes = [C.POINTER(kl_problem)] + [c_double_p] * 9
@@ -120,6 +121,11 @@ class Oracle:
         f = np.zeros(self.n_dofs)
         self.L.klo_force(self.h, _dp(f))
         return f
+
+    def mass(self, density):
+        v, l = np.zeros(self.nnz), np.zeros(self.n_dofs)
+        self.L.klo_mass(self.h, float(density), _dp(v), _dp(l))
+        return v, l
 
     def jacobian_residual(self, x, values=None, r=None):
         x = np.ascontiguousarray(x, dtype=np.float64)

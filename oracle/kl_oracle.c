@@ -795,6 +795,43 @@ int klo_jacobian_residual(const klo* o, const double* x, double* values, double*
     return rc;
 }
 
+/* mass matrix (pattern of K; only c == d blocks are non-zero) and lumped mass = row sums over ALL basis functions
+ * (assembleMass / assembleMass(true), unittests/gsStaticSolver_test.cpp:249-253) */
+int klo_mass(const klo* o, double density, double* values, double* lumped) {
+    double* disp = (double*)calloc(3 * o->ncp, sizeof(double));
+    if (values) memset(values, 0, sizeof(double) * o->nnz);
+    if (lumped) memset(lumped, 0, sizeof(double) * o->nfree);
+    int nq1 = o->P.quA * o->p[0] + o->P.quB, nq2 = o->P.quA * o->p[1] + o->P.quB;
+    double xq1[MAXQ], wq1[MAXQ], xq2[MAXQ], wq2[MAXQ];
+    gauss_legendre(nq1, xq1, wq1);
+    gauss_legendre(nq2, xq2, wq2);
+    qpdata q;
+    for (int e2 = 0; e2 < o->nel[1]; ++e2) for (int e1 = 0; e1 < o->nel[0]; ++e1) {
+        double ua = o->U[0][o->span[0][e1]], ub = o->U[0][o->span[0][e1] + 1];
+        double va = o->U[1][o->span[1][e2]], vb = o->U[1][o->span[1][e2] + 1];
+        for (int q2 = 0; q2 < nq2; ++q2) for (int q1 = 0; q1 < nq1; ++q1) {
+            double u = 0.5 * (ua + ub) + 0.5 * (ub - ua) * xq1[q1];
+            double v = 0.5 * (va + vb) + 0.5 * (vb - va) * xq2[q2];
+            double wt = 0.25 * (ub - ua) * (vb - va) * wq1[q1] * wq2[q2];
+            eval_qp(o, e1, e2, u, v, disp, &q);
+            double Nn[3]; cross3(q.A1, q.A2, Nn);
+            double wJ = wt * sqrt(dot3(Nn, Nn)) * density * o->P.thickness;
+            for (int a = 0; a < q.nloc; ++a) for (int c = 0; c < 3; ++c) {
+                int gr = o->map[c * o->ncp + q.cpidx[a]];
+                if (gr >= o->nfree) continue;
+                for (int b = 0; b < q.nloc; ++b) {
+                    double m = wJ * q.R[a] * q.R[b];
+                    if (lumped) lumped[gr] += m;
+                    int gc = o->map[c * o->ncp + q.cpidx[b]];
+                    if (values && gc < o->nfree) values[find_pos(o, gr, gc)] += m;
+                }
+            }
+        }
+    }
+    free(disp);
+    return 0;
+}
+
 /* basis evaluation exported for tests against scipy.interpolate.BSpline */
 int klo_basis_ders(int p, int nk, const double* U, double u, int* span_out, double* ders /* 3*(p+1) */) {
     int n = nk - p - 1;

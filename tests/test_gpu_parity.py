@@ -203,3 +203,21 @@ def test_full_size_properties_1m_dof(gpu):
     ok, r2 = asm.al_residual(x, 1.75)
     f = asm.force()
     assert np.abs((r1 - r2) - 1.5 * f).max() <= 1e-12 * max(np.abs(f).max(), np.abs(r1).max())
+
+
+@pytest.mark.parametrize("case", ["paraboloid", "balloon", "tension"])
+def test_mass_matrix_and_lumped_mass(gpu, case):
+    """assembleMass() / assembleMass(true) (unittests/gsStaticSolver_test.cpp:249-253)."""
+    from oracle.binding import Oracle
+    pr = {"paraboloid": lambda: W.tutorial_paraboloid(5), "balloon": lambda: W.balloon(6), "tension": lambda: W.tension_sheet(5)}[case]()
+    asm, orc = gpu(pr), Oracle(pr)
+    vo, lo = orc.mass(7.5)
+    M = asm.mass(7.5)
+    l = asm.mass(7.5, lumped=True)
+    assert np.abs(M.values - vo).max() <= RTOL * np.abs(vo).max()
+    assert np.abs(l - lo).max() <= RTOL * np.abs(lo).max()
+    # K is untouched by the mass assembly sharing its device buffer: next Jacobian still matches
+    x = W.displacement_state(asm.n_dofs, 1e-4)
+    ok, K = asm.jacobian(x)
+    Ko = orc.jacobian_values(x)
+    assert ok and np.abs(K.values - Ko).max() <= RTOL * np.abs(Ko).max()

@@ -112,3 +112,16 @@ def test_rigid_body_motion_gives_zero_internal_force():
     for c in range(3):
         t = np.zeros(o.n_dofs); t[pr.dof_map[c * ncp:(c + 1) * ncp]] = 1.0
         assert np.abs(K @ t).max() < 1e-12 * abs(K).max()
+
+
+def test_mass_known_answers():
+    """total lumped mass = density * thickness * area; consistent mass symmetric, row sums = lumped away from eliminated DoFs."""
+    import scipy.sparse as sp
+    s = G.plate(2.0, 3.0).degree_elevate(2).uniform_refine(2)
+    pr = ShellProblem(s, BoundaryConditions(), material=KL_MAT_SVK, E=1.0, nu=0.3, thickness=0.05)
+    o = Oracle(pr)
+    v, l = o.mass(4.0)
+    assert abs(l.sum() - 3 * 4.0 * 0.05 * 6.0) < 1e-12
+    M = sp.csc_matrix((v, o.inner, o.outer), shape=(o.n_dofs, o.n_dofs))
+    assert abs(M - M.T).max() < 1e-16
+    assert np.abs(np.asarray(M.sum(1)).ravel() - l).max() < 1e-14
