@@ -276,8 +276,17 @@ def main():
     except Exception:
         peak_src = "fallback 6453.1 GB/s (MEASURED_PEAKS.json absent on this box); FP64 peak measured live"
     achieved_tf = fpq * nqp / (jac_kernel_ms * 1e-3) / 1e12
+    traffic = None      # dram__bytes_read+write of the kernel from the committed ncu --set full capture of this workload
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if args.nel == 576 and args.material == "svk":
+            traffic = tj["traffic"]
+    except Exception:
+        pass
     roofline = {"kernel": "k_jacobian<3>", "bound": "fp64", "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak.value, "traffic": None, "kernel_ms": jac_kernel_ms, "flops_per_qp": fpq,
+                "frac": achieved_tf / peak.value, "traffic": traffic, "kernel_ms": jac_kernel_ms, "flops_per_qp": fpq,
+                "note": "FP64 flops are the binding roofline of the fused assembly (13.4 kflop vs 224 B per point); ncu shows the "
+                        "kernel limited by the LSU data pipe (84 % of peak) with the FP64 pipe 41 % busy - DESIGN.md section 5",
                 "hbm": {"algorithmic_bytes": bytes_alg, "bytes_per_qp": bytes_alg / nqp,
                         "achieved": bytes_alg / (jac_kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_alg / (jac_kernel_ms * 1e-3) / 1e9 / hbm_peak},
