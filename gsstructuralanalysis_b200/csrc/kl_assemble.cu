@@ -47,7 +47,7 @@ struct PointCfg {
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <int P>
-__global__ void __launch_bounds__(PointCfg<P>::NT) k_points(KLDev d, int e2_begin, int e2_end) {
+__global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_points(KLDev d, int e2_begin, int e2_end) {
     using Cfg = PointCfg<P>;
     constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;
     extern __shared__ __align__(16) unsigned char smem_pts[];
@@ -97,7 +97,7 @@ __device__ __forceinline__ void stage_basis(const KLDev& d, int e1, int e2, Basi
 }
 
 template <int P>
-__global__ void __launch_bounds__(PointCfg<P>::NT) k_residual(KLDev d, double* __restrict__ r, int e2_begin, int e2_end) {
+__global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_residual(KLDev d, double* __restrict__ r, int e2_begin, int e2_end) {
     using Cfg = PointCfg<P>;
     constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;
     __shared__ ElemStage<P> stage[EPG];
