@@ -303,7 +303,16 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     if (P->material != KL_MAT_SVK && P->material != KL_MAT_NH && P->material != KL_MAT_MR) { kl_set_error("kl_create: unsupported material"); return KL_E_ARG; }
     if (!P->knots[0] || !P->knots[1] || !P->cp || !P->dof_map) { kl_set_error("kl_create: null array"); return KL_E_ARG; }
     kl_ctx* ctx = new kl_ctx();
-    KL_CUDA(cudaGetDevice(&ctx->device));
+#define KL_CUDA_CTX(call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            kl_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                  \
+            kl_destroy(ctx);                                                                   \
+            return KL_E_CUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+    KL_CUDA_CTX(cudaGetDevice(&ctx->device));
     ctx->prob = *P;
     KLDev& d = ctx->d;
     d.p = p; d.nq = p + 1;
@@ -320,21 +329,21 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     if ((rc = upload(ctx, &d.map, P->dof_map, (size_t)3 * d.ncp))) { kl_destroy(ctx); return rc; }
     d.fixed = nullptr;
     if (P->fixed_values && P->n_fixed > 0 && (rc = upload(ctx, &d.fixed, P->fixed_values, (size_t)P->n_fixed))) { kl_destroy(ctx); return rc; }
-    KL_CUDA(cudaMalloc((void**)&d.disp, sizeof(double) * 3 * d.ncp)); ctx->owned.push_back(d.disp);
-    KL_CUDA(cudaMemset(d.disp, 0, sizeof(double) * 3 * d.ncp));
+    KL_CUDA_CTX(cudaMalloc((void**)&d.disp, sizeof(double) * 3 * d.ncp)); ctx->owned.push_back(d.disp);
+    KL_CUDA_CTX(cudaMemset(d.disp, 0, sizeof(double) * 3 * d.ncp));
     {
         const size_t npts = (size_t)d.nel1 * d.nel2 * d.nq * d.nq;
         void* pdbuf = nullptr;
-        KL_CUDA(cudaMalloc(&pdbuf, kl_pointdata_bytes() * (npts ? npts : 1)));
+        KL_CUDA_CTX(cudaMalloc(&pdbuf, kl_pointdata_bytes() * (npts ? npts : 1)));
         ctx->owned.push_back(pdbuf);
         d.pd = (PointData*)pdbuf;
     }
-    KL_CUDA(cudaMalloc((void**)&d.flag, sizeof(int))); ctx->owned.push_back(d.flag);
-    KL_CUDA(cudaMemset(d.flag, 0, sizeof(int)));
-    KL_CUDA(cudaMalloc((void**)&ctx->d_x, sizeof(double) * std::max(d.nfree, 1))); ctx->owned.push_back(ctx->d_x);
-    KL_CUDA(cudaMalloc((void**)&ctx->d_r, sizeof(double) * std::max(d.nfree, 1))); ctx->owned.push_back(ctx->d_r);
-    KL_CUDA(cudaMallocHost((void**)&ctx->h_pinned_x, sizeof(double) * std::max(d.nfree, 1)));
-    KL_CUDA(cudaMallocHost((void**)&ctx->h_pinned_r, sizeof(double) * std::max(d.nfree, 1)));
+    KL_CUDA_CTX(cudaMalloc((void**)&d.flag, sizeof(int))); ctx->owned.push_back(d.flag);
+    KL_CUDA_CTX(cudaMemset(d.flag, 0, sizeof(int)));
+    KL_CUDA_CTX(cudaMalloc((void**)&ctx->d_x, sizeof(double) * std::max(d.nfree, 1))); ctx->owned.push_back(ctx->d_x);
+    KL_CUDA_CTX(cudaMalloc((void**)&ctx->d_r, sizeof(double) * std::max(d.nfree, 1))); ctx->owned.push_back(ctx->d_r);
+    KL_CUDA_CTX(cudaMallocHost((void**)&ctx->h_pinned_x, sizeof(double) * std::max(d.nfree, 1)));
+    KL_CUDA_CTX(cudaMallocHost((void**)&ctx->h_pinned_r, sizeof(double) * std::max(d.nfree, 1)));
     // material constants
     KLMaterial& m = d.mat;
     m.material = P->material; m.compressible = P->compressible; m.bending = P->bending; m.metric_z2 = P->metric_z2;
@@ -355,11 +364,12 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     if ((rc = kl_build_pattern(ctx))) { kl_destroy(ctx); return rc; }
     if ((rc = build_fext(ctx, P))) { kl_destroy(ctx); return rc; }
     if ((rc = build_d2h_plan(ctx, P))) { kl_destroy(ctx); return rc; }
-    KL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    KL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    KL_CUDA_CTX(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    KL_CUDA_CTX(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->ev) KL_CUDA(cudaEventCreate(&e));
     *out = ctx;
     return KL_OK;
+#undef KL_CUDA_CTX
 }
 
 extern "C" void kl_destroy(kl_ctx* ctx) {
