@@ -53,6 +53,15 @@ def make_problem(nel, material):
     return pr
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def flops_per_qp(p, material):
     """FP64 operations of the Jacobian kernel per quadrature point for the algorithm of DESIGN.md §5 (FMA = 2 flops):
     phase 3 (upper-triangle tiles, sum-factorised): tiles * [ (p+1)*45 + 27*(p+1) ] FMA per fixed-q1 column
@@ -125,7 +134,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     v = orc.n_qp / dt
     sample = f"roof {nel}x{nel} elements ({orc.n_dofs} DOFs, {orc.n_qp} quadrature points) per step, same material/BCs"
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -156,6 +165,11 @@ def main():
     ap.add_argument("--mode", default="replicas", choices=["replicas", "strips"],
                     help="N>1: independent replicas (weak scaling, default) or ONE matrix split into element-row strips with the halo exchange (strong scaling)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything libraries print (NCCL banner, ...) is diverted to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -169,7 +183,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("KL_NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from gsstructuralanalysis_b200 import build as kbuild, capi
     if rank == 0:
@@ -347,7 +360,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
