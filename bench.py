@@ -76,6 +76,23 @@ def flops_per_qp(p, material):
     return int(ph3 + ph2)
 
 
+def bind_to_gpu_numa_node(index):
+    """Restrict this rank to the CPUs NVML reports as local to the GPU, so that pinned allocations are NUMA-local."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1 and 64 * w + b < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus ({cpus[0]}..{cpus[-1]})"
+    except Exception as e:      # affinity is an optimisation only
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -181,6 +198,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)     # pinned host buffers of the e2e leg end up next to this GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -352,7 +370,7 @@ def main():
                    "l2": "matrix values (8*nnz bytes = %.2f GB) exceed the 126 MB L2 every step" % (8 * nnz / 1e9),
                    "multi_gpu": ("one matrix in element-row strips, point-to-point halo exchange of the interface columns" if strips else
                                  "one replica per GPU at its own displacement state (APALM interval style), no collective"),
-                   "setup_s": t_setup},
+                   "setup_s": t_setup, "cpu_affinity": numa},
         "clocks": clk.summary(),
         "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps,
