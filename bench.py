@@ -198,6 +198,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(local)     # pinned host buffers of the e2e leg end up next to this GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -345,6 +346,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle.binding import Oracle
+        os.sched_setaffinity(0, all_cpus)      # the CPU baseline gets every host core back
         nel_s = args.ref_nel
         prs = make_problem(nel_s, args.material)
         orc = Oracle(prs, threads=os.cpu_count())
