@@ -221,3 +221,17 @@ def test_mass_matrix_and_lumped_mass(gpu, case):
     ok, K = asm.jacobian(x)
     Ko = orc.jacobian_values(x)
     assert ok and np.abs(K.values - Ko).max() <= RTOL * np.abs(Ko).max()
+
+
+def test_run_to_run_reproducibility(gpu):
+    """The scatter uses FP64 RED (order not fixed): two assemblies of the same state agree to rounding, far inside 1e-12."""
+    pr = W.roof(24)
+    asm = gpu(pr)
+    x = W.displacement_state(asm.n_dofs, 0.01)
+    ok, K1 = asm.jacobian(x)
+    v1 = K1.values.copy()
+    ok, r1 = asm.residual(x)
+    ok, K2 = asm.jacobian(x)
+    ok, r2 = asm.residual(x)
+    assert np.abs(K2.values - v1).max() <= 1e-14 * np.abs(v1).max()
+    assert np.abs(r2 - r1).max() <= 1e-14 * max(np.abs(r1).max(), 1e-300)
