@@ -361,6 +361,7 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     gauss_rule(m.ngauss, m.zg, m.wg);
     m.pressure = P->pressure;
     ctx->e2_begin = 0; ctx->e2_end = d.nel2;
+    d.ablate = getenv("KL_ABLATE") ? atoi(getenv("KL_ABLATE")) : 0;
     if ((rc = kl_build_pattern(ctx))) { kl_destroy(ctx); return rc; }
     if ((rc = build_fext(ctx, P))) { kl_destroy(ctx); return rc; }
     if ((rc = build_d2h_plan(ctx, P))) { kl_destroy(ctx); return rc; }

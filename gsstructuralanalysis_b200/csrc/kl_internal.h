@@ -51,6 +51,7 @@ struct KLDev {
     const int* colbase;    // [ncp][4]: outer[map[d][J]] for d=0..2 (-1 if eliminated), [3] = 1 if the column block of J is regular
     int* flag;             // device error flag
     PointData* pd;         // [elements][nq*nq] per-point records written by k_points
+    int ablate;            // profiling only (env KL_ABLATE): 1 skip scatter, 2 skip phase 3, 4 skip phase 2
     KLMaterial mat;
 };
 
