@@ -19,7 +19,20 @@ KL_ERRORS = {0: "KL_OK", -1: "KL_E_ARG", -2: "KL_E_CUDA", -3: "KL_E_NONFINITE", 
 SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern_host", "kl_pattern_device",
            "kl_jacobian", "kl_residual", "kl_al_residual", "kl_force", "kl_jacobian_device", "kl_residual_device",
            "kl_check", "kl_values_device", "kl_set_strip", "kl_last_timing", "kl_last_error", "kl_kernel_launches",
-           "kl_jacobian_kernel_ms", "kl_points_kernel_ms", "kl_measure_fp64_peak", "kl_mass"]
+           "kl_jacobian_kernel_ms", "kl_points_kernel_ms", "kl_measure_fp64_peak", "kl_mass",
+           "kl_cg_solve", "kl_cg_solve_device", "kl_spmv", "kl_cg_last_timing", "kl_newton_solve"]
+
+
+class kl_newton_options(C.Structure):
+    _fields_ = [("tolU", C.c_double), ("tolF", C.c_double), ("relaxation", C.c_double), ("max_it", C.c_int32),
+                ("linear_start", C.c_int32), ("cg_tol", C.c_double), ("cg_max_iter", C.c_int32)]
+
+
+class kl_newton_info(C.Structure):
+    _fields_ = [("status", C.c_int32), ("iterations", C.c_int32), ("cg_iterations", C.c_int64),
+                ("residual", C.c_double), ("residual_ini", C.c_double), ("dU_norm", C.c_double), ("DU_norm", C.c_double),
+                ("ms_assembly", C.c_float), ("ms_solve", C.c_float)]
+
 
 _LIB = None
 
@@ -63,6 +76,11 @@ def lib():
     L.kl_jacobian_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.kl_points_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.kl_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.kl_cg_solve.argtypes = [vp, c_double_p, c_double_p, C.c_double, C.c_int32, c_int_p, c_double_p]
+    L.kl_cg_solve_device.argtypes = [vp, vp, vp, C.c_double, C.c_int32, c_int_p, c_double_p, vp]
+    L.kl_spmv.argtypes = [vp, c_double_p, c_double_p]
+    L.kl_cg_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.kl_newton_solve.argtypes = [vp, c_double_p, C.POINTER(kl_newton_options), C.POINTER(kl_newton_info)]
     _LIB = L
     return L
 

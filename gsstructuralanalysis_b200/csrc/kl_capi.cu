@@ -377,6 +377,7 @@ extern "C" void kl_destroy(kl_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    kl_solve_free(ctx);
     if (ctx->registered) cudaHostUnregister(ctx->registered);
     for (void* p : ctx->owned) cudaFree(p);
     if (ctx->h_pinned_x) cudaFreeHost(ctx->h_pinned_x);

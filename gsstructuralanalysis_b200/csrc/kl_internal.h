@@ -15,6 +15,7 @@
 #define KLF_METRIC 8      // det of a (through-thickness) metric <= 0 inside the material law
 
 struct PointData;
+struct KLSolveWS;   // kl_solve.cu: workspace of the device-resident CG / Newton loop
 
 struct KLMaterial {
     int material, compressible, ngauss, bending, metric_z2;
@@ -85,6 +86,7 @@ struct kl_ctx {
     struct D2HStrip { int e2_begin, e2_end; std::vector<std::pair<size_t, size_t>> ranges; };   // value ranges complete after the strip
     std::vector<D2HStrip> d2h_plan;
     std::vector<cudaEvent_t> strip_ev;
+    KLSolveWS* solve_ws = nullptr;   // created on the first kl_cg_solve / kl_newton_solve
 };
 
 void kl_set_error(const std::string& s);
@@ -97,6 +99,8 @@ void kl_set_error(const std::string& s);
         }                                                                                      \
     } while (0)
 
+// kl_solve.cu
+void kl_solve_free(kl_ctx* ctx);
 // kl_pattern.cu
 int kl_build_pattern(kl_ctx* ctx);
 // kl_assemble.cu

@@ -1,0 +1,486 @@
+// kl_solve.cu — device-resident Jacobi-preconditioned conjugate gradients and the Newton loop around the assembly path.
+//
+// the reference's Newton solver defaults to gsSparseSolver<>::CGDiagonal
+// (src/gsStaticSolvers/gsStaticNewton.hpp:23) = Eigen::ConjugateGradient with DiagonalPreconditioner (Eigen 3.4, vendored by
+// G+Smo as gsEigen; third-party, not in the reference tree).  Its published iteration is restated here for the GPU:
+//     r = b (x0 = 0), p = D^-1 r, absNew = r.p
+//     loop: tmp = A p; alpha = absNew / p.tmp; x += alpha p; r -= alpha tmp; stop if |r|^2 < max(tol^2 |b|^2, DBL_MIN);
+//           z = D^-1 r; absOld = absNew; absNew = r.z; p = z + (absNew/absOld) p
+// All scalars stay on the device; a batch of iterations is one CUDA graph launch and the host only polls a `done` word.
+// Reductions are two-stage with a fixed grid, so the iteration is bit-reproducible run to run.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include "kl_internal.h"
+
+namespace {
+
+constexpr int CG_THREADS = 256;
+constexpr int CG_BATCH = 8;          // iterations per graph launch
+
+struct CGState {
+    double pAp, absNew, absOld, rn2, threshold, rhsNorm2, alpha, beta;
+    int iters, done, maxit, pad;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// deterministic block sum (fixed tree); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* sm) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) s += sm[k];
+    return s;
+}
+
+// y = A^T x (= A x for the symmetric matrices CG accepts): one warp per compressed column, lanes stride its entries.
+// DOT: also the block partial of x.y (p.Ap of the CG iteration) -> part[blockIdx.x].
+template <bool DOT>
+__global__ void __launch_bounds__(CG_THREADS) k_spmv(const int* __restrict__ outer, const int* __restrict__ inner, const double* __restrict__ val,
+                                                     const double* __restrict__ x, double* __restrict__ y, int n, double* __restrict__ part,
+                                                     const CGState* __restrict__ st) {
+    __shared__ double sm[CG_THREADS / 32];
+    if (st && st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (CG_THREADS / 32) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (CG_THREADS / 32);
+    double dot = 0.0;
+    for (int col = warp; col < n; col += nwarps) {
+        const int b = outer[col], e = outer[col + 1];
+        double s0 = 0.0, s1 = 0.0;
+        int k = b + lane;
+        for (; k + 32 < e; k += 64) {
+            const double v0 = val[k], v1 = val[k + 32];
+            const int i0 = inner[k], i1 = inner[k + 32];
+            s0 = fma(v0, x[i0], s0);
+            s1 = fma(v1, x[i1], s1);
+        }
+        if (k < e) s0 = fma(val[k], x[inner[k]], s0);
+        const double s = warp_sum(s0 + s1);
+        if (lane == 0) {
+            y[col] = s;
+            if (DOT) dot = fma(s, x[col], dot);
+        }
+    }
+    if (DOT) {
+        const double t = block_sum(dot, sm);
+        if (threadIdx.x == 0) part[blockIdx.x] = t;
+    }
+}
+
+// 1 / diagonal (1 where it is zero or absent) — Eigen::DiagonalPreconditioner
+__global__ void k_cg_invdiag(const int* __restrict__ outer, const int* __restrict__ inner, const double* __restrict__ val, double* __restrict__ invdiag, int n) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n) return;
+    int lo = outer[col], hi = outer[col + 1] - 1;
+    double dg = 0.0;
+    while (lo <= hi) {   // inner indices of a column are sorted
+        const int mid = (lo + hi) >> 1;
+        const int r = inner[mid];
+        if (r == col) { dg = val[mid]; break; }
+        if (r < col) lo = mid + 1; else hi = mid - 1;
+    }
+    invdiag[col] = dg != 0.0 ? 1.0 / dg : 1.0;
+}
+
+// x = 0, r = b, p = D^-1 r; partials of |b|^2 and r.p
+__global__ void __launch_bounds__(CG_THREADS) k_cg_init(const double* __restrict__ b, const double* __restrict__ invdiag, double* __restrict__ x,
+                                                        double* __restrict__ r, double* __restrict__ p, int n, double* __restrict__ part, int nb) {
+    __shared__ double sm[CG_THREADS / 32];
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double bi = b[i], pi = invdiag[i] * bi;
+        x[i] = 0.0; r[i] = bi; p[i] = pi;
+        s0 = fma(bi, bi, s0);
+        s1 = fma(bi, pi, s1);
+    }
+    const double t0 = block_sum(s0, sm);
+    const double t1 = block_sum(s1, sm);
+    if (threadIdx.x == 0) { part[blockIdx.x] = t0; part[nb + blockIdx.x] = t1; }
+}
+
+__device__ __forceinline__ double sum_partials(const double* part, int nb, double* sm) {
+    double s = 0.0;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s += part[k];
+    return block_sum(s, sm);
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_cg_scal_init(CGState* st, const double* __restrict__ part, int nb, double tol, int maxit) {
+    __shared__ double sm[CG_THREADS / 32];
+    const double b2 = sum_partials(part, nb, sm);
+    const double rp = sum_partials(part + nb, nb, sm);
+    if (threadIdx.x == 0) {
+        st->rhsNorm2 = b2; st->rn2 = b2; st->absNew = rp; st->absOld = rp;
+        st->threshold = fmax(tol * tol * b2, DBL_MIN);
+        st->iters = 0; st->maxit = maxit; st->alpha = st->beta = st->pAp = 0.0;
+        st->done = (b2 == 0.0 || b2 < st->threshold || maxit <= 0) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_cg_scal_alpha(CGState* st, const double* __restrict__ part, int nb) {
+    __shared__ double sm[CG_THREADS / 32];
+    if (st->done) return;
+    const double pAp = sum_partials(part, nb, sm);
+    if (threadIdx.x == 0) { st->pAp = pAp; st->alpha = st->absNew / pAp; }
+}
+
+// x += alpha p; r -= alpha tmp; z = D^-1 r; partials of |r|^2 and r.z
+__global__ void __launch_bounds__(CG_THREADS) k_cg_update(const CGState* __restrict__ st, const double* __restrict__ p, const double* __restrict__ tmp,
+                                                          const double* __restrict__ invdiag, double* __restrict__ x, double* __restrict__ r,
+                                                          double* __restrict__ z, int n, double* __restrict__ part, int nb) {
+    __shared__ double sm[CG_THREADS / 32];
+    if (st->done) return;
+    const double alpha = st->alpha;
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, tmp[i], r[i]);
+        const double zi = invdiag[i] * ri;
+        r[i] = ri; z[i] = zi;
+        s0 = fma(ri, ri, s0);
+        s1 = fma(ri, zi, s1);
+    }
+    const double t0 = block_sum(s0, sm);
+    const double t1 = block_sum(s1, sm);
+    if (threadIdx.x == 0) { part[blockIdx.x] = t0; part[nb + blockIdx.x] = t1; }
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_cg_scal_beta(CGState* st, const double* __restrict__ part, int nb) {
+    __shared__ double sm[CG_THREADS / 32];
+    if (st->done) return;
+    const double rn2 = sum_partials(part, nb, sm);
+    const double rz = sum_partials(part + nb, nb, sm);
+    if (threadIdx.x == 0) {
+        st->rn2 = rn2;
+        if (rn2 < st->threshold) { st->done = 1; return; }   // Eigen leaves the loop before counting this iteration
+        st->absOld = st->absNew; st->absNew = rz; st->beta = rz / st->absOld;
+        st->iters += 1;
+        if (st->iters >= st->maxit) st->done = 1;
+    }
+}
+
+__global__ void __launch_bounds__(CG_THREADS) k_cg_dir(const CGState* __restrict__ st, const double* __restrict__ z, double* __restrict__ p, int n) {
+    if (st->done) return;
+    const double beta = st->beta;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = fma(beta, p[i], z[i]);
+}
+
+// Newton helpers: out = a + s*b; partial of |v|^2
+__global__ void __launch_bounds__(CG_THREADS) k_vec_axpy_out(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b, double s, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = fma(s, b[i], a[i]);
+}
+__global__ void __launch_bounds__(CG_THREADS) k_vec_norm2(const double* __restrict__ v, int n, double* __restrict__ part) {
+    __shared__ double sm[CG_THREADS / 32];
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s = fma(v[i], v[i], s);
+    const double t = block_sum(s, sm);
+    if (threadIdx.x == 0) part[blockIdx.x] = t;
+}
+__global__ void __launch_bounds__(CG_THREADS) k_vec_norm_final(const double* __restrict__ part, int nb, double* out) {
+    __shared__ double sm[CG_THREADS / 32];
+    const double s = sum_partials(part, nb, sm);
+    if (threadIdx.x == 0) *out = sqrt(s);
+}
+
+}  // namespace
+
+struct KLSolveWS {
+    int n = 0, nb = 0, nb_spmv = 0;
+    double *p = nullptr, *tmp = nullptr, *z = nullptr, *r = nullptr, *x = nullptr, *invdiag = nullptr, *part = nullptr, *b = nullptr;
+    CGState* st = nullptr;        // device
+    CGState* st_host = nullptr;   // pinned
+    double* scal = nullptr;       // device scratch scalar (norms)
+    double* scal_host = nullptr;  // pinned
+    cudaGraphExec_t graph = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    double *nU = nullptr, *nDU = nullptr, *ndU = nullptr, *nR = nullptr, *nX = nullptr;   // Newton vectors
+    float ms_total = 0, ms_iter = 0, ms_spmv = 0;
+};
+
+static int ws_get(kl_ctx* ctx, KLSolveWS** out) {
+    if (ctx->solve_ws) { *out = ctx->solve_ws; return KL_OK; }
+    KLSolveWS* w = new KLSolveWS();
+    ctx->solve_ws = w;
+    const int n = ctx->d.nfree;
+    w->n = n;
+    int dev = 0, nsm = 0;
+    KL_CUDA(cudaGetDevice(&dev));
+    KL_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const int want = (n + CG_THREADS - 1) / CG_THREADS;
+    w->nb = want < nsm * 4 ? (want > 0 ? want : 1) : nsm * 4;
+    const int wantw = (n + CG_THREADS / 32 - 1) / (CG_THREADS / 32);
+    w->nb_spmv = wantw < nsm * 8 ? (wantw > 0 ? wantw : 1) : nsm * 8;
+    const size_t vb = sizeof(double) * (size_t)(n > 0 ? n : 1);
+    double** vecs[] = {&w->p, &w->tmp, &w->z, &w->r, &w->x, &w->invdiag, &w->b, &w->nU, &w->nDU, &w->ndU, &w->nR, &w->nX};
+    for (double** v : vecs) KL_CUDA(cudaMalloc((void**)v, vb));
+    const int npart = 2 * (w->nb > w->nb_spmv ? w->nb : w->nb_spmv);
+    KL_CUDA(cudaMalloc((void**)&w->part, sizeof(double) * npart));
+    KL_CUDA(cudaMalloc((void**)&w->st, sizeof(CGState)));
+    KL_CUDA(cudaMalloc((void**)&w->scal, sizeof(double) * 4));
+    KL_CUDA(cudaMallocHost((void**)&w->st_host, sizeof(CGState)));
+    KL_CUDA(cudaMallocHost((void**)&w->scal_host, sizeof(double) * 4));
+    KL_CUDA(cudaEventCreate(&w->e0));
+    KL_CUDA(cudaEventCreate(&w->e1));
+    KL_CUDA(cudaEventCreate(&w->e2));
+    KL_CUDA(cudaEventCreate(&w->e3));
+    *out = w;
+    return KL_OK;
+}
+
+void kl_solve_free(kl_ctx* ctx) {
+    KLSolveWS* w = ctx->solve_ws;
+    if (!w) return;
+    double* vecs[] = {w->p, w->tmp, w->z, w->r, w->x, w->invdiag, w->b, w->nU, w->nDU, w->ndU, w->nR, w->nX, w->part, w->scal};
+    for (double* v : vecs) if (v) cudaFree(v);
+    if (w->st) cudaFree(w->st);
+    if (w->st_host) cudaFreeHost(w->st_host);
+    if (w->scal_host) cudaFreeHost(w->scal_host);
+    if (w->graph) cudaGraphExecDestroy(w->graph);
+    for (cudaEvent_t e : {w->e0, w->e1, w->e2, w->e3}) if (e) cudaEventDestroy(e);
+    delete w;
+    ctx->solve_ws = nullptr;
+}
+
+static int cg_iteration_launch(kl_ctx* ctx, KLSolveWS* w, cudaStream_t s) {
+    const KLDev& d = ctx->d;
+    const int n = w->n;
+    k_spmv<true><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, w->p, w->tmp, n, w->part, w->st);
+    k_cg_scal_alpha<<<1, CG_THREADS, 0, s>>>(w->st, w->part, w->nb_spmv);
+    k_cg_update<<<w->nb, CG_THREADS, 0, s>>>(w->st, w->p, w->tmp, w->invdiag, w->x, w->r, w->z, n, w->part, w->nb);
+    k_cg_scal_beta<<<1, CG_THREADS, 0, s>>>(w->st, w->part, w->nb);
+    k_cg_dir<<<w->nb, CG_THREADS, 0, s>>>(w->st, w->z, w->p, n);
+    KL_CUDA(cudaGetLastError());
+    return KL_OK;
+}
+
+// solves K x = b with b in w->b, result in w->x (both device, context-owned so that the iteration graph is captured once)
+static int cg_run(kl_ctx* ctx, KLSolveWS* w, double tol, int max_iter, int* iters, double* rel_err, cudaStream_t s) {
+    const KLDev& d = ctx->d;
+    const int n = w->n;
+    if (ctx->d.mat.pressure != 0.0) {
+        kl_set_error("kl_cg_solve: the follower-pressure tangent is unsymmetric; conjugate gradients need a symmetric matrix");
+        return KL_E_ARG;
+    }
+    if (tol <= 0.0) tol = DBL_EPSILON;
+    if (max_iter <= 0) max_iter = 2 * n;
+    KL_CUDA(cudaEventRecord(w->e0, s));
+    k_cg_invdiag<<<(n + 255) / 256, 256, 0, s>>>(d.outer, d.inner, d.values, w->invdiag, n);
+    k_cg_init<<<w->nb, CG_THREADS, 0, s>>>(w->b, w->invdiag, w->x, w->r, w->p, n, w->part, w->nb);
+    k_cg_scal_init<<<1, CG_THREADS, 0, s>>>(w->st, w->part, w->nb, tol, max_iter);
+    KL_CUDA(cudaGetLastError());
+    ctx->launches += 3;
+    const bool use_graph = s != nullptr && s != cudaStreamLegacy;   // the legacy default stream cannot be captured
+    if (use_graph && !w->graph) {
+        cudaGraph_t g = nullptr;
+        KL_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        int rc = KL_OK;
+        for (int k = 0; k < CG_BATCH && rc == KL_OK; ++k) rc = cg_iteration_launch(ctx, w, s);
+        cudaError_t ce = cudaStreamEndCapture(s, &g);
+        if (rc != KL_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        KL_CUDA(ce);
+        KL_CUDA(cudaGraphInstantiate(&w->graph, g, 0));
+        KL_CUDA(cudaGraphDestroy(g));
+    }
+    long batches = 0;
+    for (;;) {
+        KL_CUDA(cudaMemcpyAsync(w->st_host, w->st, sizeof(CGState), cudaMemcpyDeviceToHost, s));
+        KL_CUDA(cudaStreamSynchronize(s));
+        if (w->st_host->done) break;
+        if (use_graph) KL_CUDA(cudaGraphLaunch(w->graph, s));
+        else
+            for (int k = 0; k < CG_BATCH; ++k)
+                if (int rc = cg_iteration_launch(ctx, w, s)) return rc;
+        ++batches;
+    }
+    KL_CUDA(cudaEventRecord(w->e1, s));
+    KL_CUDA(cudaStreamSynchronize(s));
+    const CGState& st = *w->st_host;
+    ctx->launches += (int)(batches * CG_BATCH * 5);
+    if (iters) *iters = st.iters;
+    if (rel_err) *rel_err = st.rhsNorm2 > 0.0 ? std::sqrt(st.rn2 / st.rhsNorm2) : 0.0;
+    if (!(st.rn2 == st.rn2) || !(st.pAp == st.pAp)) {
+        kl_set_error("kl_cg_solve: non-finite value in the iteration (matrix not assembled or not positive definite?)");
+        return KL_E_NONFINITE;
+    }
+    cudaEventElapsedTime(&w->ms_total, w->e0, w->e1);
+    const long done_iters = st.iters + (st.rn2 < st.threshold && st.rhsNorm2 > 0.0 ? 1 : 0);
+    w->ms_iter = done_iters > 0 ? w->ms_total / (float)done_iters : 0.f;
+    return KL_OK;
+}
+
+extern "C" int kl_cg_solve_device(kl_ctx* ctx, const double* b_dev, double* x_dev, double tol, int32_t max_iter, int32_t* iters,
+                                  double* rel_err, void* stream) {
+    if (!ctx || !b_dev || !x_dev) { kl_set_error("kl_cg_solve_device: null argument"); return KL_E_ARG; }
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KLSolveWS* w = nullptr;
+    int rc = ws_get(ctx, &w);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t vb = sizeof(double) * (size_t)w->n;
+    KL_CUDA(cudaMemcpyAsync(w->b, b_dev, vb, cudaMemcpyDeviceToDevice, s));
+    if ((rc = cg_run(ctx, w, tol, max_iter, iters, rel_err, s))) return rc;
+    KL_CUDA(cudaMemcpyAsync(x_dev, w->x, vb, cudaMemcpyDeviceToDevice, s));
+    KL_CUDA(cudaStreamSynchronize(s));
+    return KL_OK;
+}
+
+extern "C" int kl_cg_solve(kl_ctx* ctx, const double* b_host, double* x_host, double tol, int32_t max_iter, int32_t* iters, double* rel_err) {
+    if (!ctx || !b_host || !x_host) { kl_set_error("kl_cg_solve: null argument"); return KL_E_ARG; }
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KLSolveWS* w = nullptr;
+    int rc = ws_get(ctx, &w);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    const size_t vb = sizeof(double) * (size_t)w->n;
+    std::memcpy(ctx->h_pinned_x, b_host, vb);
+    KL_CUDA(cudaMemcpyAsync(w->b, ctx->h_pinned_x, vb, cudaMemcpyHostToDevice, s));
+    if ((rc = cg_run(ctx, w, tol, max_iter, iters, rel_err, s))) return rc;
+    KL_CUDA(cudaMemcpyAsync(ctx->h_pinned_r, w->x, vb, cudaMemcpyDeviceToHost, s));
+    KL_CUDA(cudaStreamSynchronize(s));
+    std::memcpy(x_host, ctx->h_pinned_r, vb);
+    return KL_OK;
+}
+
+extern "C" int kl_spmv(kl_ctx* ctx, const double* x_host, double* y_host) {
+    if (!ctx || !x_host || !y_host) { kl_set_error("kl_spmv: null argument"); return KL_E_ARG; }
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KLSolveWS* w = nullptr;
+    int rc = ws_get(ctx, &w);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    const size_t vb = sizeof(double) * (size_t)w->n;
+    std::memcpy(ctx->h_pinned_x, x_host, vb);
+    KL_CUDA(cudaMemcpyAsync(w->p, ctx->h_pinned_x, vb, cudaMemcpyHostToDevice, s));
+    KL_CUDA(cudaEventRecord(w->e2, s));
+    k_spmv<false><<<w->nb_spmv, CG_THREADS, 0, s>>>(ctx->d.outer, ctx->d.inner, ctx->d.values, w->p, w->tmp, w->n, nullptr, nullptr);
+    KL_CUDA(cudaEventRecord(w->e3, s));
+    KL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    KL_CUDA(cudaMemcpyAsync(ctx->h_pinned_r, w->tmp, vb, cudaMemcpyDeviceToHost, s));
+    KL_CUDA(cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&w->ms_spmv, w->e2, w->e3);
+    std::memcpy(y_host, ctx->h_pinned_r, vb);
+    return KL_OK;
+}
+
+extern "C" int kl_cg_last_timing(const kl_ctx* ctx, float* ms_total, float* ms_per_iter, float* ms_spmv) {
+    if (!ctx || !ctx->solve_ws) return KL_E_ARG;
+    if (ms_total) *ms_total = ctx->solve_ws->ms_total;
+    if (ms_per_iter) *ms_per_iter = ctx->solve_ws->ms_iter;
+    if (ms_spmv) *ms_spmv = ctx->solve_ws->ms_spmv;
+    return KL_OK;
+}
+
+// ---- Newton loop (gsStaticNewton<T>::_solveNonlinear, src/gsStaticSolvers/gsStaticNewton.hpp:141-196; _start :282-325) ----
+static int dev_norm(kl_ctx* ctx, KLSolveWS* w, const double* v, double* out, cudaStream_t s) {
+    k_vec_norm2<<<w->nb, CG_THREADS, 0, s>>>(v, w->n, w->part);
+    k_vec_norm_final<<<1, CG_THREADS, 0, s>>>(w->part, w->nb, w->scal);
+    KL_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    KL_CUDA(cudaMemcpyAsync(w->scal_host, w->scal, sizeof(double), cudaMemcpyDeviceToHost, s));
+    KL_CUDA(cudaStreamSynchronize(s));
+    *out = w->scal_host[0];
+    return KL_OK;
+}
+
+extern "C" int kl_newton_solve(kl_ctx* ctx, double* U_host, const kl_newton_options* opt, kl_newton_info* info) {
+    if (!ctx || !U_host || !opt || !info) { kl_set_error("kl_newton_solve: null argument"); return KL_E_ARG; }
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KLSolveWS* w = nullptr;
+    int rc = ws_get(ctx, &w);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    const int n = w->n;
+    const size_t vb = sizeof(double) * (size_t)n;
+    const double relax = opt->relaxation != 0.0 ? opt->relaxation : 1.0;
+    std::memset(info, 0, sizeof(*info));
+    float ms_asm = 0.f, ms_sol = 0.f, ms = 0.f;
+    cudaEvent_t ea = ctx->ev[0], eb = ctx->ev[1];
+    int it_cg = 0;
+    double err_cg = 0.0;
+#define NW_ASM(call)                                                                                   \
+    do {                                                                                               \
+        KL_CUDA(cudaEventRecord(ea, s));                                                               \
+        int rc_ = (call);                                                                              \
+        if (rc_ == KL_OK) rc_ = kl_check(ctx, s);                                                      \
+        KL_CUDA(cudaEventRecord(eb, s));                                                               \
+        KL_CUDA(cudaStreamSynchronize(s));                                                             \
+        cudaEventElapsedTime(&ms, ea, eb); ms_asm += ms;                                               \
+        if (rc_ == KL_E_CUDA || rc_ == KL_E_ARG) return rc_;                                           \
+        if (rc_ != KL_OK) { info->status = 2; info->ms_assembly = ms_asm; info->ms_solve = ms_sol; return KL_OK; } \
+    } while (0)
+#define NW_CG()                                                                                        \
+    do {                                                                                               \
+        int rc_ = cg_run(ctx, w, opt->cg_tol, opt->cg_max_iter, &it_cg, &err_cg, s);                   \
+        ms_sol += w->ms_total; info->cg_iterations += it_cg;                                           \
+        if (rc_ == KL_E_CUDA || rc_ == KL_E_ARG) return rc_;                                           \
+        if (rc_ != KL_OK) { info->status = 3; info->ms_assembly = ms_asm; info->ms_solve = ms_sol; return KL_OK; } \
+    } while (0)
+
+    // m_U
+    std::memcpy(ctx->h_pinned_x, U_host, vb);
+    KL_CUDA(cudaMemcpyAsync(w->nU, ctx->h_pinned_x, vb, cudaMemcpyHostToDevice, s));
+    double residual = 0.0, residualIni = 0.0;
+    if (opt->linear_start) {
+        // deltaU = DeltaU = K(0)^-1 F; U = 0; relative residual based on the linear solution (headstart)
+        NW_ASM(kl_jacobian_device(ctx, nullptr, s));
+        KL_CUDA(cudaMemcpyAsync(w->b, ctx->d_fext, vb, cudaMemcpyDeviceToDevice, s));
+        NW_CG();
+        KL_CUDA(cudaMemcpyAsync(w->nDU, w->x, vb, cudaMemcpyDeviceToDevice, s));
+        KL_CUDA(cudaMemsetAsync(w->nU, 0, vb, s));
+        k_vec_axpy_out<<<w->nb, CG_THREADS, 0, s>>>(w->nX, w->nU, w->nDU, 1.0, n);
+        NW_ASM(kl_residual_device(ctx, w->nX, 1.0, -1.0, w->nR, s));
+        if ((rc = dev_norm(ctx, w, w->nR, &residual, s))) return rc;
+        if (residual == 0.0) residual = 1.0;
+        NW_ASM(kl_residual_device(ctx, w->nU, 1.0, -1.0, w->ndU, s));     // Residual(U) only for its norm
+        if ((rc = dev_norm(ctx, w, w->ndU, &residualIni, s))) return rc;
+        if (residualIni == 0.0) residualIni = 1.0;
+    } else {
+        KL_CUDA(cudaMemsetAsync(w->nDU, 0, vb, s));
+        NW_ASM(kl_residual_device(ctx, w->nU, 1.0, -1.0, w->nR, s));
+        if ((rc = dev_norm(ctx, w, w->nR, &residual, s))) return rc;
+        if (residual == 0.0) residual = 1.0;
+        residualIni = residual;
+    }
+    info->residual_ini = residualIni;
+    info->status = 1;
+    const int maxit = opt->max_it > 0 ? opt->max_it : 25;
+    int k = 0;
+    for (; k != maxit; ++k) {
+        k_vec_axpy_out<<<w->nb, CG_THREADS, 0, s>>>(w->nX, w->nU, w->nDU, 1.0, n);
+        NW_ASM(kl_jacobian_device(ctx, w->nX, s));
+        KL_CUDA(cudaMemcpyAsync(w->b, w->nR, vb, cudaMemcpyDeviceToDevice, s));
+        NW_CG();
+        KL_CUDA(cudaMemcpyAsync(w->ndU, w->x, vb, cudaMemcpyDeviceToDevice, s));
+        k_vec_axpy_out<<<w->nb, CG_THREADS, 0, s>>>(w->nDU, w->nDU, w->ndU, relax, n);
+        k_vec_axpy_out<<<w->nb, CG_THREADS, 0, s>>>(w->nX, w->nU, w->nDU, 1.0, n);
+        ctx->launches += 3;
+        NW_ASM(kl_residual_device(ctx, w->nX, 1.0, -1.0, w->nR, s));
+        double ndU = 0.0, nDU = 0.0;
+        if ((rc = dev_norm(ctx, w, w->nR, &residual, s))) return rc;
+        if ((rc = dev_norm(ctx, w, w->ndU, &ndU, s))) return rc;
+        if ((rc = dev_norm(ctx, w, w->nDU, &nDU, s))) return rc;
+        info->residual = residual; info->dU_norm = relax * ndU; info->DU_norm = nDU;
+        if (relax * ndU / nDU < opt->tolU && residual / residualIni < opt->tolF) { info->status = 0; break; }
+    }
+    info->iterations = k;      // m_numIterations: index of the converging iteration, or maxIt
+    // U += DeltaU in both outcomes (gsStaticNewton.hpp:180,185)
+    k_vec_axpy_out<<<w->nb, CG_THREADS, 0, s>>>(w->nU, w->nU, w->nDU, 1.0, n);
+    KL_CUDA(cudaGetLastError());
+    KL_CUDA(cudaMemcpyAsync(ctx->h_pinned_r, w->nU, vb, cudaMemcpyDeviceToHost, s));
+    KL_CUDA(cudaStreamSynchronize(s));
+    std::memcpy(U_host, ctx->h_pinned_r, vb);
+    info->ms_assembly = ms_asm;
+    info->ms_solve = ms_sol;
+    return KL_OK;
+#undef NW_ASM
+#undef NW_CG
+}

@@ -134,6 +134,37 @@ class ShellAssembler:
     def values_device_ptr(self):
         return self.L.kl_values_device(self.h)
 
+    # -- device-resident linear solve / Newton loop ---------------------------
+    def cg_solve(self, b, tol=0.0, max_iter=0):
+        """gsSparseSolver<>::CGDiagonal on the matrix of the last jacobian()/mass() call: (x, iterations, error).
+        tol <= 0 / max_iter <= 0 select Eigen's defaults (machine epsilon, 2 n)."""
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        assert b.shape == (self.n_dofs,)
+        x = np.zeros(self.n_dofs)
+        it, err = C.c_int32(), C.c_double()
+        capi.check(self.L.kl_cg_solve(self.h, _dp(b), _dp(x), float(tol), int(max_iter), C.byref(it), C.byref(err)))
+        return x, it.value, err.value
+
+    def spmv(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.zeros(self.n_dofs)
+        capi.check(self.L.kl_spmv(self.h, _dp(x), _dp(y)))
+        return y
+
+    def cg_last_timing(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self.L.kl_cg_last_timing(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return {"total_ms": a.value, "iter_ms": b.value, "spmv_ms": c.value}
+
+    def newton_solve(self, U=None, tolU=1e-6, tolF=1e-6, max_it=25, relaxation=1.0, linear_start=True, cg_tol=0.0,
+                     cg_max_iter=0):
+        """gsStaticNewton::solveNonlinear with the CGDiagonal default, device resident: (U, info dict)."""
+        U = np.zeros(self.n_dofs) if U is None else np.array(U, dtype=np.float64)
+        opt = capi.kl_newton_options(tolU, tolF, relaxation, max_it, 1 if linear_start else 0, cg_tol, cg_max_iter)
+        info = capi.kl_newton_info()
+        capi.check(self.L.kl_newton_solve(self.h, _dp(U), C.byref(opt), C.byref(info)))
+        return U, {k: getattr(info, k) for k, _ in capi.kl_newton_info._fields_}
+
     def set_strip(self, e2_begin, e2_end):
         capi.check(self.L.kl_set_strip(self.h, e2_begin, e2_end))
 

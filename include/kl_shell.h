@@ -158,6 +158,45 @@ int kl_set_strip(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end);
 
 /* Kernel-only timing of the last call in ms (CUDA events on the launch stream). */
 int kl_last_timing(const kl_ctx* ctx, float* ms_kernel, float* ms_h2d, float* ms_d2h);
+/* ---- device-resident linear solve and Newton loop ---------------------------
+ * The reference's Newton solver defaults to gsSparseSolver<>::CGDiagonal
+ * (src/gsStaticSolvers/gsStaticNewton.hpp:23), i.e. Eigen::ConjugateGradient<SparseMatrix, Lower|Upper,
+ * DiagonalPreconditioner> (third-party, Eigen 3.4 as vendored by G+Smo; not in /root/reference): start at
+ * x = 0, stop when |r|^2 < max(tol^2 |b|^2, DBL_MIN) or after max_iter iterations; the preconditioner is
+ * 1/diag (1 where the diagonal is 0); defaults tol = DBL_EPSILON, max_iter = 2 n (pass tol <= 0 / max_iter <= 0).
+ * The matrix is the one left on the device by the last kl_jacobian / kl_jacobian_device / kl_mass call; it must
+ * be symmetric (no follower pressure), as Eigen's solver requires.  Only the vectors cross PCIe. */
+int kl_cg_solve(kl_ctx* ctx, const double* b_host, double* x_host, double tol, int32_t max_iter,
+                int32_t* iters, double* rel_err);
+int kl_cg_solve_device(kl_ctx* ctx, const double* b_dev, double* x_dev, double tol, int32_t max_iter,
+                       int32_t* iters, double* rel_err, void* stream);
+/* y = K x with the device matrix (gather form: exact for the symmetric matrices CG accepts).  Host pointers. */
+int kl_spmv(kl_ctx* ctx, const double* x_host, double* y_host);
+/* average duration in ms of one CG iteration / of its matrix-vector product in the last solve */
+int kl_cg_last_timing(const kl_ctx* ctx, float* ms_total, float* ms_per_iter, float* ms_spmv);
+
+/* gsStaticNewton<T>::_solveNonlinear (src/gsStaticSolvers/gsStaticNewton.hpp:141-196) with the CGDiagonal
+ * default, everything device resident: per iteration one Jacobian, one CG solve, one residual; only norms
+ * come back to the host.  Option names follow gsStaticBase::defaultOptions (gsStaticBase.h:66-75). */
+typedef struct kl_newton_options {
+    double tolU, tolF;          /* "tolU" / "tolF" (reference default: "tol" = 1e-6 for both)        */
+    double relaxation;          /* "Relaxation" (1)                                                   */
+    int32_t max_it;             /* "maxIt" (25)                                                       */
+    int32_t linear_start;       /* 1 = DeltaU empty on entry: start from the linear solution K(0) DU = F and U = 0
+                                   (gsStaticNewton.hpp:147-152); 0 = start from U with DeltaU = 0     */
+    double cg_tol;              /* <= 0: Eigen default DBL_EPSILON                                    */
+    int32_t cg_max_iter;        /* <= 0: Eigen default 2 n                                            */
+} kl_newton_options;
+typedef struct kl_newton_info {
+    int32_t status;             /* gsStatus: 0 Success, 1 NotConverged, 2 AssemblyError, 3 SolverError */
+    int32_t iterations;         /* m_numIterations                                                    */
+    int64_t cg_iterations;      /* summed over all linear solves                                      */
+    double residual, residual_ini;   /* |R|, |R0|                                                     */
+    double dU_norm, DU_norm;    /* |relax dU|, |DU| of the last iteration                             */
+    float ms_assembly, ms_solve;     /* device time spent in assembly kernels / in CG                 */
+} kl_newton_info;
+int kl_newton_solve(kl_ctx* ctx, double* U_host_inout, const kl_newton_options* opt, kl_newton_info* info);
+
 /* Duration in ms of the last Jacobian kernel launch itself (CUDA events on its stream; syncs). */
 int kl_jacobian_kernel_ms(kl_ctx* ctx, float* ms);
 /* Same for the per-quadrature-point kernel (geometry + material) that precedes it. */

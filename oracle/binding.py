@@ -45,6 +45,8 @@ def lib():
         L.klo_material.argtypes = [C.POINTER(kl_problem)] + [c_double_p] * 9
         L.klo_basis_ders.argtypes = [C.c_int, C.c_int, c_double_p, C.c_double, C.POINTER(C.c_int), c_double_p]
         L.klo_gauss.argtypes = [C.c_int, c_double_p, c_double_p]
+        L.klo_cg_solve.argtypes = [C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int,
+                                   C.POINTER(C.c_int), c_double_p]
         _LIB = L
     return _LIB
 
@@ -135,6 +137,77 @@ class Oracle:
         if rc:
             raise RuntimeError(f"oracle rc={rc}")
         return values, r
+
+
+def cg_solve(n, outer, inner, values, b, tol=0.0, max_iter=0):
+    """Eigen's ConjugateGradient + DiagonalPreconditioner (= gsSparseSolver<>::CGDiagonal) restated on the CPU:
+    (x, iterations, error)."""
+    L = lib()
+    outer = np.ascontiguousarray(outer, dtype=np.int32)
+    inner = np.ascontiguousarray(inner, dtype=np.int32)
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.zeros(n)
+    it, err = C.c_int(), C.c_double()
+    L.klo_cg_solve(n, outer.ctypes.data_as(c_int_p), inner.ctypes.data_as(c_int_p), _dp(values), _dp(b), _dp(x), float(tol),
+                   int(max_iter), C.byref(it), C.byref(err))
+    return x, it.value, err.value
+
+
+def newton_solve(ops, U=None, tolU=1e-6, tolF=1e-6, max_it=25, relaxation=1.0, linear_start=True, cg_tol=0.0, cg_max_iter=0):
+    """gsStaticNewton<T>::_solveNonlinear (src/gsStaticSolvers/gsStaticNewton.hpp:141-196, _start :282-325) with the
+    CGDiagonal default, on any object with jacobian(x) -> (ok, SparseView-like) / residual(x) / force()."""
+    n = ops.n_dofs
+    U = np.zeros(n) if U is None else np.array(U, dtype=np.float64)
+    info = dict(status=1, iterations=0, cg_iterations=0, residual=0.0, residual_ini=0.0, dU_norm=0.0, DU_norm=0.0)
+
+    def solve(K, rhs):
+        o, i, v = (K.indptr, K.indices, K.data) if hasattr(K, "indptr") else (K.outer, K.inner, K.values)
+        x, it, _ = cg_solve(n, o, i, v, rhs, cg_tol, cg_max_iter)
+        info["cg_iterations"] += it
+        return x
+
+    def res(x):
+        ok, r = ops.residual(x)
+        if not ok:
+            raise FloatingPointError
+        return r
+
+    def jac(x):
+        ok, K = ops.jacobian(x)
+        if not ok:
+            raise FloatingPointError
+        return K
+
+    try:
+        if linear_start:
+            DU = solve(jac(np.zeros(n)), ops.force())
+            U = np.zeros(n)
+            R = res(U + DU)
+            residual = np.linalg.norm(R) or 1.0
+            residual_ini = np.linalg.norm(res(U)) or 1.0
+        else:
+            DU = np.zeros(n)
+            R = res(U)
+            residual = np.linalg.norm(R) or 1.0
+            residual_ini = residual
+        info["residual_ini"] = residual_ini
+        k = 0
+        while k != max_it:
+            dU = solve(jac(U + DU), R)
+            DU = DU + relaxation * dU
+            R = res(U + DU)
+            residual = np.linalg.norm(R)
+            info.update(residual=residual, dU_norm=relaxation * np.linalg.norm(dU), DU_norm=np.linalg.norm(DU))
+            if info["dU_norm"] / info["DU_norm"] < tolU and residual / residual_ini < tolF:
+                info["status"] = 0
+                break
+            k += 1
+        info["iterations"] = k
+        U = U + DU
+    except FloatingPointError:
+        info["status"] = 2
+    return U, info
 
 
 def material(prob: ShellProblem, Ac, Bc, ac, bc):

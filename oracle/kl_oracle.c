@@ -843,3 +843,61 @@ int klo_basis_ders(int p, int nk, const double* U, double u, int* span_out, doub
     return 0;
 }
 int klo_gauss(int n, double* x, double* w) { gauss_legendre(n, x, w); return 0; }
+
+/* ---- linear solve of the Newton loop --------------------------------------------------------------
+ * The reference's gsStaticNewton defaults to gsSparseSolver<>::CGDiagonal (src/gsStaticSolvers/gsStaticNewton.hpp:23), i.e.
+ * Eigen::ConjugateGradient<SparseMatrix, Lower|Upper, DiagonalPreconditioner> of Eigen 3.4 (third-party; vendored by G+Smo
+ * as gsEigen, absent from /root/reference).  This is a scalar restatement of Eigen's published iteration
+ * (Eigen/src/IterativeLinearSolvers/ConjugateGradient.h, "conjugate_gradient"): x0 = 0, threshold
+ * max(tol^2 |b|^2, DBL_MIN) on |r|^2, preconditioner 1/diag (1 where the diagonal vanishes), the iteration count is the
+ * number of completed loop bodies (the converging one is not counted), error = sqrt(|r|^2/|b|^2).
+ * The matrix is compressed-column (outer/inner/values); A*p is formed column-wise (the true product, no symmetry assumed). */
+#include <float.h>
+static void csc_mult(int n, const int* outer, const int* inner, const double* val, const double* p, double* y) {
+    for (int i = 0; i < n; ++i) y[i] = 0.0;
+    for (int j = 0; j < n; ++j) {
+        const double pj = p[j];
+        for (int k = outer[j]; k < outer[j + 1]; ++k) y[inner[k]] += val[k] * pj;
+    }
+}
+int klo_cg_solve(int n, const int* outer, const int* inner, const double* val, const double* b, double* x, double tol, int max_iter,
+                 int* iters, double* rel_err) {
+    if (tol <= 0.0) tol = DBL_EPSILON;
+    if (max_iter <= 0) max_iter = 2 * n;
+    double* w = (double*)malloc(sizeof(double) * 5 * (size_t)(n > 0 ? n : 1));
+    double *r = w, *p = w + n, *z = w + 2 * n, *tmp = w + 3 * n, *invd = w + 4 * n;
+    for (int j = 0; j < n; ++j) {
+        double dg = 0.0;
+        for (int k = outer[j]; k < outer[j + 1]; ++k) if (inner[k] == j) { dg = val[k]; break; }
+        invd[j] = dg != 0.0 ? 1.0 / dg : 1.0;
+    }
+    double rhs2 = 0.0;
+    for (int i = 0; i < n; ++i) { x[i] = 0.0; r[i] = b[i]; rhs2 += b[i] * b[i]; }
+    int i = 0;
+    double rn2 = rhs2;
+    if (rhs2 == 0.0) { *iters = 0; *rel_err = 0.0; free(w); return 0; }
+    const double threshold = fmax(tol * tol * rhs2, DBL_MIN);
+    if (rn2 >= threshold) {
+        double absNew = 0.0;
+        for (int k = 0; k < n; ++k) { p[k] = invd[k] * r[k]; absNew += r[k] * p[k]; }
+        while (i < max_iter) {
+            csc_mult(n, outer, inner, val, p, tmp);
+            double pAp = 0.0;
+            for (int k = 0; k < n; ++k) pAp += p[k] * tmp[k];
+            const double alpha = absNew / pAp;
+            rn2 = 0.0;
+            for (int k = 0; k < n; ++k) { x[k] += alpha * p[k]; r[k] -= alpha * tmp[k]; rn2 += r[k] * r[k]; }
+            if (rn2 < threshold) break;
+            const double absOld = absNew;
+            absNew = 0.0;
+            for (int k = 0; k < n; ++k) { z[k] = invd[k] * r[k]; absNew += r[k] * z[k]; }
+            const double beta = absNew / absOld;
+            for (int k = 0; k < n; ++k) p[k] = z[k] + beta * p[k];
+            ++i;
+        }
+    }
+    *iters = i;
+    *rel_err = sqrt(rn2 / rhs2);
+    free(w);
+    return 0;
+}
