@@ -1,10 +1,13 @@
 /** examples/newton_shell.cpp — the reference's tutorial driver shape (tutorials/nonlinear_shell_static.cpp:115-160)
     on top of the B200 operators: define Jacobian / Residual closures, solve K du = R with a Newton loop
     (src/gsStaticSolvers/gsStaticNewton.hpp:142-193) and the reference's default "CGDiagonal" linear solver
-    (Jacobi-preconditioned CG, gsStaticNewton.hpp:23).  The linear solve stays on the host, as in the reference.
+    (Jacobi-preconditioned CG, gsStaticNewton.hpp:23).  The first pass keeps the linear solve on the host, as in the reference; the
+    second pass repeats it with gsThinShellAssemblerB200::newtonSolve (device-resident Jacobian + CGDiagonal + residual).
 
     usage: newton_shell problem.klp [max_iterations]        (problem.klp written by ShellProblem.save)
     exit code 0 = converged (or no GPU present: prints the reason and exits 0 so that CPU-only CI can build/run it). */
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -99,5 +102,19 @@ int main(int argc, char** argv) {
         if (dU.norm() / U.norm() < 1e-6 && R.norm() / R0 < 1e-9) { status = gsStatus::Success; break; }   // tolU, tolF
     }
     std::printf("STATUS %s |U| = %.12e\n", status == gsStatus::Success ? "Success" : "NotConverged", U.norm());
+
+    // The same solve with everything resident on the GPU (Jacobian, CGDiagonal, residual, norms): only U comes back.
+    kl_newton_options opt = gsThinShellAssemblerB200::defaultNewtonOptions();
+    opt.tolU = 1e-6; opt.tolF = 1e-9; opt.max_it = maxIt; opt.cg_tol = 1e-12; opt.cg_max_iter = 20 * n;
+    kl_newton_info info;
+    gsVector<> Ud(n);
+    Ud.setZero(n);
+    const gsStatus dstatus = assembler->newtonSolve(Ud, opt, &info);
+    double diff = 0;
+    for (index_t i = 0; i < n; ++i) diff = std::max(diff, std::fabs(Ud[i] - U[i]));
+    std::printf("DEVICE_NEWTON %s iterations %d cg %lld |U| = %.12e  max|U_dev - U_host| = %.3e  assembly %.2f ms  solve %.2f ms\n",
+                dstatus == gsStatus::Success ? "Success" : "NotConverged", info.iterations, (long long)info.cg_iterations, Ud.norm(),
+                diff, info.ms_assembly, info.ms_solve);
+    if (dstatus != gsStatus::Success || diff > 1e-6 * U.norm()) return 1;
     return status == gsStatus::Success ? 0 : 1;
 }

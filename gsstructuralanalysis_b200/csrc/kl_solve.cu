@@ -10,6 +10,7 @@
 // Reductions are two-stage with a fixed grid, so the iteration is bit-reproducible run to run.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "kl_internal.h"
 
@@ -64,6 +65,83 @@ __global__ void __launch_bounds__(CG_THREADS) k_spmv(const int* __restrict__ out
             s1 = fma(v1, x[i1], s1);
         }
         if (k < e) s0 = fma(val[k], x[inner[k]], s0);
+        const double s = warp_sum(s0 + s1);
+        if (lane == 0) {
+            y[col] = s;
+            if (DOT) dot = fma(s, x[col], dot);
+        }
+    }
+    if (DOT) {
+        const double t = block_sum(dot, sm);
+        if (threadIdx.x == 0) part[blockIdx.x] = t;
+    }
+}
+
+// Regular columns (the full (2p+1)^2 x 3 stencil in canonical order, 99 % of a large mesh) do not need the row-index
+// array: the rows of column (J,d) are 3 x (2p+1) runs of 2p+1 consecutive DoFs whose first indices depend on J only.
+// runbase[J][c][di2] holds them (84 B per control point instead of 588 B of `inner` per column); colinfo[col] = J or -1.
+__global__ void k_spmv_tables(int ncp, int nfree, int nst, int W, const int* __restrict__ map, const int* __restrict__ colbase,
+                              const int* __restrict__ inner, int* __restrict__ colinfo, int* __restrict__ runbase) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x;
+    if (J >= ncp) return;
+    const int4 cb = reinterpret_cast<const int4*>(colbase)[J];
+    bool ok = cb.w != 0;
+    if (ok) {
+        const int base[3] = {cb.x, cb.y, cb.z};
+        for (int c = 0; c < 3 && ok; ++c)
+            for (int r = 0; r < W && ok; ++r) {
+                const int start = inner[base[0] + c * nst + r * W];
+                runbase[(size_t)J * 3 * W + c * W + r] = start;
+                for (int d = 0; d < 3 && ok; ++d)
+                    for (int k = 0; k < W; ++k)
+                        if (inner[base[d] + c * nst + r * W + k] != start + k) { ok = false; break; }
+            }
+    }
+    for (int d = 0; d < 3; ++d) {
+        const int col = map[d * ncp + J];
+        if (col < nfree) colinfo[col] = ok ? J : -1;
+    }
+}
+
+template <int P, bool DOT>
+__global__ void __launch_bounds__(CG_THREADS) k_spmv_reg(const int* __restrict__ outer, const int* __restrict__ inner, const double* __restrict__ val,
+                                                         const int* __restrict__ colinfo, const int* __restrict__ runbase,
+                                                         const double* __restrict__ x, double* __restrict__ y, int n, double* __restrict__ part,
+                                                         const CGState* __restrict__ st) {
+    constexpr int W = 2 * P + 1, NST = W * W, NE = 3 * NST;
+    __shared__ double sm[CG_THREADS / 32];
+    if (st && st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (CG_THREADS / 32) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (CG_THREADS / 32);
+    double dot = 0.0;
+    for (int col = warp; col < n; col += nwarps) {
+        const int b = outer[col];
+        const int J = colinfo[col];
+        double s0 = 0.0, s1 = 0.0;
+        if (J >= 0) {
+            const int* rb = runbase + (size_t)J * 3 * W;
+#pragma unroll
+            for (int m = 0; m < (NE + 31) / 32; ++m) {
+                const int e = lane + 32 * m;
+                if (e < NE) {
+                    const int run = e / W, k = e - run * W;      // run = c*W + di2
+                    const double v = val[b + e];
+                    const int row = rb[run] + k;
+                    if (m & 1) s1 = fma(v, x[row], s1); else s0 = fma(v, x[row], s0);
+                }
+            }
+        } else {
+            const int e = outer[col + 1];
+            int k = b + lane;
+            for (; k + 32 < e; k += 64) {
+                const double v0 = val[k], v1 = val[k + 32];
+                const int i0 = inner[k], i1 = inner[k + 32];
+                s0 = fma(v0, x[i0], s0);
+                s1 = fma(v1, x[i1], s1);
+            }
+            if (k < e) s0 = fma(val[k], x[inner[k]], s0);
+        }
         const double s = warp_sum(s0 + s1);
         if (lane == 0) {
             y[col] = s;
@@ -195,6 +273,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_vec_norm_final(const double* __r
 struct KLSolveWS {
     int n = 0, nb = 0, nb_spmv = 0;
     double *p = nullptr, *tmp = nullptr, *z = nullptr, *r = nullptr, *x = nullptr, *invdiag = nullptr, *part = nullptr, *b = nullptr;
+    int *colinfo = nullptr, *runbase = nullptr;   // index-free SpMV of regular columns
     CGState* st = nullptr;        // device
     CGState* st_host = nullptr;   // pinned
     double* scal = nullptr;       // device scratch scalar (norms)
@@ -227,6 +306,17 @@ static int ws_get(kl_ctx* ctx, KLSolveWS** out) {
     KL_CUDA(cudaMalloc((void**)&w->scal, sizeof(double) * 4));
     KL_CUDA(cudaMallocHost((void**)&w->st_host, sizeof(CGState)));
     KL_CUDA(cudaMallocHost((void**)&w->scal_host, sizeof(double) * 4));
+    static const bool no_fast = getenv("KL_SPMV_GENERIC") != nullptr;
+    if (!no_fast && n > 0) {
+        const int W = 2 * ctx->d.p + 1;
+        KL_CUDA(cudaMalloc((void**)&w->colinfo, sizeof(int) * (size_t)n));
+        KL_CUDA(cudaMalloc((void**)&w->runbase, sizeof(int) * (size_t)ctx->d.ncp * 3 * W));
+        KL_CUDA(cudaMemset(w->colinfo, 0xff, sizeof(int) * (size_t)n));
+        k_spmv_tables<<<(ctx->d.ncp + 127) / 128, 128>>>(ctx->d.ncp, n, ctx->d.nst, W, ctx->d.map, ctx->d.colbase, ctx->d.inner, w->colinfo, w->runbase);
+        KL_CUDA(cudaGetLastError());
+        KL_CUDA(cudaDeviceSynchronize());
+        ctx->launches++;
+    }
     KL_CUDA(cudaEventCreate(&w->e0));
     KL_CUDA(cudaEventCreate(&w->e1));
     KL_CUDA(cudaEventCreate(&w->e2));
@@ -241,6 +331,8 @@ void kl_solve_free(kl_ctx* ctx) {
     double* vecs[] = {w->p, w->tmp, w->z, w->r, w->x, w->invdiag, w->b, w->nU, w->nDU, w->ndU, w->nR, w->nX, w->part, w->scal};
     for (double* v : vecs) if (v) cudaFree(v);
     if (w->st) cudaFree(w->st);
+    if (w->colinfo) cudaFree(w->colinfo);
+    if (w->runbase) cudaFree(w->runbase);
     if (w->st_host) cudaFreeHost(w->st_host);
     if (w->scal_host) cudaFreeHost(w->scal_host);
     if (w->graph) cudaGraphExecDestroy(w->graph);
@@ -249,10 +341,27 @@ void kl_solve_free(kl_ctx* ctx) {
     ctx->solve_ws = nullptr;
 }
 
+template <bool DOT>
+static int launch_spmv(kl_ctx* ctx, KLSolveWS* w, const double* x, double* y, double* part, const CGState* st, cudaStream_t s) {
+    const KLDev& d = ctx->d;
+    if (w->colinfo) {
+        switch (d.p) {
+            case 2: k_spmv_reg<2, DOT><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, w->colinfo, w->runbase, x, y, w->n, part, st); break;
+            case 3: k_spmv_reg<3, DOT><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, w->colinfo, w->runbase, x, y, w->n, part, st); break;
+            case 4: k_spmv_reg<4, DOT><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, w->colinfo, w->runbase, x, y, w->n, part, st); break;
+            default: kl_set_error("unsupported degree"); return KL_E_ARG;
+        }
+    } else {
+        k_spmv<DOT><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, x, y, w->n, part, st);
+    }
+    KL_CUDA(cudaGetLastError());
+    return KL_OK;
+}
+
 static int cg_iteration_launch(kl_ctx* ctx, KLSolveWS* w, cudaStream_t s) {
     const KLDev& d = ctx->d;
     const int n = w->n;
-    k_spmv<true><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, w->p, w->tmp, n, w->part, w->st);
+    if (int rc = launch_spmv<true>(ctx, w, w->p, w->tmp, w->part, w->st, s)) return rc;
     k_cg_scal_alpha<<<1, CG_THREADS, 0, s>>>(w->st, w->part, w->nb_spmv);
     k_cg_update<<<w->nb, CG_THREADS, 0, s>>>(w->st, w->p, w->tmp, w->invdiag, w->x, w->r, w->z, n, w->part, w->nb);
     k_cg_scal_beta<<<1, CG_THREADS, 0, s>>>(w->st, w->part, w->nb);
@@ -360,7 +469,7 @@ extern "C" int kl_spmv(kl_ctx* ctx, const double* x_host, double* y_host) {
     std::memcpy(ctx->h_pinned_x, x_host, vb);
     KL_CUDA(cudaMemcpyAsync(w->p, ctx->h_pinned_x, vb, cudaMemcpyHostToDevice, s));
     KL_CUDA(cudaEventRecord(w->e2, s));
-    k_spmv<false><<<w->nb_spmv, CG_THREADS, 0, s>>>(ctx->d.outer, ctx->d.inner, ctx->d.values, w->p, w->tmp, w->n, nullptr, nullptr);
+    if ((rc = launch_spmv<false>(ctx, w, w->p, w->tmp, nullptr, nullptr, s))) return rc;
     KL_CUDA(cudaEventRecord(w->e3, s));
     KL_CUDA(cudaGetLastError());
     ctx->launches++;

@@ -211,6 +211,41 @@ public:
         };
     }
 
+    /** Device-resident replacement of `m_solver->compute(jacMat); m_solver->solve(F)` for the CGDiagonal default
+        (gsStaticBase.h:164, gsStaticNewton.hpp:230-240): solves with the matrix the last jacobian()/mass() call left on
+        the GPU; only the two vectors cross PCIe.  tol <= 0 / maxIter <= 0 = Eigen's defaults.  Returns false on error. */
+    bool cgSolve(gsVector<T> const& rhs, gsVector<T>& x, T tol = 0, index_t maxIter = 0, index_t* iterations = nullptr,
+                 T* error = nullptr) const {
+        x.resize(m_s->ndofs);
+        int32_t it = 0;
+        double err = 0;
+        const int rc = kl_cg_solve(m_s->ctx, rhs.data(), x.data(), tol, maxIter, &it, &err);
+        if (iterations) *iterations = it;
+        if (error) *error = err;
+        return rc == KL_OK;
+    }
+    /** gsStaticNewton::solveNonlinear (gsStaticNewton.hpp:101-196) run entirely on the device (Jacobian, CGDiagonal solve,
+        residual, norms); U is m_U on entry and the solution on exit.  The returned status is the solver's gsStatus. */
+    gsStatus newtonSolve(gsVector<T>& U, const kl_newton_options& options, kl_newton_info* info = nullptr) const {
+        kl_newton_info local;
+        if (!info) info = &local;
+        if ((index_t)U.size() != (index_t)m_s->ndofs) { U.resize(m_s->ndofs); U.setZero(); }
+        if (kl_newton_solve(m_s->ctx, U.data(), &options, info) != KL_OK) return gsStatus::OtherError;
+        switch (info->status) {
+            case 0: return gsStatus::Success;
+            case 1: return gsStatus::NotConverged;
+            case 2: return gsStatus::AssemblyError;
+            case 3: return gsStatus::SolverError;
+        }
+        return gsStatus::OtherError;
+    }
+    /// gsStaticBase::defaultOptions (gsStaticBase.h:66-75) + gsStaticNewton::defaultOptions (gsStaticNewton.hpp:20-25)
+    static kl_newton_options defaultNewtonOptions() {
+        kl_newton_options o;
+        o.tolU = 1e-6; o.tolF = 1e-6; o.relaxation = 1.0; o.max_it = 25; o.linear_start = 1; o.cg_tol = 0.0; o.cg_max_iter = 0;
+        return o;
+    }
+
 private:
     static void adoptPattern(gsSparseMatrix<T>& m, index_t n, int64_t nnz, const int32_t* outer, const int32_t* inner) {
         if (m.rows() == n && m.cols() == n && (int64_t)m.nonZeros() == nnz && m.isCompressed()) return;   // values only

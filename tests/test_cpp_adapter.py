@@ -43,6 +43,7 @@ def test_cpp_newton_converges_on_gpu(tmp_path):
     r = subprocess.run([EXE, _problem(str(tmp_path)), "25"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "STATUS Success" in r.stdout, r.stdout
+    assert "DEVICE_NEWTON Success" in r.stdout, r.stdout
 
 
 APALM = os.path.join(ROOT, "examples", "apalm_dispatch")
