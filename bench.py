@@ -307,6 +307,22 @@ def main():
         e2e = {"value": world * nqp / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 8 * nnz + 8 * n,
                "ms_per_step": dt * 1e3, "jacobian_breakdown_ms": tj, "steps": ksteps}
 
+    # ---- device-resident linear solve on the matrix just assembled (not part of `value`):
+    #      a bounded number of Jacobi-PCG iterations, timed by CUDA events inside the library
+    solver = None
+    if rank == 0 and not strips:
+        try:
+            asm.jacobian_device(x_dev.data_ptr(), stream)
+            torch.cuda.synchronize()
+            xs_, its_, err_ = asm.cg_solve(asm.force(), tol=1e-30, max_iter=96)
+            tcg = asm.cg_last_timing()
+            regular_bytes = 8 * nnz + 3 * 8 * n          # values + x gather + y (row indices are arithmetic for regular columns)
+            solver = {"kind": "Jacobi-PCG = gsSparseSolver CGDiagonal, device resident", "iterations_timed": its_,
+                      "ms_per_iteration": tcg["iter_ms"], "algorithmic_GBps": regular_bytes / (tcg["iter_ms"] * 1e-3) / 1e9,
+                      "pcie_bytes_per_solve": 2 * 8 * n}
+        except Exception as exc:      # the follower-pressure tangent is unsymmetric: CG is refused
+            solver = {"unavailable": str(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -379,6 +395,7 @@ def main():
         "jacobian_ms": jac_kernel_ms,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "linear_solve": solver,
     }
     emit(out)
     if world > 1:

@@ -103,7 +103,7 @@ extern "C" int kl_build_dofmap(int32_t n1, int32_t n2, const kl_bc* bc, int32_t*
 // ------------------------------------------------------------------------------------------------
 // 1-D B-spline values and derivatives on a knot span by the Cox–de Boor triangle
 // (gsBSplineBasis::evalAllDers_into):  T[m][q][j] = m-th derivative of N_{k-q+j, q}(u)
-static void bspline_span_ders(const std::vector<double>& U, int p, int k, double u, double out[3][KL_MAXP + 1]) {
+void bspline_span_ders(const std::vector<double>& U, int p, int k, double u, double out[3][KL_MAXP + 1]) {
     double T[3][KL_MAXP + 1][KL_MAXP + 1];
     std::memset(T, 0, sizeof(T));
     T[0][0][0] = 1.0;
@@ -128,7 +128,7 @@ static void bspline_span_ders(const std::vector<double>& U, int p, int k, double
 }
 
 // Gauss–Legendre nodes/weights on [-1,1] (quRule = 1), Newton iteration in extended precision
-static void gauss_rule(int n, double* x, double* w) {
+void gauss_rule(int n, double* x, double* w) {
     for (int i = 0; i < (n + 1) / 2; ++i) {
         long double z = cosl(3.141592653589793238462643383279502884L * (i + 0.75L) / (n + 0.5L)), pp = 0;
         for (int it = 0; it < 60; ++it) {

@@ -99,6 +99,9 @@ void kl_set_error(const std::string& s);
         }                                                                                      \
     } while (0)
 
+// kl_capi.cu: host-side 1-D basis / quadrature helpers shared with ks_solid.cu
+void bspline_span_ders(const std::vector<double>& U, int p, int k, double u, double out[3][KL_MAXP + 1]);
+void gauss_rule(int n, double* x, double* w);
 // kl_solve.cu
 void kl_solve_free(kl_ctx* ctx);
 // kl_pattern.cu

@@ -1,0 +1,933 @@
+// ks_solid.cu — gsElasticity solid path: total-Lagrangian K(u) and rhs(u) on one trivariate B-spline patch.
+//
+// Replaces gsElasticityAssembler::assemble(x, fixedDofs) behind the solid closures of tutorials/nonlinear_solid_static.cpp:101-114
+// (formulation [UPSTREAM-RECALLED], gsElasticity/gsVisitorNonLinearElasticity: F = I + grad u, S(C), CC = 2 dS/dC,
+// K_ab = int B_a^T CC B_b + (grad N_a . S grad N_b) I, rhs_a = F_ext - int B_a^T S).
+//
+// The kernels never form B matrices.  With the parametric gradient g_a = dN_a/dxi (3 numbers) the block of a pair is the
+// bilinear form K_ab^{cd} = sum_q g_a[p] T_pq^{cd} g_b[q], T^{cd} = M^c^T CC M^d + delta_cd G S G^T  (81 numbers per point),
+// and rhs_a^c = -sum_q g_a[p] f^c[p], f^c = M^c^T S  (9 numbers per point):
+//   k3_points    one thread per quadrature point: geometry Jacobian, F, material law -> record {T, f} (90 doubles) in HBM
+//   k3_jacobian  one CTA per (element, block of 8 column functions b); per slab of fixed q1:
+//                  Z_b = T . g_b            (27 numbers per (b, point))                      -> smem
+//                  U_p = sum_q3  N3|N3'(q3) Z_b[p]      sum factorisation, direction 3       -> smem
+//                  W   = sum_q2  N2|N2'(q2) U           direction 2                          registers
+//                  acc += N1|N1'(q1) W                  direction 1                          registers
+//                then FP64 RED into the compressed values (arithmetic addresses for regular columns, binary search else)
+//   k3_residual  one CTA per element: rhs_a^c -= sum_q g_a . f^c
+#include <cstdlib>
+#include <cstring>
+#include <cub/cub.cuh>
+#include "kl_internal.h"
+#include "../../include/ks_solid.h"
+
+#define KS_MAXP 3
+#define KS_PD 90            // doubles per quadrature-point record: T[3][3][3][3] + f[3][3]
+#define KS_JB 8             // column functions per CTA
+#define KS_NT 384
+#define KS_KMAX 3           // tasks (i2,i3,b,cd) per thread: 4*4*8*9 / 384
+
+struct KSDev {
+    int p[3], nq[3], n[3], nel[3];
+    int ncp, nfree, nloc, nqp, nblk;
+    int W[3], nst;
+    const int* span[3];
+    const double* bas[3];     // [nel_d][nq_d][2][p_d+1] value / first derivative of the active functions at the Gauss nodes
+    const double* wq[3];      // [nel_d][nq_d] weight * half span length
+    const double* cp;
+    const int* map;
+    const double* fixed;
+    double* disp;
+    const int* outer;
+    const int* inner;
+    double* values;
+    const int* colbase;       // [ncp][4]: outer of column (J,d), d = 0..2 (-1 eliminated); [3] = regular stencil
+    double* pd;
+    int* flag;
+    int law;
+    double lambda, mu;
+};
+
+struct ks_ctx {
+    int device = 0;
+    KSDev d{};
+    std::vector<double> U[3];
+    std::vector<int> span[3];
+    int nfixed = 0;
+    int64_t nnz = 0;
+    std::vector<void*> owned;
+    double *d_x = nullptr, *d_r = nullptr, *d_fext = nullptr;
+    double *h_x = nullptr, *h_r = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6]{};
+    float ms_points = 0, ms_jac = 0, ms_res = 0;
+    int launches = 0;
+    bool attr_done = false;
+};
+
+namespace {
+
+template <class T>
+int dev_upload(ks_ctx* ctx, const T** dst, const T* src, size_t n) {
+    T* p = nullptr;
+    KL_CUDA(cudaMalloc((void**)&p, sizeof(T) * (n ? n : 1)));
+    ctx->owned.push_back((void*)p);
+    if (n) KL_CUDA(cudaMemcpy(p, src, sizeof(T) * n, cudaMemcpyHostToDevice));
+    *dst = p;
+    return 0;
+}
+template <class T>
+int dev_alloc(ks_ctx* ctx, T** p, size_t n) {
+    KL_CUDA(cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)));
+    ctx->owned.push_back((void*)*p);
+    return 0;
+}
+
+// ---- symbolic pattern ---------------------------------------------------------------------------------------------
+struct Pat3 {
+    int n[3], ncp, nfree;
+    const int* map;
+    const int *lo[3], *hi[3];      // node range coupled with node j in direction d (share a non-empty element)
+};
+
+__device__ __forceinline__ void node_ijk(const Pat3& a, int J, int& j1, int& j2, int& j3) {
+    j1 = J % a.n[0];
+    j2 = (J / a.n[0]) % a.n[1];
+    j3 = J / (a.n[0] * a.n[1]);
+}
+
+// count[col] = number of free rows coupled with column (J,d)
+__global__ void k3_count(Pat3 a, int* __restrict__ count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * a.ncp) return;
+    const int d = t / a.ncp, J = t - d * a.ncp;
+    const int col = a.map[t];
+    if (col >= a.nfree) return;
+    int j1, j2, j3;
+    node_ijk(a, J, j1, j2, j3);
+    int cnt = 0;
+    for (int c = 0; c < 3; ++c)
+        for (int i3 = a.lo[2][j3]; i3 <= a.hi[2][j3]; ++i3)
+            for (int i2 = a.lo[1][j2]; i2 <= a.hi[1][j2]; ++i2)
+                for (int i1 = a.lo[0][j1]; i1 <= a.hi[0][j1]; ++i1)
+                    cnt += a.map[c * a.ncp + i1 + a.n[0] * (i2 + a.n[1] * i3)] < a.nfree;
+    count[col] = cnt;
+}
+
+// rows in the order (c, i3, i2, i1) = ascending global index for a component-wise monotone numbering (checked)
+__global__ void k3_fill(Pat3 a, const int* __restrict__ outer, int* __restrict__ inner, int* __restrict__ unsorted) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * a.ncp) return;
+    const int d = t / a.ncp, J = t - d * a.ncp;
+    const int col = a.map[t];
+    if (col >= a.nfree) return;
+    int j1, j2, j3;
+    node_ijk(a, J, j1, j2, j3);
+    int k = outer[col], prev = -1;
+    for (int c = 0; c < 3; ++c)
+        for (int i3 = a.lo[2][j3]; i3 <= a.hi[2][j3]; ++i3)
+            for (int i2 = a.lo[1][j2]; i2 <= a.hi[1][j2]; ++i2)
+                for (int i1 = a.lo[0][j1]; i1 <= a.hi[0][j1]; ++i1) {
+                    const int row = a.map[c * a.ncp + i1 + a.n[0] * (i2 + a.n[1] * i3)];
+                    if (row >= a.nfree) continue;
+                    if (row <= prev) *unsorted = 1;
+                    prev = row;
+                    inner[k++] = row;
+                }
+}
+
+// colbase[J] = {outer[col(J,0..2)] or -1, regular}: regular = full (2p+1)^3 box with all 3 components free everywhere
+__global__ void k3_colbase(Pat3 a, int W1, int W2, int W3, const int* __restrict__ outer, int* __restrict__ colbase) {
+    const int J = blockIdx.x * blockDim.x + threadIdx.x;
+    if (J >= a.ncp) return;
+    int j1, j2, j3;
+    node_ijk(a, J, j1, j2, j3);
+    const int nst = W1 * W2 * W3;
+    int regular = (a.hi[0][j1] - a.lo[0][j1] + 1 == W1) && (a.hi[1][j2] - a.lo[1][j2] + 1 == W2) && (a.hi[2][j3] - a.lo[2][j3] + 1 == W3) &&
+                  (a.lo[0][j1] == j1 - W1 / 2) && (a.lo[1][j2] == j2 - W2 / 2) && (a.lo[2][j3] == j3 - W3 / 2);
+    for (int d = 0; d < 3; ++d) {
+        const int col = a.map[d * a.ncp + J];
+        const int base = col < a.nfree ? outer[col] : -1;
+        colbase[4 * J + d] = base;
+        if (base < 0) regular = 0;
+        else if (outer[col + 1] - base != 3 * nst) regular = 0;
+    }
+    colbase[4 * J + 3] = regular;
+}
+
+// ---- assembly kernels ---------------------------------------------------------------------------------------------
+__global__ void k3_construct(KSDev d, const double* __restrict__ x) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 3 * d.ncp) return;
+    const int c = k / d.ncp, i = k - c * d.ncp;
+    const int g = d.map[k];
+    d.disp[3 * i + c] = g < d.nfree ? (x ? x[g] : 0.0) : (d.fixed ? d.fixed[g - d.nfree] : 0.0);
+}
+
+__global__ void k3_axpby(double* __restrict__ r, const double* __restrict__ f, double a, double b, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) r[k] = a * r[k] + b * f[k];
+}
+
+struct ElemTables {
+    double b[3][KS_MAXP + 1][2][KS_MAXP + 1];   // [direction][q][value|derivative][a]
+    double w[3][KS_MAXP + 1];
+    int first[3];                                // first active node per direction
+};
+
+__device__ __forceinline__ void elem_of(const KSDev& d, int e, int& e1, int& e2, int& e3) {
+    e1 = e % d.nel[0];
+    e2 = (e / d.nel[0]) % d.nel[1];
+    e3 = e / (d.nel[0] * d.nel[1]);
+}
+
+__device__ __forceinline__ void stage_tables(const KSDev& d, int e1, int e2, int e3, ElemTables& E, int tid, int nthr) {
+    const int ee[3] = {e1, e2, e3};
+    for (int dir = 0; dir < 3; ++dir) {
+        const int np1 = d.p[dir] + 1, nq = d.nq[dir];
+        const double* g = d.bas[dir] + (size_t)ee[dir] * nq * 2 * np1;
+        for (int k = tid; k < nq * 2 * np1; k += nthr) {
+            const int a = k % np1, m = (k / np1) % 2, q = k / (2 * np1);
+            E.b[dir][q][m][a] = g[k];
+        }
+        for (int k = tid; k < nq; k += nthr) E.w[dir][k] = d.wq[dir][(size_t)ee[dir] * nq + k];
+        if (tid == 0) E.first[dir] = d.span[dir][ee[dir]] - d.p[dir];
+    }
+}
+
+__device__ __forceinline__ double det3(const double (&A)[3][3]) {
+    return A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
+           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+}
+__device__ __forceinline__ void inv3(const double (&A)[3][3], double det, double (&B)[3][3]) {
+    const double r = 1.0 / det;
+    B[0][0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) * r;
+    B[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * r;
+    B[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * r;
+    B[1][0] = (A[1][2] * A[2][0] - A[1][0] * A[2][2]) * r;
+    B[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * r;
+    B[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * r;
+    B[2][0] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) * r;
+    B[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * r;
+    B[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * r;
+}
+
+// point index inside an element: q1 slowest so that a slab of fixed q1 is contiguous
+__device__ __forceinline__ int point_index(const KSDev& d, int q1, int q2, int q3) { return (q1 * d.nq[1] + q2) * d.nq[2] + q3; }
+
+// One thread per quadrature point.  MODE 0: record {T, f}; MODE 1: body-force integrand only (N_a * detJ * w).
+__global__ void __launch_bounds__(64) k3_points(KSDev d) {
+    __shared__ ElemTables E;
+    __shared__ double s_cp[(KS_MAXP + 1) * (KS_MAXP + 1) * (KS_MAXP + 1)][3];
+    __shared__ double s_u[(KS_MAXP + 1) * (KS_MAXP + 1) * (KS_MAXP + 1)][3];
+    extern __shared__ double s_out[];       // [nqp][KS_PD]
+    const int tid = threadIdx.x, e = blockIdx.x;
+    int e1, e2, e3;
+    elem_of(d, e, e1, e2, e3);
+    stage_tables(d, e1, e2, e3, E, tid, blockDim.x);
+    __syncthreads();
+    const int np1 = d.p[0] + 1, np2 = d.p[1] + 1, np3 = d.p[2] + 1;
+    for (int a = tid; a < d.nloc; a += blockDim.x) {
+        const int a1 = a % np1, a2 = (a / np1) % np2, a3 = a / (np1 * np2);
+        const int node = (E.first[0] + a1) + d.n[0] * ((E.first[1] + a2) + d.n[1] * (E.first[2] + a3));
+        for (int k = 0; k < 3; ++k) { s_cp[a][k] = d.cp[3 * node + k]; s_u[a][k] = d.disp[3 * node + k]; }
+    }
+    __syncthreads();
+    if (tid < d.nqp) {
+        const int q3 = tid % d.nq[2], q2 = (tid / d.nq[2]) % d.nq[1], q1 = tid / (d.nq[2] * d.nq[1]);   // = point_index order
+        double Jg[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Hu[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int a3 = 0; a3 < np3; ++a3)
+            for (int a2 = 0; a2 < np2; ++a2)
+                for (int a1 = 0; a1 < np1; ++a1) {
+                    const int a = a1 + np1 * (a2 + np2 * a3);
+                    const double x0 = E.b[0][q1][0][a1], x1 = E.b[0][q1][1][a1], y0 = E.b[1][q2][0][a2], y1 = E.b[1][q2][1][a2],
+                                 z0 = E.b[2][q3][0][a3], z1 = E.b[2][q3][1][a3];
+                    const double g[3] = {x1 * y0 * z0, x0 * y1 * z0, x0 * y0 * z1};
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+#pragma unroll
+                        for (int l = 0; l < 3; ++l) { Jg[k][l] = fma(s_cp[a][k], g[l], Jg[k][l]); Hu[k][l] = fma(s_u[a][k], g[l], Hu[k][l]); }
+                }
+        const double dJ = det3(Jg);
+        int flag = 0;
+        if (!(fabs(dJ) > 0.0)) flag |= KLF_JACOBIAN;
+        double G[3][3];                       // G[l][k] = d xi_l / d x_k
+        inv3(Jg, dJ, G);
+        const double w = E.w[0][q1] * E.w[1][q2] * E.w[2][q3] * fabs(dJ);
+        double F[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) F[c][k] = (c == k ? 1.0 : 0.0) + Hu[c][0] * G[0][k] + Hu[c][1] * G[1][k] + Hu[c][2] * G[2][k];
+        const bool linear = d.law == KS_LAW_HOOKE;
+        const double lam = d.lambda, mu = d.mu;
+        // S = a Ci + b1 I + s_E E ;  CC_ijkl = c1 X_ij X_kl + c2 (X_ik X_jl + X_il X_jk), X = I (SvK, Hooke) or C^-1 (neo-Hooke)
+        double S[3][3], X[3][3], c1, c2;
+        if (linear || d.law == KS_LAW_SVK) {
+            double Eg[3][3], tr = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    double v;
+                    if (linear) v = 0.5 * (F[i][j] + F[j][i]) - (i == j ? 1.0 : 0.0);
+                    else v = 0.5 * (F[0][i] * F[0][j] + F[1][i] * F[1][j] + F[2][i] * F[2][j] - (i == j ? 1.0 : 0.0));
+                    Eg[i][j] = v;
+                }
+            tr = Eg[0][0] + Eg[1][1] + Eg[2][2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { S[i][j] = 2.0 * mu * Eg[i][j] + (i == j ? lam * tr : 0.0); X[i][j] = i == j ? 1.0 : 0.0; }
+            c1 = lam; c2 = mu;
+        } else {
+            const double Jd = det3(F);
+            if (!(Jd > 0.0)) flag |= KLF_JACOBIAN;
+            double C[3][3], Ci[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) C[i][j] = F[0][i] * F[0][j] + F[1][i] * F[1][j] + F[2][i] * F[2][j];
+            inv3(C, det3(C), Ci);
+            double a;
+            if (d.law == KS_LAW_NEO_HOOKE_LN) { a = lam * log(Jd) - mu; c1 = lam; }
+            else { a = 0.5 * lam * (Jd * Jd - 1.0) - mu; c1 = lam * Jd * Jd; }
+            c2 = -a;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { S[i][j] = a * Ci[i][j] + (i == j ? mu : 0.0); X[i][j] = Ci[i][j]; }
+        }
+        // P^c[i][p] = Fb[c][i] (strain direction i) paired with G[p][j]:  dE_ij = sym( sum_c Fb[c][i] G[p][j] g[p] du_c )
+        // T^{cd}_{pq} = sum_ijkl Fb[c][i] G[p][j] CC_ijkl Fb[d][k] G[q][l] + delta_cd (G S G^T)_{pq}
+        // with CC = c1 X (x) X + c2 (X_ik X_jl + X_il X_jk):
+        //   = c1 (Fb[c].X.G[p]) (Fb[d].X.G[q]) + c2 [ (Fb[c].X.Fb[d]) (G[p].X.G[q]) + (Fb[c].X.G[q]) (G[p].X.Fb[d]) ]
+        double Fb[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) Fb[c][k] = linear ? (c == k ? 1.0 : 0.0) : F[c][k];
+        double XF[3][3], XG[3][3];      // XF[i][d] = sum_k X[i][k] Fb[d][k];  XG[i][q] = sum_l X[i][l] G[q][l]
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                XF[i][k] = X[i][0] * Fb[k][0] + X[i][1] * Fb[k][1] + X[i][2] * Fb[k][2];
+                XG[i][k] = X[i][0] * G[k][0] + X[i][1] * G[k][1] + X[i][2] * G[k][2];
+            }
+        double FXF[3][3], GXG[3][3], FXG[3][3], GSG[3][3], SG[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                FXF[i][k] = Fb[i][0] * XF[0][k] + Fb[i][1] * XF[1][k] + Fb[i][2] * XF[2][k];     // Fb[c].X.Fb[d]
+                GXG[i][k] = G[i][0] * XG[0][k] + G[i][1] * XG[1][k] + G[i][2] * XG[2][k];        // G[p].X.G[q]
+                FXG[i][k] = Fb[i][0] * XG[0][k] + Fb[i][1] * XG[1][k] + Fb[i][2] * XG[2][k];     // Fb[c].X.G[q]
+                SG[i][k] = S[i][0] * G[k][0] + S[i][1] * G[k][1] + S[i][2] * G[k][2];            // (S G^T)[i][q]
+            }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) GSG[i][k] = G[i][0] * SG[0][k] + G[i][1] * SG[1][k] + G[i][2] * SG[2][k];
+        double* out = s_out + (size_t)tid * KS_PD;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dd = 0; dd < 3; ++dd)
+#pragma unroll
+                for (int p = 0; p < 3; ++p)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        double t = c1 * FXG[c][p] * FXG[dd][q] + c2 * (FXF[c][dd] * GXG[p][q] + FXG[c][q] * FXG[dd][p]);
+                        if (c == dd && !linear) t += GSG[p][q];
+                        out[((c * 3 + dd) * 3 + p) * 3 + q] = w * t;
+                    }
+        // f^c[p] = sum_ij Fb[c][i] S_ij G[p][j]
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int p = 0; p < 3; ++p) out[81 + c * 3 + p] = w * (Fb[c][0] * SG[0][p] + Fb[c][1] * SG[1][p] + Fb[c][2] * SG[2][p]);
+        bool bad = false;
+        for (int k = 0; k < KS_PD; ++k) bad |= !(fabs(out[k]) <= 1.79e308);
+        if (bad) flag |= KLF_NONFINITE;
+        if (flag) atomicOr(d.flag, flag);
+    }
+    __syncthreads();
+    double* g = d.pd + (size_t)e * d.nqp * KS_PD;
+    for (int k = tid; k < d.nqp * KS_PD; k += blockDim.x) g[k] = s_out[k];
+}
+
+// body force: f_a^c += b_c * sum_q N_a w |detJ|
+__global__ void __launch_bounds__(64) k3_bodyforce(KSDev d, double b0, double b1, double b2, double* __restrict__ f) {
+    __shared__ ElemTables E;
+    __shared__ double s_cp[(KS_MAXP + 1) * (KS_MAXP + 1) * (KS_MAXP + 1)][3];
+    __shared__ double s_w[(KS_MAXP + 1) * (KS_MAXP + 1) * (KS_MAXP + 1)];
+    const int tid = threadIdx.x, e = blockIdx.x;
+    int e1, e2, e3;
+    elem_of(d, e, e1, e2, e3);
+    stage_tables(d, e1, e2, e3, E, tid, blockDim.x);
+    __syncthreads();
+    const int np1 = d.p[0] + 1, np2 = d.p[1] + 1, np3 = d.p[2] + 1;
+    for (int a = tid; a < d.nloc; a += blockDim.x) {
+        const int a1 = a % np1, a2 = (a / np1) % np2, a3 = a / (np1 * np2);
+        const int node = (E.first[0] + a1) + d.n[0] * ((E.first[1] + a2) + d.n[1] * (E.first[2] + a3));
+        for (int k = 0; k < 3; ++k) s_cp[a][k] = d.cp[3 * node + k];
+    }
+    __syncthreads();
+    if (tid < d.nqp) {
+        const int q3 = tid % d.nq[2], q2 = (tid / d.nq[2]) % d.nq[1], q1 = tid / (d.nq[2] * d.nq[1]);
+        double Jg[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int a3 = 0; a3 < np3; ++a3)
+            for (int a2 = 0; a2 < np2; ++a2)
+                for (int a1 = 0; a1 < np1; ++a1) {
+                    const int a = a1 + np1 * (a2 + np2 * a3);
+                    const double x0 = E.b[0][q1][0][a1], x1 = E.b[0][q1][1][a1], y0 = E.b[1][q2][0][a2], y1 = E.b[1][q2][1][a2],
+                                 z0 = E.b[2][q3][0][a3], z1 = E.b[2][q3][1][a3];
+                    const double g[3] = {x1 * y0 * z0, x0 * y1 * z0, x0 * y0 * z1};
+                    for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) Jg[k][l] = fma(s_cp[a][k], g[l], Jg[k][l]);
+                }
+        s_w[tid] = E.w[0][q1] * E.w[1][q2] * E.w[2][q3] * fabs(det3(Jg));
+    }
+    __syncthreads();
+    for (int a = tid; a < d.nloc; a += blockDim.x) {
+        const int a1 = a % np1, a2 = (a / np1) % np2, a3 = a / (np1 * np2);
+        double s = 0.0;
+        for (int q = 0; q < d.nqp; ++q) {
+            const int q3 = q % d.nq[2], q2 = (q / d.nq[2]) % d.nq[1], q1 = q / (d.nq[2] * d.nq[1]);
+            s = fma(E.b[0][q1][0][a1] * E.b[1][q2][0][a2] * E.b[2][q3][0][a3], s_w[q], s);
+        }
+        const int node = (E.first[0] + a1) + d.n[0] * ((E.first[1] + a2) + d.n[1] * (E.first[2] + a3));
+        const double bb[3] = {b0, b1, b2};
+        for (int c = 0; c < 3; ++c) {
+            const int g = d.map[c * d.ncp + node];
+            if (g < d.nfree && bb[c] != 0.0) atomicAdd(&f[g], s * bb[c]);
+        }
+    }
+}
+
+// rhs_a^c -= sum_q g_a(q) . f^c(q)     (one CTA per element, one thread per (a, c))
+__global__ void __launch_bounds__(192) k3_residual(KSDev d, double* __restrict__ r) {
+    __shared__ ElemTables E;
+    __shared__ double s_f[(KS_MAXP + 1) * (KS_MAXP + 1) * (KS_MAXP + 1)][9];
+    const int tid = threadIdx.x, e = blockIdx.x;
+    int e1, e2, e3;
+    elem_of(d, e, e1, e2, e3);
+    stage_tables(d, e1, e2, e3, E, tid, blockDim.x);
+    const double* g = d.pd + (size_t)e * d.nqp * KS_PD;
+    for (int k = tid; k < d.nqp * 9; k += blockDim.x) s_f[k / 9][k % 9] = g[(size_t)(k / 9) * KS_PD + 81 + k % 9];
+    __syncthreads();
+    const int np1 = d.p[0] + 1, np2 = d.p[1] + 1;
+    for (int t = tid; t < d.nloc * 3; t += blockDim.x) {
+        const int a = t / 3, c = t - 3 * a;
+        const int a1 = a % np1, a2 = (a / np1) % np2, a3 = a / (np1 * np2);
+        double s = 0.0;
+        for (int q1 = 0; q1 < d.nq[0]; ++q1)
+            for (int q2 = 0; q2 < d.nq[1]; ++q2)
+                for (int q3 = 0; q3 < d.nq[2]; ++q3) {
+                    const double x0 = E.b[0][q1][0][a1], x1 = E.b[0][q1][1][a1], y0 = E.b[1][q2][0][a2], y1 = E.b[1][q2][1][a2],
+                                 z0 = E.b[2][q3][0][a3], z1 = E.b[2][q3][1][a3];
+                    const double* f = s_f[point_index(d, q1, q2, q3)] + 3 * c;
+                    s += x1 * y0 * z0 * f[0] + x0 * y1 * z0 * f[1] + x0 * y0 * z1 * f[2];
+                }
+        const int node = (E.first[0] + a1) + d.n[0] * ((E.first[1] + a2) + d.n[1] * (E.first[2] + a3));
+        const int gr = d.map[c * d.ncp + node];
+        if (gr < d.nfree) atomicAdd(&r[gr], -s);
+    }
+}
+
+struct JacSmem {
+    ElemTables E;
+    double T[(KS_MAXP + 1) * (KS_MAXP + 1)][81];                       // records of the current slab (fixed q1)
+    double Z[(KS_MAXP + 1) * (KS_MAXP + 1)][KS_JB][27];                // [pt (q2,q3)][b][cd][p]
+    double U[KS_MAXP + 1][KS_MAXP + 1][KS_JB][9][3];                   // [q2][i3][b][cd][p]
+};
+
+__global__ void __launch_bounds__(KS_NT) k3_jacobian(KSDev d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    JacSmem& S = *reinterpret_cast<JacSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int e = blockIdx.x / d.nblk, blk = blockIdx.x - e * d.nblk;
+    int e1, e2, e3;
+    elem_of(d, e, e1, e2, e3);
+    stage_tables(d, e1, e2, e3, S.E, tid, KS_NT);
+    const int np1 = d.p[0] + 1, np2 = d.p[1] + 1, np3 = d.p[2] + 1;
+    const int nq1 = d.nq[0], nq2 = d.nq[1], nq3 = d.nq[2];
+    const int b0 = blk * KS_JB;
+    const int nb = min(KS_JB, d.nloc - b0);                 // column functions of this block
+    const int nZ = nq2 * nq3 * nb * 3;                      // tasks (pt, b, c)
+    const int nU = nq2 * np3 * nb * 9;                      // tasks (q2, i3, b, cd)
+    const int nW = np2 * np3 * nb * 9;                      // tasks (i2, i3, b, cd)
+    double acc[KS_KMAX][KS_MAXP + 1];
+#pragma unroll
+    for (int k = 0; k < KS_KMAX; ++k)
+#pragma unroll
+        for (int a = 0; a <= KS_MAXP; ++a) acc[k][a] = 0.0;
+    const double* pdE = d.pd + (size_t)e * d.nqp * KS_PD;
+    for (int q1 = 0; q1 < nq1; ++q1) {
+        __syncthreads();                                    // tables staged / previous slab consumed
+        for (int k = tid; k < nq2 * nq3 * 81; k += KS_NT) {
+            const int pt = k / 81, m = k - pt * 81;
+            S.T[pt][m] = pdE[(size_t)(q1 * nq2 * nq3 + pt) * KS_PD + m];
+        }
+        __syncthreads();
+        // ---- Z_b[c][dd][p] = sum_q T^{c dd}[p][q] g_b[q]
+        for (int t = tid; t < nZ; t += KS_NT) {
+            const int c = t % 3, bl = (t / 3) % nb, pt = t / (3 * nb);
+            const int q3 = pt % nq3, q2 = pt / nq3;
+            const int b = b0 + bl, a1 = b % np1, a2 = (b / np1) % np2, a3 = b / (np1 * np2);
+            const double x0 = S.E.b[0][q1][0][a1], x1 = S.E.b[0][q1][1][a1], y0 = S.E.b[1][q2][0][a2], y1 = S.E.b[1][q2][1][a2],
+                         z0 = S.E.b[2][q3][0][a3], z1 = S.E.b[2][q3][1][a3];
+            const double g0 = x1 * y0 * z0, g1 = x0 * y1 * z0, g2 = x0 * y0 * z1;
+            const double* Tp = S.T[pt] + c * 27;
+            double* Zo = S.Z[pt][bl] + c * 9;
+#pragma unroll
+            for (int m = 0; m < 9; ++m) Zo[m] = Tp[3 * m] * g0 + Tp[3 * m + 1] * g1 + Tp[3 * m + 2] * g2;
+        }
+        __syncthreads();
+        // ---- direction 3: U_p[q2][i3] = sum_q3 N3(q3) Z[p] (p = 0,1), N3'(q3) Z[2]
+        for (int t = tid; t < nU; t += KS_NT) {
+            const int cd = t % 9, bl = (t / 9) % nb, i3 = (t / (9 * nb)) % np3, q2 = t / (9 * nb * np3);
+            double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+            for (int q3 = 0; q3 < nq3; ++q3) {
+                const double* z = S.Z[q2 * nq3 + q3][bl] + cd * 3;
+                const double v = S.E.b[2][q3][0][i3], dv = S.E.b[2][q3][1][i3];
+                u0 = fma(v, z[0], u0);
+                u1 = fma(v, z[1], u1);
+                u2 = fma(dv, z[2], u2);
+            }
+            double* u = S.U[q2][i3][bl][cd];
+            u[0] = u0; u[1] = u1; u[2] = u2;
+        }
+        __syncthreads();
+        // ---- direction 2 and 1: W0 = sum_q2 N2 U0 (pairs with N1'), W12 = sum_q2 N2' U1 + N2 U2 (pairs with N1)
+#pragma unroll
+        for (int k = 0; k < KS_KMAX; ++k) {
+            const int t = tid + k * KS_NT;
+            if (t < nW) {
+                const int cd = t % 9, bl = (t / 9) % nb, i3 = (t / (9 * nb)) % np3, i2 = t / (9 * nb * np3);
+                double w0 = 0.0, w12 = 0.0;
+                for (int q2 = 0; q2 < nq2; ++q2) {
+                    const double* u = S.U[q2][i3][bl][cd];
+                    const double v = S.E.b[1][q2][0][i2], dv = S.E.b[1][q2][1][i2];
+                    w0 = fma(v, u[0], w0);
+                    w12 = fma(dv, u[1], fma(v, u[2], w12));
+                }
+#pragma unroll
+                for (int a = 0; a <= KS_MAXP; ++a)
+                    if (a < np1) acc[k][a] = fma(S.E.b[0][q1][1][a], w0, fma(S.E.b[0][q1][0][a], w12, acc[k][a]));
+            }
+        }
+    }
+    // ---- scatter: entry (row (I,c), col (J,dd)), Z index cd = c*3 + dd
+    const int W1 = d.W[0], W2 = d.W[1], NST = d.nst;
+#pragma unroll
+    for (int k = 0; k < KS_KMAX; ++k) {
+        const int t = tid + k * KS_NT;
+        if (t >= nW) continue;
+        const int cd = t % 9, bl = (t / 9) % nb, i3 = (t / (9 * nb)) % np3, i2 = t / (9 * nb * np3);
+        const int c = cd / 3, dd = cd - 3 * c;
+        const int b = b0 + bl, j1 = b % np1, j2 = (b / np1) % np2, j3 = b / (np1 * np2);
+        const int J = (S.E.first[0] + j1) + d.n[0] * ((S.E.first[1] + j2) + d.n[1] * (S.E.first[2] + j3));
+        const int4 cb = reinterpret_cast<const int4*>(d.colbase)[J];
+        const int base = dd == 0 ? cb.x : (dd == 1 ? cb.y : cb.z);
+        if (base < 0) continue;                              // eliminated column
+        if (cb.w) {
+            const int slot0 = ((i3 - j3 + d.p[2]) * W2 + (i2 - j2 + d.p[1])) * W1 + (0 - j1 + d.p[0]);
+            double* dst = d.values + base + c * NST + slot0;
+#pragma unroll
+            for (int a = 0; a <= KS_MAXP; ++a)
+                if (a < np1) atomicAdd(dst + a, acc[k][a]);
+        } else {
+            const int col = d.map[dd * d.ncp + J];
+            const int lo0 = base, hi0 = d.outer[col + 1] - 1;
+#pragma unroll
+            for (int a = 0; a <= KS_MAXP; ++a) {
+                if (a >= np1) continue;
+                const int I = (S.E.first[0] + a) + d.n[0] * ((S.E.first[1] + i2) + d.n[1] * (S.E.first[2] + i3));
+                const int row = d.map[c * d.ncp + I];
+                if (row >= d.nfree) continue;
+                int lo = lo0, hi = hi0;
+                while (lo <= hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int rr = d.inner[mid];
+                    if (rr == row) { atomicAdd(d.values + mid, acc[k][a]); break; }
+                    if (rr < row) lo = mid + 1; else hi = mid - 1;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+// ---- host side ---------------------------------------------------------------------------------------------------------
+extern "C" int ks_build_dofmap(int32_t n1, int32_t n2, int32_t n3, const ks_bc* bc, int32_t* map, int32_t* n_free, int32_t* n_fixed) {
+    if (!bc || !map || n1 < 2 || n2 < 2 || n3 < 2) { kl_set_error("ks_build_dofmap: bad argument"); return KL_E_ARG; }
+    const int ncp = n1 * n2 * n3;
+    const int n[3] = {n1, n2, n3};
+    std::vector<char> elim((size_t)3 * ncp, 0);
+    for (int c = 0; c < 3; ++c)
+        for (int i3 = 0; i3 < n3; ++i3)
+            for (int i2 = 0; i2 < n2; ++i2)
+                for (int i1 = 0; i1 < n1; ++i1) {
+                    const int id[3] = {i1, i2, i3};
+                    bool e = false;
+                    for (int d = 0; d < 3; ++d) {
+                        if (id[d] == 0 && bc->side[2 * d][c]) e = true;
+                        if (id[d] == n[d] - 1 && bc->side[2 * d + 1][c]) e = true;
+                    }
+                    const bool corner = (i1 == 0 || i1 == n1 - 1) && (i2 == 0 || i2 == n2 - 1) && (i3 == 0 || i3 == n3 - 1);
+                    if (corner && bc->corner[(i1 ? 1 : 0) | (i2 ? 2 : 0) | (i3 ? 4 : 0)][c]) e = true;
+                    elim[(size_t)c * ncp + i1 + n1 * (i2 + n2 * i3)] = e;
+                }
+    int nf = 0, ne = 0;
+    for (size_t k = 0; k < elim.size(); ++k) if (!elim[k]) map[k] = nf++;
+    for (size_t k = 0; k < elim.size(); ++k) if (elim[k]) map[k] = nf + ne++;
+    if (n_free) *n_free = nf;
+    if (n_fixed) *n_fixed = ne;
+    return KL_OK;
+}
+
+static int ks_build_pattern(ks_ctx* ctx) {
+    KSDev& d = ctx->d;
+    Pat3 a{};
+    for (int k = 0; k < 3; ++k) a.n[k] = d.n[k];
+    a.ncp = d.ncp; a.nfree = d.nfree; a.map = d.map;
+    for (int dir = 0; dir < 3; ++dir) {
+        std::vector<int> lo(d.n[dir], d.n[dir]), hi(d.n[dir], -1);
+        for (int s : ctx->span[dir])
+            for (int i = s - d.p[dir]; i <= s; ++i) { lo[i] = std::min(lo[i], s - d.p[dir]); hi[i] = std::max(hi[i], s); }
+        if (int rc = dev_upload(ctx, &a.lo[dir], lo.data(), lo.size())) return rc;
+        if (int rc = dev_upload(ctx, &a.hi[dir], hi.data(), hi.size())) return rc;
+    }
+    const int T = 128, nt = 3 * d.ncp;
+    int *count = nullptr, *outer = nullptr, *unsorted = nullptr;
+    if (int rc = dev_alloc(ctx, &count, (size_t)d.nfree + 1)) return rc;
+    if (int rc = dev_alloc(ctx, &outer, (size_t)d.nfree + 1)) return rc;
+    if (int rc = dev_alloc(ctx, &unsorted, 1)) return rc;
+    KL_CUDA(cudaMemset(count, 0, sizeof(int) * ((size_t)d.nfree + 1)));
+    KL_CUDA(cudaMemset(unsorted, 0, sizeof(int)));
+    k3_count<<<(nt + T - 1) / T, T>>>(a, count);
+    KL_CUDA(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    KL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, count, outer, d.nfree + 1));
+    void* tmp = nullptr;
+    KL_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    cudaError_t ce = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, count, outer, d.nfree + 1);
+    cudaFree(tmp);
+    KL_CUDA(ce);
+    int nnz = 0;
+    KL_CUDA(cudaMemcpy(&nnz, outer + d.nfree, sizeof(int), cudaMemcpyDeviceToHost));
+    ctx->nnz = nnz;
+    int* inner = nullptr;
+    if (int rc = dev_alloc(ctx, &inner, (size_t)nnz)) return rc;
+    k3_fill<<<(nt + T - 1) / T, T>>>(a, outer, inner, unsorted);
+    KL_CUDA(cudaGetLastError());
+    int* colbase = nullptr;
+    if (int rc = dev_alloc(ctx, &colbase, (size_t)4 * d.ncp)) return rc;
+    k3_colbase<<<(d.ncp + T - 1) / T, T>>>(a, d.W[0], d.W[1], d.W[2], outer, colbase);
+    KL_CUDA(cudaGetLastError());
+    int uns = 0;
+    KL_CUDA(cudaMemcpy(&uns, unsorted, sizeof(int), cudaMemcpyDeviceToHost));
+    if (uns) { kl_set_error("ks_create: dof_map must number the free DoFs of each component in control-point order"); return KL_E_ARG; }
+    double* values = nullptr;
+    if (int rc = dev_alloc(ctx, &values, (size_t)nnz)) return rc;
+    KL_CUDA(cudaMemset(values, 0, sizeof(double) * (size_t)(nnz ? nnz : 1)));
+    ctx->launches += 3;
+    d.outer = outer; d.inner = inner; d.colbase = colbase; d.values = values;
+    return KL_OK;
+}
+
+// dead surface tractions: F_a^c += t_c int_face N_a dGamma   (host, once; faces are 2-D)
+static void add_tractions(const ks_ctx* ctx, const ks_problem* P, const std::vector<double>& cp, const std::vector<int>& map, std::vector<double>& f) {
+    const KSDev& d = ctx->d;
+    for (int t = 0; t < P->n_tractions; ++t) {
+        const int side = P->traction_side[t], dn = side / 2, hiSide = side & 1;
+        const int da = (dn + 1) % 3, db = (dn + 2) % 3;
+        const double* tv = P->traction_val + 3 * t;
+        const std::vector<double>& Un = ctx->U[dn];
+        const int sn = hiSide ? ctx->span[dn].back() : ctx->span[dn].front();
+        const double un = hiSide ? Un.back() : Un.front();
+        double bn[3][KL_MAXP + 1];
+        bspline_span_ders(Un, d.p[dn], sn, un, bn);
+        std::vector<double> xa(d.p[da] + 1), wa(d.p[da] + 1), xb(d.p[db] + 1), wb(d.p[db] + 1);
+        gauss_rule(d.p[da] + 1, xa.data(), wa.data());
+        gauss_rule(d.p[db] + 1, xb.data(), wb.data());
+        for (int sa : ctx->span[da])
+            for (int sb : ctx->span[db]) {
+                const double a0 = ctx->U[da][sa], ha = ctx->U[da][sa + 1] - a0, b0 = ctx->U[db][sb], hb = ctx->U[db][sb + 1] - b0;
+                for (int qa = 0; qa <= d.p[da]; ++qa)
+                    for (int qb = 0; qb <= d.p[db]; ++qb) {
+                        double ba[3][KL_MAXP + 1], bb[3][KL_MAXP + 1];
+                        bspline_span_ders(ctx->U[da], d.p[da], sa, a0 + 0.5 * ha * (xa[qa] + 1.0), ba);
+                        bspline_span_ders(ctx->U[db], d.p[db], sb, b0 + 0.5 * hb * (xb[qb] + 1.0), bb);
+                        double ta[3] = {0, 0, 0}, tb[3] = {0, 0, 0};
+                        int s3[3];
+                        s3[dn] = sn; s3[da] = sa; s3[db] = sb;
+                        double(*B3[3])[KL_MAXP + 1];
+                        B3[dn] = bn; B3[da] = ba; B3[db] = bb;
+                        for (int a3 = 0; a3 <= d.p[2]; ++a3)
+                            for (int a2 = 0; a2 <= d.p[1]; ++a2)
+                                for (int a1 = 0; a1 <= d.p[0]; ++a1) {
+                                    const int aa[3] = {a1, a2, a3};
+                                    const int node = (s3[0] - d.p[0] + a1) + d.n[0] * ((s3[1] - d.p[1] + a2) + d.n[1] * (s3[2] - d.p[2] + a3));
+                                    const double Nn = B3[dn][0][aa[dn]];
+                                    const double ga = Nn * B3[da][1][aa[da]] * B3[db][0][aa[db]], gb = Nn * B3[da][0][aa[da]] * B3[db][1][aa[db]];
+                                    for (int k = 0; k < 3; ++k) { ta[k] += cp[3 * node + k] * ga; tb[k] += cp[3 * node + k] * gb; }
+                                }
+                        const double nx = ta[1] * tb[2] - ta[2] * tb[1], ny = ta[2] * tb[0] - ta[0] * tb[2], nz = ta[0] * tb[1] - ta[1] * tb[0];
+                        const double w = wa[qa] * wb[qb] * 0.25 * ha * hb * std::sqrt(nx * nx + ny * ny + nz * nz);
+                        for (int a3 = 0; a3 <= d.p[2]; ++a3)
+                            for (int a2 = 0; a2 <= d.p[1]; ++a2)
+                                for (int a1 = 0; a1 <= d.p[0]; ++a1) {
+                                    const int aa[3] = {a1, a2, a3};
+                                    const int node = (s3[0] - d.p[0] + a1) + d.n[0] * ((s3[1] - d.p[1] + a2) + d.n[1] * (s3[2] - d.p[2] + a3));
+                                    const double N = B3[0][0][aa[0]] * B3[1][0][aa[1]] * B3[2][0][aa[2]];
+                                    for (int c = 0; c < 3; ++c) {
+                                        const int g = map[(size_t)c * d.ncp + node];
+                                        if (g < d.nfree) f[g] += w * N * tv[c];
+                                    }
+                                }
+                    }
+            }
+    }
+}
+
+extern "C" void ks_destroy(ks_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void* p : ctx->owned) cudaFree(p);
+    if (ctx->h_x) cudaFreeHost(ctx->h_x);
+    if (ctx->h_r) cudaFreeHost(ctx->h_r);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    delete ctx;
+}
+
+extern "C" int ks_create(const ks_problem* P, int device, ks_ctx** out) {
+    if (!P || !out) { kl_set_error("ks_create: null argument"); return KL_E_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        kl_set_error("no CUDA device: libkl_shell has no CPU fallback");
+        return KL_E_NOGPU;
+    }
+    if (device >= 0) KL_CUDA(cudaSetDevice(device));
+    if (P->weights) { kl_set_error("ks_create: rational (NURBS) volumes are not supported in this version"); return KL_E_ARG; }
+    if (P->material_law < KS_LAW_HOOKE || P->material_law > KS_LAW_NEO_HOOKE_QUAD) { kl_set_error("ks_create: unknown MaterialLaw"); return KL_E_ARG; }
+    for (int k = 0; k < 3; ++k)
+        if (P->degree[k] < 1 || P->degree[k] > KS_MAXP || !P->knots[k] || P->n_knots[k] < 2 * (P->degree[k] + 1)) {
+            kl_set_error("ks_create: degrees must be in [1,3] with open knot vectors");
+            return KL_E_ARG;
+        }
+    if (!P->cp || !P->dof_map) { kl_set_error("ks_create: null control net / dof map"); return KL_E_ARG; }
+    ks_ctx* ctx = new ks_ctx();
+    int rc = KL_OK;
+    struct Guard { ks_ctx* c; bool ok = false; ~Guard() { if (!ok) ks_destroy(c); } } guard{ctx};
+    KL_CUDA(cudaGetDevice(&ctx->device));
+    KSDev& d = ctx->d;
+    d.ncp = 1; d.nloc = 1; d.nqp = 1; d.nst = 1;
+    for (int k = 0; k < 3; ++k) {
+        d.p[k] = P->degree[k]; d.nq[k] = d.p[k] + 1; d.n[k] = P->n_knots[k] - d.p[k] - 1;
+        ctx->U[k].assign(P->knots[k], P->knots[k] + P->n_knots[k]);
+        for (int s = d.p[k]; s < d.n[k]; ++s) if (ctx->U[k][s + 1] > ctx->U[k][s]) ctx->span[k].push_back(s);
+        d.nel[k] = (int)ctx->span[k].size();
+        if (d.nel[k] < 1 || d.n[k] < d.p[k] + 1) { kl_set_error("ks_create: empty knot vector"); return KL_E_ARG; }
+        d.ncp *= d.n[k]; d.nloc *= d.p[k] + 1; d.nqp *= d.nq[k];
+        d.W[k] = 2 * d.p[k] + 1; d.nst *= d.W[k];
+    }
+    d.nblk = (d.nloc + KS_JB - 1) / KS_JB;
+    d.nfree = P->n_free; ctx->nfixed = P->n_fixed;
+    d.law = P->material_law;
+    d.lambda = P->E * P->nu / ((1.0 + P->nu) * (1.0 - 2.0 * P->nu));
+    d.mu = P->E / (2.0 * (1.0 + P->nu));
+    for (size_t k = 0; k < (size_t)3 * d.ncp; ++k)
+        if (P->dof_map[k] < 0 || P->dof_map[k] >= P->n_free + P->n_fixed) { kl_set_error("ks_create: dof_map entry out of range"); return KL_E_ARG; }
+    // 1-D tables at the Gauss nodes of every non-empty span
+    for (int k = 0; k < 3; ++k) {
+        const int nq = d.nq[k], np1 = d.p[k] + 1;
+        std::vector<double> xg(nq), wg(nq), bas((size_t)d.nel[k] * nq * 2 * np1), wq((size_t)d.nel[k] * nq);
+        gauss_rule(nq, xg.data(), wg.data());
+        for (int e = 0; e < d.nel[k]; ++e) {
+            const int s = ctx->span[k][e];
+            const double a = ctx->U[k][s], h = ctx->U[k][s + 1] - a;
+            for (int q = 0; q < nq; ++q) {
+                double o[3][KL_MAXP + 1];
+                bspline_span_ders(ctx->U[k], d.p[k], s, a + 0.5 * h * (xg[q] + 1.0), o);
+                for (int m = 0; m < 2; ++m)
+                    for (int j = 0; j < np1; ++j) bas[(((size_t)e * nq + q) * 2 + m) * np1 + j] = o[m][j];
+                wq[(size_t)e * nq + q] = 0.5 * h * wg[q];
+            }
+        }
+        if ((rc = dev_upload(ctx, &d.bas[k], bas.data(), bas.size()))) return rc;
+        if ((rc = dev_upload(ctx, &d.wq[k], wq.data(), wq.size()))) return rc;
+        if ((rc = dev_upload(ctx, &d.span[k], ctx->span[k].data(), ctx->span[k].size()))) return rc;
+    }
+    std::vector<double> cp(P->cp, P->cp + (size_t)3 * d.ncp);
+    std::vector<int> map(P->dof_map, P->dof_map + (size_t)3 * d.ncp);
+    if ((rc = dev_upload(ctx, &d.cp, cp.data(), cp.size()))) return rc;
+    if ((rc = dev_upload(ctx, &d.map, map.data(), map.size()))) return rc;
+    if (P->n_fixed > 0) {
+        std::vector<double> fx((size_t)P->n_fixed, 0.0);
+        if (P->fixed_values) fx.assign(P->fixed_values, P->fixed_values + P->n_fixed);
+        if ((rc = dev_upload(ctx, &d.fixed, fx.data(), fx.size()))) return rc;
+    }
+    if ((rc = dev_alloc(ctx, &d.disp, (size_t)3 * d.ncp))) return rc;
+    if ((rc = dev_alloc(ctx, &d.flag, 1))) return rc;
+    KL_CUDA(cudaMemset(d.flag, 0, sizeof(int)));
+    const size_t nelem = (size_t)d.nel[0] * d.nel[1] * d.nel[2];
+    if ((rc = dev_alloc(ctx, &d.pd, nelem * d.nqp * KS_PD))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_x, (size_t)d.nfree))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_r, (size_t)d.nfree))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->d_fext, (size_t)d.nfree))) return rc;
+    KL_CUDA(cudaMallocHost((void**)&ctx->h_x, sizeof(double) * (size_t)(d.nfree > 0 ? d.nfree : 1)));
+    KL_CUDA(cudaMallocHost((void**)&ctx->h_r, sizeof(double) * (size_t)(d.nfree > 0 ? d.nfree : 1)));
+    KL_CUDA(cudaStreamCreate(&ctx->stream));
+    for (auto& e : ctx->ev) KL_CUDA(cudaEventCreate(&e));
+    if ((rc = ks_build_pattern(ctx))) return rc;
+    // F_ext = tractions (host, faces only) + body force (device)
+    std::vector<double> f((size_t)(d.nfree > 0 ? d.nfree : 1), 0.0);
+    if (P->n_tractions > 0) {
+        if (!P->traction_side || !P->traction_val) { kl_set_error("ks_create: null traction arrays"); return KL_E_ARG; }
+        for (int t = 0; t < P->n_tractions; ++t)
+            if (P->traction_side[t] < 0 || P->traction_side[t] > 5) { kl_set_error("ks_create: bad traction side"); return KL_E_ARG; }
+        add_tractions(ctx, P, cp, map, f);
+    }
+    KL_CUDA(cudaMemcpy(ctx->d_fext, f.data(), sizeof(double) * (size_t)d.nfree, cudaMemcpyHostToDevice));
+    if (P->body_force[0] != 0.0 || P->body_force[1] != 0.0 || P->body_force[2] != 0.0) {
+        k3_bodyforce<<<(unsigned)nelem, 64>>>(d, P->body_force[0], P->body_force[1], P->body_force[2], ctx->d_fext);
+        KL_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    KL_CUDA(cudaDeviceSynchronize());
+    guard.ok = true;
+    *out = ctx;
+    return KL_OK;
+}
+
+extern "C" int ks_sizes(const ks_ctx* ctx, int32_t* n_dofs, int64_t* nnz, int64_t* n_elements, int64_t* n_qp) {
+    if (!ctx) return KL_E_ARG;
+    const int64_t ne = (int64_t)ctx->d.nel[0] * ctx->d.nel[1] * ctx->d.nel[2];
+    if (n_dofs) *n_dofs = ctx->d.nfree;
+    if (nnz) *nnz = ctx->nnz;
+    if (n_elements) *n_elements = ne;
+    if (n_qp) *n_qp = ne * ctx->d.nqp;
+    return KL_OK;
+}
+extern "C" int ks_pattern_host(const ks_ctx* ctx, int32_t* outer, int32_t* inner) {
+    if (!ctx || !outer || !inner) return KL_E_ARG;
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KL_CUDA(cudaMemcpy(outer, ctx->d.outer, sizeof(int) * ((size_t)ctx->d.nfree + 1), cudaMemcpyDeviceToHost));
+    KL_CUDA(cudaMemcpy(inner, ctx->d.inner, sizeof(int) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost));
+    return KL_OK;
+}
+extern "C" double* ks_values_device(ks_ctx* ctx) { return ctx ? ctx->d.values : nullptr; }
+extern "C" int ks_kernel_launches(const ks_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int ks_force(ks_ctx* ctx, double* f_host) {
+    if (!ctx || !f_host) return KL_E_ARG;
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KL_CUDA(cudaMemcpy(f_host, ctx->d_fext, sizeof(double) * (size_t)ctx->d.nfree, cudaMemcpyDeviceToHost));
+    return KL_OK;
+}
+
+extern "C" int ks_check(ks_ctx* ctx, void* stream) {
+    if (!ctx) return KL_E_ARG;
+    int flag = 0;
+    KL_CUDA(cudaMemcpyAsync(&flag, ctx->d.flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    KL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flag) {
+        KL_CUDA(cudaMemsetAsync(ctx->d.flag, 0, sizeof(int), (cudaStream_t)stream));
+        if (flag & KLF_JACOBIAN) { kl_set_error("inverted element: det F <= 0 or det of the geometry Jacobian = 0"); return KL_E_JACOBIAN; }
+        kl_set_error("non-finite value at a quadrature point");
+        return KL_E_NONFINITE;
+    }
+    return KL_OK;
+}
+
+// r_dev = a_r * (-F_int) + b_f * F_ext
+static int assemble_dev(ks_ctx* ctx, const double* x_dev, int want_matrix, double* r_dev, double a_r, double b_f, void* stream) {
+    if (!ctx) return KL_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const KSDev& d = ctx->d;
+    const unsigned nelem = (unsigned)((size_t)d.nel[0] * d.nel[1] * d.nel[2]);
+    const int n3 = 3 * d.ncp;
+    k3_construct<<<(n3 + 255) / 256, 256, 0, s>>>(d, x_dev);
+    KL_CUDA(cudaEventRecord(ctx->ev[0], s));
+    const size_t smem_pts = sizeof(double) * (size_t)d.nqp * KS_PD;
+    if (!ctx->attr_done) {
+        KL_CUDA(cudaFuncSetAttribute(k3_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * KS_PD)));
+        KL_CUDA(cudaFuncSetAttribute(k3_jacobian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacSmem)));
+        ctx->attr_done = true;
+    }
+    k3_points<<<nelem, 64, smem_pts, s>>>(d);
+    KL_CUDA(cudaEventRecord(ctx->ev[1], s));
+    ctx->launches += 2;
+    if (want_matrix) {
+        KL_CUDA(cudaMemsetAsync(d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
+        KL_CUDA(cudaEventRecord(ctx->ev[2], s));
+        k3_jacobian<<<nelem * d.nblk, KS_NT, sizeof(JacSmem), s>>>(d);
+        KL_CUDA(cudaEventRecord(ctx->ev[3], s));
+        ctx->launches++;
+    }
+    if (r_dev) {
+        KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * (size_t)d.nfree, s));
+        KL_CUDA(cudaEventRecord(ctx->ev[4], s));
+        k3_residual<<<nelem, 192, 0, s>>>(d, r_dev);
+        KL_CUDA(cudaEventRecord(ctx->ev[5], s));
+        if (d.nfree > 0) k3_axpby<<<(d.nfree + 255) / 256, 256, 0, s>>>(r_dev, ctx->d_fext, a_r, b_f, d.nfree);
+        ctx->launches += 2;
+    }
+    KL_CUDA(cudaGetLastError());
+    return KL_OK;
+}
+extern "C" int ks_assemble_device(ks_ctx* ctx, const double* x_dev, int want_matrix, double* r_dev, void* stream) {
+    return assemble_dev(ctx, x_dev, want_matrix, r_dev, 1.0, 1.0, stream);
+}
+
+// host-pointer entry: r = a_r * (-F_int) + b_f * F_ext
+static int run_host(ks_ctx* ctx, const double* x_host, double* values_host, double* r_host, double a_r, double b_f) {
+    if (!ctx) { kl_set_error("null context"); return KL_E_ARG; }
+    KL_CUDA(cudaSetDevice(ctx->device));
+    const int n = ctx->d.nfree;
+    cudaStream_t s = ctx->stream;
+    const double* xd = nullptr;
+    if (x_host) {
+        std::memcpy(ctx->h_x, x_host, sizeof(double) * (size_t)n);
+        KL_CUDA(cudaMemcpyAsync(ctx->d_x, ctx->h_x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, s));
+        xd = ctx->d_x;
+    }
+    int rc = assemble_dev(ctx, xd, values_host != nullptr, r_host ? ctx->d_r : nullptr, a_r, b_f, s);
+    if (rc) return rc;
+    if (r_host) {
+        KL_CUDA(cudaMemcpyAsync(ctx->h_r, ctx->d_r, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    }
+    if (values_host) KL_CUDA(cudaMemcpyAsync(values_host, ctx->d.values, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost, s));
+    rc = ks_check(ctx, s);
+    if (r_host) std::memcpy(r_host, ctx->h_r, sizeof(double) * (size_t)n);
+    cudaEventElapsedTime(&ctx->ms_points, ctx->ev[0], ctx->ev[1]);
+    if (values_host) cudaEventElapsedTime(&ctx->ms_jac, ctx->ev[2], ctx->ev[3]);
+    if (r_host) cudaEventElapsedTime(&ctx->ms_res, ctx->ev[4], ctx->ev[5]);
+    return rc;
+}
+
+extern "C" int ks_assemble(ks_ctx* ctx, const double* x_host, double* values_host, double* r_host) { return run_host(ctx, x_host, values_host, r_host, 1.0, 1.0); }
+extern "C" int ks_jacobian(ks_ctx* ctx, const double* x_host, double* values_host) {
+    if (!values_host) { kl_set_error("ks_jacobian: null values"); return KL_E_ARG; }
+    return run_host(ctx, x_host, values_host, nullptr, 1.0, 1.0);
+}
+extern "C" int ks_residual(ks_ctx* ctx, const double* x_host, double* r_host) {
+    if (!r_host) { kl_set_error("ks_residual: null output"); return KL_E_ARG; }
+    return run_host(ctx, x_host, nullptr, r_host, 1.0, 1.0);
+}
+extern "C" int ks_al_residual(ks_ctx* ctx, const double* x_host, double lam, double* r_host) {
+    if (!r_host) { kl_set_error("ks_al_residual: null output"); return KL_E_ARG; }
+    return run_host(ctx, x_host, nullptr, r_host, -1.0, -lam);    // F_int - lam F_ext  (k3_residual leaves -F_int in r)
+}
+extern "C" int ks_last_timing(const ks_ctx* ctx, float* ms_points, float* ms_jacobian, float* ms_residual) {
+    if (!ctx) return KL_E_ARG;
+    if (ms_points) *ms_points = ctx->ms_points;
+    if (ms_jacobian) *ms_jacobian = ctx->ms_jac;
+    if (ms_residual) *ms_residual = ctx->ms_res;
+    return KL_OK;
+}

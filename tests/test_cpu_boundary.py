@@ -89,3 +89,41 @@ def test_no_cpu_fallback(L):
     rc = L.kl_create(C.byref(P), -1, C.byref(h))
     assert rc == -6 and not h.value
     assert b"no CPU fallback" in L.kl_last_error()
+
+
+# ---- solid path (include/ks_solid.h) ------------------------------------------------------------------------------------
+def test_solid_header_symbols_exported(L):
+    from gsstructuralanalysis_b200 import solid as S
+    hdr = open(os.path.join(ROOT, "include", "ks_solid.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b(ks_[a-z_0-9]+)\s*\(", hdr))
+    assert names == set(S.SYMBOLS), names ^ set(S.SYMBOLS)
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_solid_dofmap_matches_oracle(L):
+    from gsstructuralanalysis_b200 import solid as S
+    from oracle.binding_solid import lib as olib
+    S._bind(L)
+    for bc in (S.SolidBC(), S.SolidBC().add_condition(S.KS_WEST).add_condition(S.KS_BACK, 1),
+               S.SolidBC().add_corner_value(0).add_corner_value(7, 2).add_condition(S.KS_SOUTH, 0)):
+        n1, n2, n3 = 4, 3, 5
+        m1, m2 = np.zeros(3 * n1 * n2 * n3, dtype=np.int32), np.zeros(3 * n1 * n2 * n3, dtype=np.int32)
+        a, b, c, d = C.c_int32(), C.c_int32(), C.c_int(), C.c_int()
+        cb = bc.to_c()
+        assert L.ks_build_dofmap(n1, n2, n3, C.byref(cb), m1.ctypes.data_as(c_int_p), C.byref(a), C.byref(b)) == 0
+        assert olib().kso_build_dofmap(n1, n2, n3, C.byref(cb), m2.ctypes.data_as(c_int_p), C.byref(c), C.byref(d)) == 0
+        assert np.array_equal(m1, m2) and a.value == c.value and b.value == d.value
+        assert sorted(m1.tolist()) == list(range(3 * n1 * n2 * n3))
+
+
+def test_solid_no_cpu_fallback(L):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gsstructuralanalysis_b200 import solid as S
+    from gsstructuralanalysis_b200.capi import KLError
+    with pytest.raises(KLError) as ei:
+        S.SolidAssembler(S.SolidProblem(S.brick(nels=(2, 1, 1)), S.SolidBC()))
+    assert ei.value.rc == -6
