@@ -10,7 +10,7 @@ import os
 from .problem import kl_problem, kl_bc, c_double_p, c_int_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkl_shell.so")
+LIB_PATH = os.environ.get("KL_LIB") or os.path.join(_HERE, "libkl_shell.so")   # KL_LIB: A/B builds of the same sources
 
 KL_ERRORS = {0: "KL_OK", -1: "KL_E_ARG", -2: "KL_E_CUDA", -3: "KL_E_NONFINITE", -4: "KL_E_JACOBIAN", -5: "KL_E_C33",
              -6: "KL_E_NOGPU"}

@@ -24,8 +24,10 @@
 #define KS_MAXP 3
 #define KS_PD 90            // doubles per quadrature-point record: T[3][3][3][3] + f[3][3]
 #define KS_JB 8             // column functions per CTA
-#define KS_NT 384
-#define KS_KMAX 3           // tasks (i2,i3,b,cd) per thread: 4*4*8*9 / 384
+#ifndef KS_MINB
+#define KS_MINB 3           // CTAs per SM the Jacobian kernel is compiled for (72 registers)
+#endif
+#define KS_NT 288           // = (p3+1) * KS_JB * 9 at p = 3: one (i3, column, cd) accumulator task per thread
 
 struct KSDev {
     int p[3], nq[3], n[3], nel[3];
@@ -41,7 +43,9 @@ struct KSDev {
     const int* outer;
     const int* inner;
     double* values;
-    const int* colbase;       // [ncp][4]: outer of column (J,d), d = 0..2 (-1 eliminated); [3] = regular stencil
+    const int* colbase;       // [ncp][4]: outer of column (J,d), d = 0..2 (-1 eliminated); [3] = 1 when no DoF in the coupled box is eliminated
+    const int* nlo[3];        // [n_d] first / last node coupled with node j in direction d (the box of a column)
+    const int* nhi[3];
     double* pd;
     int* flag;
     int law;
@@ -136,23 +140,23 @@ __global__ void k3_fill(Pat3 a, const int* __restrict__ outer, int* __restrict__
                 }
 }
 
-// colbase[J] = {outer[col(J,0..2)] or -1, regular}: regular = full (2p+1)^3 box with all 3 components free everywhere
-__global__ void k3_colbase(Pat3 a, int W1, int W2, int W3, const int* __restrict__ outer, int* __restrict__ colbase) {
+// colbase[J] = {outer[col(J,0..2)] or -1, boxed}: boxed = every DoF of the coupled node box [lo,hi]^3 is free, so the rows of
+// the three columns of J are exactly 3 x box in canonical order and entry addresses are arithmetic
+__global__ void k3_colbase(Pat3 a, const int* __restrict__ outer, int* __restrict__ colbase) {
     const int J = blockIdx.x * blockDim.x + threadIdx.x;
     if (J >= a.ncp) return;
     int j1, j2, j3;
     node_ijk(a, J, j1, j2, j3);
-    const int nst = W1 * W2 * W3;
-    int regular = (a.hi[0][j1] - a.lo[0][j1] + 1 == W1) && (a.hi[1][j2] - a.lo[1][j2] + 1 == W2) && (a.hi[2][j3] - a.lo[2][j3] + 1 == W3) &&
-                  (a.lo[0][j1] == j1 - W1 / 2) && (a.lo[1][j2] == j2 - W2 / 2) && (a.lo[2][j3] == j3 - W3 / 2);
+    const int nbox = (a.hi[0][j1] - a.lo[0][j1] + 1) * (a.hi[1][j2] - a.lo[1][j2] + 1) * (a.hi[2][j3] - a.lo[2][j3] + 1);
+    int boxed = 1;
     for (int d = 0; d < 3; ++d) {
         const int col = a.map[d * a.ncp + J];
         const int base = col < a.nfree ? outer[col] : -1;
         colbase[4 * J + d] = base;
-        if (base < 0) regular = 0;
-        else if (outer[col + 1] - base != 3 * nst) regular = 0;
+        if (base < 0) boxed = 0;
+        else if (outer[col + 1] - base != 3 * nbox) boxed = 0;
     }
-    colbase[4 * J + 3] = regular;
+    colbase[4 * J + 3] = boxed;
 }
 
 // ---- assembly kernels ---------------------------------------------------------------------------------------------
@@ -183,6 +187,11 @@ __device__ __forceinline__ void elem_of(const KSDev& d, int e, int& e1, int& e2,
 
 __device__ __forceinline__ void stage_tables(const KSDev& d, int e1, int e2, int e3, ElemTables& E, int tid, int nthr) {
     const int ee[3] = {e1, e2, e3};
+    {   // entries beyond p / nq stay zero: unrolled loops over KS_MAXP+1 functions then add exact zeros
+        double* z = &E.b[0][0][0][0];
+        for (int k = tid; k < 3 * (KS_MAXP + 1) * 2 * (KS_MAXP + 1); k += nthr) z[k] = 0.0;
+    }
+    __syncthreads();
     for (int dir = 0; dir < 3; ++dir) {
         const int np1 = d.p[dir] + 1, nq = d.nq[dir];
         const double* g = d.bas[dir] + (size_t)ee[dir] * nq * 2 * np1;
@@ -442,34 +451,58 @@ struct JacSmem {
     double U[KS_MAXP + 1][KS_MAXP + 1][KS_JB][9][3];                   // [q2][i3][b][cd][p]
 };
 
-__global__ void __launch_bounds__(KS_NT) k3_jacobian(KSDev d) {
+// TP1..TP3 = compile-time degrees (0 = read them from KSDev at run time): with constants the index arithmetic of the task
+// decoding folds into shifts and the inner loops unroll (the run-time version executes 7 instructions per FMA)
+template <int TP1, int TP2, int TP3>
+__global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     JacSmem& S = *reinterpret_cast<JacSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int e = blockIdx.x / d.nblk, blk = blockIdx.x - e * d.nblk;
+    const int np1 = TP1 ? TP1 + 1 : d.p[0] + 1, np2 = TP2 ? TP2 + 1 : d.p[1] + 1, np3 = TP3 ? TP3 + 1 : d.p[2] + 1;
+    const int nq1 = np1, nq2 = np2, nq3 = np3;              // p+1 Gauss nodes per direction
+    const int nloc = np1 * np2 * np3;
+    const int nblk = (nloc + KS_JB - 1) / KS_JB;
+    const int e = blockIdx.x / nblk, blk = blockIdx.x - e * nblk;
     int e1, e2, e3;
     elem_of(d, e, e1, e2, e3);
     stage_tables(d, e1, e2, e3, S.E, tid, KS_NT);
-    const int np1 = d.p[0] + 1, np2 = d.p[1] + 1, np3 = d.p[2] + 1;
-    const int nq1 = d.nq[0], nq2 = d.nq[1], nq3 = d.nq[2];
     const int b0 = blk * KS_JB;
-    const int nb = min(KS_JB, d.nloc - b0);                 // column functions of this block
+    const int nb = (TP1 && nloc % KS_JB == 0) ? KS_JB : min(KS_JB, nloc - b0);      // column functions of this block
     const int nZ = nq2 * nq3 * nb * 3;                      // tasks (pt, b, c)
-    const int nU = nq2 * np3 * nb * 9;                      // tasks (q2, i3, b, cd)
-    const int nW = np2 * np3 * nb * 9;                      // tasks (i2, i3, b, cd)
-    double acc[KS_KMAX][KS_MAXP + 1];
+    const int nU = nq2 * nb * 9;                            // tasks (q2, b, cd): all i3 of one (q2, b, cd) in registers
+    const int nW = np3 * nb * 9;                            // tasks (i3, b, cd): all (i2, i1) of one (i3, b, cd) in registers
+    // this thread's W task (at most one: np3 * nb * 9 <= 4 * 8 * 9 = KS_NT)
+    const bool hasW = tid < nW;
+    const int w_cd = tid % 9, w_bl = (tid / 9) % nb, w_i3 = tid / (9 * nb);
+    double acc[KS_MAXP + 1][KS_MAXP + 1];                   // [i2][i1]
 #pragma unroll
-    for (int k = 0; k < KS_KMAX; ++k)
+    for (int k = 0; k <= KS_MAXP; ++k)
 #pragma unroll
         for (int a = 0; a <= KS_MAXP; ++a) acc[k][a] = 0.0;
-    const double* pdE = d.pd + (size_t)e * d.nqp * KS_PD;
-    for (int q1 = 0; q1 < nq1; ++q1) {
-        __syncthreads();                                    // tables staged / previous slab consumed
-        for (int k = tid; k < nq2 * nq3 * 81; k += KS_NT) {
-            const int pt = k / 81, m = k - pt * 81;
-            S.T[pt][m] = pdE[(size_t)(q1 * nq2 * nq3 + pt) * KS_PD + m];
+    const double* pdE = d.pd + (size_t)e * (nq1 * nq2 * nq3) * KS_PD;
+    // T of a slab (fixed q1) = nq2*nq3 records; the next slab is fetched into registers while this one is processed
+    constexpr int NPRE = ((KS_MAXP + 1) * (KS_MAXP + 1) * 81 + KS_NT - 1) / KS_NT;
+    const int nT = nq2 * nq3 * 81;
+    double tpre[NPRE];
+    auto fetch = [&](int q1) {
+#pragma unroll
+        for (int k = 0; k < NPRE; ++k) {
+            const int idx = tid + k * KS_NT;
+            if (idx < nT) { const int pt = idx / 81, m = idx - pt * 81; tpre[k] = __ldg(pdE + (size_t)(q1 * nq2 * nq3 + pt) * KS_PD + m); }
         }
-        __syncthreads();
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int k = 0; k < NPRE; ++k) {
+            const int idx = tid + k * KS_NT;
+            if (idx < nT) (&S.T[0][0])[idx] = tpre[k];
+        }
+    };
+    fetch(0);
+    stash();
+    for (int q1 = 0; q1 < nq1; ++q1) {
+        __syncthreads();                                    // tables and T staged / previous slab consumed
+        if (q1 + 1 < nq1) fetch(q1 + 1);
         // ---- Z_b[c][dd][p] = sum_q T^{c dd}[p][q] g_b[q]
         for (int t = tid; t < nZ; t += KS_NT) {
             const int c = t % 3, bl = (t / 3) % nb, pt = t / (3 * nb);
@@ -484,62 +517,83 @@ __global__ void __launch_bounds__(KS_NT) k3_jacobian(KSDev d) {
             for (int m = 0; m < 9; ++m) Zo[m] = Tp[3 * m] * g0 + Tp[3 * m + 1] * g1 + Tp[3 * m + 2] * g2;
         }
         __syncthreads();
-        // ---- direction 3: U_p[q2][i3] = sum_q3 N3(q3) Z[p] (p = 0,1), N3'(q3) Z[2]
+        // ---- direction 3: U_p[q2][i3] = sum_q3 N3(q3) Z[p] (p = 0,1), N3'(q3) Z[2]; every Z value loaded once feeds all i3
         for (int t = tid; t < nU; t += KS_NT) {
-            const int cd = t % 9, bl = (t / 9) % nb, i3 = (t / (9 * nb)) % np3, q2 = t / (9 * nb * np3);
-            double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+            const int cd = t % 9, bl = (t / 9) % nb, q2 = t / (9 * nb);
+            double u[KS_MAXP + 1][3];
+#pragma unroll
+            for (int i3 = 0; i3 <= KS_MAXP; ++i3) u[i3][0] = u[i3][1] = u[i3][2] = 0.0;
             for (int q3 = 0; q3 < nq3; ++q3) {
                 const double* z = S.Z[q2 * nq3 + q3][bl] + cd * 3;
-                const double v = S.E.b[2][q3][0][i3], dv = S.E.b[2][q3][1][i3];
-                u0 = fma(v, z[0], u0);
-                u1 = fma(v, z[1], u1);
-                u2 = fma(dv, z[2], u2);
+                const double z0 = z[0], z1 = z[1], z2 = z[2];
+#pragma unroll
+                for (int i3 = 0; i3 <= KS_MAXP; ++i3) {
+                    const double v = S.E.b[2][q3][0][i3], dv = S.E.b[2][q3][1][i3];     // zero beyond p3 (tables are zero-filled)
+                    u[i3][0] = fma(v, z0, u[i3][0]);
+                    u[i3][1] = fma(v, z1, u[i3][1]);
+                    u[i3][2] = fma(dv, z2, u[i3][2]);
+                }
             }
-            double* u = S.U[q2][i3][bl][cd];
-            u[0] = u0; u[1] = u1; u[2] = u2;
+#pragma unroll
+            for (int i3 = 0; i3 <= KS_MAXP; ++i3)
+                if (i3 < np3) {
+                    double* uo = S.U[q2][i3][bl][cd];
+                    uo[0] = u[i3][0]; uo[1] = u[i3][1]; uo[2] = u[i3][2];
+                }
         }
         __syncthreads();
         // ---- direction 2 and 1: W0 = sum_q2 N2 U0 (pairs with N1'), W12 = sum_q2 N2' U1 + N2 U2 (pairs with N1)
+        if (hasW) {
+            double w0[KS_MAXP + 1], w12[KS_MAXP + 1];
 #pragma unroll
-        for (int k = 0; k < KS_KMAX; ++k) {
-            const int t = tid + k * KS_NT;
-            if (t < nW) {
-                const int cd = t % 9, bl = (t / 9) % nb, i3 = (t / (9 * nb)) % np3, i2 = t / (9 * nb * np3);
-                double w0 = 0.0, w12 = 0.0;
-                for (int q2 = 0; q2 < nq2; ++q2) {
-                    const double* u = S.U[q2][i3][bl][cd];
+            for (int i2 = 0; i2 <= KS_MAXP; ++i2) w0[i2] = w12[i2] = 0.0;
+            for (int q2 = 0; q2 < nq2; ++q2) {
+                const double* u = S.U[q2][w_i3][w_bl][w_cd];
+                const double u0 = u[0], u1 = u[1], u2 = u[2];
+#pragma unroll
+                for (int i2 = 0; i2 <= KS_MAXP; ++i2) {
                     const double v = S.E.b[1][q2][0][i2], dv = S.E.b[1][q2][1][i2];
-                    w0 = fma(v, u[0], w0);
-                    w12 = fma(dv, u[1], fma(v, u[2], w12));
+                    w0[i2] = fma(v, u0, w0[i2]);
+                    w12[i2] = fma(dv, u1, fma(v, u2, w12[i2]));
                 }
+            }
 #pragma unroll
-                for (int a = 0; a <= KS_MAXP; ++a)
-                    if (a < np1) acc[k][a] = fma(S.E.b[0][q1][1][a], w0, fma(S.E.b[0][q1][0][a], w12, acc[k][a]));
+            for (int a = 0; a <= KS_MAXP; ++a) {
+                const double xv = S.E.b[0][q1][0][a], xd = S.E.b[0][q1][1][a];
+#pragma unroll
+                for (int i2 = 0; i2 <= KS_MAXP; ++i2) acc[i2][a] = fma(xd, w0[i2], fma(xv, w12[i2], acc[i2][a]));
             }
         }
+        if (q1 + 1 < nq1) stash();                          // T was last read before the post-Z barrier of this slab
     }
     // ---- scatter: entry (row (I,c), col (J,dd)), Z index cd = c*3 + dd
-    const int W1 = d.W[0], W2 = d.W[1], NST = d.nst;
+    if (!hasW) return;
+    const int c = w_cd / 3, dd = w_cd - 3 * c, i3 = w_i3;
+    const int b = b0 + w_bl, j1 = b % np1, j2 = (b / np1) % np2, j3 = b / (np1 * np2);
+    const int J1 = S.E.first[0] + j1, J2 = S.E.first[1] + j2, J3 = S.E.first[2] + j3;
+    const int J = J1 + d.n[0] * (J2 + d.n[1] * J3);
+    const int4 cb = reinterpret_cast<const int4*>(d.colbase)[J];
+    const int base = dd == 0 ? cb.x : (dd == 1 ? cb.y : cb.z);
+    if (base < 0) return;                                    // eliminated column
+    if (cb.w) {
+        // rows of the column = 3 x node box [lo,hi]^3 in the order (c, i3, i2, i1)
+        const int lo1 = d.nlo[0][J1], lo2 = d.nlo[1][J2], lo3 = d.nlo[2][J3];
+        const int w1 = d.nhi[0][J1] - lo1 + 1, w2 = d.nhi[1][J2] - lo2 + 1, w3 = d.nhi[2][J3] - lo3 + 1;
+        double* col0 = d.values + base + c * (w1 * w2 * w3) + ((S.E.first[2] + i3 - lo3) * w2 - lo2) * w1 + (S.E.first[0] - lo1);
 #pragma unroll
-    for (int k = 0; k < KS_KMAX; ++k) {
-        const int t = tid + k * KS_NT;
-        if (t >= nW) continue;
-        const int cd = t % 9, bl = (t / 9) % nb, i3 = (t / (9 * nb)) % np3, i2 = t / (9 * nb * np3);
-        const int c = cd / 3, dd = cd - 3 * c;
-        const int b = b0 + bl, j1 = b % np1, j2 = (b / np1) % np2, j3 = b / (np1 * np2);
-        const int J = (S.E.first[0] + j1) + d.n[0] * ((S.E.first[1] + j2) + d.n[1] * (S.E.first[2] + j3));
-        const int4 cb = reinterpret_cast<const int4*>(d.colbase)[J];
-        const int base = dd == 0 ? cb.x : (dd == 1 ? cb.y : cb.z);
-        if (base < 0) continue;                              // eliminated column
-        if (cb.w) {
-            const int slot0 = ((i3 - j3 + d.p[2]) * W2 + (i2 - j2 + d.p[1])) * W1 + (0 - j1 + d.p[0]);
-            double* dst = d.values + base + c * NST + slot0;
+        for (int i2 = 0; i2 <= KS_MAXP; ++i2) {
+            if (i2 >= np2) continue;
+            double* dst = col0 + (S.E.first[1] + i2) * w1;
 #pragma unroll
             for (int a = 0; a <= KS_MAXP; ++a)
-                if (a < np1) atomicAdd(dst + a, acc[k][a]);
-        } else {
-            const int col = d.map[dd * d.ncp + J];
-            const int lo0 = base, hi0 = d.outer[col + 1] - 1;
+                if (a < np1) atomicAdd(dst + a, acc[i2][a]);
+        }
+    } else {
+        const int col = d.map[dd * d.ncp + J];
+        const int lo0 = base, hi0 = d.outer[col + 1] - 1;
+#pragma unroll
+        for (int i2 = 0; i2 <= KS_MAXP; ++i2) {
+            if (i2 >= np2) continue;
 #pragma unroll
             for (int a = 0; a <= KS_MAXP; ++a) {
                 if (a >= np1) continue;
@@ -550,7 +604,7 @@ __global__ void __launch_bounds__(KS_NT) k3_jacobian(KSDev d) {
                 while (lo <= hi) {
                     const int mid = (lo + hi) >> 1;
                     const int rr = d.inner[mid];
-                    if (rr == row) { atomicAdd(d.values + mid, acc[k][a]); break; }
+                    if (rr == row) { atomicAdd(d.values + mid, acc[i2][a]); break; }
                     if (rr < row) lo = mid + 1; else hi = mid - 1;
                 }
             }
@@ -625,7 +679,7 @@ static int ks_build_pattern(ks_ctx* ctx) {
     KL_CUDA(cudaGetLastError());
     int* colbase = nullptr;
     if (int rc = dev_alloc(ctx, &colbase, (size_t)4 * d.ncp)) return rc;
-    k3_colbase<<<(d.ncp + T - 1) / T, T>>>(a, d.W[0], d.W[1], d.W[2], outer, colbase);
+    k3_colbase<<<(d.ncp + T - 1) / T, T>>>(a, outer, colbase);
     KL_CUDA(cudaGetLastError());
     int uns = 0;
     KL_CUDA(cudaMemcpy(&uns, unsorted, sizeof(int), cudaMemcpyDeviceToHost));
@@ -635,6 +689,7 @@ static int ks_build_pattern(ks_ctx* ctx) {
     KL_CUDA(cudaMemset(values, 0, sizeof(double) * (size_t)(nnz ? nnz : 1)));
     ctx->launches += 3;
     d.outer = outer; d.inner = inner; d.colbase = colbase; d.values = values;
+    for (int k = 0; k < 3; ++k) { d.nlo[k] = a.lo[k]; d.nhi[k] = a.hi[k]; }
     return KL_OK;
 }
 
@@ -857,7 +912,12 @@ static int assemble_dev(ks_ctx* ctx, const double* x_dev, int want_matrix, doubl
     const size_t smem_pts = sizeof(double) * (size_t)d.nqp * KS_PD;
     if (!ctx->attr_done) {
         KL_CUDA(cudaFuncSetAttribute(k3_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 64 * KS_PD)));
-        KL_CUDA(cudaFuncSetAttribute(k3_jacobian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacSmem)));
+#define KS_ATTR(K)                                                                                                \
+    KL_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacSmem)));          \
+    KL_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        KS_ATTR((k3_jacobian<0, 0, 0>)) KS_ATTR((k3_jacobian<3, 3, 3>)) KS_ATTR((k3_jacobian<2, 2, 2>)) KS_ATTR((k3_jacobian<3, 3, 2>))
+        KS_ATTR((k3_jacobian<1, 1, 1>))
+#undef KS_ATTR
         ctx->attr_done = true;
     }
     k3_points<<<nelem, 64, smem_pts, s>>>(d);
@@ -866,7 +926,14 @@ static int assemble_dev(ks_ctx* ctx, const double* x_dev, int want_matrix, doubl
     if (want_matrix) {
         KL_CUDA(cudaMemsetAsync(d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
         KL_CUDA(cudaEventRecord(ctx->ev[2], s));
-        k3_jacobian<<<nelem * d.nblk, KS_NT, sizeof(JacSmem), s>>>(d);
+        const unsigned grid = nelem * d.nblk;
+        const int pk = d.p[0] * 100 + d.p[1] * 10 + d.p[2];
+        static const bool generic = getenv("KS_GENERIC") != nullptr;      // testing aid: force the run-time-degree kernel
+        if (pk == 333 && !generic) k3_jacobian<3, 3, 3><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
+        else if (pk == 222 && !generic) k3_jacobian<2, 2, 2><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
+        else if (pk == 332 && !generic) k3_jacobian<3, 3, 2><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
+        else if (pk == 111 && !generic) k3_jacobian<1, 1, 1><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
+        else k3_jacobian<0, 0, 0><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
         KL_CUDA(cudaEventRecord(ctx->ev[3], s));
         ctx->launches++;
     }
