@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "kl_shell.h"
+#include "ks_solid.h"
 
 #if defined(__has_include)
 #if __has_include(<gismo.h>)
@@ -268,6 +269,92 @@ private:
         ~Shared() { if (ctx) kl_destroy(ctx); }
     };
     std::shared_ptr<Shared> m_s;   // shared by every handle handed out, so handles may outlive this object
+};
+
+/** gsElasticityAssembler<real_t> behind the solid closures (tutorials/nonlinear_solid_static.cpp:101-114,
+    benchmarks/benchmark_Elasticity_Beam_APALM.cpp:307-325) on libkl_shell.so (include/ks_solid.h).  The reference's two
+    closures each run the full assemble(x, fixedDofs); here each computes only its half, and assemble() gives both in one pass. */
+class gsElasticityAssemblerB200 {
+public:
+    typedef double T;
+    typedef gsStructuralAnalysisOps<T> Ops;
+
+    gsElasticityAssemblerB200(const ks_problem& prob, int device = -1) {
+        ks_ctx* c = nullptr;
+        if (ks_create(&prob, device, &c) != KL_OK) throw std::runtime_error(std::string("ks_create: ") + kl_last_error());
+        m_s = std::make_shared<Shared>();
+        m_s->ctx = c;
+        int64_t nnz = 0, ne = 0, nq = 0;
+        ks_sizes(c, &m_s->ndofs, &nnz, &ne, &nq);
+        m_s->nnz = nnz;
+        m_s->outer.resize((size_t)m_s->ndofs + 1);
+        m_s->inner.resize((size_t)nnz);
+        if (ks_pattern_host(c, m_s->outer.data(), m_s->inner.data()) != KL_OK)
+            throw std::runtime_error(std::string("ks_pattern_host: ") + kl_last_error());
+    }
+    index_t numDofs() const { return m_s->ndofs; }
+    int64_t nonZeros() const { return m_s->nnz; }
+    ks_ctx* context() const { return m_s->ctx; }
+
+    /// assembler.assemble(x, fixedDofs); m = assembler.matrix();
+    Ops::Jacobian_t jacobian() const {
+        auto s = m_s;
+        return [s](gsVector<T> const& x, gsSparseMatrix<T>& m) {
+            adopt(m, *s);
+            return ks_jacobian(s->ctx, x.data(), m.valuePtr()) == KL_OK;
+        };
+    }
+    /// assembler.assemble(x, fixedDofs); v = assembler.rhs();
+    Ops::Residual_t residual() const {
+        auto s = m_s;
+        return [s](gsVector<T> const& x, gsVector<T>& r) {
+            r.resize(s->ndofs);
+            return ks_residual(s->ctx, x.data(), r.data()) == KL_OK;
+        };
+    }
+    /// Force - lam*Force - assembler.rhs()
+    Ops::ALResidual_t alResidual() const {
+        auto s = m_s;
+        return [s](gsVector<T> const& x, const T lam, gsVector<T>& r) {
+            r.resize(s->ndofs);
+            return ks_al_residual(s->ctx, x.data(), lam, r.data()) == KL_OK;
+        };
+    }
+    /// assembler.assemble(); F = assembler.rhs()
+    Ops::Force_t force() const {
+        auto s = m_s;
+        return [s](gsVector<T>& f) {
+            f.resize(s->ndofs);
+            return ks_force(s->ctx, f.data()) == KL_OK;
+        };
+    }
+    /// one pass for both outputs of assemble(x, fixedDofs)
+    bool assemble(gsVector<T> const& x, gsSparseMatrix<T>& m, gsVector<T>& rhs) const {
+        adopt(m, *m_s);
+        rhs.resize(m_s->ndofs);
+        return ks_assemble(m_s->ctx, x.data(), m.valuePtr(), rhs.data()) == KL_OK;
+    }
+
+private:
+    struct Shared {
+        ks_ctx* ctx = nullptr;
+        int32_t ndofs = 0;
+        int64_t nnz = 0;
+        std::vector<int32_t> outer, inner;
+        ~Shared() { if (ctx) ks_destroy(ctx); }
+    };
+    static void adopt(gsSparseMatrix<T>& m, const Shared& s) {
+        if (m.rows() == s.ndofs && m.cols() == s.ndofs && (int64_t)m.nonZeros() == s.nnz && m.isCompressed()) return;
+#ifdef KL_HAVE_GISMO
+        typedef gsEigen::Map<const gsEigen::SparseMatrix<T, gsEigen::ColMajor, index_t> > MapT;
+        std::vector<T> zeros((size_t)s.nnz, T(0));
+        m = MapT(s.ndofs, s.ndofs, (index_t)s.nnz, s.outer.data(), s.inner.data(), zeros.data());
+        m.makeCompressed();
+#else
+        m.setPattern(s.ndofs, s.outer.data(), s.inner.data());
+#endif
+    }
+    std::shared_ptr<Shared> m_s;
 };
 
 }  // namespace gismo

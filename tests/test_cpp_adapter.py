@@ -88,3 +88,31 @@ def test_apalm_intervals_one_per_gpu(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     d = _parse(r.stdout.strip().splitlines()[-1])
     assert int(d["jobs"]) == 4 * n and int(d["failed"]) == 0
+
+
+SOLID_EXE = os.path.join(ROOT, "examples", "solid_newton")
+
+
+def _build_solid():
+    from gsstructuralanalysis_b200 import build as kbuild
+    kbuild.build()
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", SOLID_EXE, os.path.join(ROOT, "examples", "solid_newton.cpp"),
+                           "-L" + os.path.join(ROOT, "gsstructuralanalysis_b200"), "-l:libkl_shell.so",
+                           "-Wl,-rpath," + os.path.join(ROOT, "gsstructuralanalysis_b200")])
+
+
+def test_cpp_solid_example_builds_and_refuses_cpu():
+    import torch
+    _build_solid()
+    r = subprocess.run([SOLID_EXE], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if not torch.cuda.is_available():
+        assert "NO_GPU" in r.stdout and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_solid_newton_converges_on_gpu():
+    _build_solid()
+    r = subprocess.run([SOLID_EXE], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "STATUS Success" in r.stdout, r.stdout
