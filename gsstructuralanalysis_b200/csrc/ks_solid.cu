@@ -9,7 +9,7 @@
 // and rhs_a^c = -sum_q g_a[p] f^c[p], f^c = M^c^T S  (9 numbers per point):
 //   k3_points    one thread per quadrature point: geometry Jacobian, F, material law -> record {T, f} (90 doubles) in HBM
 //   k3_jacobian  one CTA per (element, block of 8 column functions b); per slab of fixed q1:
-//                  Z_b = T . g_b            (27 numbers per (b, point))                      -> smem
+//                  Z_b = T . g_b            (27 numbers per (b, point))                      registers
 //                  U_p = sum_q3  N3|N3'(q3) Z_b[p]      sum factorisation, direction 3       -> smem
 //                  W   = sum_q2  N2|N2'(q2) U           direction 2                          registers
 //                  acc += N1|N1'(q1) W                  direction 1                          registers
@@ -22,10 +22,12 @@
 #include "../../include/ks_solid.h"
 
 #define KS_MAXP 3
+static_assert(KS_MAXP == 3, "the vectorised basis-row loads assume rows of 4 doubles");
 #define KS_PD 90            // doubles per quadrature-point record: T[3][3][3][3] + f[3][3]
 #define KS_JB 8             // column functions per CTA
+#define KS_TS 82            // doubles of a record staged per point: T (81) rounded up to whole 16-byte chunks
 #ifndef KS_MINB
-#define KS_MINB 3           // CTAs per SM the Jacobian kernel is compiled for (72 registers)
+#define KS_MINB 2           // CTAs per SM the Jacobian kernel is compiled for (measured: 2 -> 145 ms, 3 -> 155 ms with spills)
 #endif
 #define KS_NT 288           // = (p3+1) * KS_JB * 9 at p = 3: one (i3, column, cd) accumulator task per thread
 
@@ -49,6 +51,7 @@ struct KSDev {
     double* pd;
     int* flag;
     int law;
+    int ablate;               // profiling only (env KS_ABLATE): 1 skip the scatter, 2 skip the W/acc step, 4 skip the Z/U step
     double lambda, mu;
 };
 
@@ -446,8 +449,7 @@ __global__ void __launch_bounds__(192) k3_residual(KSDev d, double* __restrict__
 
 struct JacSmem {
     ElemTables E;
-    double T[(KS_MAXP + 1) * (KS_MAXP + 1)][81];                       // records of the current slab (fixed q1)
-    double Z[(KS_MAXP + 1) * (KS_MAXP + 1)][KS_JB][27];                // [pt (q2,q3)][b][cd][p]
+    double T[2][(KS_MAXP + 1) * (KS_MAXP + 1)][KS_TS];                 // records of the current / next slab (fixed q1)
     double U[KS_MAXP + 1][KS_MAXP + 1][KS_JB][9][3];                   // [q2][i3][b][cd][p]
 };
 
@@ -468,7 +470,6 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
     stage_tables(d, e1, e2, e3, S.E, tid, KS_NT);
     const int b0 = blk * KS_JB;
     const int nb = (TP1 && nloc % KS_JB == 0) ? KS_JB : min(KS_JB, nloc - b0);      // column functions of this block
-    const int nZ = nq2 * nq3 * nb * 3;                      // tasks (pt, b, c)
     const int nU = nq2 * nb * 9;                            // tasks (q2, b, cd): all i3 of one (q2, b, cd) in registers
     const int nW = np3 * nb * 9;                            // tasks (i3, b, cd): all (i2, i1) of one (i3, b, cd) in registers
     // this thread's W task (at most one: np3 * nb * 9 <= 4 * 8 * 9 = KS_NT)
@@ -480,58 +481,50 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
 #pragma unroll
         for (int a = 0; a <= KS_MAXP; ++a) acc[k][a] = 0.0;
     const double* pdE = d.pd + (size_t)e * (nq1 * nq2 * nq3) * KS_PD;
-    // T of a slab (fixed q1) = nq2*nq3 records; the next slab is fetched into registers while this one is processed
-    constexpr int NPRE = ((KS_MAXP + 1) * (KS_MAXP + 1) * 81 + KS_NT - 1) / KS_NT;
-    const int nT = nq2 * nq3 * 81;
-    double tpre[NPRE];
-    auto fetch = [&](int q1) {
-#pragma unroll
-        for (int k = 0; k < NPRE; ++k) {
-            const int idx = tid + k * KS_NT;
-            if (idx < nT) { const int pt = idx / 81, m = idx - pt * 81; tpre[k] = __ldg(pdE + (size_t)(q1 * nq2 * nq3 + pt) * KS_PD + m); }
+    // T of a slab (fixed q1) = the first 81 doubles of nq2*nq3 records; the next slab is copied asynchronously (cp.async, 16-byte
+    // chunks, 41 per record) into the other half of the double buffer while this one is processed
+    const int nchunk = nq2 * nq3 * (KS_TS / 2);
+    auto fetch = [&](int q1, int buf) {
+        for (int idx = tid; idx < nchunk; idx += KS_NT) {
+            const int pt = idx / (KS_TS / 2), m = idx - pt * (KS_TS / 2);
+            const double* src = pdE + (size_t)(q1 * nq2 * nq3 + pt) * KS_PD + 2 * m;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&S.T[buf][pt][2 * m]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto stash = [&]() {
-#pragma unroll
-        for (int k = 0; k < NPRE; ++k) {
-            const int idx = tid + k * KS_NT;
-            if (idx < nT) (&S.T[0][0])[idx] = tpre[k];
-        }
-    };
-    fetch(0);
-    stash();
+    fetch(0, 0);
     for (int q1 = 0; q1 < nq1; ++q1) {
-        __syncthreads();                                    // tables and T staged / previous slab consumed
-        if (q1 + 1 < nq1) fetch(q1 + 1);
-        // ---- Z_b[c][dd][p] = sum_q T^{c dd}[p][q] g_b[q]
-        for (int t = tid; t < nZ; t += KS_NT) {
-            const int c = t % 3, bl = (t / 3) % nb, pt = t / (3 * nb);
-            const int q3 = pt % nq3, q2 = pt / nq3;
-            const int b = b0 + bl, a1 = b % np1, a2 = (b / np1) % np2, a3 = b / (np1 * np2);
-            const double x0 = S.E.b[0][q1][0][a1], x1 = S.E.b[0][q1][1][a1], y0 = S.E.b[1][q2][0][a2], y1 = S.E.b[1][q2][1][a2],
-                         z0 = S.E.b[2][q3][0][a3], z1 = S.E.b[2][q3][1][a3];
-            const double g0 = x1 * y0 * z0, g1 = x0 * y1 * z0, g2 = x0 * y0 * z1;
-            const double* Tp = S.T[pt] + c * 27;
-            double* Zo = S.Z[pt][bl] + c * 9;
-#pragma unroll
-            for (int m = 0; m < 9; ++m) Zo[m] = Tp[3 * m] * g0 + Tp[3 * m + 1] * g1 + Tp[3 * m + 2] * g2;
-        }
-        __syncthreads();
-        // ---- direction 3: U_p[q2][i3] = sum_q3 N3(q3) Z[p] (p = 0,1), N3'(q3) Z[2]; every Z value loaded once feeds all i3
+        const int buf = q1 & 1;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                    // tables and T[buf] staged / previous slab consumed
+        if (q1 + 1 < nq1) fetch(q1 + 1, buf ^ 1);
+        // ---- Z_b[cd][p] = sum_q T^{cd}[p][q] g_b[q] at the nq3 points of a (q1,q2) line, contracted at once over q3:
+        //      U_p[q2][i3] = sum_q3 N3(q3) Z[p] (p = 0,1), N3'(q3) Z[2]; Z never leaves registers and feeds all i3
+        if (!(d.ablate & 4))
         for (int t = tid; t < nU; t += KS_NT) {
             const int cd = t % 9, bl = (t / 9) % nb, q2 = t / (9 * nb);
+            const int b = b0 + bl, a1 = b % np1, a2 = (b / np1) % np2, a3 = b / (np1 * np2);
+            const double x0 = S.E.b[0][q1][0][a1], x1 = S.E.b[0][q1][1][a1], y0 = S.E.b[1][q2][0][a2], y1 = S.E.b[1][q2][1][a2];
+            const double gx = x1 * y0, gy = x0 * y1, gz = x0 * y0;
             double u[KS_MAXP + 1][3];
 #pragma unroll
             for (int i3 = 0; i3 <= KS_MAXP; ++i3) u[i3][0] = u[i3][1] = u[i3][2] = 0.0;
             for (int q3 = 0; q3 < nq3; ++q3) {
-                const double* z = S.Z[q2 * nq3 + q3][bl] + cd * 3;
-                const double z0 = z[0], z1 = z[1], z2 = z[2];
+                const double z0 = S.E.b[2][q3][0][a3], z1 = S.E.b[2][q3][1][a3];
+                const double g0 = gx * z0, g1 = gy * z0, g2 = gz * z1;
+                const double* Tp = S.T[buf][q2 * nq3 + q3] + cd * 9;
+                const double zz0 = Tp[0] * g0 + Tp[1] * g1 + Tp[2] * g2;
+                const double zz1 = Tp[3] * g0 + Tp[4] * g1 + Tp[5] * g2;
+                const double zz2 = Tp[6] * g0 + Tp[7] * g1 + Tp[8] * g2;
+                const double2* vr = reinterpret_cast<const double2*>(S.E.b[2][q3][0]);     // N3(q3) of all i3, then N3'(q3)
+                const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];
+                const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
                 for (int i3 = 0; i3 <= KS_MAXP; ++i3) {
-                    const double v = S.E.b[2][q3][0][i3], dv = S.E.b[2][q3][1][i3];     // zero beyond p3 (tables are zero-filled)
-                    u[i3][0] = fma(v, z0, u[i3][0]);
-                    u[i3][1] = fma(v, z1, u[i3][1]);
-                    u[i3][2] = fma(dv, z2, u[i3][2]);
+                    u[i3][0] = fma(v[i3], zz0, u[i3][0]);
+                    u[i3][1] = fma(v[i3], zz1, u[i3][1]);
+                    u[i3][2] = fma(dv[i3], zz2, u[i3][2]);
                 }
             }
 #pragma unroll
@@ -543,31 +536,41 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
         }
         __syncthreads();
         // ---- direction 2 and 1: W0 = sum_q2 N2 U0 (pairs with N1'), W12 = sum_q2 N2' U1 + N2 U2 (pairs with N1)
-        if (hasW) {
+        if (hasW && !(d.ablate & 2)) {
             double w0[KS_MAXP + 1], w12[KS_MAXP + 1];
 #pragma unroll
             for (int i2 = 0; i2 <= KS_MAXP; ++i2) w0[i2] = w12[i2] = 0.0;
             for (int q2 = 0; q2 < nq2; ++q2) {
                 const double* u = S.U[q2][w_i3][w_bl][w_cd];
                 const double u0 = u[0], u1 = u[1], u2 = u[2];
+                const double2* vr = reinterpret_cast<const double2*>(S.E.b[1][q2][0]);     // N2(q2) of all i2, then N2'(q2)
+                const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];
+                const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
                 for (int i2 = 0; i2 <= KS_MAXP; ++i2) {
-                    const double v = S.E.b[1][q2][0][i2], dv = S.E.b[1][q2][1][i2];
-                    w0[i2] = fma(v, u0, w0[i2]);
-                    w12[i2] = fma(dv, u1, fma(v, u2, w12[i2]));
+                    w0[i2] = fma(v[i2], u0, w0[i2]);
+                    w12[i2] = fma(dv[i2], u1, fma(v[i2], u2, w12[i2]));
                 }
             }
+            {
+                const double2* xr = reinterpret_cast<const double2*>(S.E.b[0][q1][0]);
+                const double2 v01 = xr[0], v23 = xr[1], d01 = xr[2], d23 = xr[3];
+                const double xv[4] = {v01.x, v01.y, v23.x, v23.y}, xd[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
-            for (int a = 0; a <= KS_MAXP; ++a) {
-                const double xv = S.E.b[0][q1][0][a], xd = S.E.b[0][q1][1][a];
+                for (int a = 0; a <= KS_MAXP; ++a)
 #pragma unroll
-                for (int i2 = 0; i2 <= KS_MAXP; ++i2) acc[i2][a] = fma(xd, w0[i2], fma(xv, w12[i2], acc[i2][a]));
+                    for (int i2 = 0; i2 <= KS_MAXP; ++i2) acc[i2][a] = fma(xd[a], w0[i2], fma(xv[a], w12[i2], acc[i2][a]));
             }
         }
-        if (q1 + 1 < nq1) stash();                          // T was last read before the post-Z barrier of this slab
     }
     // ---- scatter: entry (row (I,c), col (J,dd)), Z index cd = c*3 + dd
     if (!hasW) return;
+    if (d.ablate & 1) {
+        double sink = 0.0;
+        for (int k = 0; k <= KS_MAXP; ++k) for (int a = 0; a <= KS_MAXP; ++a) sink += acc[k][a];
+        if (sink == 1.2345e-300) d.values[0] = sink;
+        return;
+    }
     const int c = w_cd / 3, dd = w_cd - 3 * c, i3 = w_i3;
     const int b = b0 + w_bl, j1 = b % np1, j2 = (b / np1) % np2, j3 = b / (np1 * np2);
     const int J1 = S.E.first[0] + j1, J2 = S.E.first[1] + j2, J3 = S.E.first[2] + j3;
@@ -795,6 +798,7 @@ extern "C" int ks_create(const ks_problem* P, int device, ks_ctx** out) {
     d.nblk = (d.nloc + KS_JB - 1) / KS_JB;
     d.nfree = P->n_free; ctx->nfixed = P->n_fixed;
     d.law = P->material_law;
+    d.ablate = getenv("KS_ABLATE") ? atoi(getenv("KS_ABLATE")) : 0;
     d.lambda = P->E * P->nu / ((1.0 + P->nu) * (1.0 - 2.0 * P->nu));
     d.mu = P->E / (2.0 * (1.0 + P->nu));
     for (size_t k = 0; k < (size_t)3 * d.ncp; ++k)
