@@ -77,6 +77,58 @@ def uat_lateral_stretch(pr, x):
     return 1.0 + x[g]
 
 
+def uat_analytical_cauchy_stress(material, compressible, lam=2.0):
+    """San of UAT_analytical (unittests/gsStaticSolver_test.cpp:355-385; mu = 1.5e6, Ratio = 7, nu = 0.45 when compressible)."""
+    mu, ratio = 1.5e6, 7.0
+    c2 = 1.0 / (ratio + 1.0)
+    c1 = 1.0 - c2
+    if not compressible:
+        if material == KL_MAT_NH:
+            return mu * (lam * lam - 1.0 / lam)
+        return -mu * (c2 * lam * lam + c2 / lam + c1) / lam + lam * (c1 * lam * mu + 2 * c2 * mu)
+    nu = 0.45
+    K = 2 * mu * (1 + nu) / (3 - 6 * nu)
+    J = UAT_J[(material, True)]
+    if material == KL_MAT_NH:
+        return lam * (0.5 * mu * (-(2 * (lam ** 2 + 2 * J / lam)) / (3 * J ** (2. / 3.) * lam) + 2 * lam / J ** (2. / 3.))
+                      + 0.25 * K * (2 * J ** 2 / lam - 2. / lam)) / J
+    return lam * (0.5 * c1 * mu * (-(2 * (lam ** 2 + 2 * J / lam)) / (3 * J ** (2. / 3.) * lam) + 2 * lam / J ** (2. / 3.))
+                  + 0.5 * c2 * mu * (-(4 * (2 * lam * J + J ** 2 / lam ** 2)) / (3 * J ** (4. / 3.) * lam) + 4 / J ** (1. / 3.))
+                  + 0.25 * K * (2 * J ** 2 / lam - 2 / lam)) / J
+
+
+def uat_cauchy_stress(make_assembler, pr, x, build_dofmap):
+    """S = sideForce / (thickness lambda(0) lambda(2)) as in UAT_numerical (unittests/gsStaticSolver_test.cpp:317-324): the
+    force on the tension boundary is the sum of the x-reactions on the east edge.  They are read from the residual of the same
+    sheet with the east x-DoFs left free (no external load, so residual = -F_int), evaluated at the converged state; by
+    isotropy the thickness stretch lambda(2) equals the lateral in-plane stretch lambda(0)."""
+    s = pr.surface
+    n1, n2 = s.n
+    ncp = n1 * n2
+    bc = BoundaryConditions()
+    bc.add_condition(WEST, KL_BC_DIRICHLET, 0).add_condition(SOUTH, KL_BC_DIRICHLET, 1)
+    for side in (WEST, EAST, SOUTH, NORTH):
+        bc.add_condition(side, KL_BC_DIRICHLET, 2)
+    pb = ShellProblem(s, bc, material=pr.material, compressible=pr.compressible, E=pr.E, nu=pr.nu, thickness=pr.thickness,
+                      mr_ratio=pr.mr_ratio)
+    pb.number_dofs(build_dofmap)
+    xb = np.zeros(pb.n_free)
+    for c in range(3):
+        for i in range(ncp):
+            gb = pb.dof_map[c * ncp + i]
+            if gb >= pb.n_free:
+                continue
+            ga = pr.dof_map[c * ncp + i]
+            xb[gb] = x[ga] if ga < pr.n_free else pr.fixed_values[ga - pr.n_free]
+    asm = make_assembler(pb)
+    ok, r = asm.residual(xb)
+    assert ok
+    east = [pb.dof_map[0 * ncp + (n1 - 1) + n1 * i2] for i2 in range(n2)]
+    side_force = -sum(r[g] for g in east)
+    lam0 = uat_lateral_stretch(pr, x)
+    return side_force / (pr.thickness * lam0 * lam0)
+
+
 def scordelis_lo_problem(nel, build_dofmap):
     """Classic roof R=25, L=50, 40 deg, E=4.32e8, nu=0, t=0.25, gravity load 90 per unit area, rigid diaphragms at the
     curved ends (filedata/pde/kirchhoff_shell_scordelis.xml:6-12,80-85)."""

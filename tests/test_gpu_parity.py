@@ -123,6 +123,9 @@ def test_gpu_uniaxial_tension_known_answer(gpu, material, compressible):
     lam2 = kp.uat_lateral_stretch(pr, x)
     expect = np.sqrt(kp.UAT_J[(material, compressible)] / 2.0)
     assert abs(lam2 - expect) / expect < 1e-7      # unittests/gsStaticSolver_test.cpp:415
+    S = kp.uat_cauchy_stress(lambda p: gpu(p), pr, x, capi.lib().kl_build_dofmap)
+    San = kp.uat_analytical_cauchy_stress(material, compressible)
+    assert abs(S - San) / San < 1e-6, (S, San)     # San: unittests/gsStaticSolver_test.cpp:355-385
 
 
 def test_gpu_scordelis_lo_known_answer(gpu):

@@ -15,6 +15,11 @@ def test_uniaxial_tension_lateral_stretch(material, compressible):
     expect = np.sqrt(kp.UAT_J[(material, compressible)] / 2.0)
     # reference tolerance: 1e-7 relative (unittests/gsStaticSolver_test.cpp:415); the tabulated J has 10 digits
     assert abs(lam2 - expect) / expect < 1e-7, (lam2, expect)
+    # the Cauchy stress of UAT_numerical against San of UAT_analytical (:317-324,355-385); the reference computes both but
+    # asserts only the stretch - here the stress level pins the material law itself (J is tabulated to 10 digits)
+    S = kp.uat_cauchy_stress(lambda p: OracleOps(p), pr, x, olib().klo_build_dofmap)
+    San = kp.uat_analytical_cauchy_stress(material, compressible)
+    assert abs(S - San) / San < 1e-6, (S, San)
 
 
 def test_scordelis_lo_linear_deflection():
