@@ -417,6 +417,67 @@ __global__ void __launch_bounds__(64) k3_bodyforce(KSDev d, double b0, double b1
     }
 }
 
+// consistent mass: M_ab^{cc} += rho sum_q N_a N_b w |detJ|.  One CTA per element; the weights w|detJ| per point come from the
+// geometry only; one thread per pair (a, b) walks the points with the three 1-D factors, then three REDs (c = 0..2).
+__global__ void __launch_bounds__(256) k3_mass(KSDev d, double rho) {
+    __shared__ ElemTables E;
+    __shared__ double s_cp[(KS_MAXP + 1) * (KS_MAXP + 1) * (KS_MAXP + 1)][3];
+    __shared__ double s_w[(KS_MAXP + 1) * (KS_MAXP + 1) * (KS_MAXP + 1)];
+    const int tid = threadIdx.x, e = blockIdx.x;
+    int e1, e2, e3;
+    elem_of(d, e, e1, e2, e3);
+    stage_tables(d, e1, e2, e3, E, tid, blockDim.x);
+    __syncthreads();
+    const int np1 = d.p[0] + 1, np2 = d.p[1] + 1, np3 = d.p[2] + 1;
+    for (int a = tid; a < d.nloc; a += blockDim.x) {
+        const int a1 = a % np1, a2 = (a / np1) % np2, a3 = a / (np1 * np2);
+        const int node = (E.first[0] + a1) + d.n[0] * ((E.first[1] + a2) + d.n[1] * (E.first[2] + a3));
+        for (int k = 0; k < 3; ++k) s_cp[a][k] = d.cp[3 * node + k];
+    }
+    __syncthreads();
+    for (int q = tid; q < d.nqp; q += blockDim.x) {
+        const int q3 = q % d.nq[2], q2 = (q / d.nq[2]) % d.nq[1], q1 = q / (d.nq[2] * d.nq[1]);
+        double Jg[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        for (int a3 = 0; a3 < np3; ++a3)
+            for (int a2 = 0; a2 < np2; ++a2)
+                for (int a1 = 0; a1 < np1; ++a1) {
+                    const int a = a1 + np1 * (a2 + np2 * a3);
+                    const double x0 = E.b[0][q1][0][a1], x1 = E.b[0][q1][1][a1], y0 = E.b[1][q2][0][a2], y1 = E.b[1][q2][1][a2],
+                                 z0 = E.b[2][q3][0][a3], z1 = E.b[2][q3][1][a3];
+                    const double g[3] = {x1 * y0 * z0, x0 * y1 * z0, x0 * y0 * z1};
+                    for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) Jg[k][l] = fma(s_cp[a][k], g[l], Jg[k][l]);
+                }
+        s_w[q] = rho * E.w[0][q1] * E.w[1][q2] * E.w[2][q3] * fabs(det3(Jg));
+    }
+    __syncthreads();
+    for (int t = tid; t < d.nloc * d.nloc; t += blockDim.x) {
+        const int a = t % d.nloc, b = t / d.nloc;
+        const int a1 = a % np1, a2 = (a / np1) % np2, a3 = a / (np1 * np2);
+        const int b1 = b % np1, b2 = (b / np1) % np2, b3 = b / (np1 * np2);
+        double m = 0.0;
+        for (int q1 = 0; q1 < d.nq[0]; ++q1) {
+            const double f1 = E.b[0][q1][0][a1] * E.b[0][q1][0][b1];
+            for (int q2 = 0; q2 < d.nq[1]; ++q2) {
+                const double f2 = f1 * E.b[1][q2][0][a2] * E.b[1][q2][0][b2];
+                for (int q3 = 0; q3 < d.nq[2]; ++q3) m = fma(f2 * E.b[2][q3][0][a3] * E.b[2][q3][0][b3], s_w[point_index(d, q1, q2, q3)], m);
+            }
+        }
+        const int I = (E.first[0] + a1) + d.n[0] * ((E.first[1] + a2) + d.n[1] * (E.first[2] + a3));
+        const int J = (E.first[0] + b1) + d.n[0] * ((E.first[1] + b2) + d.n[1] * (E.first[2] + b3));
+        for (int c = 0; c < 3; ++c) {
+            const int row = d.map[c * d.ncp + I], col = d.map[c * d.ncp + J];
+            if (row >= d.nfree || col >= d.nfree) continue;
+            int lo = d.outer[col], hi = d.outer[col + 1] - 1;
+            while (lo <= hi) {
+                const int mid = (lo + hi) >> 1;
+                const int rr = d.inner[mid];
+                if (rr == row) { atomicAdd(d.values + mid, m); break; }
+                if (rr < row) lo = mid + 1; else hi = mid - 1;
+            }
+        }
+    }
+}
+
 // rhs_a^c -= sum_q g_a(q) . f^c(q)     (one CTA per element, one thread per (a, c))
 __global__ void __launch_bounds__(192) k3_residual(KSDev d, double* __restrict__ r) {
     __shared__ ElemTables E;
@@ -887,6 +948,22 @@ extern "C" int ks_force(ks_ctx* ctx, double* f_host) {
     if (!ctx || !f_host) return KL_E_ARG;
     KL_CUDA(cudaSetDevice(ctx->device));
     KL_CUDA(cudaMemcpy(f_host, ctx->d_fext, sizeof(double) * (size_t)ctx->d.nfree, cudaMemcpyDeviceToHost));
+    return KL_OK;
+}
+
+extern "C" int ks_mass(ks_ctx* ctx, double density, double* values_host) {
+    if (!ctx || !values_host) { kl_set_error("ks_mass: null argument"); return KL_E_ARG; }
+    KL_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const KSDev& d = ctx->d;
+    const unsigned nelem = (unsigned)((size_t)d.nel[0] * d.nel[1] * d.nel[2]);
+    // a set-up quantity: it shares the device value array of K (which is re-assembled on every call)
+    KL_CUDA(cudaMemsetAsync(d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
+    k3_mass<<<nelem, 256, 0, s>>>(d, density);
+    KL_CUDA(cudaGetLastError());
+    ctx->launches++;
+    KL_CUDA(cudaMemcpyAsync(values_host, d.values, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost, s));
+    KL_CUDA(cudaStreamSynchronize(s));
     return KL_OK;
 }
 

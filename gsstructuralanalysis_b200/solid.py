@@ -167,6 +167,7 @@ def _bind(L):
     L.ks_residual.argtypes = [vp, c_double_p, c_double_p]
     L.ks_al_residual.argtypes = [vp, c_double_p, C.c_double, c_double_p]
     L.ks_force.argtypes = [vp, c_double_p]
+    L.ks_mass.argtypes = [vp, C.c_double, c_double_p]
     L.ks_assemble_device.argtypes = [vp, vp, C.c_int, vp, vp]
     L.ks_values_device.argtypes = [vp]
     L.ks_values_device.restype = vp
@@ -179,7 +180,7 @@ def _bind(L):
 
 # every symbol include/ks_solid.h declares
 SYMBOLS = ["ks_build_dofmap", "ks_create", "ks_destroy", "ks_sizes", "ks_pattern_host", "ks_assemble", "ks_jacobian",
-           "ks_residual", "ks_al_residual", "ks_force", "ks_assemble_device", "ks_values_device", "ks_check",
+           "ks_residual", "ks_al_residual", "ks_force", "ks_mass", "ks_assemble_device", "ks_values_device", "ks_check",
            "ks_last_timing", "ks_kernel_launches"]
 
 
@@ -258,6 +259,13 @@ class SolidAssembler:
         f = np.zeros(self.n_dofs)
         capi.check(self.L.ks_force(self.h, _dp(f)))
         return f
+
+    def mass(self, density):
+        """gsMassAssembler with option Density: consistent mass matrix on the pattern of K."""
+        v = np.zeros(max(self.nnz, 1))
+        capi.check(self.L.ks_mass(self.h, float(density), _dp(v)))
+        outer, inner = self.pattern()
+        return SparseView(self.n_dofs, outer, inner, v[:self.nnz])
 
     def assemble_device(self, x_dev_ptr, r_dev_ptr=0, want_matrix=True, stream=0):
         capi.check(self.L.ks_assemble_device(self.h, C.c_void_p(x_dev_ptr), 1 if want_matrix else 0,

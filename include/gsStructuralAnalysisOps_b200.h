@@ -203,6 +203,14 @@ public:
             return kl_mass(s->ctx, density, nullptr, v.data()) == KL_OK;
         };
     }
+    /// linear stiffness (Stiffness_t): assemble(); K = matrix()  (tutorials/nonlinear_shell_dynamic.cpp:116-118) = K(0)
+    Ops::Stiffness_t stiffness() const {
+        auto s = m_s;
+        return [s](gsSparseMatrix<T>& m) {
+            adoptPattern(m, s->ndofs, s->nnz, s->outer.data(), s->inner.data());
+            return kl_jacobian(s->ctx, nullptr, m.valuePtr()) == KL_OK;
+        };
+    }
     /// F (what assemble(); rhs() gives at u = 0)
     Ops::Force_t force() const {
         auto s = m_s;
@@ -326,6 +334,14 @@ public:
         return [s](gsVector<T>& f) {
             f.resize(s->ndofs);
             return ks_force(s->ctx, f.data()) == KL_OK;
+        };
+    }
+    /// gsMassAssembler with option "Density": assemble(); M = matrix()  (tutorials/nonlinear_solid_dynamic.cpp:98-109,137)
+    Ops::Mass_t mass(T density) const {
+        auto s = m_s;
+        return [s, density](gsSparseMatrix<T>& m) {
+            adopt(m, *s);
+            return ks_mass(s->ctx, density, m.valuePtr()) == KL_OK;
         };
     }
     /// one pass for both outputs of assemble(x, fixedDofs)

@@ -71,6 +71,9 @@ int ks_jacobian(ks_ctx* ctx, const double* x_host, double* values_host);        
 int ks_residual(ks_ctx* ctx, const double* x_host, double* r_host);                      /* Residual_t body   */
 int ks_al_residual(ks_ctx* ctx, const double* x_host, double lam, double* r_host);       /* F_int - lam F_ext */
 int ks_force(ks_ctx* ctx, double* f_host);                                               /* assemble(); rhs() */
+/* gsMassAssembler<real_t>(ori, basis, bc, body_force) with options "Density": assemble(); matrix()
+ * (tutorials/nonlinear_solid_dynamic.cpp:98-109) on the pattern of K: M_ab^{cd} = delta_cd density int N_a N_b */
+int ks_mass(ks_ctx* ctx, double density, double* values_host);
 /* device-resident variant: x_dev / r_dev device pointers (r_dev may be NULL), matrix stays at ks_values_device */
 int ks_assemble_device(ks_ctx* ctx, const double* x_dev, int want_matrix, double* r_dev, void* stream);
 double* ks_values_device(ks_ctx* ctx);

@@ -30,6 +30,7 @@ def lib():
         L.kso_pattern.argtypes = [vp, c_int_p, c_int_p]
         L.kso_force.argtypes = [vp, c_double_p]
         L.kso_assemble.argtypes = [vp, c_double_p, c_double_p, c_double_p, c_double_p]
+        L.kso_mass.argtypes = [vp, C.c_double, c_double_p]
         L.kso_build_dofmap.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(ks_bc), c_int_p, c_int_p, c_int_p]
         _LIB = L
     return _LIB
@@ -87,6 +88,11 @@ class SolidOracle:
 
     def energy(self, x):
         return self.assemble(x, False, False, True)
+
+    def mass(self, density):
+        v = np.zeros(max(self.nnz, 1))
+        self.L.kso_mass(self.h, float(density), _dp(v))
+        return v[:self.nnz]
 
     def force(self):
         f = np.zeros(self.n_dofs)

@@ -450,3 +450,37 @@ int kso_assemble(const kso* o, const double* x, double* values, double* r, doubl
     free(disp);
     return bad ? -4 : 0;
 }
+
+/* gsMassAssembler (tutorials/nonlinear_solid_dynamic.cpp:98-109): M_ab^{cd} = delta_cd density int N_a N_b, on the pattern of K */
+int kso_mass(const kso* o, double density, double* values) {
+    memset(values, 0, sizeof(double) * (size_t)o->nnz);
+    double xq[3][MAXP + 2], wq[3][MAXP + 2];
+    for (int d = 0; d < 3; ++d) gauss_legendre(o->p[d] + 1, xq[d], wq[d]);
+    double N[KS_MAXLOC], dN[KS_MAXLOC][3];
+    int node[KS_MAXLOC];
+    for (int e3 = 0; e3 < o->nel[2]; ++e3)
+        for (int e2 = 0; e2 < o->nel[1]; ++e2)
+            for (int e1 = 0; e1 < o->nel[0]; ++e1) {
+                const int s[3] = {o->span[0][e1], o->span[1][e2], o->span[2][e3]};
+                double a[3], h[3];
+                for (int d = 0; d < 3; ++d) { a[d] = o->U[d][s[d]]; h[d] = o->U[d][s[d] + 1] - a[d]; }
+                for (int q3 = 0; q3 <= o->p[2]; ++q3)
+                    for (int q2 = 0; q2 <= o->p[1]; ++q2)
+                        for (int q1 = 0; q1 <= o->p[0]; ++q1) {
+                            const double uvw[3] = {a[0] + 0.5 * h[0] * (xq[0][q1] + 1), a[1] + 0.5 * h[1] * (xq[1][q2] + 1),
+                                                   a[2] + 0.5 * h[2] * (xq[2][q3] + 1)};
+                            const int nl = eval_basis(o, s, uvw, N, dN, node);
+                            double Jg[3][3] = {{0}};
+                            for (int b = 0; b < nl; ++b)
+                                for (int k = 0; k < 3; ++k) for (int l = 0; l < 3; ++l) Jg[k][l] += o->cp[3 * node[b] + k] * dN[b][l];
+                            const double w = density * wq[0][q1] * wq[1][q2] * wq[2][q3] * 0.125 * h[0] * h[1] * h[2] * fabs(det3(Jg));
+                            for (int aa = 0; aa < nl; ++aa)
+                                for (int b = 0; b < nl; ++b)
+                                    for (int c = 0; c < 3; ++c) {
+                                        const int gr = o->map[c * o->ncp + node[aa]], gc = o->map[c * o->ncp + node[b]];
+                                        if (gr < o->nfree && gc < o->nfree) values[find_pos(o, gr, gc)] += w * N[aa] * N[b];
+                                    }
+                        }
+            }
+    return 0;
+}

@@ -48,6 +48,8 @@ def _compare(Asm, prob, scale, tag):
         assert ok and ok2 and np.abs(K2.values - Ko).max() <= RTOL * np.abs(Ko).max() and np.abs(r2 - ro).max() <= RTOL * max(np.abs(ro).max(), np.abs(fo).max())
         ok, ra = asm.al_residual(x, 0.37)
         assert ok and np.abs(ra - (fo - 0.37 * fo - ro)).max() <= RTOL * max(np.abs(ro).max(), np.abs(fo).max()), tag
+    Mg, Mo = asm.mass(3.5), orc.mass(3.5)
+    assert np.abs(Mg.values - Mo).max() <= RTOL * np.abs(Mo).max(), tag
     return asm
 
 

@@ -130,3 +130,17 @@ def test_inverted_state_is_reported():
     o = SolidOracle(pr)
     with pytest.raises(RuntimeError):
         o.residual(np.full(o.n_dofs, 1.0) * np.random.default_rng(3).standard_normal(o.n_dofs) * 10.0)
+
+
+def test_mass_matrix_sums_to_density_times_volume():
+    """gsMassAssembler (tutorials/nonlinear_solid_dynamic.cpp:98-109): partition of unity => sum of one component block of M
+    = density x volume; M is symmetric positive definite on the pattern of K."""
+    import scipy.sparse as sp
+    v = S.brick(2.0, 1.0, 0.5, degrees=(2, 3, 1), nels=(3, 2, 2))
+    pr = S.SolidProblem(v, S.SolidBC(), law=S.KS_LAW_SVK)
+    o = SolidOracle(pr)
+    M = sp.csc_matrix((o.mass(7.0), o.inner, o.outer), shape=(o.n_dofs, o.n_dofs))
+    assert abs(M.sum() - 3 * 7.0 * 2.0 * 1.0 * 0.5) <= 1e-12 * M.sum()
+    assert abs(M - M.T).max() <= 1e-14 * abs(M).max()
+    x = np.random.default_rng(0).standard_normal(o.n_dofs)
+    assert x @ (M @ x) > 0
