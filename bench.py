@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--scale", type=float, default=0.002, help="displacement amplitude as a fraction of the element size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--separate-calls", action="store_true", help="device leg: kl_jacobian_device + kl_residual_device back to back instead of kl_assemble_device")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "strips"],
                     help="N>1: independent replicas (weak scaling, default) or ONE matrix split into element-row strips with the halo exchange (strong scaling)")
     args = ap.parse_args()
@@ -239,6 +240,10 @@ def main():
         x_dev = torch.from_numpy(x_host).cuda()
 
     def step_device():
+        if not strips and not args.separate_calls:
+            # one Jacobian + one residual at the same state through the fused entry (residual kernels on a second stream)
+            asm.assemble_device(x_dev.data_ptr(), r_dev.data_ptr(), 1.0, -1.0, stream)
+            return
         asm.jacobian_device(x_dev.data_ptr(), stream)
         if strips:
             # partial internal force of the strip; the owner adds F_ext after the exchange (not timed: one axpy)
@@ -388,7 +393,9 @@ def main():
                    "l2": "matrix values (8*nnz bytes = %.2f GB) exceed the 126 MB L2 every step" % (8 * nnz / 1e9),
                    "multi_gpu": ("one matrix in element-row strips, point-to-point halo exchange of the interface columns" if strips else
                                  "one replica per GPU at its own displacement state (APALM interval style), no collective"),
-                   "setup_s": t_setup, "cpu_affinity": numa},
+                   "setup_s": t_setup, "cpu_affinity": numa,
+                   "step": ("kl_jacobian_device + kl_residual_device" if (strips or args.separate_calls) else
+                            "kl_assemble_device: one Jacobian + one residual at the same state, residual kernels on a second stream")},
         "clocks": clk.summary(),
         "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps,

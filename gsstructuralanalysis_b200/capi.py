@@ -20,7 +20,7 @@ SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern
            "kl_jacobian", "kl_residual", "kl_al_residual", "kl_force", "kl_jacobian_device", "kl_residual_device",
            "kl_check", "kl_values_device", "kl_set_strip", "kl_last_timing", "kl_last_error", "kl_kernel_launches",
            "kl_jacobian_kernel_ms", "kl_points_kernel_ms", "kl_measure_fp64_peak", "kl_mass",
-           "kl_cg_solve", "kl_cg_solve_device", "kl_spmv", "kl_cg_last_timing", "kl_newton_solve"]
+           "kl_assemble_device", "kl_cg_solve", "kl_cg_solve_device", "kl_spmv", "kl_cg_last_timing", "kl_newton_solve"]
 
 
 class kl_newton_options(C.Structure):
@@ -66,6 +66,7 @@ def lib():
     L.kl_mass.argtypes = [vp, C.c_double, c_double_p, c_double_p]
     L.kl_jacobian_device.argtypes = [vp, vp, vp]
     L.kl_residual_device.argtypes = [vp, vp, C.c_double, C.c_double, vp, vp]
+    L.kl_assemble_device.argtypes = [vp, vp, C.c_double, C.c_double, vp, vp]
     L.kl_check.argtypes = [vp, vp]
     L.kl_values_device.argtypes = [vp]
     L.kl_values_device.restype = vp

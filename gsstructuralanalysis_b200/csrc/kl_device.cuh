@@ -31,26 +31,40 @@ struct ElemStage {
     double Wt[NLOC];           // weights (rational geometry only)
 };
 
-// cooperative load of one element's staging data by `nthr` threads with lane id `t`
+// cooperative load of one element's staging data by (P+1)^2 threads with lane id `t` (one control point per thread).
+// All global loads are issued before the first shared-memory store, so the thread pays one memory latency instead of one
+// per loop trip (the staging prologue was 41 % of the stall samples of k_points with 12 resident warps per SM).
 template <int P>
-__device__ __forceinline__ void stage_element(const KLDev& d, int e1, int e2, ElemStage<P>& E, int t, int nthr) {
-    constexpr int NQ = P + 1, NLOC = (P + 1) * (P + 1), NB = NQ * 3 * (P + 1);
+__device__ __forceinline__ void stage_element(const KLDev& d, int e1, int e2, ElemStage<P>& E, int t, int /*nthr = (P+1)^2*/) {
+    constexpr int NQ = P + 1, NLOC = (P + 1) * (P + 1), NB = NQ * 3 * (P + 1), NT = NLOC, RB = (NB + NT - 1) / NT;
     const double* g1 = d.bas1 + (size_t)e1 * NB;
     const double* g2 = d.bas2 + (size_t)e2 * NB;
+    const int i0 = __ldg(&d.span1[e1]) - P, j0 = __ldg(&d.span2[e2]) - P;
+    double vb1[RB], vb2[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        const int k = t + r * NT;
+        vb1[r] = k < NB ? __ldg(g1 + k) : 0.0;
+        vb2[r] = k < NB ? __ldg(g2 + k) : 0.0;
+    }
+    const double wq1 = t < NQ ? __ldg(&d.wq1[e1 * NQ + t]) : 0.0, wq2 = t < NQ ? __ldg(&d.wq2[e2 * NQ + t]) : 0.0;
+    const int a = t % (P + 1), b = t / (P + 1);
+    const int cpi = (i0 + a) + d.n1 * (j0 + b);
+    const double wv = d.rational ? __ldg(&d.w[cpi]) : 1.0;
+    double x[3], u[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { x[c] = __ldg(&d.cp[3 * cpi + c]); u[c] = d.disp[3 * cpi + c]; }
     double* s1 = &E.b1[0][0][0];
     double* s2 = &E.b2[0][0][0];
-    for (int k = t; k < NB; k += nthr) { s1[k] = g1[k]; s2[k] = g2[k]; }
-    for (int k = t; k < NQ; k += nthr) { E.w1[k] = d.wq1[e1 * NQ + k]; E.w2[k] = d.wq2[e2 * NQ + k]; }
-    const int i0 = d.span1[e1] - P, j0 = d.span2[e2] - P;
-    for (int k = t; k < NLOC * 3; k += nthr) {
-        int l = k / 3, c = k - 3 * l;
-        int a = l % (P + 1), b = l / (P + 1);
-        int cpi = (i0 + a) + d.n1 * (j0 + b);
-        double wv = d.rational ? d.w[cpi] : 1.0;
-        E.X[l][c] = d.cp[3 * cpi + c] * wv;
-        E.U[l][c] = d.disp[3 * cpi + c];
-        if (c == 0) E.Wt[l] = wv;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+        const int k = t + r * NT;
+        if (k < NB) { s1[k] = vb1[r]; s2[k] = vb2[r]; }
     }
+    if (t < NQ) { E.w1[t] = wq1; E.w2[t] = wq2; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { E.X[t][c] = x[c] * wv; E.U[t][c] = u[c]; }
+    E.Wt[t] = wv;
 }
 
 // sum-factorised evaluation of a 3-component field: out[k][c], k = (val, d1, d2, d11, d22, d12)

@@ -77,6 +77,8 @@ struct kl_ctx {
     size_t registered_bytes = 0;
     cudaStream_t stream = nullptr;   // own stream for the host-pointer entry points
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // residual kernels of kl_assemble_device run here, next to the Jacobian kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[8]{};
     float ms_kernel = 0, ms_h2d = 0, ms_d2h = 0;
     int launches = 0;

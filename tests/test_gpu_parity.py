@@ -238,3 +238,32 @@ def test_run_to_run_reproducibility(gpu):
     ok, r2 = asm.residual(x)
     assert np.abs(K2.values - v1).max() <= 1e-14 * np.abs(v1).max()
     assert np.abs(r2 - r1).max() <= 1e-14 * max(np.abs(r1).max(), 1e-300)
+
+
+def test_fused_assemble_device_matches_separate_calls(gpu):
+    """kl_assemble_device (K and residual at one state, residual kernels on a second stream) against the two device entry
+    points it combines and against the oracle."""
+    import torch
+    from oracle.binding import Oracle
+    prob = W.tutorial_paraboloid(7, 3, KL_MAT_NH)
+    asm, orc = gpu(prob), Oracle(prob)
+    n = asm.n_dofs
+    x = W.displacement_state(n, 2e-3)
+    xd = torch.from_numpy(x).cuda()
+    rd = torch.zeros(n, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):       # repeated calls reuse the side stream and events
+        asm.assemble_device(xd.data_ptr(), rd.data_ptr(), 1.0, -1.0, stream)
+    assert asm.check(stream) == 0
+    torch.cuda.synchronize()
+    from gsstructuralanalysis_b200.parallel import DevicePointerView
+    K = DevicePointerView(asm.values_device_ptr(), asm.nnz).tensor().cpu().numpy().copy()
+    r = rd.cpu().numpy()
+    Ko, ro = orc.jacobian_values(x), orc.residual(x)
+    assert np.abs(K - Ko).max() <= RTOL * np.abs(Ko).max()
+    assert np.abs(r - ro).max() <= RTOL * max(np.abs(ro).max(), np.abs(orc.force()).max())
+    # arc-length form through the same entry: F_int - lam F_ext
+    asm.assemble_device(xd.data_ptr(), rd.data_ptr(), -0.4, 1.0, stream)
+    torch.cuda.synchronize()
+    ra = orc.al_residual(x, 0.4)
+    assert np.abs(rd.cpu().numpy() - ra).max() <= RTOL * max(np.abs(ra).max(), np.abs(orc.force()).max())
