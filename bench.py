@@ -241,7 +241,7 @@ def main():
 
     def step_device():
         if not strips and not args.separate_calls:
-            # one Jacobian + one residual at the same state through the fused entry (residual kernels on a second stream)
+            # one Jacobian + one residual at the same state through the fused entry (internal force integrated by the point kernel)
             asm.assemble_device(x_dev.data_ptr(), r_dev.data_ptr(), 1.0, -1.0, stream)
             return
         asm.jacobian_device(x_dev.data_ptr(), stream)
@@ -395,7 +395,7 @@ def main():
                                  "one replica per GPU at its own displacement state (APALM interval style), no collective"),
                    "setup_s": t_setup, "cpu_affinity": numa,
                    "step": ("kl_jacobian_device + kl_residual_device" if (strips or args.separate_calls) else
-                            "kl_assemble_device: one Jacobian + one residual at the same state, residual kernels on a second stream")},
+                            "kl_assemble_device: one Jacobian + one residual at the same state, internal force integrated by the point kernel")},
         "clocks": clk.summary(),
         "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps,

@@ -46,8 +46,10 @@ struct PointCfg {
 // per thread.
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <int P>
-__global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_points(KLDev d, int e2_begin, int e2_end) {
+// WITH_RES: also integrate the internal force F_int - F_pressure into r from the staged records (RED), which makes the separate
+// k_residual pass unnecessary when Jacobian and residual are wanted at the same state (kl_assemble_device).
+template <int P, bool WITH_RES>
+__global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_points(KLDev d, int e2_begin, int e2_end, double* __restrict__ r) {
     using Cfg = PointCfg<P>;
     constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;
     extern __shared__ __align__(16) unsigned char smem_pts[];
@@ -72,8 +74,34 @@ __global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_points(KLDev d, int e2_b
         const unsigned bytes = (unsigned)(ne * NQ2 * sizeof(PointData));
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(out)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay valid until the engine has read it
     }
+    if (WITH_RES && active) {
+        // one thread per local basis function: integrate over the element's points (same integrand as k_residual)
+        const int a = lq % (P + 1), b = lq / (P + 1);
+        double f[3] = {0, 0, 0};
+        const ElemStage<P>& E = stage[le];
+#pragma unroll
+        for (int q2 = 0; q2 < NQ; ++q2)
+#pragma unroll
+            for (int q1 = 0; q1 < NQ; ++q1) {
+                const PointData& pd = out[le * NQ2 + q2 + NQ * q1];
+                const double x0 = E.b1[q1][0][a], x1 = E.b1[q1][1][a], x2 = E.b1[q1][2][a];
+                const double y0 = E.b2[q2][0][b], y1 = E.b2[q2][1][b], y2 = E.b2[q2][2][b];
+                const double R = x0 * y0, R1 = x1 * y0, R2 = x0 * y1, R11 = x2 * y0, R22 = x0 * y2, R12 = x1 * y1;
+                const double mb = R11 * pd.Mt[0] + R22 * pd.Mt[1] + R12 * pd.Mt[2];
+                const double cn = R1 * pd.Ha1 + R2 * pd.Ha2 - mb - R * d.mat.pressure * pd.wJ;      // coefficient of n_c
+                const double c1 = R1 * pd.N[0] + R2 * pd.N[2], c2 = R2 * pd.N[1] + R1 * pd.N[2];     // of a1_c, a2_c
+#pragma unroll
+                for (int c = 0; c < 3; ++c) f[c] += c1 * pd.a1[c] + c2 * pd.a2[c] + cn * pd.n[c];
+            }
+        const int cpi = (d.span1[e1] - P + a) + d.n1 * (d.span2[e2] - P + b);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int g = d.map[c * d.ncp + cpi];
+            if (g < d.nfree) atomicAdd(&r[g], f[c]);
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay valid until the engine has read it
 }
 
 // residual: F_int - F_pressure accumulated into r (atomic); reads PointData
@@ -1143,25 +1171,27 @@ int kl_launch_axpby(kl_ctx* ctx, double* r, const double* fext, double a_r, doub
 }
 
 template <int P>
-static int launch_points(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
+static int launch_points(kl_ctx* ctx, int e2b, int e2e, double* r, cudaStream_t s) {
     using Cfg = PointCfg<P>;
     const int nel = ctx->d.nel1 * (e2e - e2b);
     if (nel <= 0) return 0;
     const size_t smem = ((sizeof(ElemStage<P>) * Cfg::EPG + 15) / 16) * 16 + sizeof(PointData) * Cfg::EPG * Cfg::NQ2;
     if (!(ctx->attr_done & 1u)) {      // function attributes are per device: tracked in the context, not in a static
-        KL_CUDA(cudaFuncSetAttribute(k_points<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KL_CUDA(cudaFuncSetAttribute(k_points<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KL_CUDA(cudaFuncSetAttribute(k_points<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->attr_done |= 1u;
     }
-    k_points<P><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
+    if (r) k_points<P, true><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e, r);
+    else k_points<P, false><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e, nullptr);
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
     return 0;
 }
-int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s) {
+int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s, double* r_dev) {
     switch (ctx->d.p) {
-        case 2: return launch_points<2>(ctx, e2_begin, e2_end, s);
-        case 3: return launch_points<3>(ctx, e2_begin, e2_end, s);
-        case 4: return launch_points<4>(ctx, e2_begin, e2_end, s);
+        case 2: return launch_points<2>(ctx, e2_begin, e2_end, r_dev, s);
+        case 3: return launch_points<3>(ctx, e2_begin, e2_end, r_dev, s);
+        case 4: return launch_points<4>(ctx, e2_begin, e2_end, r_dev, s);
     }
     kl_set_error("unsupported degree");
     return KL_E_ARG;

@@ -384,9 +384,6 @@ extern "C" void kl_destroy(kl_ctx* ctx) {
     if (ctx->h_pinned_r) cudaFreeHost(ctx->h_pinned_r);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->side_stream) cudaStreamDestroy(ctx->side_stream);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->strip_ev) if (e) cudaEventDestroy(e);
     delete ctx;
@@ -467,29 +464,16 @@ extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_f
 extern "C" int kl_assemble_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, void* stream) {
     if (!ctx || !r_dev) return KL_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!ctx->side_stream) {
-        KL_CUDA(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-        KL_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-        KL_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    }
     int rc;
     if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
-    KL_CUDA(cudaEventRecord(ctx->ev_fork, s));
-    // residual branch
-    cudaStream_t t = ctx->side_stream;
-    KL_CUDA(cudaStreamWaitEvent(t, ctx->ev_fork, 0));
-    KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, t));
-    if ((rc = kl_launch_residual(ctx, r_dev, t))) return rc;
-    if ((rc = kl_launch_axpby(ctx, r_dev, ctx->d_fext, sign_fint, lam_fext, ctx->d.nfree, t))) return rc;
-    KL_CUDA(cudaEventRecord(ctx->ev_join, t));
-    // Jacobian branch
+    KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, s));
     KL_CUDA(cudaEventRecord(ctx->ev[6], s));
-    if ((rc = kl_launch_points(ctx, ctx->e2_begin, ctx->e2_end, s))) return rc;
+    // the point kernel integrates the internal force from the records it has just staged: no separate residual pass
+    if ((rc = kl_launch_points(ctx, ctx->e2_begin, ctx->e2_end, s, r_dev))) return rc;
     KL_CUDA(cudaEventRecord(ctx->ev[7], s));
+    if ((rc = kl_launch_axpby(ctx, r_dev, ctx->d_fext, sign_fint, lam_fext, ctx->d.nfree, s))) return rc;
     KL_CUDA(cudaMemsetAsync(ctx->d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
-    if ((rc = kl_launch_jacobian(ctx, ctx->e2_begin, ctx->e2_end, s))) return rc;
-    KL_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));
-    return KL_OK;
+    return kl_launch_jacobian(ctx, ctx->e2_begin, ctx->e2_end, s);
 }
 
 // ---- host-pointer entry points (what the Jacobian_t / Residual_t closures call) -------------------

@@ -77,8 +77,6 @@ struct kl_ctx {
     size_t registered_bytes = 0;
     cudaStream_t stream = nullptr;   // own stream for the host-pointer entry points
     cudaStream_t copy_stream = nullptr;
-    cudaStream_t side_stream = nullptr;   // residual kernels of kl_assemble_device run here, next to the Jacobian kernel
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[8]{};
     float ms_kernel = 0, ms_h2d = 0, ms_d2h = 0;
     int launches = 0;
@@ -111,7 +109,7 @@ int kl_build_pattern(kl_ctx* ctx);
 // kl_assemble.cu
 int kl_launch_construct(kl_ctx* ctx, const double* x_dev, cudaStream_t s);
 int kl_launch_jacobian(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s);
-int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s);
+int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s, double* r_dev = nullptr);   // r_dev: also r += F_int - F_pressure
 int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s);   // r += F_int - F_pressure (atomic)
 size_t kl_pointdata_bytes(void);
 int kl_launch_bodyforce(kl_ctx* ctx, double* f_dev, const double bf[3], cudaStream_t s);

@@ -129,7 +129,7 @@ class ShellAssembler:
                                              C.c_void_p(stream)))
 
     def assemble_device(self, x_dev_ptr, r_dev_ptr, lam_fext=1.0, sign_fint=-1.0, stream=0):
-        """K(x) and the residual at the same state; the residual kernels overlap the Jacobian kernel."""
+        """K(x) and the residual at the same state in one pass (the point kernel also integrates the internal force)."""
         capi.check(self.L.kl_assemble_device(self.h, C.c_void_p(x_dev_ptr), lam_fext, sign_fint, C.c_void_p(r_dev_ptr),
                                              C.c_void_p(stream)))
 

@@ -159,8 +159,8 @@ int kl_set_strip(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end);
 /* Kernel-only timing of the last call in ms (CUDA events on the launch stream). */
 int kl_last_timing(const kl_ctx* ctx, float* ms_kernel, float* ms_h2d, float* ms_d2h);
 /* One Newton iteration's worth of assembly at ONE state: K(x) into the device values (as kl_jacobian_device) and
- * r = lam_fext*F_ext + sign_fint*F_int (as kl_residual_device); constructSolution runs once and the residual kernels
- * overlap the Jacobian kernel on a second stream (they are latency-bound, the Jacobian kernel is LSU-bound). */
+ * r = lam_fext*F_ext + sign_fint*F_int (as kl_residual_device); constructSolution runs once and the internal force is
+ * integrated by the per-point kernel from the records it has just staged, so the separate residual pass disappears. */
 int kl_assemble_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, void* stream);
 
 /* ---- device-resident linear solve and Newton loop ---------------------------
