@@ -551,6 +551,12 @@ __device__ __forceinline__ void tile_scatter(const KLDev& d, const int4* cb, int
     }
 }
 
+// phase ablation (profiling only): compiled in with -DKL_ABLATION, selected at run time by the env variable KL_ABLATE
+#ifdef KL_ABLATION
+#define KL_ABL(d) ((d).ablate)
+#else
+#define KL_ABL(d) 0
+#endif
 template <int P, bool HASB>
 __global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLDev d, int e2_begin, int e2_end) {
     using Cfg = JacCfg<P>;
@@ -608,7 +614,7 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLD
         __syncthreads();   // basis staged / previous chunk's Z consumed
         mbar_wait(&S.bar, ch & 1);   // this chunk's per-point records have landed in shared memory
         // ---- phase 2: Z_j for the points of this chunk
-        if (!(d.ablate & 4))
+        if (!(KL_ABL(d) & 4))
         for (int k = tid; k < EPG * QCH * NLOC; k += NT) {
             const int j = k % NLOC;
             const int qc = (k / NLOC) % QCH;
@@ -622,11 +628,11 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLD
         }
         // ---- phase 3: tile (ti2, tj).  The first-direction factors X(q1) are constant over the chunk, so
         //      V_m^{cd} = sum_{q2} W_m^{cd}(q1,q2) is formed first and applied once per chunk (sum factorisation).
-        if (has_tile && !(d.ablate & 2)) tile_chunk<P>(S.stage[le_t], S.Z[le_t], ch, ti2, tj, acc);
+        if (has_tile && !(KL_ABL(d) & 2)) tile_chunk<P>(S.stage[le_t], S.Z[le_t], ch, ti2, tj, acc);
     }
     const int e = ebase + le_t;
-    if (has_tile && e < nel && !(d.ablate & 1)) tile_scatter<P>(d, S.cb[le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
-    if (d.ablate & 1) { double sink = 0; for (int a = 0; a <= P; ++a) for (int k = 0; k < 9; ++k) sink += acc[a][k]; if (sink == 1.2345e-300) d.values[0] = sink; }
+    if (has_tile && e < nel && !(KL_ABL(d) & 1)) tile_scatter<P>(d, S.cb[le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
+    if (KL_ABL(d) & 1) { double sink = 0; for (int a = 0; a <= P; ++a) for (int k = 0; k < 9; ++k) sink += acc[a][k]; if (sink == 1.2345e-300) d.values[0] = sink; }
 }
 
 
