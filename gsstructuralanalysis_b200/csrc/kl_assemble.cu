@@ -372,8 +372,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 //      The F* flags say which inputs are present; absent ones are folded away at compile time (they are written as the
 //      additive identity -0.0 so that no multiplication by zero is ever emitted).  All flags true = a basis function.
 #define TZ(f, e) ((f) ? (e) : -0.0)
-// ZPERM: rows of the second (c,d) half first ([cd 5..8][cd 0..4]) so that both halves start 16-byte aligned
-template <bool HASB, bool F1, bool F2, bool F11, bool F22, bool F12, bool ZPERM = false>
+template <bool HASB, bool F1, bool F2, bool F11, bool F22, bool F12>
 __device__ __forceinline__ void compute_Zc(const PointData& pd, double N1, double N2, double N11, double N22, double N12, double* Zo) {
     constexpr bool FG = F1 || F2;              // first derivatives present
     constexpr bool FS = F11 || F22 || F12;     // second derivatives present
@@ -421,7 +420,7 @@ __device__ __forceinline__ void compute_Zc(const PointData& pd, double N1, doubl
         const double en = TZ(FG, eta * n[dd]);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            double* z = Zo + (ZPERM ? ((c * 3 + dd) < 5 ? 20 + (c * 3 + dd) * 5 : ((c * 3 + dd) - 5) * 5) : (c * 3 + dd) * 5);
+            double* z = Zo + (c * 3 + dd) * 5;
             double z0 = TZ(FSIG, a1[c] * sig[0] + a2[c] * sig[2]) + n[c] * s1 + TZ(FG, -(en * c1[c]));
             double z1 = TZ(FSIG, a2[c] * sig[1] + a1[c] * sig[2]) + n[c] * s2 + TZ(FG, -(en * c2[c]));
             if (c == dd) {
@@ -637,485 +636,6 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLD
 
 
 // ------------------------------------------------------------------------------------------------
-// Jacobian kernel, sum-factorised in BOTH index directions of the column function j = (j1,j2).
-//   Z_j(q1,q2) = x0(j1,q1) U0 + x1(j1,q1) U1 + x2(j1,q1) U2   with  U_a(q1,q2,j2) = T.(pseudo input built from Y_{j2}(q2) only)
-//   => phase A  U_a for (q2, j2, a): 12 evaluations per point instead of 16, and with mostly-zero inputs (folded at compile time)
-//      phase B  W_{m,a}(i2,j2) = sum_{q2} Y_{i2}(q2) . U_a(q2,j2)        (30 tasks per element and column; depends on (i2,j2) only)
-//      phase C  tile (i2, j):  V_m = sum_a x_a(j1) W_{m,a}(i2,j2),  acc += X_m(i1) V_m       (36 accumulators per thread as before)
-// One CTA = EPG elements; per fixed-q1 column: B | barrier | C + A(next column) | barrier.
-template <int P>
-struct Jac3Cfg {
-    static constexpr int NQ = P + 1, NQ2 = NQ * NQ, NLOC = (P + 1) * (P + 1);
-    static constexpr int TILES = (P + 1) * (P + 1) * (P + 2) / 2;
-    static constexpr int NPAIR = (P + 1) * (P + 2) / 2;                 // (i2 <= j2)
-    static constexpr int EPG = (P == 4) ? 1 : 2;
-    static constexpr int NT = TILES * EPG;                              // 36 / 80 / 75
-    static constexpr int NL = EPG * NQ * (P + 1);                       // (element, q2, j2) combinations
-    static constexpr int NW = EPG * NPAIR * 3;                          // phase-B tasks
-    static constexpr int ZS = 46, WS = 30;                              // row strides (doubles): conflict-free LDS.128
-    static constexpr int MINB = (P == 3) ? 4 : 1;
-};
-template <int P>
-struct Jac3Shared {
-    using Cfg = Jac3Cfg<P>;
-    BasisStage<P> stage[Cfg::EPG];
-    double U[Cfg::EPG][Cfg::NQ][P + 1][3][Cfg::ZS];
-    double Wm[Cfg::EPG][Cfg::NPAIR][3][Cfg::WS];      // [a][m*10 + cd]
-    int4 cb[Cfg::EPG][Cfg::NLOC];
-    PointData pd[Cfg::EPG][Cfg::NQ];
-    unsigned long long bar;
-};
-
-template <int P, bool HASB>
-__global__ void __launch_bounds__(Jac3Cfg<P>::NT, Jac3Cfg<P>::MINB) k_jacobian3(KLDev d, int e2_begin, int e2_end) {
-    using Cfg = Jac3Cfg<P>;
-    constexpr int NQ = Cfg::NQ, NQ2 = Cfg::NQ2, NLOC = Cfg::NLOC, TILES = Cfg::TILES, NPAIR = Cfg::NPAIR, EPG = Cfg::EPG, NT = Cfg::NT,
-                  NL = Cfg::NL, NW = Cfg::NW;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Jac3Shared<P>& S = *reinterpret_cast<Jac3Shared<P>*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int nel = d.nel1 * (e2_end - e2_begin);
-    const int ebase = blockIdx.x * EPG;
-
-    auto issue_pd = [&](int ch) {
-        mbar_expect_tx(&S.bar, (unsigned)(EPG * NQ * sizeof(PointData)));
-        for (int le = 0; le < EPG; ++le) {
-            int e = ebase + le;
-            if (e >= nel) e = nel - 1;
-            const size_t ge = (size_t)(e % d.nel1) + (size_t)d.nel1 * (e2_begin + e / d.nel1);
-            tma_bulk_g2s(&S.pd[le][0], d.pd + ge * NQ2 + (size_t)ch * NQ, (unsigned)(NQ * sizeof(PointData)), &S.bar);
-        }
-    };
-    // phase A: one (element, q2, j2, a) evaluation
-    auto phaseA_task = [&](int a, int idx) {
-        const int j2 = idx % (P + 1), q2 = (idx / (P + 1)) % NQ, le = idx / ((P + 1) * NQ);
-        const BasisStage<P>& E = S.stage[le];
-        const double y0 = E.b2[q2][0][j2], y1 = E.b2[q2][1][j2], y2 = E.b2[q2][2][j2];
-        double* out = S.U[le][q2][j2][a];
-        if (a == 0) compute_Zc<HASB, false, true, false, true, false>(S.pd[le][q2], -0.0, y1, -0.0, y2, -0.0, out);        // multiplies N_{j1}
-        else if (a == 1) compute_Zc<HASB, true, false, false, false, true>(S.pd[le][q2], y0, -0.0, -0.0, -0.0, y1, out);   // multiplies N'_{j1}
-        else compute_Zc<HASB, false, false, true, false, false>(S.pd[le][q2], -0.0, -0.0, y0, -0.0, -0.0, out);            // multiplies N''_{j1}
-    };
-    auto phaseA = [&]() {
-        if (NT > 2 * NL) {
-            // the two heavy variants first (uniform per group of NL threads), the cheap a = 2 variant shared by the remaining threads
-            if (tid < 2 * NL) phaseA_task(tid / NL, tid % NL);
-            else for (int idx = tid - 2 * NL; idx < NL; idx += NT - 2 * NL) phaseA_task(2, idx);
-        } else {
-            for (int k = tid; k < 3 * NL; k += NT) phaseA_task(k / NL, k % NL);
-        }
-    };
-
-    if (tid == 0) mbar_init(&S.bar, 1);
-    __syncthreads();
-    if (tid == 0) issue_pd(0);
-    for (int le = 0; le < EPG; ++le) {
-        int e = ebase + le;
-        if (e >= nel) e = nel - 1;
-        stage_basis<P>(d, e % d.nel1, e2_begin + e / d.nel1, S.stage[le], tid, NT);
-    }
-    for (int k = tid; k < EPG * NLOC; k += NT) {
-        const int le = k / NLOC, l = k - le * NLOC;
-        int e = ebase + le;
-        if (e >= nel) e = nel - 1;
-        const int cpi = (d.span1[e % d.nel1] - P + l % (P + 1)) + d.n1 * (d.span2[e2_begin + e / d.nel1] - P + l / (P + 1));
-        S.cb[le][l] = reinterpret_cast<const int4*>(d.colbase)[cpi];
-    }
-    // tile of this thread
-    const int le_t = tid / TILES, tt = tid - le_t * TILES;
-    int tj = 0, ti2 = 0;
-    {
-        int rem = tt;
-        for (int j2 = 0; j2 <= P; ++j2) {
-            const int cnt = (P + 1) * (j2 + 1);
-            if (rem < cnt) { tj = (P + 1) * j2 + rem / (j2 + 1); ti2 = rem % (j2 + 1); break; }
-            rem -= cnt;
-        }
-    }
-    const int tj1 = tj % (P + 1), tj2 = tj / (P + 1);
-    const int tpi = tj2 * (tj2 + 1) / 2 + ti2;
-    double acc[P + 1][9];
-#pragma unroll
-    for (int a = 0; a <= P; ++a)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) acc[a][k] = 0.0;
-
-    __syncthreads();             // basis tables staged
-    mbar_wait(&S.bar, 0);
-    phaseA();                    // column 0
-    __syncthreads();
-
-    for (int ch = 0; ch < NQ; ++ch) {
-        if (tid == 0 && ch + 1 < NQ) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_pd(ch + 1);    // S.pd is free: phase A of this column is complete
-        }
-        // ---- phase B: W_{m,a}(i2,j2) = sum_{q2} Y_{i2}(q2) . U_a(q2, j2)
-        for (int t = tid; t < NW; t += NT) {
-            const int a = t % 3, pi = (t / 3) % NPAIR, le = t / (3 * NPAIR);
-            int j2 = 0;
-            while ((j2 + 1) * (j2 + 2) / 2 <= pi) ++j2;
-            const int i2 = pi - j2 * (j2 + 1) / 2;
-            const BasisStage<P>& E = S.stage[le];
-            double V0[9], V1[9], V2[9];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) { V0[k] = 0.0; V1[k] = 0.0; V2[k] = 0.0; }
-#pragma unroll
-            for (int q2 = 0; q2 < NQ; ++q2) {
-                const double y0 = E.b2[q2][0][i2], y1 = E.b2[q2][1][i2], y2 = E.b2[q2][2][i2];
-                const double2* Zi = reinterpret_cast<const double2*>(S.U[le][q2][j2][a]);
-#pragma unroll
-                for (int m = 0; m < 5; ++m) {
-                    double zz[10];
-#pragma unroll
-                    for (int k = 0; k < (m < 4 ? 5 : 3); ++k) { const double2 v = Zi[m * 5 + k]; zz[2 * k] = v.x; zz[2 * k + 1] = v.y; }
-#pragma unroll
-                    for (int h = 0; h < (m < 4 ? 2 : 1); ++h) {
-                        const int cd = 2 * m + h;
-                        const double z1 = zz[5 * h], z2 = zz[5 * h + 1], z11 = zz[5 * h + 2], z22 = zz[5 * h + 3], z12 = zz[5 * h + 4];
-                        V0[cd] = fma(y2, z22, fma(y1, z2, V0[cd]));
-                        V1[cd] = fma(y1, z12, fma(y0, z1, V1[cd]));
-                        V2[cd] = fma(y0, z11, V2[cd]);
-                    }
-                }
-            }
-            double* w = S.Wm[le][pi][a];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) { w[k] = V0[k]; w[10 + k] = V1[k]; w[20 + k] = V2[k]; }
-        }
-        __syncthreads();
-        // ---- phase C: tile (ti2, tj): V_m = sum_a x_a(j1,q1) W_{m,a};  acc += X_m(i1,q1) V_m
-        {
-            const BasisStage<P>& E = S.stage[le_t];
-            const double xa0 = E.b1[ch][0][tj1], xa1 = E.b1[ch][1][tj1], xa2 = E.b1[ch][2][tj1];
-            double X0[P + 1], X1[P + 1], X2[P + 1];
-#pragma unroll
-            for (int a = 0; a <= P; ++a) { X0[a] = E.b1[ch][0][a]; X1[a] = E.b1[ch][1][a]; X2[a] = E.b1[ch][2][a]; }
-            const double* w0 = S.Wm[le_t][tpi][0];
-            const double* w1 = S.Wm[le_t][tpi][1];
-            const double* w2 = S.Wm[le_t][tpi][2];
-#pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                constexpr int NG[3] = {4, 4, 1};
-                const int ng = NG[g];
-                double V[3][4];
-#pragma unroll
-                for (int m = 0; m < 3; ++m) {
-                    double r0[4], r1[4], r2[4];
-                    if (ng == 4) {
-                        const double2 a0 = *reinterpret_cast<const double2*>(w0 + m * 10 + 4 * g), a1 = *reinterpret_cast<const double2*>(w0 + m * 10 + 4 * g + 2);
-                        const double2 b0 = *reinterpret_cast<const double2*>(w1 + m * 10 + 4 * g), b1 = *reinterpret_cast<const double2*>(w1 + m * 10 + 4 * g + 2);
-                        const double2 c0 = *reinterpret_cast<const double2*>(w2 + m * 10 + 4 * g), c1 = *reinterpret_cast<const double2*>(w2 + m * 10 + 4 * g + 2);
-                        r0[0] = a0.x; r0[1] = a0.y; r0[2] = a1.x; r0[3] = a1.y;
-                        r1[0] = b0.x; r1[1] = b0.y; r1[2] = b1.x; r1[3] = b1.y;
-                        r2[0] = c0.x; r2[1] = c0.y; r2[2] = c1.x; r2[3] = c1.y;
-                    } else {
-                        r0[0] = w0[m * 10 + 8]; r1[0] = w1[m * 10 + 8]; r2[0] = w2[m * 10 + 8];
-                    }
-#pragma unroll
-                    for (int h = 0; h < ng; ++h) V[m][h] = fma(xa2, r2[h], fma(xa1, r1[h], xa0 * r0[h]));
-                }
-#pragma unroll
-                for (int a = 0; a <= P; ++a)
-#pragma unroll
-                    for (int h = 0; h < ng; ++h) acc[a][4 * g + h] = fma(X2[a], V[2][h], fma(X1[a], V[1][h], fma(X0[a], V[0][h], acc[a][4 * g + h])));
-            }
-        }
-        // ---- phase A of the next column (U is free since the barrier above)
-        if (ch + 1 < NQ) {
-            mbar_wait(&S.bar, (ch + 1) & 1);
-            phaseA();
-        }
-        __syncthreads();
-    }
-    const int e = ebase + le_t;
-    if (e < nel) tile_scatter<P>(d, S.cb[le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Jacobian kernel, degree 3, "i2-pair" tiles: a thread owns column function j, TWO rows of basis functions (i2 = 2g, 2g+1)
-// and one half of the nine (c,d) entries (cd 0..4 or 5..8).  It keeps 2 x 4 x 5 accumulators (as many as before) but every
-// Z value it loads from shared memory now feeds two FMAs, which cuts the shared-memory traffic of phase 3 by 40 % — the
-// kernel is LSU-bound.  48 threads per element, 2 elements per CTA = 3 full warps.
-struct Jac4Shared {
-    static constexpr int EPG = 2, NQ = 4, NLOC = 16, ZS = 46;
-    BasisStage<3> stage[EPG];
-    double Z[EPG][NQ][NLOC][ZS];      // rows permuted: [cd 5..8][cd 0..4]
-    int4 cb[EPG][NLOC];
-    PointData pd[EPG][NQ];
-    unsigned long long bar;
-};
-
-template <bool HASB>
-__global__ void __launch_bounds__(96, 4) k_jacobian4(KLDev d, int e2_begin, int e2_end) {
-    constexpr int P = 3, NQ = 4, NQ2 = 16, NLOC = 16, EPG = 2, NT = 96, TPE = 48, W = 7, NST = 49, S3 = NST * 3;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Jac4Shared& S = *reinterpret_cast<Jac4Shared*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int nel = d.nel1 * (e2_end - e2_begin);
-    const int ebase = blockIdx.x * EPG;
-
-    auto issue_pd = [&](int ch) {
-        mbar_expect_tx(&S.bar, (unsigned)(EPG * NQ * sizeof(PointData)));
-        for (int le = 0; le < EPG; ++le) {
-            int e = ebase + le;
-            if (e >= nel) e = nel - 1;
-            const size_t ge = (size_t)(e % d.nel1) + (size_t)d.nel1 * (e2_begin + e / d.nel1);
-            tma_bulk_g2s(&S.pd[le][0], d.pd + ge * NQ2 + (size_t)ch * NQ, (unsigned)(NQ * sizeof(PointData)), &S.bar);
-        }
-    };
-    if (tid == 0) mbar_init(&S.bar, 1);
-    __syncthreads();
-    if (tid == 0) issue_pd(0);
-    for (int le = 0; le < EPG; ++le) {
-        int e = ebase + le;
-        if (e >= nel) e = nel - 1;
-        stage_basis<P>(d, e % d.nel1, e2_begin + e / d.nel1, S.stage[le], tid, NT);
-    }
-    for (int k = tid; k < EPG * NLOC; k += NT) {
-        const int le = k / NLOC, l = k - le * NLOC;
-        int e = ebase + le;
-        if (e >= nel) e = nel - 1;
-        const int cpi = (d.span1[e % d.nel1] - P + l % (P + 1)) + d.n1 * (d.span2[e2_begin + e / d.nel1] - P + l / (P + 1));
-        S.cb[le][l] = reinterpret_cast<const int4*>(d.colbase)[cpi];
-    }
-    // tile of this thread: element, (c,d) half, column function j, row pair g
-    const int le_t = tid / TPE, tt = tid - le_t * TPE;
-    const int half = tt / 24, pt = tt - half * 24;
-    int tj, tg;
-    if (pt < 8) { tj = pt; tg = 0; }                                  // j2 = 0,1: one pair-tile each
-    else { tj = 8 + (pt - 8) / 2; tg = (pt - 8) & 1; }               // j2 = 2,3: two pair-tiles each
-    const int tj2 = tj >> 2;
-    const int ia = 2 * tg, ib = 2 * tg + 1;                           // the two rows; row ib only exists if ib <= j2
-    const bool hasB = ib <= tj2;
-    const int ncd = half == 0 ? 5 : 4, cd0 = half == 0 ? 0 : 5;       // (c,d) entries of this thread
-    double acc[2][P + 1][5];
-#pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int a = 0; a <= P; ++a)
-#pragma unroll
-            for (int k = 0; k < 5; ++k) acc[r][a][k] = 0.0;
-
-    for (int ch = 0; ch < NQ; ++ch) {
-        __syncthreads();
-        mbar_wait(&S.bar, ch & 1);
-        // ---- phase 2: Z_j (permuted rows) for the points of this column
-        for (int k = tid; k < EPG * NQ * NLOC; k += NT) {
-            const int j = k % NLOC, qc = (k / NLOC) % NQ, le = k / (NLOC * NQ);
-            const BasisStage<P>& E = S.stage[le];
-            const int ja = j % (P + 1), jb = j / (P + 1);
-            const double x0 = E.b1[ch][0][ja], x1 = E.b1[ch][1][ja], x2 = E.b1[ch][2][ja];
-            const double y0 = E.b2[qc][0][jb], y1 = E.b2[qc][1][jb], y2 = E.b2[qc][2][jb];
-            compute_Zc<HASB, true, true, true, true, true, true>(S.pd[le][qc], x1 * y0, x0 * y1, x2 * y0, x0 * y2, x1 * y1, S.Z[le][qc][j]);
-        }
-        __syncthreads();
-        if (tid == 0 && ch + 1 < NQ) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_pd(ch + 1);
-        }
-        // ---- phase 3: both rows share every loaded Z value
-        {
-            const BasisStage<P>& E = S.stage[le_t];
-            double V[2][3][5];
-#pragma unroll
-            for (int r = 0; r < 2; ++r)
-#pragma unroll
-                for (int m = 0; m < 3; ++m)
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) V[r][m][k] = 0.0;
-#pragma unroll
-            for (int qc = 0; qc < NQ; ++qc) {
-                const double ya0 = E.b2[qc][0][ia], ya1 = E.b2[qc][1][ia], ya2 = E.b2[qc][2][ia];
-                const double yb0 = hasB ? E.b2[qc][0][ib] : 0.0, yb1 = hasB ? E.b2[qc][1][ib] : 0.0, yb2 = hasB ? E.b2[qc][2][ib] : 0.0;
-                // this half's rows: half 1 = doubles [0,20), half 0 = doubles [20,45)
-                const double2* Zi = reinterpret_cast<const double2*>(S.Z[le_t][qc][tj] + (half == 0 ? 20 : 0));
-#pragma unroll
-                for (int m2 = 0; m2 < 3; ++m2) {
-                    // two (c,d) entries = 10 doubles = 5 x 16 bytes; the last group of half 0 holds one entry (+ the pad)
-                    if (m2 == 2 && half == 1) break;
-                    double zz[10];
-                    const int nld = (m2 < 2) ? 5 : 3;
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) if (k < nld) { const double2 t = Zi[m2 * 5 + k]; zz[2 * k] = t.x; zz[2 * k + 1] = t.y; }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int k = 2 * m2 + h;
-                        if (k >= ncd) break;
-                        const double z1 = zz[5 * h], z2 = zz[5 * h + 1], z11 = zz[5 * h + 2], z22 = zz[5 * h + 3], z12 = zz[5 * h + 4];
-                        V[0][0][k] = fma(ya2, z22, fma(ya1, z2, V[0][0][k]));
-                        V[0][1][k] = fma(ya1, z12, fma(ya0, z1, V[0][1][k]));
-                        V[0][2][k] = fma(ya0, z11, V[0][2][k]);
-                        V[1][0][k] = fma(yb2, z22, fma(yb1, z2, V[1][0][k]));
-                        V[1][1][k] = fma(yb1, z12, fma(yb0, z1, V[1][1][k]));
-                        V[1][2][k] = fma(yb0, z11, V[1][2][k]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int a = 0; a <= P; ++a) {
-                const double X0 = E.b1[ch][0][a], X1 = E.b1[ch][1][a], X2 = E.b1[ch][2][a];
-#pragma unroll
-                for (int r = 0; r < 2; ++r)
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) acc[r][a][k] = fma(X2, V[r][2][k], fma(X1, V[r][1][k], fma(X0, V[r][0][k], acc[r][a][k])));
-            }
-        }
-    }
-    // ---- scatter
-    const int e = ebase + le_t;
-    if (e >= nel) return;
-    const int e1 = e % d.nel1, e2 = e2_begin + e / d.nel1;
-    const int i0 = d.span1[e1] - P, j0 = d.span2[e2] - P;
-    const int J1 = i0 + (tj & 3), J2 = j0 + tj2, Jc = J1 + d.n1 * J2;
-    double* __restrict__ val = d.values;
-    const int4 cbJ = S.cb[le_t][tj];
-    const int baseJ[3] = {cbJ.x, cbJ.y, cbJ.z};
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int i2 = 2 * tg + r;
-        if (i2 > tj2) break;
-#pragma unroll
-        for (int a = 0; a <= P; ++a) {
-            const int i = a + (P + 1) * i2;
-            if (i > tj) continue;
-            const int I1 = i0 + a, I2 = j0 + i2, Ic = I1 + d.n1 * I2;
-            const int st_ij = (I1 - J1 + P) + W * (I2 - J2 + P);
-            const int st_ji = (J1 - I1 + P) + W * (J2 - I2 + P);
-            const int4 cbI = S.cb[le_t][i];
-            const int baseI[3] = {cbI.x, cbI.y, cbI.z};
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                if (k >= ncd) break;
-                const int cd = cd0 + k, c = cd / 3, dd = cd - 3 * c;
-                const double v = acc[r][a][k];
-                int p1, p2 = -1;
-                if (cbJ.w) p1 = baseJ[dd] + c * NST + st_ij;
-                else p1 = __ldg(&d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c]);
-                if (i != tj) {
-                    if (cbI.w) p2 = baseI[c] + dd * NST + st_ji;
-                    else p2 = __ldg(&d.pos[(size_t)(Ic * 3 + c) * S3 + st_ji * 3 + dd]);
-                }
-                if (p1 >= 0) atomicAdd(&val[p1], v);
-                if (p2 >= 0) atomicAdd(&val[p2], v);
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Warp-specialised persistent Jacobian kernel (degree 3): one CTA per SM, 13 warps.
-//   warps 0..4   consumers: 160 tile threads (4 elements x 40 upper-triangle tiles) keep the 3x3 blocks in registers
-//   warps 5..12  producers: 256 threads, one (element, q2, basis function) Z task each per chunk
-// Z is double-buffered in shared memory and handed over with mbarriers (full/empty), so the two phases of the
-// non-specialised kernel overlap instead of alternating behind CTA-wide barriers; the per-point records arrive
-// by TMA bulk copies two chunks ahead.
-struct JacWSShared {
-    static constexpr int EPG = 4, QCH = 4, NLOC = 16, ZS = 46;
-    double Z[2][EPG][QCH][NLOC][ZS];
-    PointData pd[2][EPG][QCH];
-    BasisStage<3> stage[2][EPG];
-    int4 cb[2][EPG][NLOC];
-    unsigned long long zfull[2], zempty[2], pdfull[2];
-};
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <bool HASB>
-__global__ void __launch_bounds__(416, 1) k_jacobian_ws(KLDev d, int e2_begin, int e2_end) {
-    constexpr int P = 3, NQ = 4, NQ2 = 16, NLOC = 16, TILES = 40, EPG = 4, QCH = 4, NCONS = 160, NPROD = 256;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    JacWSShared& S = *reinterpret_cast<JacWSShared*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int nel = d.nel1 * (e2_end - e2_begin);
-    const int ngroups = (nel + EPG - 1) / EPG;
-    const int my_groups = ((int)blockIdx.x < ngroups) ? (ngroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int nchunks = my_groups * (NQ2 / QCH);
-    if (tid == 0) {
-        for (int b = 0; b < 2; ++b) { mbar_init(&S.zfull[b], NPROD); mbar_init(&S.zempty[b], NCONS); mbar_init(&S.pdfull[b], 1); }
-    }
-    __syncthreads();
-    if (nchunks == 0) return;
-
-    if (tid >= NCONS) {
-        // ================================ producers ================================
-        const int pt = tid - NCONS;
-        const int j = pt % NLOC, qc = (pt / NLOC) % QCH, le = pt / (NLOC * QCH);
-        auto issue_pd = [&](int n) {   // chunk n of this CTA -> buffer n&1
-            const int b = n & 1, it = n / (NQ2 / QCH), ch = n % (NQ2 / QCH);
-            const int ebase = ((int)blockIdx.x + it * (int)gridDim.x) * EPG;
-            mbar_expect_tx(&S.pdfull[b], (unsigned)(EPG * QCH * sizeof(PointData)));
-            for (int l = 0; l < EPG; ++l) {
-                int e = ebase + l;
-                if (e >= nel) e = nel - 1;
-                const size_t ge = (size_t)(e % d.nel1) + (size_t)d.nel1 * (e2_begin + e / d.nel1);
-                tma_bulk_g2s(&S.pd[b][l][0], d.pd + ge * NQ2 + (size_t)ch * QCH, (unsigned)(QCH * sizeof(PointData)), &S.pdfull[b]);
-            }
-        };
-        if (pt == 0) { issue_pd(0); if (nchunks > 1) issue_pd(1); }
-        for (int n = 0; n < nchunks; ++n) {
-            const int b = n & 1, k = n >> 1, it = n / (NQ2 / QCH), ch = n % (NQ2 / QCH), gb = it & 1;
-            mbar_wait(&S.zempty[b], (k & 1) ^ 1);      // consumers have released Z[b] (passes at once the first time)
-            if (ch == 0) {
-                // basis tables and scatter bases of this group (consumers are past group it-2, see zempty wait above)
-                const int ebase = ((int)blockIdx.x + it * (int)gridDim.x) * EPG;
-                for (int l = 0; l < EPG; ++l) {
-                    int e = ebase + l;
-                    if (e >= nel) e = nel - 1;
-                    stage_basis<P>(d, e % d.nel1, e2_begin + e / d.nel1, S.stage[gb][l], pt, NPROD);
-                }
-                if (pt < EPG * NLOC) {
-                    const int l = pt / NLOC, f = pt - l * NLOC;
-                    int e = ebase + l;
-                    if (e >= nel) e = nel - 1;
-                    const int cpi = (d.span1[e % d.nel1] - P + f % (P + 1)) + d.n1 * (d.span2[e2_begin + e / d.nel1] - P + f / (P + 1));
-                    S.cb[gb][l][f] = reinterpret_cast<const int4*>(d.colbase)[cpi];
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
-            mbar_wait(&S.pdfull[b], k & 1);            // per-point records of this chunk have landed
-            compute_Z<P, HASB>(S.pd[b][le][qc], S.stage[gb][le], ch, qc, j, S.Z[b][le][qc][j]);
-            mbar_arrive(&S.zfull[b]);                  // release: Z[b] (and, for ch==0, stage/cb) visible to the consumers
-            asm volatile("bar.sync 1, 256;" ::: "memory");   // every producer is done reading pd[b]
-            if (pt == 0 && n + 2 < nchunks) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue_pd(n + 2);
-            }
-        }
-    } else {
-        // ================================ consumers ================================
-        const int le_t = tid / TILES, tt = tid - le_t * TILES;
-        int tj = 0, ti2 = 0;
-        {
-            int rem = tt;
-            for (int j2 = 0; j2 <= P; ++j2) {
-                const int cnt = (P + 1) * (j2 + 1);
-                if (rem < cnt) { tj = (P + 1) * j2 + rem / (j2 + 1); ti2 = rem % (j2 + 1); break; }
-                rem -= cnt;
-            }
-        }
-        for (int it = 0; it < my_groups; ++it) {
-            const int gb = it & 1;
-            double acc[P + 1][9];
-#pragma unroll
-            for (int a = 0; a <= P; ++a)
-#pragma unroll
-                for (int q = 0; q < 9; ++q) acc[a][q] = 0.0;
-#pragma unroll 1
-            for (int ch = 0; ch < NQ2 / QCH; ++ch) {
-                const int n = it * (NQ2 / QCH) + ch, b = n & 1, k = n >> 1;
-                mbar_wait(&S.zfull[b], k & 1);
-                tile_chunk<P>(S.stage[gb][le_t], S.Z[b][le_t], ch, ti2, tj, acc);
-                mbar_arrive(&S.zempty[b]);
-            }
-            const int e = ((int)blockIdx.x + it * (int)gridDim.x) * EPG + le_t;
-            if (e < nel) tile_scatter<P>(d, S.cb[gb][le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // follower-pressure tangent  -p R_i dn_jd[c] = +p R_i n_d g_j[c]  (unsymmetric, full i x j loop; cheap)
 template <int P>
 __global__ void __launch_bounds__(256) k_pressure_tangent(KLDev d, int e2_begin, int e2_end) {
@@ -1219,68 +739,8 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
     // the membrane-bending coupling block B vanishes identically for the linear (SvK) law and for membranes
     const bool hasB = ctx->d.mat.material != KL_MAT_SVK && ctx->d.mat.bending;
-    static const bool use_ws = getenv("KL_JAC_WS") != nullptr;
-    static const bool use_k3 = getenv("KL_JAC") != nullptr && atoi(getenv("KL_JAC")) == 3;
-    static const bool use_k4 = getenv("KL_JAC") != nullptr && atoi(getenv("KL_JAC")) == 4;
-    if (use_k4 && P == 3) {
-        if (!(ctx->attr_done & 16u)) {
-            KL_CUDA(cudaFuncSetAttribute(k_jacobian4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jac4Shared)));
-            KL_CUDA(cudaFuncSetAttribute(k_jacobian4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jac4Shared)));
-            KL_CUDA(cudaFuncSetAttribute(k_jacobian4<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            KL_CUDA(cudaFuncSetAttribute(k_jacobian4<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            ctx->attr_done |= 16u;
-        }
-        const int g4 = (nel + 1) / 2;
-        KL_CUDA(cudaEventRecord(ctx->ev[4], s));
-        if (hasB) k_jacobian4<true><<<g4, 96, sizeof(Jac4Shared), s>>>(ctx->d, e2b, e2e);
-        else k_jacobian4<false><<<g4, 96, sizeof(Jac4Shared), s>>>(ctx->d, e2b, e2e);
-        KL_CUDA(cudaEventRecord(ctx->ev[5], s));
-        ctx->launches++;
-        KL_CUDA(cudaGetLastError());
-        if (ctx->d.mat.pressure != 0.0) {
-            k_pressure_tangent<P><<<nel, 256, 0, s>>>(ctx->d, e2b, e2e);
-            ctx->launches++;
-            KL_CUDA(cudaGetLastError());
-        }
-        return 0;
-    }
-    if (use_k3) {
-        using C3 = Jac3Cfg<P>;
-        if (!(ctx->attr_done & 4u)) {
-            KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jac3Shared<P>)));
-            KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Jac3Shared<P>)));
-            KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            KL_CUDA(cudaFuncSetAttribute(k_jacobian3<P, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-            ctx->attr_done |= 4u;
-        }
-        const int g3 = (nel + C3::EPG - 1) / C3::EPG;
-        KL_CUDA(cudaEventRecord(ctx->ev[4], s));
-        if (hasB) k_jacobian3<P, true><<<g3, C3::NT, sizeof(Jac3Shared<P>), s>>>(ctx->d, e2b, e2e);
-        else k_jacobian3<P, false><<<g3, C3::NT, sizeof(Jac3Shared<P>), s>>>(ctx->d, e2b, e2e);
-        KL_CUDA(cudaEventRecord(ctx->ev[5], s));
-        ctx->launches++;
-        KL_CUDA(cudaGetLastError());
-        if (ctx->d.mat.pressure != 0.0) {
-            k_pressure_tangent<P><<<nel, 256, 0, s>>>(ctx->d, e2b, e2e);
-            ctx->launches++;
-            KL_CUDA(cudaGetLastError());
-        }
-        return 0;
-    }   // experimental warp-specialised variant (slower so far: profiles/)
     KL_CUDA(cudaEventRecord(ctx->ev[4], s));
-    if (P == 3 && use_ws) {
-        if (!(ctx->attr_done & 8u)) {
-            KL_CUDA(cudaFuncSetAttribute(k_jacobian_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacWSShared)));
-            KL_CUDA(cudaFuncSetAttribute(k_jacobian_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacWSShared)));
-            int dev = 0;
-            KL_CUDA(cudaGetDevice(&dev));
-            KL_CUDA(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev));
-            ctx->attr_done |= 8u;
-        }
-        const int g = grid < ctx->n_sm ? grid : ctx->n_sm;
-        if (hasB) k_jacobian_ws<true><<<g, 416, sizeof(JacWSShared), s>>>(ctx->d, e2b, e2e);
-        else k_jacobian_ws<false><<<g, 416, sizeof(JacWSShared), s>>>(ctx->d, e2b, e2e);
-    } else if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
+    if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     else k_jacobian<P, false><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     KL_CUDA(cudaEventRecord(ctx->ev[5], s));
     ctx->launches++;

@@ -127,6 +127,7 @@ int kl_build_pattern(kl_ctx* ctx) {
     a.lo1 = lo1; a.hi1 = hi1; a.lo2 = lo2; a.hi2 = hi2;
 
     const long long total = 9LL * d.nst * d.ncp;
+    if (total >= (1LL << 31)) { kl_set_error("kl_create: 9 * (2p+1)^2 * n_cp exceeds int32 (index_t); the mesh is too large for one context"); return KL_E_ARG; }
     unsigned long long *keys = nullptr, *keys_alt = nullptr, *ukeys = nullptr;
     long long* d_num = nullptr;
     KL_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * total));

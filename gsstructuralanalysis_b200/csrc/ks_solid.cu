@@ -91,6 +91,7 @@ int dev_alloc(ks_ctx* ctx, T** p, size_t n) {
 }
 
 // ---- symbolic pattern ---------------------------------------------------------------------------------------------
+struct ToLL { __host__ __device__ long long operator()(int v) const { return (long long)v; } };
 struct Pat3 {
     int n[3], ncp, nfree;
     const int* map;
@@ -727,6 +728,21 @@ static int ks_build_pattern(ks_ctx* ctx) {
     KL_CUDA(cudaMemset(unsorted, 0, sizeof(int)));
     k3_count<<<(nt + T - 1) / T, T>>>(a, count);
     KL_CUDA(cudaGetLastError());
+    {   // nnz must fit index_t: sum the column counts in 64 bits before the int32 scan
+        long long* d_tot = nullptr;
+        KL_CUDA(cudaMalloc((void**)&d_tot, sizeof(long long)));
+        size_t rb = 0;
+        cub::DeviceReduce::Sum(nullptr, rb, cub::TransformInputIterator<long long, ToLL, const int*>(count, ToLL()), d_tot, d.nfree);
+        void* rt = nullptr;
+        KL_CUDA(cudaMalloc(&rt, rb ? rb : 1));
+        cudaError_t re = cub::DeviceReduce::Sum(rt, rb, cub::TransformInputIterator<long long, ToLL, const int*>(count, ToLL()), d_tot, d.nfree);
+        long long tot = 0;
+        if (re == cudaSuccess) re = cudaMemcpy(&tot, d_tot, sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(rt);
+        cudaFree(d_tot);
+        KL_CUDA(re);
+        if (tot >= (1LL << 31)) { kl_set_error("ks_create: nnz exceeds int32 (index_t); the mesh is too large for one context"); return KL_E_ARG; }
+    }
     size_t tmp_bytes = 0;
     KL_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, count, outer, d.nfree + 1));
     void* tmp = nullptr;
@@ -896,6 +912,7 @@ extern "C" int ks_create(const ks_problem* P, int device, ks_ctx** out) {
     if ((rc = dev_alloc(ctx, &d.disp, (size_t)3 * d.ncp))) return rc;
     if ((rc = dev_alloc(ctx, &d.flag, 1))) return rc;
     KL_CUDA(cudaMemset(d.flag, 0, sizeof(int)));
+    if ((rc = ks_build_pattern(ctx))) return rc;      // first: fails fast when nnz does not fit index_t
     const size_t nelem = (size_t)d.nel[0] * d.nel[1] * d.nel[2];
     if ((rc = dev_alloc(ctx, &d.pd, nelem * d.nqp * KS_PD))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->d_x, (size_t)d.nfree))) return rc;
@@ -905,7 +922,6 @@ extern "C" int ks_create(const ks_problem* P, int device, ks_ctx** out) {
     KL_CUDA(cudaMallocHost((void**)&ctx->h_r, sizeof(double) * (size_t)(d.nfree > 0 ? d.nfree : 1)));
     KL_CUDA(cudaStreamCreate(&ctx->stream));
     for (auto& e : ctx->ev) KL_CUDA(cudaEventCreate(&e));
-    if ((rc = ks_build_pattern(ctx))) return rc;
     // F_ext = tractions (host, faces only) + body force (device)
     std::vector<double> f((size_t)(d.nfree > 0 ? d.nfree : 1), 0.0);
     if (P->n_tractions > 0) {

@@ -115,3 +115,15 @@ def test_full_size_properties(gpu):
         assert np.abs(Ks @ t).max() <= 1e-10 * scale
     ok, rr = asm.residual(x)                           # rigid motion: no internal force
     assert ok and np.abs(rr).max() <= 1e-10 * scale
+
+
+def test_too_large_mesh_is_refused(gpu):
+    """nnz must fit index_t = int32: a 92^3 tri-cubic mesh has 2.4 G entries; ks_create fails before the big allocations."""
+    from gsstructuralanalysis_b200.capi import KLError
+    v = S.Volume((3, 3, 3), tuple(__import__("gsstructuralanalysis_b200.geometry", fromlist=["x"]).open_uniform_knots(3, 92) for _ in range(3)),
+                 np.zeros((95 ** 3, 3)))
+    g = np.linspace(0.0, 1.0, 95)
+    v.cp[:] = np.stack(np.meshgrid(g, g, g, indexing="ij")[::-1], axis=-1).reshape(-1, 3)
+    with pytest.raises(KLError) as ei:
+        gpu(S.SolidProblem(v, S.SolidBC(), law=S.KS_LAW_SVK))
+    assert ei.value.rc == -1 and "int32" in str(ei.value)
