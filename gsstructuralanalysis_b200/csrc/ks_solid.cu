@@ -48,6 +48,8 @@ struct KSDev {
     const int* colbase;       // [ncp][4]: outer of column (J,d), d = 0..2 (-1 eliminated); [3] = 1 when no DoF in the coupled box is eliminated
     const int* nlo[3];        // [n_d] first / last node coupled with node j in direction d (the box of a column)
     const int* nhi[3];
+    const int* dof2node;      // [nfree] 3*node + component of a free DoF (mirror pass)
+    int symmetric;            // 1: assemble node pairs I <= J only, k3_mirror fills the rest (K is symmetric: dead loads)
     double* pd;
     int* flag;
     int law;
@@ -535,8 +537,10 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
     const int nU = nq2 * nb * 9;                            // tasks (q2, b, cd): all i3 of one (q2, b, cd) in registers
     const int nW = np3 * nb * 9;                            // tasks (i3, b, cd): all (i2, i1) of one (i3, b, cd) in registers
     // this thread's W task (at most one: np3 * nb * 9 <= 4 * 8 * 9 = KS_NT)
-    const bool hasW = tid < nW;
     const int w_cd = tid % 9, w_bl = (tid / 9) % nb, w_i3 = tid / (9 * nb);
+    // symmetric mode: only row functions a <= b (lexicographic in (i3, i2, i1), = node index order) are assembled
+    const int w_j3 = (b0 + w_bl) / (np1 * np2);
+    const bool hasW = tid < nW && !(d.symmetric && w_i3 > w_j3);
     double acc[KS_MAXP + 1][KS_MAXP + 1];                   // [i2][i1]
 #pragma unroll
     for (int k = 0; k <= KS_MAXP; ++k)
@@ -569,6 +573,7 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
             const int b = b0 + bl, a1 = b % np1, a2 = (b / np1) % np2, a3 = b / (np1 * np2);
             const double x0 = S.E.b[0][q1][0][a1], x1 = S.E.b[0][q1][1][a1], y0 = S.E.b[1][q2][0][a2], y1 = S.E.b[1][q2][1][a2];
             const double gx = x1 * y0, gy = x0 * y1, gz = x0 * y0;
+            const int i3max = d.symmetric ? a3 : KS_MAXP;
             double u[KS_MAXP + 1][3];
 #pragma unroll
             for (int i3 = 0; i3 <= KS_MAXP; ++i3) u[i3][0] = u[i3][1] = u[i3][2] = 0.0;
@@ -584,6 +589,7 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
                 const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
                 for (int i3 = 0; i3 <= KS_MAXP; ++i3) {
+                    if (i3 > i3max) continue;              // symmetric mode: rows with i3 > j3 are never used
                     u[i3][0] = fma(v[i3], zz0, u[i3][0]);
                     u[i3][1] = fma(v[i3], zz1, u[i3][1]);
                     u[i3][2] = fma(dv[i3], zz2, u[i3][2]);
@@ -637,6 +643,8 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
     const int b = b0 + w_bl, j1 = b % np1, j2 = (b / np1) % np2, j3 = b / (np1 * np2);
     const int J1 = S.E.first[0] + j1, J2 = S.E.first[1] + j2, J3 = S.E.first[2] + j3;
     const int J = J1 + d.n[0] * (J2 + d.n[1] * J3);
+    // rows (i1, i2) of this thread's i3 layer that are kept: all of them below j3, up to the column function itself on its layer
+    const int amax = (d.symmetric && i3 == j3) ? j1 + np1 * j2 : np1 * np2;
     const int4 cb = reinterpret_cast<const int4*>(d.colbase)[J];
     const int base = dd == 0 ? cb.x : (dd == 1 ? cb.y : cb.z);
     if (base < 0) return;                                    // eliminated column
@@ -651,7 +659,7 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
             double* dst = col0 + (S.E.first[1] + i2) * w1;
 #pragma unroll
             for (int a = 0; a <= KS_MAXP; ++a)
-                if (a < np1) atomicAdd(dst + a, acc[i2][a]);
+                if (a < np1 && a + np1 * i2 <= amax) atomicAdd(dst + a, acc[i2][a]);
         }
     } else {
         const int col = d.map[dd * d.ncp + J];
@@ -662,6 +670,7 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
 #pragma unroll
             for (int a = 0; a <= KS_MAXP; ++a) {
                 if (a >= np1) continue;
+                if (a + np1 * i2 > amax) continue;
                 const int I = (S.E.first[0] + a) + d.n[0] * ((S.E.first[1] + i2) + d.n[1] * (S.E.first[2] + i3));
                 const int row = d.map[c * d.ncp + I];
                 if (row >= d.nfree) continue;
@@ -673,6 +682,42 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
                     if (rr < row) lo = mid + 1; else hi = mid - 1;
                 }
             }
+        }
+    }
+}
+
+// symmetric mode: values of the node pairs I > J are copies of the transposed entries (row (J,d), col (I,c)) assembled by
+// k3_jacobian.  One warp per column, lanes stride its entries; the transposed position is arithmetic for boxed columns.
+__global__ void __launch_bounds__(256) k3_mirror(KSDev d) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
+    const int n1 = d.n[0], n2 = d.n[1];
+    for (int col = warp; col < d.nfree; col += nwarps) {
+        const int ncJ = d.dof2node[col], J = ncJ / 3, dd = ncJ - 3 * J;
+        const int J1 = J % n1, J2 = (J / n1) % n2, J3 = J / (n1 * n2);
+        const int kb = d.outer[col], ke = d.outer[col + 1];
+        for (int k = kb + lane; k < ke; k += 32) {
+            const int row = d.inner[k];
+            const int ncI = d.dof2node[row], I = ncI / 3, c = ncI - 3 * I;
+            if (I <= J) continue;
+            const int4 cb = reinterpret_cast<const int4*>(d.colbase)[I];
+            const int base = c == 0 ? cb.x : (c == 1 ? cb.y : cb.z);
+            int pos = -1;
+            if (cb.w) {
+                const int I1 = I % n1, I2 = (I / n1) % n2, I3 = I / (n1 * n2);
+                const int lo1 = d.nlo[0][I1], lo2 = d.nlo[1][I2], lo3 = d.nlo[2][I3];
+                const int w1 = d.nhi[0][I1] - lo1 + 1, w2 = d.nhi[1][I2] - lo2 + 1, w3 = d.nhi[2][I3] - lo3 + 1;
+                pos = base + dd * (w1 * w2 * w3) + ((J3 - lo3) * w2 + (J2 - lo2)) * w1 + (J1 - lo1);
+            } else {
+                int lo = base, hi = d.outer[row + 1] - 1;
+                while (lo <= hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const int rr = d.inner[mid];
+                    if (rr == col) { pos = mid; break; }
+                    if (rr < col) lo = mid + 1; else hi = mid - 1;
+                }
+            }
+            if (pos >= 0) d.values[k] = d.values[pos];
         }
     }
 }
@@ -876,6 +921,7 @@ extern "C" int ks_create(const ks_problem* P, int device, ks_ctx** out) {
     d.nfree = P->n_free; ctx->nfixed = P->n_fixed;
     d.law = P->material_law;
     d.ablate = getenv("KS_ABLATE") ? atoi(getenv("KS_ABLATE")) : 0;
+    d.symmetric = getenv("KS_FULL") ? 0 : 1;      // KS_FULL=1: assemble every node pair (A/B and debugging)
     d.lambda = P->E * P->nu / ((1.0 + P->nu) * (1.0 - 2.0 * P->nu));
     d.mu = P->E / (2.0 * (1.0 + P->nu));
     for (size_t k = 0; k < (size_t)3 * d.ncp; ++k)
@@ -904,6 +950,15 @@ extern "C" int ks_create(const ks_problem* P, int device, ks_ctx** out) {
     std::vector<int> map(P->dof_map, P->dof_map + (size_t)3 * d.ncp);
     if ((rc = dev_upload(ctx, &d.cp, cp.data(), cp.size()))) return rc;
     if ((rc = dev_upload(ctx, &d.map, map.data(), map.size()))) return rc;
+    {
+        std::vector<int> d2n((size_t)(d.nfree > 0 ? d.nfree : 1), 0);
+        for (int c = 0; c < 3; ++c)
+            for (int i = 0; i < d.ncp; ++i) {
+                const int g = map[(size_t)c * d.ncp + i];
+                if (g < d.nfree) d2n[g] = 3 * i + c;
+            }
+        if ((rc = dev_upload(ctx, &d.dof2node, d2n.data(), d2n.size()))) return rc;
+    }
     if (P->n_fixed > 0) {
         std::vector<double> fx((size_t)P->n_fixed, 0.0);
         if (P->fixed_values) fx.assign(P->fixed_values, P->fixed_values + P->n_fixed);
@@ -1031,8 +1086,14 @@ static int assemble_dev(ks_ctx* ctx, const double* x_dev, int want_matrix, doubl
         else if (pk == 332 && !generic) k3_jacobian<3, 3, 2><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
         else if (pk == 111 && !generic) k3_jacobian<1, 1, 1><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
         else k3_jacobian<0, 0, 0><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
-        KL_CUDA(cudaEventRecord(ctx->ev[3], s));
         ctx->launches++;
+        if (d.symmetric) {
+            int nsm = 0;
+            KL_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+            k3_mirror<<<nsm * 8, 256, 0, s>>>(d);
+            ctx->launches++;
+        }
+        KL_CUDA(cudaEventRecord(ctx->ev[3], s));
     }
     if (r_dev) {
         KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * (size_t)d.nfree, s));
