@@ -116,5 +116,18 @@ int main(int argc, char** argv) {
                 dstatus == gsStatus::Success ? "Success" : "NotConverged", info.iterations, (long long)info.cg_iterations, Ud.norm(),
                 diff, info.ms_assembly, info.ms_solve);
     if (dstatus != gsStatus::Success || diff > 1e-6 * U.norm()) return 1;
+
+    // Post-processing of the converged state as the reference's drivers do it (unittests/gsStaticSolver_test.cpp:313-324,
+    // benchmarks/benchmark_Balloon.cpp:381-408): principal stretches, boundary reaction, membrane Cauchy stress.
+    const std::vector<real_t> pt = {0.5, 0.5};
+    std::vector<real_t> lambdas, sigma;
+    real_t fw[3];
+    if (!assembler->computePrincipalStretches(pt, U, 0.0, lambdas) || !assembler->boundaryForce(U, KL_WEST, fw) ||
+        !assembler->evalStress(U, KL_STRESS_MEMBRANE, pt, sigma)) {
+        std::printf("POSTPROCESS failed: %s\n", kl_last_error());
+        return 1;
+    }
+    std::printf("STRETCHES %.12e %.12e %.12e  WEST_FORCE %.6e %.6e %.6e  MEMBRANE %.6e %.6e %.6e\n", lambdas[0], lambdas[1],
+                lambdas[2], fw[0], fw[1], fw[2], sigma[0], sigma[1], sigma[2]);
     return status == gsStatus::Success ? 0 : 1;
 }

@@ -20,7 +20,14 @@ SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern
            "kl_jacobian", "kl_residual", "kl_al_residual", "kl_force", "kl_jacobian_device", "kl_residual_device",
            "kl_check", "kl_values_device", "kl_set_strip", "kl_last_timing", "kl_last_error", "kl_kernel_launches",
            "kl_jacobian_kernel_ms", "kl_points_kernel_ms", "kl_measure_fp64_peak", "kl_mass",
-           "kl_assemble_device", "kl_cg_solve", "kl_cg_solve_device", "kl_spmv", "kl_cg_last_timing", "kl_newton_solve"]
+           "kl_assemble_device", "kl_cg_solve", "kl_cg_solve_device", "kl_spmv", "kl_cg_last_timing", "kl_newton_solve",
+           "kl_stress_dim", "kl_eval_stress", "kl_principal_stretches", "kl_boundary_force"]
+
+# stress_type of constructStress (include/kl_shell.h)
+STRESS_TYPES = {"displacement": 0, "membrane_force": 1, "flexural_moment": 2, "membrane": 3, "flexural": 4,
+                "membrane_strain": 5, "flexural_strain": 6, "principal_stretch": 7, "principal_stretch_dir": 8,
+                "principal_stress_membrane": 9, "principal_stress_flexural": 10, "principal_membrane_strain": 11,
+                "principal_flexural_strain": 12, "von_mises_membrane": 13, "tension_field": 14}
 
 
 class kl_newton_options(C.Structure):
@@ -82,6 +89,10 @@ def lib():
     L.kl_spmv.argtypes = [vp, c_double_p, c_double_p]
     L.kl_cg_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.kl_newton_solve.argtypes = [vp, c_double_p, C.POINTER(kl_newton_options), C.POINTER(kl_newton_info)]
+    L.kl_stress_dim.argtypes = [C.c_int32]
+    L.kl_eval_stress.argtypes = [vp, c_double_p, C.c_int32, C.c_int32, c_double_p, C.c_double, c_double_p]
+    L.kl_principal_stretches.argtypes = [vp, c_double_p, C.c_int32, c_double_p, C.c_double, c_double_p]
+    L.kl_boundary_force.argtypes = [vp, c_double_p, C.c_int32, c_double_p]
     _LIB = L
     return L
 

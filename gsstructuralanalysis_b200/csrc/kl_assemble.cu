@@ -124,7 +124,8 @@ __device__ __forceinline__ void stage_basis(const KLDev& d, int e1, int e2, Basi
     for (int k = t; k < NB; k += nthr) { s1[k] = g1[k]; s2[k] = g2[k]; }
 }
 
-template <int P>
+// FULL: internal force only (no follower pressure) at ALL control points, r = [3][ncp] — what boundaryForce sums over a side
+template <int P, bool FULL = false>
 __global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_residual(KLDev d, double* __restrict__ r, int e2_begin, int e2_end) {
     using Cfg = PointCfg<P>;
     constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_residual(KLDev d, double
         const int flag = eval_point<P, false>(d, stage[le], lq % NQ, lq / NQ, pd);
         if (flag && active) atomicOr(d.flag, flag);
         ResPoint& o = rp[le][lq];
-        const double pw = d.mat.pressure * pd.wJ;
+        const double pw = FULL ? 0.0 : d.mat.pressure * pd.wJ;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             // coefficient of N_a,1 and N_a,2:  N:dEm  +  n_c * (H . a^gamma)   (the Christoffel part of M:dEf)
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_residual(KLDev d, double
         const int cpi = (d.span1[e1] - P + a) + d.n1 * (d.span2[e2] - P + b);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
+            if (FULL) { atomicAdd(&r[c * d.ncp + cpi], f[c]); continue; }
             const int g = d.map[c * d.ncp + cpi];
             if (g < d.nfree) atomicAdd(&r[g], f[c]);
         }
@@ -764,22 +766,23 @@ int kl_launch_jacobian(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s) {
 }
 
 template <int P>
-static int launch_res(kl_ctx* ctx, double* r, cudaStream_t s) {
+static int launch_res(kl_ctx* ctx, double* r, cudaStream_t s, bool full) {
     using Cfg = PointCfg<P>;
     const int nel = ctx->d.nel1 * (ctx->e2_end - ctx->e2_begin);
     if (nel <= 0) return 0;
     const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
-    k_residual<P><<<grid, Cfg::NT, 0, s>>>(ctx->d, r, ctx->e2_begin, ctx->e2_end);
+    if (full) k_residual<P, true><<<grid, Cfg::NT, 0, s>>>(ctx->d, r, ctx->e2_begin, ctx->e2_end);
+    else k_residual<P><<<grid, Cfg::NT, 0, s>>>(ctx->d, r, ctx->e2_begin, ctx->e2_end);
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
     return 0;
 }
 
-int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s) {
+int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s, bool full) {
     switch (ctx->d.p) {
-        case 2: return launch_res<2>(ctx, r_dev, s);
-        case 3: return launch_res<3>(ctx, r_dev, s);
-        case 4: return launch_res<4>(ctx, r_dev, s);
+        case 2: return launch_res<2>(ctx, r_dev, s, full);
+        case 3: return launch_res<3>(ctx, r_dev, s, full);
+        case 4: return launch_res<4>(ctx, r_dev, s, full);
     }
     kl_set_error("unsupported degree");
     return KL_E_ARG;

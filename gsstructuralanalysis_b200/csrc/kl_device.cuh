@@ -164,7 +164,7 @@ __device__ __forceinline__ void hyper_incomp(const KLMaterial& m, const double G
 // Newton on C33 until S33 = 0, then static condensation.  Returns false if not converged.
 template <bool TANGENT>
 __device__ __forceinline__ bool hyper_comp(const KLMaterial& m, const double Gi[3], const double gc[3], const double gi[3],
-                                           double J0sq, double S[3], double C[6]) {
+                                           double J0sq, double S[3], double C[6], double* c33_out = nullptr) {
     // contravariant push of the in-plane C: Cup = Gi * gc * Gi  (2x2, symmetric)
     const double t00 = Gi[0] * gc[0] + Gi[2] * gc[2], t01 = Gi[0] * gc[2] + Gi[2] * gc[1];
     const double t10 = Gi[2] * gc[0] + Gi[1] * gc[2], t11 = Gi[2] * gc[2] + Gi[1] * gc[1];
@@ -192,6 +192,7 @@ __device__ __forceinline__ bool hyper_comp(const KLMaterial& m, const double Gi[
         if (fabs(dc) <= 1e-14 * fabs(c33)) conv = true;
     }
     if (!conv) return false;
+    if (c33_out) *c33_out = c33;   // thickness stretch^2 (stress recovery, kl_stress.cu)
     // in-plane stress and the tensor components needed for condensation
     double dI2v[3], Sv[3], Cab33[3];
 #pragma unroll

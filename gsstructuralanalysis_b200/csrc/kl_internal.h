@@ -110,7 +110,7 @@ int kl_build_pattern(kl_ctx* ctx);
 int kl_launch_construct(kl_ctx* ctx, const double* x_dev, cudaStream_t s);
 int kl_launch_jacobian(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s);
 int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s, double* r_dev = nullptr);   // r_dev: also r += F_int - F_pressure
-int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s);   // r += F_int - F_pressure (atomic)
+int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s, bool full = false);   // r += F_int - F_pressure (atomic); full: r = [3][ncp], internal force at every control point
 size_t kl_pointdata_bytes(void);
 int kl_launch_bodyforce(kl_ctx* ctx, double* f_dev, const double bf[3], cudaStream_t s);
 int kl_launch_mass(kl_ctx* ctx, double rho_t, double* values, double* lumped, cudaStream_t s);

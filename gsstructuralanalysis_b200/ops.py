@@ -170,6 +170,34 @@ class ShellAssembler:
         capi.check(self.L.kl_newton_solve(self.h, _dp(U), C.byref(opt), C.byref(info)))
         return U, {k: getattr(info, k) for k, _ in capi.kl_newton_info._fields_}
 
+    # -- stress / stretch recovery --------------------------------------------
+    def eval_stress(self, x, stress_type, uv, z=0.0):
+        """constructStress(mp_def, field, stress_type::X) evaluated at the parametric points uv [n,2]: array [n, dim]
+        (benchmarks/benchmark_Balloon.cpp:381-408).  stress_type: a name of capi.STRESS_TYPES or its number."""
+        t = capi.STRESS_TYPES[stress_type] if isinstance(stress_type, str) else int(stress_type)
+        dim = self.L.kl_stress_dim(t)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros((uv.shape[0], max(dim, 1)))
+        capi.check(self.L.kl_eval_stress(self.h, _dp(x), t, uv.shape[0], _dp(uv), float(z), _dp(out)))
+        return out
+
+    def computePrincipalStretches(self, uv, x, z=0.0):
+        """assembler->computePrincipalStretches(pts, mp_def, z) (unittests/gsStaticSolver_test.cpp:317): [n,3],
+        lambda(0) <= lambda(1) in-plane, lambda(2) the thickness stretch."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros((uv.shape[0], 3))
+        capi.check(self.L.kl_principal_stretches(self.h, _dp(x), uv.shape[0], _dp(uv), float(z), _dp(out)))
+        return out
+
+    def boundaryForce(self, x, side):
+        """assembler->boundaryForce(mp_def, patchSide(0, side)) (unittests/gsStaticSolver_test.cpp:321): (Fx, Fy, Fz)."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros(3)
+        capi.check(self.L.kl_boundary_force(self.h, _dp(x), int(side), _dp(out)))
+        return out
+
     def set_strip(self, e2_begin, e2_end):
         capi.check(self.L.kl_set_strip(self.h, e2_begin, e2_end))
 

@@ -248,6 +248,25 @@ public:
         }
         return gsStatus::OtherError;
     }
+    /** assembler->computePrincipalStretches(pts, mp_def, z) (unittests/gsStaticSolver_test.cpp:317): `uv` holds the
+        parametric points column by column (u0,v0,u1,v1,...), the result 3 stretches per point — lambda(0) <= lambda(1)
+        in-plane, lambda(2) the thickness stretch.  `solVector` is the DoF vector that constructSolution would take. */
+    bool computePrincipalStretches(const std::vector<T>& uv, gsVector<T> const& solVector, T z, std::vector<T>& lambdas) const {
+        const int32_t n = (int32_t)(uv.size() / 2);
+        lambdas.assign((size_t)3 * n, T(0));
+        return kl_principal_stretches(m_s->ctx, solVector.data(), n, uv.data(), z, lambdas.data()) == KL_OK;
+    }
+    /** assembler->boundaryForce(mp_def, patchSide(0, side)) (unittests/gsStaticSolver_test.cpp:321); side = KL_WEST.. */
+    bool boundaryForce(gsVector<T> const& solVector, int side, T force[3]) const {
+        return kl_boundary_force(m_s->ctx, solVector.data(), side, force) == KL_OK;
+    }
+    /** assembler->constructStress(mp_def, field, stress_type::X) evaluated at parametric points
+        (benchmarks/benchmark_Balloon.cpp:381-408): `type` = KL_STRESS_*, result kl_stress_dim(type) values per point. */
+    bool evalStress(gsVector<T> const& solVector, int type, const std::vector<T>& uv, std::vector<T>& result, T z = 0) const {
+        const int32_t n = (int32_t)(uv.size() / 2);
+        result.assign((size_t)kl_stress_dim(type) * n, T(0));
+        return kl_eval_stress(m_s->ctx, solVector.data(), type, n, uv.data(), z, result.data()) == KL_OK;
+    }
     /// gsStaticBase::defaultOptions (gsStaticBase.h:66-75) + gsStaticNewton::defaultOptions (gsStaticNewton.hpp:20-25)
     static kl_newton_options defaultNewtonOptions() {
         kl_newton_options o;

@@ -202,6 +202,51 @@ typedef struct kl_newton_info {
 } kl_newton_info;
 int kl_newton_solve(kl_ctx* ctx, double* U_host_inout, const kl_newton_options* opt, kl_newton_info* info);
 
+/* ---- stress / stretch recovery -----------------------------------------------
+ * Replaces assembler->constructStress(mp_def, field, stress_type::X) followed by field evaluation
+ * (benchmarks/benchmark_Balloon.cpp:381-408, benchmark_TensionWrinkling.cpp:505-540, benchmark_Pillow.cpp:431,484-505),
+ * assembler->computePrincipalStretches(pts, mp_def, z) and assembler->boundaryForce(mp_def, patchSide)
+ * (unittests/gsStaticSolver_test.cpp:317,321).  The gsKLShell sources that define these quantities are not in the
+ * reference tree; the definitions below are the ones this library and its oracle implement (PARITY UNPINNED against
+ * upstream; pinned by the reference's own uniaxial-tension test: lambda, S = F_side/(t lambda0 lambda2)).
+ * Voigt order of 3-component outputs: (11, 22, 12), tensor components (no engineering factor 2).
+ *   DISPLACEMENT              3  u = x_def - x_ori
+ *   MEMBRANE_FORCE            3  N^ab, thickness-integrated 2nd Piola-Kirchhoff stress (MaterialOutput::VectorN), curvilinear
+ *   FLEXURAL_MOMENT           3  M^ab (MaterialOutput::VectorM), curvilinear
+ *   MEMBRANE                  3  Cauchy membrane stress N^ab/(t J) pushed to the local Cartesian frame of the DEFORMED
+ *                                mid-surface (e1 = a_1/|a_1|, e2 = a^2/|a^2|), J = J0 lambda3
+ *   FLEXURAL                  3  outer-fibre Cauchy bending stress 6 M^ab/(t^2 J) in the same frame
+ *   MEMBRANE_STRAIN           3  Green-Lagrange E_ab = (a_ab - A_ab)/2 in the local Cartesian frame of the UNDEFORMED surface
+ *   FLEXURAL_STRAIN           3  K_ab = B_ab - b_ab in the same frame
+ *   PRINCIPAL_STRETCH         3  lambda(0) <= lambda(1) in-plane at height z, lambda(2) ALWAYS the thickness stretch
+ *                                (ordering of unittests/gsStaticSolver_test.cpp:313): 1/J0 for SvK and incompressible laws,
+ *                                sqrt(C33) of the plane-stress iteration for compressible laws
+ *   PRINCIPAL_STRETCH_DIR     9  spatial unit vectors n_0, n_1 (= F N_i / lambda_i) and the deformed normal; sign arbitrary
+ *   PRINCIPAL_STRESS_MEMBRANE 2  eigenvalues of MEMBRANE, ascending;  PRINCIPAL_STRESS_FLEXURAL likewise of FLEXURAL
+ *   PRINCIPAL_MEMBRANE_STRAIN 2  eigenvalues of MEMBRANE_STRAIN;      PRINCIPAL_FLEXURAL_STRAIN of FLEXURAL_STRAIN
+ *   VON_MISES_MEMBRANE        1  sqrt(s11^2 + s22^2 - s11 s22 + 3 s12^2) of MEMBRANE
+ *   TENSION_FIELD             1  1 taut (min principal membrane stress > 0), -1 slack (max principal membrane strain <= 0),
+ *                                0 wrinkled otherwise                                                               */
+enum {
+    KL_STRESS_DISPLACEMENT = 0, KL_STRESS_MEMBRANE_FORCE = 1, KL_STRESS_FLEXURAL_MOMENT = 2, KL_STRESS_MEMBRANE = 3,
+    KL_STRESS_FLEXURAL = 4, KL_STRESS_MEMBRANE_STRAIN = 5, KL_STRESS_FLEXURAL_STRAIN = 6, KL_STRESS_PRINCIPAL_STRETCH = 7,
+    KL_STRESS_PRINCIPAL_STRETCH_DIR = 8, KL_STRESS_PRINCIPAL_STRESS_MEMBRANE = 9, KL_STRESS_PRINCIPAL_STRESS_FLEXURAL = 10,
+    KL_STRESS_PRINCIPAL_MEMBRANE_STRAIN = 11, KL_STRESS_PRINCIPAL_FLEXURAL_STRAIN = 12, KL_STRESS_VON_MISES_MEMBRANE = 13,
+    KL_STRESS_TENSION_FIELD = 14, KL_STRESS_NTYPES = 15
+};
+int kl_stress_dim(int32_t type);                  /* components per point, 0 for an unknown type */
+/* Evaluate one quantity at n_pts parametric points uv[2*k..] of the patch for the state x (free DoFs, host); z = height
+ * through the thickness used by the stretch outputs (computePrincipalStretches' third argument).  out: [n_pts*dim], point-major. */
+int kl_eval_stress(kl_ctx* ctx, const double* x_host, int32_t type, int32_t n_pts, const double* uv_host, double z,
+                   double* out_host);
+/* assembler->computePrincipalStretches(pts, mp_def, z): out [n_pts*3] */
+int kl_principal_stretches(kl_ctx* ctx, const double* x_host, int32_t n_pts, const double* uv_host, double z, double* out_host);
+/* assembler->boundaryForce(mp_def, patchSide(0, side)): -F_int (the sign of rhs() = F_ext - F_int; no follower pressure)
+ * summed per component over ALL control points of the side, eliminated ones included, so that the Cauchy stress of the
+ * reference's test reads S = -sideForce / (thickness lambda(0) lambda(2)) (unittests/gsStaticSolver_test.cpp:321-323).
+ * out3: (Fx, Fy, Fz). */
+int kl_boundary_force(kl_ctx* ctx, const double* x_host, int32_t side, double* out3_host);
+
 /* Duration in ms of the last Jacobian kernel launch itself (CUDA events on its stream; syncs). */
 int kl_jacobian_kernel_ms(kl_ctx* ctx, float* ms);
 /* Same for the per-quadrature-point kernel (geometry + material) that precedes it. */

@@ -47,6 +47,9 @@ def lib():
         L.klo_gauss.argtypes = [C.c_int, c_double_p, c_double_p]
         L.klo_cg_solve.argtypes = [C.c_int, c_int_p, c_int_p, c_double_p, c_double_p, c_double_p, C.c_double, C.c_int,
                                    C.POINTER(C.c_int), c_double_p]
+        L.klo_stress_dim.argtypes = [C.c_int]
+        L.klo_eval_stress.argtypes = [C.c_void_p, c_double_p, C.c_int, C.c_int, c_double_p, C.c_double, c_double_p]
+        L.klo_boundary_force.argtypes = [C.c_void_p, c_double_p, C.c_int, c_double_p]
         _LIB = L
     return _LIB
 
@@ -128,6 +131,29 @@ class Oracle:
         v, l = np.zeros(self.nnz), np.zeros(self.n_dofs)
         self.L.klo_mass(self.h, float(density), _dp(v), _dp(l))
         return v, l
+
+    def eval_stress(self, x, stress_type, uv, z=0.0):
+        from gsstructuralanalysis_b200.capi import STRESS_TYPES
+        t = STRESS_TYPES[stress_type] if isinstance(stress_type, str) else int(stress_type)
+        dim = self.L.klo_stress_dim(t)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        uv = np.ascontiguousarray(uv, dtype=np.float64).reshape(-1, 2)
+        out = np.zeros((uv.shape[0], max(dim, 1)))
+        rc = self.L.klo_eval_stress(self.h, _dp(x), t, uv.shape[0], _dp(uv), float(z), _dp(out))
+        if rc:
+            raise RuntimeError(f"oracle eval_stress rc={rc}")
+        return out
+
+    def computePrincipalStretches(self, uv, x, z=0.0):
+        return self.eval_stress(x, "principal_stretch", uv, z)
+
+    def boundaryForce(self, x, side):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros(3)
+        rc = self.L.klo_boundary_force(self.h, _dp(x), int(side), _dp(out))
+        if rc:
+            raise RuntimeError(f"oracle boundary_force rc={rc}")
+        return out
 
     def jacobian_residual(self, x, values=None, r=None):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -86,7 +86,7 @@ static inline double s2(const double m[3], int i, int j) { return i == j ? m[i] 
 
 /* 3D hyperelastic point evaluation with plane-stress treatment.  G,g: covariant in-plane
  * metrics at thickness coordinate z (Voigt).  Out: S[3], C[3][3] (condensed).           */
-static int hyper_point(const kl_problem* P, const double Gc[3], const double gc[3], double S[3], double C[3][3]) {
+static int hyper_point(const kl_problem* P, const double Gc[3], const double gc[3], double S[3], double C[3][3], double* c33_out) {
     double Gi[3], gi[3], detG, detg;
     inv2(Gc, Gi, &detG);
     inv2(gc, gi, &detg);
@@ -101,6 +101,7 @@ static int hyper_point(const kl_problem* P, const double Gc[3], const double gc[
         double trs = 0.0;
         for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) trs += s2(gc, a, b) * s2(Gi, a, b);
         double c33 = 1.0 / J0sq;
+        if (c33_out) *c33_out = c33;
         double dpsi33 = 0.5 * c1 + 0.5 * c2 * trs;
         for (int v = 0; v < 3; ++v) {
             int a = VI[v], b = VJ[v];
@@ -165,6 +166,7 @@ static int hyper_point(const kl_problem* P, const double Gc[3], const double gc[
         if (fabs(dc33) <= 1e-14 * fabs(c33)) converged = 1;   /* one more pass evaluates at the root */
     }
     if (!converged) return KL_E_C33;
+    if (c33_out) *c33_out = c33;
     for (int v = 0; v < 3; ++v) {
         int a = VI[v], b = VJ[v];
         S[v] = S3[a][b];
@@ -228,7 +230,7 @@ static int material_eval(const kl_problem* P, const double Ac[3], const double B
             }
         }
         double S[3], C[3][3];
-        int rc = hyper_point(P, Gc, gc, S, C);
+        int rc = hyper_point(P, Gc, gc, S, C, NULL);
         if (rc) return rc;
         for (int v = 0; v < 3; ++v) {
             N[v] += wz * S[v];
@@ -464,7 +466,7 @@ static void construct_disp(const klo* o, const double* x, double* disp) {
 }
 
 /* mode bit 1: matrix, bit 2: internal force vector.  fint gets F_int - F_pressure (free rows). */
-static int assemble(const klo* o, const double* x, double* Kval, double* fint) {
+static int assemble_full(const klo* o, const double* x, double* Kval, double* fint, double* ffull /* [3*ncp] internal force at ALL control points, no pressure */) {
     int err = 0;
     double* disp = (double*)malloc(sizeof(double) * 3 * o->ncp);
     construct_disp(o, x, disp);
@@ -486,8 +488,9 @@ static int assemble(const klo* o, const double* x, double* Kval, double* fint) {
         qpdata q;
         int nloc = (o->p[0] + 1) * (o->p[1] + 1), nd = 3 * nloc;
         double* Ke = Kval ? (double*)calloc((size_t)nd * nd, sizeof(double)) : NULL;
-        double fe[3 * MAXLOC];
+        double fe[3 * MAXLOC], fi[3 * MAXLOC];
         memset(fe, 0, sizeof(fe));
+        memset(fi, 0, sizeof(fi));
         for (int q2 = 0; q2 < nq2 && !err; ++q2) for (int q1 = 0; q1 < nq1 && !err; ++q1) {
             double u = 0.5 * (ua + ub) + 0.5 * (ub - ua) * xq1[q1];
             double v = 0.5 * (va + vb) + 0.5 * (vb - va) * xq2[q2];
@@ -532,6 +535,7 @@ static int assemble(const klo* o, const double* x, double* Kval, double* fint) {
                 double s = 0.0;
                 for (int k = 0; k < 3; ++k) s += N[k] * dEm[r][k] + M[k] * dEf[r][k];
                 fe[r] += wJ * s;
+                fi[r] += wJ * s;
                 if (pr != 0.0) fe[r] -= wJ * pr * q.R[r / 3] * nn[r % 3];
             }
             if (!Ke) continue;
@@ -574,6 +578,10 @@ static int assemble(const klo* o, const double* x, double* Kval, double* fint) {
         }
         if (!err) {
             for (int r = 0; r < nd; ++r) {
+                if (ffull) {
+#pragma omp atomic
+                    ffull[(r % 3) * ncp + q.cpidx[r / 3]] += fi[r];
+                }
                 int gr = o->map[(r % 3) * ncp + q.cpidx[r / 3]];
                 if (gr >= nf) continue;
                 if (fint) {
@@ -594,6 +602,8 @@ static int assemble(const klo* o, const double* x, double* Kval, double* fint) {
     free(disp);
     return err;
 }
+
+static int assemble(const klo* o, const double* x, double* Kval, double* fint) { return assemble_full(o, x, Kval, fint, NULL); }
 
 /* external force: constant body force * N_i * meas(ori) + point loads (setPointLoads) */
 static void build_fext(klo* o) {
@@ -820,4 +830,202 @@ int klo_cg_solve(int n, const int* outer, const int* inner, const double* val, c
     *rel_err = sqrt(rn2 / rhs2);
     free(w);
     return 0;
+}
+
+/* ---- stress / stretch recovery --------------------------------------------------------------------
+ * Restates what constructStress / computePrincipalStretches / boundaryForce are used for in the reference
+ * (unittests/gsStaticSolver_test.cpp:313-324; benchmarks/benchmark_Balloon.cpp:381-408; benchmark_Pillow.cpp:431,484-505)
+ * with the definitions written in include/kl_shell.h.  Deliberately a different route than the device code: everything
+ * goes through full 3-D tensors (deformation gradient F = a_i (x) A^i with a_3 = lambda3 n, sigma = F S F^T / det F,
+ * E = (F^T F - I)/2) projected on explicit orthonormal frames, and the principal values come from a Cholesky
+ * transformation + Jacobi rotation instead of the closed-form roots of the characteristic polynomial. */
+static double det3(double M[3][3]) {
+    return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0])
+         + M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+}
+/* eigen decomposition of the symmetric 2x2 (s11,s22,s12): ascending values w, orthonormal vectors V[k] */
+static void eig2(double s11, double s22, double s12, double w[2], double V[2][2]) {
+    double th = 0.5 * atan2(2.0 * s12, s11 - s22), c = cos(th), s = sin(th);
+    double wa = c * c * s11 + 2 * c * s * s12 + s * s * s22, wb = s * s * s11 - 2 * c * s * s12 + c * c * s22;
+    if (wa <= wb) { w[0] = wa; w[1] = wb; V[0][0] = c; V[0][1] = s; V[1][0] = -s; V[1][1] = c; }
+    else { w[0] = wb; w[1] = wa; V[0][0] = -s; V[0][1] = c; V[1][0] = c; V[1][1] = s; }
+}
+int klo_stress_dim(int type) {
+    static const int dim[KL_STRESS_NTYPES] = {3, 3, 3, 3, 3, 3, 3, 3, 9, 2, 2, 2, 2, 1, 1};
+    return (type >= 0 && type < KL_STRESS_NTYPES) ? dim[type] : 0;
+}
+int klo_eval_stress(const klo* o, const double* x, int type, int npts, const double* uv, double z, double* out) {
+    int dim = klo_stress_dim(type);
+    if (!dim) return KL_E_ARG;
+    double* disp = (double*)malloc(sizeof(double) * 3 * o->ncp);
+    construct_disp(o, x, disp);
+    int err = 0;
+    for (int k = 0; k < npts && !err; ++k) {
+        double u = uv[2 * k], v = uv[2 * k + 1], *res = out + (size_t)dim * k;
+        int s1 = find_span(o->n[0], o->p[0], u, o->U[0]), s2_ = find_span(o->n[1], o->p[1], v, o->U[1]);
+        int e1 = 0, e2 = 0;
+        for (int e = 0; e < o->nel[0]; ++e) if (o->span[0][e] == s1) e1 = e;
+        for (int e = 0; e < o->nel[1]; ++e) if (o->span[1][e] == s2_) e2 = e;
+        qpdata q;
+        eval_qp(o, e1, e2, u, v, disp, &q);
+        if (type == KL_STRESS_DISPLACEMENT) {
+            for (int c = 0; c < 3; ++c) { double s = 0; for (int l = 0; l < q.nloc; ++l) s += q.R[l] * disp[3 * q.cpidx[l] + c]; res[c] = s; }
+            continue;
+        }
+        double Nn[3], nn[3];
+        cross3(q.A1, q.A2, Nn); cross3(q.a1, q.a2, nn);
+        double JA = sqrt(dot3(Nn, Nn)), Ja = sqrt(dot3(nn, nn));
+        if (!(JA > 0.0) || !(Ja > 0.0)) { err = KL_E_JACOBIAN; break; }
+        for (int c = 0; c < 3; ++c) { Nn[c] /= JA; nn[c] /= Ja; }
+        double Ac[3] = {dot3(q.A1, q.A1), dot3(q.A2, q.A2), dot3(q.A1, q.A2)};
+        double ac[3] = {dot3(q.a1, q.a1), dot3(q.a2, q.a2), dot3(q.a1, q.a2)};
+        double Bc[3], bc[3];
+        for (int i = 0; i < 3; ++i) { Bc[i] = dot3(q.H[i], Nn); bc[i] = dot3(q.h[i], nn); }
+        if (!o->P.bending) for (int i = 0; i < 3; ++i) { Bc[i] = 0; bc[i] = 0; }
+        double Ai[3], ai[3], dA, da;
+        inv2(Ac, Ai, &dA); inv2(ac, ai, &da);
+        /* contravariant vectors of the undeformed mid-surface, orthonormal frames (E1,E2,N), (e1,e2,n) */
+        double Au[2][3], E1[3], E2[3], e1v[3], e2v[3];
+        for (int c = 0; c < 3; ++c) { Au[0][c] = Ai[0] * q.A1[c] + Ai[2] * q.A2[c]; Au[1][c] = Ai[2] * q.A1[c] + Ai[1] * q.A2[c]; }
+        for (int c = 0; c < 3; ++c) { E1[c] = q.A1[c] / sqrt(Ac[0]); e1v[c] = q.a1[c] / sqrt(ac[0]); }
+        cross3(Nn, E1, E2); cross3(nn, e1v, e2v);
+        /* thickness stretch at the mid-surface */
+        double J0sq0 = da / dA, c33mid = 1.0 / J0sq0;
+        if (o->P.material != KL_MAT_SVK && o->P.compressible) {
+            double S_[3], C_[3][3];
+            int rc = hyper_point(&o->P, Ac, ac, S_, C_, &c33mid);
+            if (rc) { err = rc; break; }
+        }
+        double lam3mid = sqrt(c33mid);
+        /* F = a_1 (x) A^1 + a_2 (x) A^2 + lambda3 n (x) N */
+        double F[3][3];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) F[i][j] = q.a1[i] * Au[0][j] + q.a2[i] * Au[1][j] + lam3mid * nn[i] * Nn[j];
+        double J = det3(F);
+        if (type == KL_STRESS_PRINCIPAL_STRETCH || type == KL_STRESS_PRINCIPAL_STRETCH_DIR) {
+            /* metric at height z exactly as the material law sees it (g_ab - 2 z b_ab [+ z^2 b_ac a^cd b_db]) */
+            double Gc[3], gc[3];
+            for (int i = 0; i < 3; ++i) { Gc[i] = Ac[i] - 2.0 * z * Bc[i]; gc[i] = ac[i] - 2.0 * z * bc[i]; }
+            if (o->P.metric_z2)
+                for (int i = 0; i < 3; ++i) {
+                    int a = VI[i], b = VJ[i];
+                    double sG = 0, sg = 0;
+                    for (int c = 0; c < 2; ++c) for (int d = 0; d < 2; ++d) {
+                        sG += s2(Bc, a, c) * s2(Ai, c, d) * s2(Bc, d, b);
+                        sg += s2(bc, a, c) * s2(ai, c, d) * s2(bc, d, b);
+                    }
+                    Gc[i] += z * z * sG; gc[i] += z * z * sg;
+                }
+            double dG = Gc[0] * Gc[1] - Gc[2] * Gc[2], dg = gc[0] * gc[1] - gc[2] * gc[2];
+            if (!(dG > 0.0) || !(dg > 0.0)) { err = KL_E_JACOBIAN; break; }
+            /* Cholesky G = L L^T;  Chat = L^-1 g L^-T is the right Cauchy-Green tensor in an orthonormal frame */
+            double l11 = sqrt(Gc[0]), l21 = Gc[2] / l11, l22 = sqrt(Gc[1] - l21 * l21);
+            double m11 = gc[0] / (l11 * l11);
+            double m12 = (gc[2] - l21 * gc[0] / l11) / (l11 * l22);
+            double m22 = (gc[1] - 2.0 * l21 * gc[2] / l11 + l21 * l21 * gc[0] / (l11 * l11)) / (l22 * l22);
+            double w[2], V[2][2];
+            eig2(m11, m22, m12, w, V);
+            double c33 = dG / dg;
+            if (o->P.material != KL_MAT_SVK && o->P.compressible) {
+                double S_[3], C_[3][3];
+                int rc = hyper_point(&o->P, Gc, gc, S_, C_, &c33);
+                if (rc) { err = rc; break; }
+            }
+            if (type == KL_STRESS_PRINCIPAL_STRETCH) { res[0] = sqrt(w[0]); res[1] = sqrt(w[1]); res[2] = sqrt(c33); continue; }
+            /* contravariant components v = L^-T what; spatial direction n_i = v^a g_a(z) / lambda_i, g_a(z) = a_a - z b_a^c a_c */
+            double gz[2][3];
+            {
+                double bm[2][2] = {{bc[0] * ai[0] + bc[2] * ai[2], bc[0] * ai[2] + bc[2] * ai[1]},
+                                   {bc[2] * ai[0] + bc[1] * ai[2], bc[2] * ai[2] + bc[1] * ai[1]}};   /* b_a^c */
+                for (int c = 0; c < 3; ++c) {
+                    gz[0][c] = q.a1[c] - z * (bm[0][0] * q.a1[c] + bm[0][1] * q.a2[c]);
+                    gz[1][c] = q.a2[c] - z * (bm[1][0] * q.a1[c] + bm[1][1] * q.a2[c]);
+                }
+            }
+            for (int i = 0; i < 2; ++i) {
+                double v2 = V[i][1] / l22, v1 = (V[i][0] - l21 * v2) / l11;
+                double d[3], nrm;
+                for (int c = 0; c < 3; ++c) d[c] = v1 * gz[0][c] + v2 * gz[1][c];
+                nrm = sqrt(dot3(d, d));
+                for (int c = 0; c < 3; ++c) res[3 * i + c] = d[c] / nrm;
+            }
+            for (int c = 0; c < 3; ++c) res[6 + c] = nn[c];
+            continue;
+        }
+        /* strains: 3-D Green-Lagrange tensor and the curvature change tensor, projected on (E1,E2) */
+        double Em[3] = {0, 0, 0}, Ef[3] = {0, 0, 0};
+        {
+            double E3[3][3], K3[3][3];
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int m = 0; m < 3; ++m) s += F[m][i] * F[m][j];
+                E3[i][j] = 0.5 * (s - (i == j ? 1.0 : 0.0));
+                double kk = 0;
+                for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) kk += (s2(Bc, a, b) - s2(bc, a, b)) * Au[a][i] * Au[b][j];
+                K3[i][j] = kk;
+            }
+            const double* Fr[2] = {E1, E2};
+            for (int vv = 0; vv < 3; ++vv) {
+                const double *p_ = Fr[VI[vv]], *q_ = Fr[VJ[vv]];
+                for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { Em[vv] += p_[i] * E3[i][j] * q_[j]; Ef[vv] += p_[i] * K3[i][j] * q_[j]; }
+            }
+        }
+        double A[3][3], B[3][3], D[3][3], N[3], M[3];
+        int rc = material_eval(&o->P, Ac, Bc, ac, bc, A, B, D, N, M);
+        if (rc) { err = rc; break; }
+        if (!o->P.bending) M[0] = M[1] = M[2] = 0.0;
+        /* Cauchy tensors sigma = F S F^T / J with S = N^ab/t A_a (x) A_b, projected on (e1,e2) */
+        double sm[3] = {0, 0, 0}, sf[3] = {0, 0, 0};
+        {
+            const double* Acov[2] = {q.A1, q.A2};
+            double S3[3][3], M3[3][3], t = o->P.thickness;
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+                double a_ = 0, b_ = 0;
+                for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) { a_ += s2(N, a, b) * Acov[a][i] * Acov[b][j]; b_ += s2(M, a, b) * Acov[a][i] * Acov[b][j]; }
+                S3[i][j] = a_ / t; M3[i][j] = 6.0 * b_ / (t * t);
+            }
+            const double* fr[2] = {e1v, e2v};
+            for (int vv = 0; vv < 3; ++vv) {
+                double Fp[3] = {0, 0, 0}, Fq[3] = {0, 0, 0};   /* F^T e */
+                for (int i = 0; i < 3; ++i) for (int m = 0; m < 3; ++m) { Fp[i] += F[m][i] * fr[VI[vv]][m]; Fq[i] += F[m][i] * fr[VJ[vv]][m]; }
+                for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { sm[vv] += Fp[i] * S3[i][j] * Fq[j] / J; sf[vv] += Fp[i] * M3[i][j] * Fq[j] / J; }
+            }
+        }
+        double w[2], V[2][2];
+        switch (type) {
+            case KL_STRESS_MEMBRANE_FORCE: for (int i = 0; i < 3; ++i) res[i] = N[i]; break;
+            case KL_STRESS_FLEXURAL_MOMENT: for (int i = 0; i < 3; ++i) res[i] = M[i]; break;
+            case KL_STRESS_MEMBRANE: for (int i = 0; i < 3; ++i) res[i] = sm[i]; break;
+            case KL_STRESS_FLEXURAL: for (int i = 0; i < 3; ++i) res[i] = sf[i]; break;
+            case KL_STRESS_MEMBRANE_STRAIN: for (int i = 0; i < 3; ++i) res[i] = Em[i]; break;
+            case KL_STRESS_FLEXURAL_STRAIN: for (int i = 0; i < 3; ++i) res[i] = Ef[i]; break;
+            case KL_STRESS_PRINCIPAL_STRESS_MEMBRANE: eig2(sm[0], sm[1], sm[2], w, V); res[0] = w[0]; res[1] = w[1]; break;
+            case KL_STRESS_PRINCIPAL_STRESS_FLEXURAL: eig2(sf[0], sf[1], sf[2], w, V); res[0] = w[0]; res[1] = w[1]; break;
+            case KL_STRESS_PRINCIPAL_MEMBRANE_STRAIN: eig2(Em[0], Em[1], Em[2], w, V); res[0] = w[0]; res[1] = w[1]; break;
+            case KL_STRESS_PRINCIPAL_FLEXURAL_STRAIN: eig2(Ef[0], Ef[1], Ef[2], w, V); res[0] = w[0]; res[1] = w[1]; break;
+            case KL_STRESS_VON_MISES_MEMBRANE: res[0] = sqrt(sm[0] * sm[0] + sm[1] * sm[1] - sm[0] * sm[1] + 3.0 * sm[2] * sm[2]); break;
+            case KL_STRESS_TENSION_FIELD: {
+                double ws[2], we[2];
+                eig2(sm[0], sm[1], sm[2], ws, V);
+                eig2(Em[0], Em[1], Em[2], we, V);
+                res[0] = ws[0] > 0.0 ? 1.0 : (we[1] <= 0.0 ? -1.0 : 0.0);
+            } break;
+            default: err = KL_E_ARG;
+        }
+    }
+    free(disp);
+    return err;
+}
+/* boundaryForce(mp_def, patchSide(0, side)): MINUS the internal force summed per component over all control points of the side */
+int klo_boundary_force(const klo* o, const double* x, int side, double* out3) {
+    double* ff = (double*)calloc((size_t)3 * o->ncp, sizeof(double));
+    int rc = assemble_full(o, x, NULL, NULL, ff);
+    int n1 = o->n[0], n2 = o->n[1];
+    for (int c = 0; c < 3; ++c) {
+        double s = 0.0;
+        if (side == KL_WEST || side == KL_EAST) { int i1 = side == KL_WEST ? 0 : n1 - 1; for (int i2 = 0; i2 < n2; ++i2) s += ff[c * o->ncp + i1 + n1 * i2]; }
+        else { int i2 = side == KL_SOUTH ? 0 : n2 - 1; for (int i1 = 0; i1 < n1; ++i1) s += ff[c * o->ncp + i1 + n1 * i2]; }
+        out3[c] = -s;   /* sign of rhs() = F_ext - F_int: the reference forms S = -sideForce / area (unittests/gsStaticSolver_test.cpp:323) */
+    }
+    free(ff);
+    return rc;
 }
