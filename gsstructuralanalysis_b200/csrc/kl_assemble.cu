@@ -374,7 +374,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 //      The F* flags say which inputs are present; absent ones are folded away at compile time (they are written as the
 //      additive identity -0.0 so that no multiplication by zero is ever emitted).  All flags true = a basis function.
 #define TZ(f, e) ((f) ? (e) : -0.0)
-template <bool HASB, bool F1, bool F2, bool F11, bool F22, bool F12, int SLOT = 5>
+template <bool HASB, bool F1, bool F2, bool F11, bool F22, bool F12>
 __device__ __forceinline__ void compute_Zc(const PointData& pd, double N1, double N2, double N11, double N22, double N12, double* Zo) {
     constexpr bool FG = F1 || F2;              // first derivatives present
     constexpr bool FS = F11 || F22 || F12;     // second derivatives present
@@ -422,7 +422,7 @@ __device__ __forceinline__ void compute_Zc(const PointData& pd, double N1, doubl
         const double en = TZ(FG, eta * n[dd]);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            double* z = Zo + (c * 3 + dd) * SLOT;
+            double* z = Zo + (c * 3 + dd) * 5;
             double z0 = TZ(FSIG, a1[c] * sig[0] + a2[c] * sig[2]) + n[c] * s1 + TZ(FG, -(en * c1[c]));
             double z1 = TZ(FSIG, a2[c] * sig[1] + a1[c] * sig[2]) + n[c] * s2 + TZ(FG, -(en * c2[c]));
             if (c == dd) {
@@ -434,29 +434,24 @@ __device__ __forceinline__ void compute_Zc(const PointData& pd, double N1, doubl
                 z0 += TZ(F2, -(N2 * eq));
                 z1 += TZ(F1, N1 * eq);
             }
+            z[0] = z0;
+            z[1] = z1;
             const double ng = TZ(FG, n[dd] * g[c]);
-            const double z2 = -(n[c] * mu[0]) + TZ(FG, Mt0 * ng);
-            const double z3 = -(n[c] * mu[1]) + TZ(FG, Mt1 * ng);
-            const double z4 = -(2.0 * n[c] * mu[2]) + TZ(FG, Mt2 * ng);
-            if (SLOT == 6) {   // 48-byte slots: two aligned 16-byte stores + one 8-byte store
-                reinterpret_cast<double2*>(z)[0] = make_double2(z0, z1);
-                reinterpret_cast<double2*>(z)[1] = make_double2(z2, z3);
-                z[4] = z4;
-            } else {
-                z[0] = z0; z[1] = z1; z[2] = z2; z[3] = z3; z[4] = z4;
-            }
+            z[2] = -(n[c] * mu[0]) + TZ(FG, Mt0 * ng);
+            z[3] = -(n[c] * mu[1]) + TZ(FG, Mt1 * ng);
+            z[4] = -(2.0 * n[c] * mu[2]) + TZ(FG, Mt2 * ng);
         }
     }
 }
 #undef TZ
 
 // Z_j of basis function j at point (q1,q2)
-template <int P, bool HASB, int SLOT = 5>
+template <int P, bool HASB>
 __device__ __forceinline__ void compute_Z(const PointData& pd, const BasisStage<P>& E, int q1, int q2, int j, double* Zo) {
     const int ja = j % (P + 1), jb = j / (P + 1);
     const double x0 = E.b1[q1][0][ja], x1 = E.b1[q1][1][ja], x2 = E.b1[q1][2][ja];
     const double y0 = E.b2[q2][0][jb], y1 = E.b2[q2][1][jb], y2 = E.b2[q2][2][jb];
-    compute_Zc<HASB, true, true, true, true, true, SLOT>(pd, x1 * y0, x0 * y1, x2 * y0, x0 * y2, x1 * y1, Zo);
+    compute_Zc<HASB, true, true, true, true, true>(pd, x1 * y0, x0 * y1, x2 * y0, x0 * y2, x1 * y1, Zo);
 }
 
 // ---- tile (ti2, tj) over one chunk (fixed q1): V_m^{cd} = sum_{q2} W_m^{cd}(q1,q2) first, then applied once with the
@@ -642,155 +637,6 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLD
 }
 
 
-
-// ================================================================================================
-// Column-entry mapping of the Jacobian kernel (k_jacobian_cd).  Phase 2 is the one of k_jacobian; in phase 3 a thread owns
-// ONE (c,d) entry of ONE column function j and accumulates it for ALL (P+1)^2 row functions i of the element:
-//   V_m^{i2} = sum_{q2} Y_m(i2,q2) Z_j^{cd}(q1,q2)   (5 FMA per i2 and point, 5 loaded coefficients feed 5(P+1) FMAs)
-//   acc[i2][i1] += X_m(i1,q1) V_m^{i2}                (once per column q1)
-// so every coefficient read from shared memory feeds P+1 FMAs instead of one (k_jacobian is bound by the shared-memory
-// pipe), the accumulators shrink from 36 to 16 doubles (more resident warps), and the whole 16x16 block of node pairs is
-// produced directly: no transposed scatter, all entries of a thread live in ONE matrix column at compile-time offsets.
-// The price is the lower triangle of node pairs that k_jacobian gets from symmetry (1.6x the phase-3 FMAs).
-#ifndef KL_CD_EPG
-#define KL_CD_EPG 1
-#endif
-#ifndef KL_CD_MINB
-#define KL_CD_MINB 3
-#endif
-template <int P>
-struct JacCdCfg {
-    static constexpr int NQ = P + 1;
-    static constexpr int NQ2 = NQ * NQ;
-    static constexpr int NLOC = (P + 1) * (P + 1);
-    static constexpr int EPG = KL_CD_EPG;                 // elements per CTA
-    static constexpr int NT = EPG * NLOC * 9;             // one thread per (element, column function, (c,d) entry)
-    static constexpr int MINB = (P == 3) ? KL_CD_MINB : 1;
-    static constexpr int SLOT = 6;                        // 5 coefficients of one (c,d) entry + 1 pad: 48-byte slots, 16-byte aligned
-    static constexpr int ZS = 9 * SLOT;
-};
-template <int P>
-struct JacCdShared {
-    using Cfg = JacCdCfg<P>;
-    BasisStage<P> stage[Cfg::EPG];
-    double Z[Cfg::EPG][Cfg::NQ][Cfg::NLOC][Cfg::ZS];
-    int4 cb[Cfg::EPG][Cfg::NLOC];
-    PointData pd[Cfg::EPG][Cfg::NQ];
-    unsigned long long bar;
-};
-
-template <int P, bool HASB>
-__global__ void __launch_bounds__(JacCdCfg<P>::NT, JacCdCfg<P>::MINB) k_jacobian_cd(KLDev d, int e2_begin, int e2_end) {
-    using Cfg = JacCdCfg<P>;
-    constexpr int NQ = Cfg::NQ, NQ2 = Cfg::NQ2, NLOC = Cfg::NLOC, EPG = Cfg::EPG, NT = Cfg::NT, SLOT = Cfg::SLOT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    JacCdShared<P>& S = *reinterpret_cast<JacCdShared<P>*>(smem_raw);
-    const int tid = threadIdx.x;
-    const int nel = d.nel1 * (e2_end - e2_begin);
-    const int ebase = blockIdx.x * EPG;
-
-    auto issue_pd = [&](int ch) {
-        mbar_expect_tx(&S.bar, (unsigned)(EPG * NQ * sizeof(PointData)));
-        for (int le = 0; le < EPG; ++le) {
-            int e = ebase + le;
-            if (e >= nel) e = nel - 1;
-            const size_t ge = (size_t)(e % d.nel1) + (size_t)d.nel1 * (e2_begin + e / d.nel1);
-            tma_bulk_g2s(&S.pd[le][0], d.pd + ge * NQ2 + (size_t)ch * NQ, (unsigned)(NQ * sizeof(PointData)), &S.bar);
-        }
-    };
-    if (tid == 0) mbar_init(&S.bar, 1);
-    __syncthreads();
-    if (tid == 0) issue_pd(0);
-    for (int le = 0; le < EPG; ++le) {
-        int e = ebase + le;
-        if (e >= nel) e = nel - 1;
-        stage_basis<P>(d, e % d.nel1, e2_begin + e / d.nel1, S.stage[le], tid, NT);
-    }
-    for (int k = tid; k < EPG * NLOC; k += NT) {
-        const int le = k / NLOC, l = k - le * NLOC;
-        int e = ebase + le;
-        if (e >= nel) e = nel - 1;
-        const int cpi = (d.span1[e % d.nel1] - P + l % (P + 1)) + d.n1 * (d.span2[e2_begin + e / d.nel1] - P + l / (P + 1));
-        S.cb[le][l] = reinterpret_cast<const int4*>(d.colbase)[cpi];
-    }
-    const int le_t = tid / (NLOC * 9), rt = tid - le_t * (NLOC * 9);
-    const int tj = rt / 9, cd = rt - tj * 9;
-    double acc[P + 1][P + 1];   // [i2][i1]
-#pragma unroll
-    for (int b = 0; b <= P; ++b)
-#pragma unroll
-        for (int a = 0; a <= P; ++a) acc[b][a] = 0.0;
-
-    for (int ch = 0; ch < NQ; ++ch) {
-        __syncthreads();                 // basis staged / previous column's Z consumed
-        mbar_wait(&S.bar, ch & 1);       // this column's per-point records have landed in shared memory
-        // ---- phase 2: Z_j at the NQ points of the column (fixed q1)
-        for (int k = tid; k < EPG * NQ * NLOC; k += NT) {
-            const int j = k % NLOC;
-            const int qc = (k / NLOC) % NQ;
-            const int le = k / (NLOC * NQ);
-            compute_Z<P, HASB, SLOT>(S.pd[le][qc], S.stage[le], ch, qc, j, S.Z[le][qc][j]);
-        }
-        __syncthreads();
-        if (tid == 0 && ch + 1 < NQ) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue_pd(ch + 1);
-        }
-        // ---- phase 3
-        const BasisStage<P>& E = S.stage[le_t];
-        double V0[P + 1], V1[P + 1], V2[P + 1];
-#pragma unroll
-        for (int b = 0; b <= P; ++b) { V0[b] = 0.0; V1[b] = 0.0; V2[b] = 0.0; }
-#pragma unroll
-        for (int qc = 0; qc < NQ; ++qc) {
-            const double* zp = &S.Z[le_t][qc][tj][cd * SLOT];
-            const double2 za = reinterpret_cast<const double2*>(zp)[0], zb = reinterpret_cast<const double2*>(zp)[1];
-            const double z1 = za.x, z2 = za.y, z11 = zb.x, z22 = zb.y, z12 = zp[4];
-#pragma unroll
-            for (int b = 0; b <= P; ++b) {
-                const double y0 = E.b2[qc][0][b], y1 = E.b2[qc][1][b], y2 = E.b2[qc][2][b];
-                V0[b] = fma(y2, z22, fma(y1, z2, V0[b]));    // multiplies N_{i1}(q1)
-                V1[b] = fma(y1, z12, fma(y0, z1, V1[b]));    // multiplies N'_{i1}(q1)
-                V2[b] = fma(y0, z11, V2[b]);                 // multiplies N''_{i1}(q1)
-            }
-        }
-#pragma unroll
-        for (int a = 0; a <= P; ++a) {
-            const double x0 = E.b1[ch][0][a], x1 = E.b1[ch][1][a], x2 = E.b1[ch][2][a];
-#pragma unroll
-            for (int b = 0; b <= P; ++b) acc[b][a] = fma(x2, V2[b], fma(x1, V1[b], fma(x0, V0[b], acc[b][a])));
-        }
-    }
-    // ---- scatter: entry (row (I,c), column (J,dd)) for all I of the element; one matrix column per thread
-    const int e = ebase + le_t;
-    if (e >= nel) return;
-    const int e1 = e % d.nel1, e2 = e2_begin + e / d.nel1;
-    const int c = cd / 3, dd = cd - 3 * c;
-    const int ja = tj % (P + 1), jb = tj / (P + 1);
-    const int NST = d.nst, W = 2 * P + 1;
-    double* __restrict__ val = d.values;
-    const int4 cbJ = S.cb[le_t][tj];
-    const int base = dd == 0 ? cbJ.x : (dd == 1 ? cbJ.y : cbJ.z);
-    if (cbJ.w) {
-        double* v0 = val + base + c * NST + (P - ja) + W * (P - jb);
-#pragma unroll
-        for (int b = 0; b <= P; ++b)
-#pragma unroll
-            for (int a = 0; a <= P; ++a) atomicAdd(v0 + a + W * b, acc[b][a]);
-    } else {
-        const int Jc = (d.span1[e1] - P + ja) + d.n1 * (d.span2[e2] - P + jb);
-        const int* __restrict__ pj = d.pos + (size_t)(Jc * 3 + dd) * (NST * 3) + c;
-#pragma unroll
-        for (int b = 0; b <= P; ++b)
-#pragma unroll
-            for (int a = 0; a <= P; ++a) {
-                const int st = (a - ja + P) + W * (b - jb + P);
-                const int pp = __ldg(pj + st * 3);
-                if (pp >= 0) atomicAdd(&val[pp], acc[b][a]);
-            }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // follower-pressure tangent  -p R_i dn_jd[c] = +p R_i n_d g_j[c]  (unsymmetric, full i x j loop; cheap)
 template <int P>
@@ -892,25 +738,11 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
         KL_CUDA(cudaFuncSetAttribute(k_jacobian<P, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         ctx->attr_done |= 2u;
     }
-    using CCfg = JacCdCfg<P>;
-    const size_t smem_cd = sizeof(JacCdShared<P>);
-    if (!(ctx->attr_done & 16u)) {
-        KL_CUDA(cudaFuncSetAttribute(k_jacobian_cd<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cd));
-        KL_CUDA(cudaFuncSetAttribute(k_jacobian_cd<P, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        KL_CUDA(cudaFuncSetAttribute(k_jacobian_cd<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cd));
-        KL_CUDA(cudaFuncSetAttribute(k_jacobian_cd<P, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        ctx->attr_done |= 16u;
-    }
-    static const int variant = getenv("KL_JAC") ? atoi(getenv("KL_JAC")) : 0;   // 0: k_jacobian (tiles), 1: k_jacobian_cd (column entries)
     const int grid = (nel + Cfg::EPG - 1) / Cfg::EPG;
-    const int grid_cd = (nel + CCfg::EPG - 1) / CCfg::EPG;
     // the membrane-bending coupling block B vanishes identically for the linear (SvK) law and for membranes
     const bool hasB = ctx->d.mat.material != KL_MAT_SVK && ctx->d.mat.bending;
     KL_CUDA(cudaEventRecord(ctx->ev[4], s));
-    if (variant == 1) {
-        if (hasB) k_jacobian_cd<P, true><<<grid_cd, CCfg::NT, smem_cd, s>>>(ctx->d, e2b, e2e);
-        else k_jacobian_cd<P, false><<<grid_cd, CCfg::NT, smem_cd, s>>>(ctx->d, e2b, e2e);
-    } else if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
+    if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     else k_jacobian<P, false><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     KL_CUDA(cudaEventRecord(ctx->ev[5], s));
     ctx->launches++;
