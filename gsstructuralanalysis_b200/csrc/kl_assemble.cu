@@ -328,7 +328,12 @@ struct JacCfg {
     static constexpr int EPG = (P == 2) ? 4 : 2;                        // elements per CTA
     static constexpr int NTILE = TILES * EPG;                           // threads that own a tile
     static constexpr int NTASK = EPG * NQ * NLOC;                       // phase-2 tasks per chunk
-    static constexpr int NT = NTILE;                                    // 72 / 80 / 150 (measured: more, smaller CTAs beat one task per thread)
+#ifndef KL_JAC_FULLWARPS
+#define KL_JAC_FULLWARPS 1
+#endif
+    // threads: the tiles rounded up to whole warps (96 / 96 / 160).  The extra lanes cost no registers (allocation is per
+    // warp) and take phase-2 tasks: 128 tasks run as 4 warp-rounds instead of 5 (measured: more, smaller CTAs beat one task per thread)
+    static constexpr int NT = KL_JAC_FULLWARPS ? (NTILE + 31) / 32 * 32 : NTILE;
     static constexpr int MINB = (P == 3) ? 4 : 1;
     static constexpr int QCH = NQ;                                      // points per chunk: fixed q1, all q2
     static constexpr int ZS = 46;                                       // 45 coefficients [cd][p] + 1 pad: stride = 28 banks mod 32
@@ -434,12 +439,11 @@ __device__ __forceinline__ void compute_Zc(const PointData& pd, double N1, doubl
                 z0 += TZ(F2, -(N2 * eq));
                 z1 += TZ(F1, N1 * eq);
             }
-            z[0] = z0;
-            z[1] = z1;
             const double ng = TZ(FG, n[dd] * g[c]);
-            z[2] = -(n[c] * mu[0]) + TZ(FG, Mt0 * ng);
-            z[3] = -(n[c] * mu[1]) + TZ(FG, Mt1 * ng);
-            z[4] = -(2.0 * n[c] * mu[2]) + TZ(FG, Mt2 * ng);
+            const double z2 = -(n[c] * mu[0]) + TZ(FG, Mt0 * ng);
+            const double z3 = -(n[c] * mu[1]) + TZ(FG, Mt1 * ng);
+            const double z4 = -(2.0 * n[c] * mu[2]) + TZ(FG, Mt2 * ng);
+            z[0] = z0; z[1] = z1; z[2] = z2; z[3] = z3; z[4] = z4;
         }
     }
 }
@@ -615,12 +619,22 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLD
         __syncthreads();   // basis staged / previous chunk's Z consumed
         mbar_wait(&S.bar, ch & 1);   // this chunk's per-point records have landed in shared memory
         // ---- phase 2: Z_j for the points of this chunk
-        if (!(KL_ABL(d) & 4))
-        for (int k = tid; k < EPG * QCH * NLOC; k += NT) {
-            const int j = k % NLOC;
-            const int qc = (k / NLOC) % QCH;
-            const int le = k / (NLOC * QCH);
-            compute_Z<P, HASB>(S.pd[le][qc], S.stage[le], ch, qc, j, S.Z[le][qc][j]);
+        if (!(KL_ABL(d) & 4)) {
+            constexpr int NTASKS = EPG * QCH * NLOC, NW = (NT + 31) / 32;
+            static_assert(NTASKS <= 2 * NT, "at most two phase-2 tasks per thread");
+            // one task per thread, the remaining NTASKS - NT go to the threads [shift, shift + NTASKS - NT): with
+            // KL_JAC_FULLWARPS == 2 that window starts at a different warp every column
+            const int shift = (KL_JAC_FULLWARPS == 2) ? 32 * (ch % NW) : 0;
+#pragma unroll 1
+            for (int r = 0; r < 2; ++r) {
+                int k = tid;
+                if (r) { const int x = tid - shift + (tid < shift ? NT : 0); k = NT + x; }
+                if (k >= NTASKS) continue;
+                const int j = k % NLOC;
+                const int qc = (k / NLOC) % QCH;
+                const int le = k / (NLOC * QCH);
+                compute_Z<P, HASB>(S.pd[le][qc], S.stage[le], ch, qc, j, S.Z[le][qc][j]);
+            }
         }
         __syncthreads();
         if (tid == 0 && ch + 1 < NQ2 / QCH) {
@@ -635,6 +649,7 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLD
     if (has_tile && e < nel && !(KL_ABL(d) & 1)) tile_scatter<P>(d, S.cb[le_t], e % d.nel1, e2_begin + e / d.nel1, ti2, tj, acc);
     if (KL_ABL(d) & 1) { double sink = 0; for (int a = 0; a <= P; ++a) for (int k = 0; k < 9; ++k) sink += acc[a][k]; if (sink == 1.2345e-300) d.values[0] = sink; }
 }
+
 
 
 // ------------------------------------------------------------------------------------------------
