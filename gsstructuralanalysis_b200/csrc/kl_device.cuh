@@ -325,7 +325,8 @@ struct PointData {
     double q[3];                                // (H - n Hn)/|a1 x a2|
     double acon[3];                             // a^11, a^22, a^12
     double wJ;                                  // weight * meas(ori)
-    double pad;                                 // odd stride -> fewer bank conflicts
+    double pad[3];                              // 58 doubles = 464 B: a multiple of 16 (TMA) with a stride of 20 banks mod 32, so the
+                                                // thread-strided 128-bit stores of k_points are conflict-free (56 doubles: 8-way conflicts)
 };
 static_assert(sizeof(PointData) % 8 == 0, "PointData must be a whole number of doubles");
 
