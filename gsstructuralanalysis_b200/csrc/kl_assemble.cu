@@ -325,7 +325,10 @@ struct JacCfg {
     static constexpr int NQ2 = NQ * NQ;
     static constexpr int NLOC = (P + 1) * (P + 1);
     static constexpr int TILES = (P + 1) * (P + 1) * (P + 2) / 2;      // (i2, j) with i2 <= j2
-    static constexpr int EPG = (P == 2) ? 4 : 2;                        // elements per CTA
+#ifndef KL_JAC_EPG
+#define KL_JAC_EPG 2
+#endif
+    static constexpr int EPG = (P == 2) ? 4 : (P == 3 ? KL_JAC_EPG : 2);  // elements per CTA
     static constexpr int NTILE = TILES * EPG;                           // threads that own a tile
     static constexpr int NTASK = EPG * NQ * NLOC;                       // phase-2 tasks per chunk
 #ifndef KL_JAC_FULLWARPS
@@ -334,7 +337,10 @@ struct JacCfg {
     // threads: the tiles rounded up to whole warps (96 / 96 / 160).  The extra lanes cost no registers (allocation is per
     // warp) and take phase-2 tasks: 128 tasks run as 4 warp-rounds instead of 5 (measured: more, smaller CTAs beat one task per thread)
     static constexpr int NT = KL_JAC_FULLWARPS ? (NTILE + 31) / 32 * 32 : NTILE;
-    static constexpr int MINB = (P == 3) ? 4 : 1;
+#ifndef KL_JAC_MINB
+#define KL_JAC_MINB 4
+#endif
+    static constexpr int MINB = (P == 3) ? KL_JAC_MINB : 1;
     static constexpr int QCH = NQ;                                      // points per chunk: fixed q1, all q2
     static constexpr int ZS = 46;                                       // 45 coefficients [cd][p] + 1 pad: stride = 28 banks mod 32
 };
@@ -563,7 +569,11 @@ __device__ __forceinline__ void tile_scatter(const KLDev& d, const int4* cb, int
 #define KL_ABL(d) 0
 #endif
 template <int P, bool HASB>
+#ifdef KL_JAC_MAXREG
+__global__ void __maxnreg__(KL_JAC_MAXREG) k_jacobian(KLDev d, int e2_begin, int e2_end) {
+#else
 __global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLDev d, int e2_begin, int e2_end) {
+#endif
     using Cfg = JacCfg<P>;
     constexpr int NQ = Cfg::NQ, NQ2 = Cfg::NQ2, NLOC = Cfg::NLOC, TILES = Cfg::TILES, EPG = Cfg::EPG, NT = Cfg::NT, QCH = Cfg::QCH;
     extern __shared__ __align__(16) unsigned char smem_raw[];
