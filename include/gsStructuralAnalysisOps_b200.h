@@ -17,6 +17,7 @@
 */
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -185,6 +186,30 @@ public:
         return [s](gsVector<T> const& x, const T lam, gsVector<T>& r) {
             r.resize(s->ndofs);
             return kl_al_residual(s->ctx, x.data(), lam, r.data()) == KL_OK;
+        };
+    }
+    /** Time-dependent signatures of the dynamic solvers (gsDynamicBase.h:294,330; TJacobian_t / TResidual_t / TForce_t,
+        gsStructuralAnalysisTypes.h:66-74,90).  The shell drivers of the reference ignore the time argument
+        (examples/example_DynamicShellNL.cpp:217-236: "to do: add time dependency of forcing"); so do these. */
+    Ops::TJacobian_t tJacobian() const {
+        Ops::Jacobian_t J = jacobian();
+        return [J](gsVector<T> const& x, const T /*time*/, gsSparseMatrix<T>& m) { return J(x, m); };
+    }
+    Ops::TResidual_t tResidual() const {
+        Ops::Residual_t R = residual();
+        return [R](gsVector<T> const& x, const T /*time*/, gsVector<T>& r) { return R(x, r); };
+    }
+    Ops::TForce_t tForce() const {
+        Ops::Force_t F = force();
+        return [F](const T /*time*/, gsVector<T>& f) { return F(f); };
+    }
+    /// C = 0 on the stiffness pattern: `C = gsSparseMatrix<>(numDofs, numDofs)` of examples/example_DynamicShellNL.cpp:251,255
+    Ops::Damping_t damping() const {
+        auto s = m_s;
+        return [s](gsVector<T> const&, gsSparseMatrix<T>& m) {
+            adoptPattern(m, s->ndofs, s->nnz, s->outer.data(), s->inner.data());
+            std::fill(m.valuePtr(), m.valuePtr() + s->nnz, T(0));
+            return true;
         };
     }
     /// M: assembler.assembleMass(); m = matrix()  (Mass_t, gsStructuralAnalysisTypes.h:77)
