@@ -188,7 +188,9 @@ static int build_tables(kl_ctx* ctx) {
                 wq[(size_t)e * nq + q] = 0.5 * (ub - ua) * wg[q];
             }
         }
-        const int* dspan; const double *dbas, *dwq;
+        const int* dspan; const double *dbas, *dwq, *dknots;
+        if (int rc = upload(ctx, &dknots, U.data(), U.size())) return rc;
+        if (dir == 0) d.knots1 = dknots; else d.knots2 = dknots;
         if (int rc = upload(ctx, &dspan, span.data(), span.size())) return rc;
         if (int rc = upload(ctx, &dbas, bas.data(), bas.size())) return rc;
         if (int rc = upload(ctx, &dwq, wq.data(), wq.size())) return rc;

@@ -34,6 +34,8 @@ struct KLDev {
     int rational;
     const int* span1;      // [nel1] knot span index per element
     const int* span2;
+    const double* knots1;  // knot vectors (point evaluation of the stress recovery)
+    const double* knots2;
     const double* bas1;    // [nel1][nq][3][p+1] values / 1st / 2nd derivative of the p+1 active functions
     const double* bas2;
     const double* wq1;     // [nel1][nq] quadrature weight * half element length

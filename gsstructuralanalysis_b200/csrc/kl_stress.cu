@@ -4,8 +4,9 @@
 //                            benchmark_Pillow.cpp:431,484-505)
 //   kl_principal_stretches  assembler->computePrincipalStretches(pts, mp_def, z)   (unittests/gsStaticSolver_test.cpp:317)
 //   kl_boundary_force       assembler->boundaryForce(mp_def, patchSide)            (unittests/gsStaticSolver_test.cpp:321)
-// Definitions of the quantities: include/kl_shell.h.  One thread per evaluation point; the 1-D basis functions of every
-// point are evaluated on the host (they do not depend on the state) and uploaded next to the knot spans.  All in-plane
+// Definitions of the quantities: include/kl_shell.h.  One thread per evaluation point: it finds its knot spans by bisection,
+// evaluates the 1-D basis functions and their first two derivatives (triangular Cox-de Boor table, as the host tables of
+// kl_capi.cu) and gathers its (p+1)^2 control points; only the parametric coordinates are uploaded.  All in-plane
 // tensors are handled in curvilinear components with closed-form 2x2 eigen-decompositions (the oracle goes through 3-D
 // tensors instead, oracle/kl_oracle.c: klo_eval_stress).
 #include <algorithm>
@@ -16,6 +17,55 @@ struct StressPoint {
     int s1, s2;
     double b1[3][KL_MAXP + 1], b2[3][KL_MAXP + 1];
 };
+
+// knot span of u: the last non-empty span whose first knot is <= u (span[] lists the non-empty spans in ascending order)
+__device__ __forceinline__ int find_span_dev(const double* __restrict__ U, const int* __restrict__ span, int nel, double u) {
+    int lo = 0, hi = nel - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (U[span[mid]] <= u) lo = mid; else hi = mid - 1;
+    }
+    return span[lo];
+}
+// values, first and second derivatives of the p+1 functions that are non-zero on span k (same recurrence as
+// bspline_span_ders in kl_capi.cu: T[m][q][j] = m-th derivative of the j-th function of degree q)
+__device__ __forceinline__ void span_ders_dev(const double* __restrict__ U, int p, int k, double u, double out[3][KL_MAXP + 1]) {
+    double T[3][KL_MAXP + 1][KL_MAXP + 1];
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int q = 0; q <= KL_MAXP; ++q)
+#pragma unroll
+            for (int j = 0; j <= KL_MAXP; ++j) T[m][q][j] = 0.0;
+    T[0][0][0] = 1.0;
+#pragma unroll
+    for (int q = 1; q <= KL_MAXP; ++q) {
+        if (q > p) break;
+#pragma unroll
+        for (int j = 0; j <= KL_MAXP; ++j) {
+            if (j > q) break;
+            const int i = k - q + j;
+            const double dl = U[i + q] - U[i], dr = U[i + q + 1] - U[i + 1];
+#pragma unroll
+            for (int m = 0; m <= 2; ++m) {
+                double v = 0.0;
+                if (m == 0) {
+                    if (j >= 1) v += (u - U[i]) / dl * T[0][q - 1][j - 1];
+                    if (j <= q - 1) v += (U[i + q + 1] - u) / dr * T[0][q - 1][j];
+                } else {
+                    if (j >= 1) v += T[m - 1][q - 1][j - 1] / dl;
+                    if (j <= q - 1) v -= T[m - 1][q - 1][j] / dr;
+                    v *= q;
+                }
+                T[m][q][j] = v;
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+        for (int j = 0; j <= KL_MAXP; ++j) out[m][j] = (j <= p) ? T[m][p < 1 ? 0 : p][j] : 0.0;
+}
 
 __host__ __device__ inline int stress_dim(int type) {
     switch (type) {
@@ -40,12 +90,19 @@ __device__ __forceinline__ void push2(const double S[3], double t11, double t12,
     out[2] = scale * (t22 * (t11 * S[2] + t12 * S[1]));
 }
 
-__global__ void __launch_bounds__(128) k_eval_stress(KLDev d, const StressPoint* __restrict__ pts, int npts, int type, double z,
+__global__ void __launch_bounds__(128) k_eval_stress(KLDev d, const double* __restrict__ uv, int npts, int type, double z,
                                                      double* __restrict__ out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= npts) return;
-    const StressPoint& sp = pts[k];
     const int p = d.p, dim = stress_dim(type);
+    StressPoint sp;
+    {
+        const double u = uv[2 * k], v = uv[2 * k + 1];
+        sp.s1 = find_span_dev(d.knots1, d.span1, d.nel1, u);
+        sp.s2 = find_span_dev(d.knots2, d.span2, d.nel2, v);
+        span_ders_dev(d.knots1, p, sp.s1, u, sp.b1);
+        span_ders_dev(d.knots2, p, sp.s2, v, sp.b2);
+    }
     double* res = out + (size_t)dim * k;
     // geometry: fo[m][c] (weighted if rational), fw[m], fu[m][c];  m = (val, d1, d2, d11, d22, d12)
     double fo[6][3] = {}, fu[6][3] = {}, fw[6] = {};
@@ -242,31 +299,19 @@ extern "C" int kl_eval_stress(kl_ctx* ctx, const double* x_host, int32_t type, i
     if (n_pts == 0) return KL_OK;
     KL_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
-    const int p = ctx->d.p;
-    // knot span and 1-D basis functions of every point (state independent)
-    std::vector<StressPoint> pts((size_t)n_pts);
+    // only the domain check happens on the host; spans and basis functions are evaluated by the kernel
     for (int k = 0; k < n_pts; ++k)
         for (int dir = 0; dir < 2; ++dir) {
-            const std::vector<double>& U = ctx->U[dir];
-            const std::vector<int>& span = ctx->span[dir];
             const double u = uv_host[2 * k + dir];
-            if (!(u >= U.front() && u <= U.back())) { kl_set_error("kl_eval_stress: point outside the parametric domain"); return KL_E_ARG; }
-            // last element whose first knot is <= u
-            int lo = 0, hi = (int)span.size() - 1;
-            while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (U[span[mid]] <= u) lo = mid; else hi = mid - 1; }
-            double ders[3][KL_MAXP + 1];
-            bspline_span_ders(U, p, span[lo], u, ders);
-            StressPoint& sp = pts[k];
-            (dir == 0 ? sp.s1 : sp.s2) = span[lo];
-            std::memcpy(dir == 0 ? sp.b1 : sp.b2, ders, sizeof(ders));
+            if (!(u >= ctx->U[dir].front() && u <= ctx->U[dir].back())) { kl_set_error("kl_eval_stress: point outside the parametric domain"); return KL_E_ARG; }
         }
-    StressPoint* d_pts = nullptr;
+    double* d_pts = nullptr;
     double* d_out = nullptr;
-    KL_CUDA(cudaMalloc((void**)&d_pts, sizeof(StressPoint) * (size_t)n_pts));
+    KL_CUDA(cudaMalloc((void**)&d_pts, sizeof(double) * 2 * (size_t)n_pts));
     if (cudaMalloc((void**)&d_out, sizeof(double) * (size_t)n_pts * dim) != cudaSuccess) { cudaFree(d_pts); kl_set_error("kl_eval_stress: cudaMalloc"); return KL_E_CUDA; }
     int rc = KL_OK;
     do {
-        if (cudaMemcpyAsync(d_pts, pts.data(), sizeof(StressPoint) * (size_t)n_pts, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = KL_E_CUDA; break; }
+        if (cudaMemcpyAsync(d_pts, uv_host, sizeof(double) * 2 * (size_t)n_pts, cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = KL_E_CUDA; break; }
         if ((rc = upload_state(ctx, x_host, s))) break;
         k_eval_stress<<<(n_pts + 127) / 128, 128, 0, s>>>(ctx->d, d_pts, n_pts, type, z, d_out);
         ctx->launches++;

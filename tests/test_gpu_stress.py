@@ -153,3 +153,29 @@ def test_gpu_homogeneous_states_known_answers():
     fe = asm.boundaryForce(x, EAST)
     sig, area = mu * (1.69 - 1 / 1.69), pr.thickness / 1.3
     assert abs(-fe[0] - sig * area) < 1e-11 * sig * area
+
+
+def test_paraview_sized_sampling():
+    """A 1000 x 1000 sampling grid (what gsWriteParaview(field, name, 1000) asks for, benchmarks/benchmark_Balloon.cpp:388) is one
+    kernel launch: spans and basis functions are evaluated on the device.  Checked against the oracle at a random subset."""
+    import time
+    from gsstructuralanalysis_b200.ops import ShellAssembler
+    from oracle.binding import Oracle
+    name, pr, amp = _problems()[1]
+    if pr.dof_map is None:
+        pr.number_dofs(capi.lib().kl_build_dofmap)
+    asm, orc = ShellAssembler(pr, device=0), Oracle(pr)
+    rng = np.random.default_rng(2)
+    x = _state(pr, asm.n_dofs, amp, rng)
+    g = np.linspace(0.0, 0.97, 1000)
+    uv = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, 2)
+    t0 = time.perf_counter()
+    sig = asm.eval_stress(x, "membrane", uv)
+    lam = asm.eval_stress(x, "principal_stretch", uv)
+    dt = time.perf_counter() - t0
+    assert sig.shape == (1000000, 3) and np.isfinite(sig).all() and np.isfinite(lam).all()
+    pick = rng.choice(len(uv), 64, replace=False)
+    so, lo = orc.eval_stress(x, "membrane", uv[pick]), orc.eval_stress(x, "principal_stretch", uv[pick])
+    assert np.abs(sig[pick] - so).max() <= 1e-11 * np.abs(so).max()
+    assert np.abs(lam[pick] - lo).max() <= 1e-12
+    print(f"2 x 1e6 evaluation points in {dt * 1e3:.1f} ms (host call, incl. PCIe)")
