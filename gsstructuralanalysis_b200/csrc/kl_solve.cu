@@ -104,7 +104,7 @@ __global__ void k_spmv_tables(int ncp, int nfree, int nst, int W, const int* __r
 }
 
 template <int P, bool DOT>
-__global__ void __launch_bounds__(CG_THREADS) k_spmv_reg(const int* __restrict__ outer, const int* __restrict__ inner, const double* __restrict__ val,
+__global__ void __launch_bounds__(CG_THREADS, 4) k_spmv_reg(const int* __restrict__ outer, const int* __restrict__ inner, const double* __restrict__ val,
                                                          const int* __restrict__ colinfo, const int* __restrict__ runbase,
                                                          const double* __restrict__ x, double* __restrict__ y, int n, double* __restrict__ part,
                                                          const CGState* __restrict__ st) {
@@ -115,37 +115,88 @@ __global__ void __launch_bounds__(CG_THREADS) k_spmv_reg(const int* __restrict__
     const int warp = blockIdx.x * (CG_THREADS / 32) + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * (CG_THREADS / 32);
     double dot = 0.0;
-    for (int col = warp; col < n; col += nwarps) {
-        const int b = outer[col];
-        const int J = colinfo[col];
-        double s0 = 0.0, s1 = 0.0;
-        if (J >= 0) {
-            const int* rb = runbase + (size_t)J * 3 * W;
+    // two columns per trip: the 2 x 5 value loads and x gathers of both are in flight together (the kernel is bound by
+    // memory latency: one column per trip left the HBM pipe at 38 % of its peak)
+    constexpr int NM = (NE + 31) / 32;
+    // column start and control-point index of the next trip are fetched one trip ahead (first level of the dependent chain
+    // outer / colinfo -> run table -> x)
+    int nb0 = 0, nb1 = 0, nJ0 = -1, nJ1 = -1;
+    if (warp < n) { nb0 = outer[warp]; nJ0 = colinfo[warp]; }
+    if (warp + nwarps < n) { nb1 = outer[warp + nwarps]; nJ1 = colinfo[warp + nwarps]; }
+    for (int col0 = warp; col0 < n; col0 += 2 * nwarps) {
+        const int col1 = col0 + nwarps;
+        const bool two = col1 < n;
+        const int b0 = nb0, b1 = nb1, J0 = nJ0, J1 = two ? nJ1 : -1;
+        {
+            const int c2 = col0 + 2 * nwarps, c3 = col1 + 2 * nwarps;
+            if (c2 < n) { nb0 = outer[c2]; nJ0 = colinfo[c2]; }
+            if (c3 < n) { nb1 = outer[c3]; nJ1 = colinfo[c3]; }
+        }
+        double s[2] = {0.0, 0.0};
+        if (J0 >= 0 && J1 >= 0) {
+            const int* rb0 = runbase + (size_t)J0 * 3 * W;
+            const int* rb1 = runbase + (size_t)J1 * 3 * W;
+            double v0[NM], v1[NM], x0[NM], x1[NM];
 #pragma unroll
-            for (int m = 0; m < (NE + 31) / 32; ++m) {
+            for (int m = 0; m < NM; ++m) {
                 const int e = lane + 32 * m;
+                v0[m] = 0.0; v1[m] = 0.0; x0[m] = 0.0; x1[m] = 0.0;
                 if (e < NE) {
                     const int run = e / W, k = e - run * W;      // run = c*W + di2
-                    const double v = val[b + e];
-                    const int row = rb[run] + k;
-                    if (m & 1) s1 = fma(v, x[row], s1); else s0 = fma(v, x[row], s0);
+                    v0[m] = val[b0 + e];
+                    v1[m] = val[b1 + e];
+                    x0[m] = x[rb0[run] + k];
+                    x1[m] = x[rb1[run] + k];
                 }
             }
-        } else {
-            const int e = outer[col + 1];
-            int k = b + lane;
-            for (; k + 32 < e; k += 64) {
-                const double v0 = val[k], v1 = val[k + 32];
-                const int i0 = inner[k], i1 = inner[k + 32];
-                s0 = fma(v0, x[i0], s0);
-                s1 = fma(v1, x[i1], s1);
+            double a0 = 0.0, a1 = 0.0, c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                if (m & 1) { a1 = fma(v0[m], x0[m], a1); c1 = fma(v1[m], x1[m], c1); }
+                else { a0 = fma(v0[m], x0[m], a0); c0 = fma(v1[m], x1[m], c0); }
             }
-            if (k < e) s0 = fma(val[k], x[inner[k]], s0);
+            s[0] = a0 + a1; s[1] = c0 + c1;
+        } else {
+#pragma unroll 1
+            for (int t = 0; t < 2; ++t) {
+                const int col = t ? col1 : col0;
+                if (t && !two) break;
+                const int b = t ? b1 : b0, J = t ? J1 : J0;
+                double s0 = 0.0, s1 = 0.0;
+                if (J >= 0) {
+                    const int* rb = runbase + (size_t)J * 3 * W;
+#pragma unroll
+                    for (int m = 0; m < NM; ++m) {
+                        const int e = lane + 32 * m;
+                        if (e < NE) {
+                            const int run = e / W, k = e - run * W;
+                            const double v = val[b + e];
+                            const int row = rb[run] + k;
+                            if (m & 1) s1 = fma(v, x[row], s1); else s0 = fma(v, x[row], s0);
+                        }
+                    }
+                } else {
+                    const int e = outer[col + 1];
+                    int k = b + lane;
+                    for (; k + 32 < e; k += 64) {
+                        const double v0 = val[k], v1 = val[k + 32];
+                        const int i0 = inner[k], i1 = inner[k + 32];
+                        s0 = fma(v0, x[i0], s0);
+                        s1 = fma(v1, x[i1], s1);
+                    }
+                    if (k < e) s0 = fma(val[k], x[inner[k]], s0);
+                }
+                s[t] = s0 + s1;
+            }
         }
-        const double s = warp_sum(s0 + s1);
+        const double r0 = warp_sum(s[0]), r1 = warp_sum(s[1]);
         if (lane == 0) {
-            y[col] = s;
-            if (DOT) dot = fma(s, x[col], dot);
+            y[col0] = r0;
+            if (DOT) dot = fma(r0, x[col0], dot);
+            if (two) {
+                y[col1] = r1;
+                if (DOT) dot = fma(r1, x[col1], dot);
+            }
         }
     }
     if (DOT) {
@@ -296,7 +347,9 @@ static int ws_get(kl_ctx* ctx, KLSolveWS** out) {
     const int want = (n + CG_THREADS - 1) / CG_THREADS;
     w->nb = want < nsm * 4 ? (want > 0 ? want : 1) : nsm * 4;
     const int wantw = (n + CG_THREADS / 32 - 1) / (CG_THREADS / 32);
-    w->nb_spmv = wantw < nsm * 8 ? (wantw > 0 ? wantw : 1) : nsm * 8;
+    // grid-stride kernel: launch exactly the blocks that are resident at once (4 per SM, __launch_bounds__ of k_spmv_reg); the
+    // former 8 per SM ran a partial second wave at a third of the occupancy
+    w->nb_spmv = wantw < nsm * 4 ? (wantw > 0 ? wantw : 1) : nsm * 4;
     const size_t vb = sizeof(double) * (size_t)(n > 0 ? n : 1);
     double** vecs[] = {&w->p, &w->tmp, &w->z, &w->r, &w->x, &w->invdiag, &w->b, &w->nU, &w->nDU, &w->ndU, &w->nR, &w->nX};
     for (double** v : vecs) KL_CUDA(cudaMalloc((void**)v, vb));
