@@ -127,3 +127,34 @@ def test_solid_no_cpu_fallback(L):
     with pytest.raises(KLError) as ei:
         S.SolidAssembler(S.SolidProblem(S.brick(nels=(2, 1, 1)), S.SolidBC()))
     assert ei.value.rc == -6
+
+
+def test_headers_are_plain_c_and_link(tmp_path):
+    """The boundary is a C ABI: both headers compile as C99 (-pedantic) and a C program links against libkl_shell.so and
+    calls the entry points that need no GPU (kl_stress_dim, kl_build_dofmap, kl_create refusing without a device)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "kl_shell.h"
+#include "ks_solid.h"
+int main(void) {
+    kl_bc bc;
+    int32_t map[3 * 4 * 4], nf = 0, nx = 0;
+    memset(&bc, 0, sizeof bc);
+    bc.side[KL_WEST][0] = KL_BC_DIRICHLET;
+    if (kl_build_dofmap(4, 4, &bc, map, &nf, &nx) != KL_OK) return 2;
+    if (nf + nx != 48 || nx != 4) return 3;
+    if (kl_stress_dim(KL_STRESS_PRINCIPAL_STRETCH_DIR) != 9 || kl_stress_dim(KL_STRESS_NTYPES) != 0) return 4;
+    printf("C ABI ok: %d free, %d eliminated\n", (int)nf, (int)nx);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "gsstructuralanalysis_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L" + libdir, "-l:libkl_shell.so", "-Wl,-rpath," + libdir])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "C ABI ok" in r.stdout
