@@ -357,7 +357,8 @@ def main():
     roofline = {"kernel": "k_jacobian<3>", "bound": "fp64", "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak.value, "traffic": traffic, "kernel_ms": jac_kernel_ms, "flops_per_qp": fpq,
                 "note": "FP64 flops are the binding roofline of the fused assembly (13.4 kflop vs 224 B per point); ncu shows the "
-                        "kernel limited by the LSU data pipe (84 % of peak) with the FP64 pipe 41 % busy - DESIGN.md section 5",
+                        "kernel limited by the L1/LSU pipe (87 % of peak) with the FP64 pipe 38 % busy, and its time follows the number "
+                        "of resident CTAs (profiles/r1_s2_jacobian_summary.txt, profiles/r1_ablation.txt) - DESIGN.md sections 5 and 8",
                 "hbm": {"algorithmic_bytes": bytes_alg, "bytes_per_qp": bytes_alg / nqp,
                         "achieved": bytes_alg / (jac_kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_alg / (jac_kernel_ms * 1e-3) / 1e9 / hbm_peak},
