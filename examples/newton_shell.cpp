@@ -133,7 +133,8 @@ int main(int argc, char** argv) {
     double dr = 0;
     for (index_t i = 0; i < n; ++i) dr = std::max(dr, std::fabs(Rt[i] - Rs[i]));
     gsSparseMatrix<> Cd;
-    if (!assembler->damping()(U, Cd) || Cd.rows() != n || dr != 0.0) { std::printf("DYNAMIC_OPS failed\n"); return 1; }
+    // the assembly accumulates with atomics: two calls agree to rounding, not bit for bit
+    if (!assembler->damping()(U, Cd) || Cd.rows() != n || dr > 1e-12 * (Rs.norm() + 1.0)) { std::printf("DYNAMIC_OPS failed\n"); return 1; }
     std::printf("STRETCHES %.12e %.12e %.12e  WEST_FORCE %.6e %.6e %.6e  MEMBRANE %.6e %.6e %.6e\n", lambdas[0], lambdas[1],
                 lambdas[2], fw[0], fw[1], fw[2], sigma[0], sigma[1], sigma[2]);
     return status == gsStatus::Success ? 0 : 1;
