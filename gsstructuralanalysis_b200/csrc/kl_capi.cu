@@ -493,6 +493,20 @@ static int ensure_registered(kl_ctx* ctx, void* p, size_t bytes) {
     return 0;
 }
 
+// page-locked (cudaMallocHost / cudaHostRegister'ed) caller memory is copied from / to directly; pageable memory goes through
+// the context's pinned staging buffers
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost) return true;
+    cudaGetLastError();
+    return false;
+}
+static const double* stage_x(kl_ctx* ctx, const double* x_host, int n) {
+    if (host_is_pinned(x_host)) return x_host;
+    std::memcpy(ctx->h_pinned_x, x_host, sizeof(double) * n);
+    return ctx->h_pinned_x;
+}
+
 static int run_residual(kl_ctx* ctx, const double* x_host, double lam_fext, double sign_fint, double* r_host) {
     if (!ctx || !r_host) { kl_set_error("null argument"); return KL_E_ARG; }
     KL_CUDA(cudaSetDevice(ctx->device));
@@ -501,18 +515,18 @@ static int run_residual(kl_ctx* ctx, const double* x_host, double lam_fext, doub
     KL_CUDA(cudaEventRecord(ctx->ev[0], s));
     const double* xd = nullptr;
     if (x_host) {
-        std::memcpy(ctx->h_pinned_x, x_host, sizeof(double) * n);
-        KL_CUDA(cudaMemcpyAsync(ctx->d_x, ctx->h_pinned_x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        KL_CUDA(cudaMemcpyAsync(ctx->d_x, stage_x(ctx, x_host, n), sizeof(double) * n, cudaMemcpyHostToDevice, s));
         xd = ctx->d_x;
     }
     KL_CUDA(cudaEventRecord(ctx->ev[1], s));
     int rc = kl_residual_device(ctx, xd, lam_fext, sign_fint, ctx->d_r, s);
     if (rc) return rc;
     KL_CUDA(cudaEventRecord(ctx->ev[2], s));
-    KL_CUDA(cudaMemcpyAsync(ctx->h_pinned_r, ctx->d_r, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    const bool direct = host_is_pinned(r_host);
+    KL_CUDA(cudaMemcpyAsync(direct ? r_host : ctx->h_pinned_r, ctx->d_r, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     KL_CUDA(cudaEventRecord(ctx->ev[3], s));
     rc = kl_check(ctx, s);
-    std::memcpy(r_host, ctx->h_pinned_r, sizeof(double) * n);
+    if (!direct) std::memcpy(r_host, ctx->h_pinned_r, sizeof(double) * n);
     cudaEventElapsedTime(&ctx->ms_h2d, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->ms_kernel, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->ms_d2h, ctx->ev[2], ctx->ev[3]);
@@ -552,8 +566,7 @@ extern "C" int kl_jacobian(kl_ctx* ctx, const double* x_host, double* values_hos
     KL_CUDA(cudaEventRecord(ctx->ev[0], s));
     const double* xd = nullptr;
     if (x_host) {
-        std::memcpy(ctx->h_pinned_x, x_host, sizeof(double) * n);
-        KL_CUDA(cudaMemcpyAsync(ctx->d_x, ctx->h_pinned_x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        KL_CUDA(cudaMemcpyAsync(ctx->d_x, stage_x(ctx, x_host, n), sizeof(double) * n, cudaMemcpyHostToDevice, s));
         xd = ctx->d_x;
     }
     KL_CUDA(cudaEventRecord(ctx->ev[1], s));

@@ -80,10 +80,12 @@ class ShellAssembler:
         outer, inner = self.pattern()
         return True, SparseView(self.n_dofs, outer, inner, v[:self.nnz])
 
-    def residual(self, x):
-        """constructSolution; assembleVector(def); v = rhs()   (= F_ext - F_int)."""
+    def residual(self, x, out=None):
+        """constructSolution; assembleVector(def); v = rhs()   (= F_ext - F_int).  `out`: the caller's result vector (the
+        reference fills a gsVector the solver owns); page-locked memory is written by the D2H copy directly."""
         x = np.ascontiguousarray(x, dtype=np.float64)
-        r = np.zeros(self.n_dofs)
+        r = np.zeros(self.n_dofs) if out is None else out
+        assert r.shape == (self.n_dofs,) and r.dtype == np.float64 and r.flags.c_contiguous
         rc = self.L.kl_residual(self.h, _dp(x), _dp(r))
         if rc != 0:
             self.last_error = self.L.kl_last_error().decode()
