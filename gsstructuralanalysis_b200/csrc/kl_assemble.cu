@@ -11,6 +11,7 @@
 //            K_ij^{cd} += sum_p d_i[p] Z_j^{p,cd}, sum-factorised over the tensor-product basis
 //   scatter  FP64 RED (atomicAdd, no return) into the compressed values through the position table,
 //            both (i,j) and the transposed (j,i) entry.
+#include <cstddef>
 #include <cstdlib>
 #include "kl_device.cuh"
 
@@ -75,30 +76,54 @@ __global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_points(KLDev d, int e2_b
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(out)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    if (WITH_RES && active) {
-        // one thread per local basis function: integrate over the element's points (same integrand as k_residual)
-        const int a = lq % (P + 1), b = lq / (P + 1);
-        double f[3] = {0, 0, 0};
+    if (WITH_RES) {
+        // internal force, sum-factorised: f_(a,b),c = sum_q2 [ y0 T0_c + y1 T1_c + y2 T2_c ](a,q2) with
+        //   T0_c = sum_q1 (x1 N0) a1_c + (x1 N2) a2_c + (x1 Ha1 - x2 Mt0 - x0 p wJ) n_c
+        //   T1_c = sum_q1 (x0 N2) a1_c + (x0 N1) a2_c + (x0 Ha2 - x1 Mt2) n_c          T2_c = sum_q1 (-x0 Mt1) n_c
+        // (x, y: 1-D values / derivatives in the two directions).  Stage A: thread (a, q2) sums over q1; stage B: thread (a, b) over
+        // q2.  137 instead of 368 shared-memory accesses per thread; the partial sums live where the control points were staged.
         const ElemStage<P>& E = stage[le];
-#pragma unroll
-        for (int q2 = 0; q2 < NQ; ++q2)
+        double* T = &stage[le].w1[0];
+        static_assert(offsetof(ElemStage<P>, scratch) + sizeof(E.scratch) - offsetof(ElemStage<P>, w1) >= sizeof(double) * 9 * NQ2,
+                      "partial sums must fit the dead part of the staging area");
+        {
+            const int a = lq % (P + 1), q2 = lq / (P + 1);
+            double T0[3] = {0, 0, 0}, T1[3] = {0, 0, 0}, T2[3] = {0, 0, 0};
 #pragma unroll
             for (int q1 = 0; q1 < NQ; ++q1) {
                 const PointData& pd = out[le * NQ2 + q2 + NQ * q1];
                 const double x0 = E.b1[q1][0][a], x1 = E.b1[q1][1][a], x2 = E.b1[q1][2][a];
-                const double y0 = E.b2[q2][0][b], y1 = E.b2[q2][1][b], y2 = E.b2[q2][2][b];
-                const double R = x0 * y0, R1 = x1 * y0, R2 = x0 * y1, R11 = x2 * y0, R22 = x0 * y2, R12 = x1 * y1;
-                const double mb = R11 * pd.Mt[0] + R22 * pd.Mt[1] + R12 * pd.Mt[2];
-                const double cn = R1 * pd.Ha1 + R2 * pd.Ha2 - mb - R * d.mat.pressure * pd.wJ;      // coefficient of n_c
-                const double c1 = R1 * pd.N[0] + R2 * pd.N[2], c2 = R2 * pd.N[1] + R1 * pd.N[2];     // of a1_c, a2_c
+                const double s0a1 = x1 * pd.N[0], s0a2 = x1 * pd.N[2], s0n = x1 * pd.Ha1 - x2 * pd.Mt[0] - x0 * d.mat.pressure * pd.wJ;
+                const double s1a1 = x0 * pd.N[2], s1a2 = x0 * pd.N[1], s1n = x0 * pd.Ha2 - x1 * pd.Mt[2];
+                const double s2n = -(x0 * pd.Mt[1]);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) f[c] += c1 * pd.a1[c] + c2 * pd.a2[c] + cn * pd.n[c];
+                for (int c = 0; c < 3; ++c) {
+                    T0[c] += s0a1 * pd.a1[c] + s0a2 * pd.a2[c] + s0n * pd.n[c];
+                    T1[c] += s1a1 * pd.a1[c] + s1a2 * pd.a2[c] + s1n * pd.n[c];
+                    T2[c] += s2n * pd.n[c];
+                }
             }
-        const int cpi = (d.span1[e1] - P + a) + d.n1 * (d.span2[e2] - P + b);
+            double* t = T + 9 * lq;     // [q2][a][9]
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int g = d.map[c * d.ncp + cpi];
-            if (g < d.nfree) atomicAdd(&r[g], f[c]);
+            for (int c = 0; c < 3; ++c) { t[c] = T0[c]; t[3 + c] = T1[c]; t[6 + c] = T2[c]; }
+        }
+        __syncthreads();
+        if (active) {
+            const int a = lq % (P + 1), b = lq / (P + 1);
+            double f[3] = {0, 0, 0};
+#pragma unroll
+            for (int q2 = 0; q2 < NQ; ++q2) {
+                const double y0 = E.b2[q2][0][b], y1 = E.b2[q2][1][b], y2 = E.b2[q2][2][b];
+                const double* t = T + 9 * (q2 * (P + 1) + a);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) f[c] += y0 * t[c] + y1 * t[3 + c] + y2 * t[6 + c];
+            }
+            const int cpi = (d.span1[e1] - P + a) + d.n1 * (d.span2[e2] - P + b);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const int g = d.map[c * d.ncp + cpi];
+                if (g < d.nfree) atomicAdd(&r[g], f[c]);
+            }
         }
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must stay valid until the engine has read it

@@ -29,6 +29,8 @@ struct ElemStage {
     double X[NLOC][3];         // undeformed control points (times weight if rational)
     double U[NLOC][3];         // displacement control points
     double Wt[NLOC];           // weights (rational geometry only)
+    double scratch[2 * P * (P + 1)];   // with w1..Wt (dead after the point evaluation) 9 (P+1)^2 doubles: the partial sums of the
+                                       // sum-factorised internal force (k_points<P, true>)
 };
 
 // cooperative load of one element's staging data by (P+1)^2 threads with lane id `t` (one control point per thread).
