@@ -182,23 +182,38 @@ __global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_residual(KLDev d, double
         }
     }
     __syncthreads();
-    // one thread per local basis function: integrate over the element's points
+    // sum-factorised integration (as in k_points<P, true>): stage A, thread (a, q2): sums over q1; stage B, thread (a, b): over q2
+    const ElemStage<P>& E = stage[le];
+    double* T = &stage[le].w1[0];     // dead part of the staging area: 9 (P+1)^2 doubles
+    {
+        const int a = lq % (P + 1), q2 = lq / (P + 1);
+        double T0[3] = {0, 0, 0}, T1[3] = {0, 0, 0}, T2[3] = {0, 0, 0};
+#pragma unroll
+        for (int q1 = 0; q1 < NQ; ++q1) {
+            const ResPoint& o = rp[le][q1 + NQ * q2];
+            const double x0 = E.b1[q1][0][a], x1 = E.b1[q1][1][a], x2 = E.b1[q1][2][a];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                T0[c] += x1 * o.q1[c] + x2 * o.nM[0][c] + x0 * o.pn[c];     // multiplies N_b(q2)
+                T1[c] += x0 * o.q2[c] + x1 * o.nM[2][c];                    // multiplies N_b'(q2)
+                T2[c] += x0 * o.nM[1][c];                                   // multiplies N_b''(q2)
+            }
+        }
+        double* t = T + 9 * lq;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { t[c] = T0[c]; t[3 + c] = T1[c]; t[6 + c] = T2[c]; }
+    }
+    __syncthreads();
     if (active) {
         const int a = lq % (P + 1), b = lq / (P + 1);
         double f[3] = {0, 0, 0};
-        const ElemStage<P>& E = stage[le];
 #pragma unroll
-        for (int q2 = 0; q2 < NQ; ++q2)
+        for (int q2 = 0; q2 < NQ; ++q2) {
+            const double y0 = E.b2[q2][0][b], y1 = E.b2[q2][1][b], y2 = E.b2[q2][2][b];
+            const double* t = T + 9 * (q2 * (P + 1) + a);
 #pragma unroll
-            for (int q1 = 0; q1 < NQ; ++q1) {
-                const ResPoint& o = rp[le][q1 + NQ * q2];
-                const double x0 = E.b1[q1][0][a], x1 = E.b1[q1][1][a], x2 = E.b1[q1][2][a];
-                const double y0 = E.b2[q2][0][b], y1 = E.b2[q2][1][b], y2 = E.b2[q2][2][b];
-                const double R = x0 * y0, R1 = x1 * y0, R2 = x0 * y1, R11 = x2 * y0, R22 = x0 * y2, R12 = x1 * y1;
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    f[c] += R1 * o.q1[c] + R2 * o.q2[c] + R11 * o.nM[0][c] + R22 * o.nM[1][c] + R12 * o.nM[2][c] + R * o.pn[c];
-            }
+            for (int c = 0; c < 3; ++c) f[c] += y0 * t[c] + y1 * t[3 + c] + y2 * t[6 + c];
+        }
         const int cpi = (d.span1[e1] - P + a) + d.n1 * (d.span2[e2] - P + b);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
