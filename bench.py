@@ -100,7 +100,25 @@ class ClockSampler:
     def __init__(self, index):
         self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
 
+    def _nvml(self):
+        """In-process NVML polling (about 200 samples per second): several samples fall inside a 70 ms timed region."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = (0x8, 0x40, 0x20, 0x4)      # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        while not self._stop.is_set():
+            sm, r = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), reasons(h)
+            self.samples.append([str(sm), str(mx), "0"] + ["Active" if r & b else "Not Active" for b in bits])
+            self._stop.wait(0.005)
+
     def _run(self):
+        try:
+            self._nvml()
+            return
+        except Exception:       # no NVML binding: fall back to polling nvidia-smi
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
