@@ -12,7 +12,7 @@
 /* ------------------------------------------------------------------------------------ */
 /* B-spline basis: Piegl & Tiller, The NURBS Book, A2.1 (FindSpan) and A2.3 (DersBasisFuns)
  * = what gsBSplineBasis::evalAllDers_into computes (values, 1st, 2nd derivatives).       */
-static int find_span(int n, int p, double u, const double* U) {
+static __attribute__((unused)) int find_span(int n, int p, double u, const double* U) {
     /* n = number of basis functions */
     if (u >= U[n]) {
         int s = n - 1;
