@@ -205,6 +205,101 @@ __global__ void __launch_bounds__(CG_THREADS, 4) k_spmv_reg(const int* __restric
     }
 }
 
+// EXPERIMENT (KL_SPMV_CP=1; not the production path).  Control-point form of the regular-column SpMV: the three columns
+// (J,0), (J,1), (J,2) of one control point share their row set, so one warp trip gathers x once and streams the three value
+// columns against it.  Motivation: ncu of k_spmv_reg shows the L1/LSU pipe at 92 % of its peak with HBM at 57 %
+// (profiles/r1_spmv_summary.txt).  Result on B200 at 1M DOF: correct (tests/test_gpu_solve.py green) but slower, 0.330 ms
+// against 0.284 ms; the three value streams of a trip lie a third of the matrix apart.  Columns that are not regular
+// (colinfo < 0: clipped stencils, coupled DoFs) are swept by a second, generic pass of the same launch.
+template <int P, bool DOT>
+__global__ void __launch_bounds__(CG_THREADS, 4) k_spmv_cp(const int* __restrict__ outer, const int* __restrict__ inner, const double* __restrict__ val,
+                                                        const int* __restrict__ colinfo, const int* __restrict__ runbase,
+                                                        const int* __restrict__ map, int ncp,
+                                                        const double* __restrict__ x, double* __restrict__ y, int n, double* __restrict__ part,
+                                                        const CGState* __restrict__ st) {
+    constexpr int W = 2 * P + 1, NST = W * W, NE = 3 * NST, NM = (NE + 31) / 32;
+    __shared__ double sm[CG_THREADS / 32];
+    if (st && st->done) return;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (CG_THREADS / 32) + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * (CG_THREADS / 32);
+    double dot = 0.0;
+    // pass A: regular columns, one control point per trip; column ids and starts of the next trip are fetched one trip ahead
+    int nc0 = -1, nc1 = -1, nc2 = -1, nb0 = 0, nb1 = 0, nb2 = 0;
+#define KL_CP_FETCH(J)                                                          \
+    {                                                                           \
+        const int c0 = map[(J)], c1 = map[ncp + (J)], c2 = map[2 * ncp + (J)];   \
+        nc0 = (c0 < n && colinfo[c0] == (J)) ? c0 : -1;                          \
+        nc1 = (c1 < n && colinfo[c1] == (J)) ? c1 : -1;                          \
+        nc2 = (c2 < n && colinfo[c2] == (J)) ? c2 : -1;                          \
+        nb0 = nc0 >= 0 ? outer[nc0] : 0;                                         \
+        nb1 = nc1 >= 0 ? outer[nc1] : 0;                                         \
+        nb2 = nc2 >= 0 ? outer[nc2] : 0;                                         \
+    }
+    if (warp < ncp) KL_CP_FETCH(warp)
+    for (int J = warp; J < ncp; J += nwarps) {
+        const int c0 = nc0, c1 = nc1, c2 = nc2, b0 = nb0, b1 = nb1, b2 = nb2;
+        if (J + nwarps < ncp) KL_CP_FETCH(J + nwarps)
+        if (c0 < 0 && c1 < 0 && c2 < 0) continue;
+        const int* rb = runbase + (size_t)J * 3 * W;
+        double v0[NM], v1[NM], v2[NM], xx[NM];
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            const int e = lane + 32 * m;
+            v0[m] = 0.0; v1[m] = 0.0; v2[m] = 0.0; xx[m] = 0.0;
+            if (e < NE) {
+                const int run = e / W, k = e - run * W;      // run = c*W + di2
+                if (c0 >= 0) v0[m] = val[b0 + e];
+                if (c1 >= 0) v1[m] = val[b1 + e];
+                if (c2 >= 0) v2[m] = val[b2 + e];
+                xx[m] = x[rb[run] + k];
+            }
+        }
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            s0 = fma(v0[m], xx[m], s0);
+            s1 = fma(v1[m], xx[m], s1);
+            s2 = fma(v2[m], xx[m], s2);
+        }
+        const double r0 = warp_sum(s0), r1 = warp_sum(s1), r2 = warp_sum(s2);
+        if (lane == 0) {
+            if (c0 >= 0) { y[c0] = r0; if (DOT) dot = fma(r0, x[c0], dot); }
+            if (c1 >= 0) { y[c1] = r1; if (DOT) dot = fma(r1, x[c1], dot); }
+            if (c2 >= 0) { y[c2] = r2; if (DOT) dot = fma(r2, x[c2], dot); }
+        }
+    }
+#undef KL_CP_FETCH
+    // pass B: the remaining columns through the row-index array; 32 column flags per warp load
+    for (int cbase = warp * 32; cbase < n; cbase += nwarps * 32) {
+        const int cmine = cbase + lane;
+        unsigned todo = __ballot_sync(0xffffffffu, cmine < n && colinfo[cmine] < 0);
+        while (todo) {
+            const int col = cbase + __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int b = outer[col], e = outer[col + 1];
+            double s0 = 0.0, s1 = 0.0;
+            int k = b + lane;
+            for (; k + 32 < e; k += 64) {
+                const double a0 = val[k], a1 = val[k + 32];
+                const int i0 = inner[k], i1 = inner[k + 32];
+                s0 = fma(a0, x[i0], s0);
+                s1 = fma(a1, x[i1], s1);
+            }
+            if (k < e) s0 = fma(val[k], x[inner[k]], s0);
+            const double r = warp_sum(s0 + s1);
+            if (lane == 0) {
+                y[col] = r;
+                if (DOT) dot = fma(r, x[col], dot);
+            }
+        }
+    }
+    if (DOT) {
+        const double t = block_sum(dot, sm);
+        if (threadIdx.x == 0) part[blockIdx.x] = t;
+    }
+}
+
 // 1 / diagonal (1 where it is zero or absent) — Eigen::DiagonalPreconditioner
 __global__ void k_cg_invdiag(const int* __restrict__ outer, const int* __restrict__ inner, const double* __restrict__ val, double* __restrict__ invdiag, int n) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,7 +492,17 @@ void kl_solve_free(kl_ctx* ctx) {
 template <bool DOT>
 static int launch_spmv(kl_ctx* ctx, KLSolveWS* w, const double* x, double* y, double* part, const CGState* st, cudaStream_t s) {
     const KLDev& d = ctx->d;
-    if (w->colinfo) {
+    // experiment, off by default: measured slower than k_spmv_reg (SpMV 0.330 vs 0.284 ms, CG iteration 0.484 vs 0.329 ms at
+    // 1M DOF, profiles/r1_ablation.txt)
+    static const bool by_cp = getenv("KL_SPMV_CP") != nullptr;
+    if (w->colinfo && by_cp) {
+        switch (d.p) {
+            case 2: k_spmv_cp<2, DOT><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, w->colinfo, w->runbase, d.map, d.ncp, x, y, w->n, part, st); break;
+            case 3: k_spmv_cp<3, DOT><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, w->colinfo, w->runbase, d.map, d.ncp, x, y, w->n, part, st); break;
+            case 4: k_spmv_cp<4, DOT><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, w->colinfo, w->runbase, d.map, d.ncp, x, y, w->n, part, st); break;
+            default: kl_set_error("unsupported degree"); return KL_E_ARG;
+        }
+    } else if (w->colinfo) {
         switch (d.p) {
             case 2: k_spmv_reg<2, DOT><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, w->colinfo, w->runbase, x, y, w->n, part, st); break;
             case 3: k_spmv_reg<3, DOT><<<w->nb_spmv, CG_THREADS, 0, s>>>(d.outer, d.inner, d.values, w->colinfo, w->runbase, x, y, w->n, part, st); break;
