@@ -24,6 +24,6 @@ for _ in range(8):
 spmv = min(samples)
 x, it, err = asm.cg_solve(f, tol=1e-30, max_iter=iters)
 t = asm.cg_last_timing()
-bytes_alg = 8 * asm.nnz + 4 * asm.nnz + 3 * 8 * n
+bytes_alg = 8 * asm.nnz + 3 * 8 * n      # values + x, y, dot operand; regular columns do not read the row-index array
 print(json.dumps({"n_dofs": n, "nnz": asm.nnz, "spmv_ms": spmv, "spmv_GBps": bytes_alg / spmv / 1e6, "spmv_samples_ms": samples, "cg_iters": it,
                   "cg_iter_ms": t["iter_ms"], "cg_total_ms": t["total_ms"], "rel_err": err}))
