@@ -11,6 +11,7 @@
 //            K_ij^{cd} += sum_p d_i[p] Z_j^{p,cd}, sum-factorised over the tensor-product basis
 //   scatter  FP64 RED (atomicAdd, no return) into the compressed values through the position table,
 //            both (i,j) and the transposed (j,i) entry.
+#include <algorithm>
 #include <cstddef>
 #include <cstdlib>
 #include "kl_device.cuh"
@@ -703,6 +704,212 @@ __global__ void __launch_bounds__(JacCfg<P>::NT, JacCfg<P>::MINB) k_jacobian(KLD
 
 
 // ------------------------------------------------------------------------------------------------
+// Jacobian, register-resident sliding-window kernel (P = 3).
+//
+// One CTA = 64 threads walks a segment of consecutive elements of ONE element row e2 along direction 1.  Thread
+// (column function j = (b, b2), lane q2) evaluates Z_j = T . d_j at the four points (q1, q2), q1 = 0..3, itself — Z never
+// touches shared memory — keeps only the component pairs c <= d (K^{cd}_{ij} = K^{dc}_{ji}), contracts with the second-direction
+// factors of all four row positions i2, and a 4-lane shuffle reduce-scatter over q2 leaves lane i2 with V_m(i2) of its
+// column function.  The first-direction factors are applied at once into 24 accumulators acc[a][cd] = K[(a, i2), j][cd].
+// Walking along direction 1 the accumulators stay in registers while an (I, J) node pair is still inside the support of
+// later elements of the row (the local index a shifts down by one per element; the column function of a thread advances
+// by p+1 when it leaves the support), so every pair is written once per element ROW: 1008 RED per element instead of 2304,
+// with compile-time shuffles instead of the 846 LDS.128 wavefronts per column of the shared-memory kernel.
+template <bool HASB>
+__device__ __forceinline__ void sw_point(const PointData& pd, double N1, double N2, double N11, double N22, double N12,
+                                         const double (&yk)[4][3], const double (&xa)[3][4], double (&acc)[4][6]) {
+    double n[3], a1[3], a2[3], c1[3], c2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { n[c] = pd.n[c]; a1[c] = pd.a1[c]; a2[c] = pd.a2[c]; c1[c] = pd.c1[c]; c2[c] = pd.c2[c]; }
+    double g[3], hh[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = N1 * c1[c] + N2 * c2[c];
+    const double G1[3] = {pd.G1[0], pd.G1[1], pd.G1[2]}, G2[3] = {pd.G2[0], pd.G2[1], pd.G2[2]};
+    hh[0] = N11 - G1[0] * N1 - G2[0] * N2;
+    hh[1] = N22 - G1[1] * N1 - G2[1] * N2;
+    hh[2] = 2.0 * (N12 - G1[2] * N1 - G2[2] * N2);
+    double AE1[3], AE2[3], BE1[3], BE2[3], Bh[3], Dh[3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        AE1[v] = N1 * pd.A[sidx(v, 0)] + N2 * pd.A[sidx(v, 2)];
+        AE2[v] = N2 * pd.A[sidx(v, 1)] + N1 * pd.A[sidx(v, 2)];
+        if (HASB) {
+            BE1[v] = N1 * pd.B[sidx(v, 0)] + N2 * pd.B[sidx(v, 2)];
+            BE2[v] = N2 * pd.B[sidx(v, 1)] + N1 * pd.B[sidx(v, 2)];
+            Bh[v] = pd.B[sidx(v, 0)] * hh[0] + pd.B[sidx(v, 1)] * hh[1] + pd.B[sidx(v, 2)] * hh[2];
+        }
+        Dh[v] = pd.D[sidx(v, 0)] * hh[0] + pd.D[sidx(v, 1)] * hh[1] + pd.D[sidx(v, 2)] * hh[2];
+    }
+    const double Mt0 = pd.Mt[0], Mt1 = pd.Mt[1], Mt2 = pd.Mt[2];
+    const double Nhat = Mt0 * N11 + Mt1 * N22 + Mt2 * N12;
+    const double Ha1 = pd.Ha1, Ha2 = pd.Ha2, Hn = pd.Hn;
+    const double eta = Ha1 * N1 + Ha2 * N2;
+    const double p1 = pd.N[0] * N1 + pd.N[2] * N2, p2 = pd.N[1] * N2 + pd.N[2] * N1;
+    const double ga1 = pd.acon[0] * N1 + pd.acon[2] * N2, ga2 = pd.acon[2] * N1 + pd.acon[1] * N2;
+    const double q[3] = {pd.q[0], pd.q[1], pd.q[2]};
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) {
+        double sig[3], mu[3];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            sig[v] = AE1[v] * a1[dd] + AE2[v] * a2[dd];
+            if (HASB) sig[v] -= n[dd] * Bh[v];
+            mu[v] = -(n[dd] * Dh[v]);
+            if (HASB) mu[v] += BE1[v] * a1[dd] + BE2[v] * a2[dd];
+        }
+        const double s1 = G1[0] * mu[0] + G1[1] * mu[1] + 2.0 * G1[2] * mu[2] + Nhat * c1[dd] - Ha1 * g[dd] + Hn * n[dd] * ga1;
+        const double s2 = G2[0] * mu[0] + G2[1] * mu[1] + 2.0 * G2[2] * mu[2] + Nhat * c2[dd] - Ha2 * g[dd] + Hn * n[dd] * ga2;
+        const double en = eta * n[dd];
+#pragma unroll
+        for (int c = 0; c <= dd; ++c) {
+            double z0 = a1[c] * sig[0] + a2[c] * sig[2] + n[c] * s1 - en * c1[c];
+            double z1 = a2[c] * sig[1] + a1[c] * sig[2] + n[c] * s2 - en * c2[c];
+            if (c == dd) {
+                z0 += p1;
+                z1 += p2;
+            } else {
+                const double eq = ((c + 1) % 3 == dd) ? q[(c + 2) % 3] : -q[(dd + 2) % 3];   // epsilon_{c dd k} q_k
+                z0 -= N2 * eq;
+                z1 += N1 * eq;
+            }
+            const double ng = n[dd] * g[c];
+            const double z2 = Mt0 * ng - n[c] * mu[0];     // multiplies N_i,11
+            const double z3 = Mt1 * ng - n[c] * mu[1];     // N_i,22
+            const double z4 = Mt2 * ng - 2.0 * n[c] * mu[2];   // N_i,12
+            // second-direction contraction for the four row positions (slot s = i2 ^ lane) and reduce-scatter over the q2 lanes:
+            //   w0 multiplies N_{i1}(q1), w1 N'_{i1}(q1), w2 N''_{i1}(q1)
+            double r0, r1, r2, t0, t1, t2;
+            r0 = fma(yk[3][2], z3, yk[3][1] * z1); r1 = fma(yk[3][1], z4, yk[3][0] * z0); r2 = yk[3][0] * z2;
+            r0 = __shfl_xor_sync(0xffffffffu, r0, 2); r1 = __shfl_xor_sync(0xffffffffu, r1, 2); r2 = __shfl_xor_sync(0xffffffffu, r2, 2);
+            r0 = fma(yk[1][2], z3, fma(yk[1][1], z1, r0)); r1 = fma(yk[1][1], z4, fma(yk[1][0], z0, r1)); r2 = fma(yk[1][0], z2, r2);
+            r0 = __shfl_xor_sync(0xffffffffu, r0, 1); r1 = __shfl_xor_sync(0xffffffffu, r1, 1); r2 = __shfl_xor_sync(0xffffffffu, r2, 1);
+            t0 = fma(yk[2][2], z3, yk[2][1] * z1); t1 = fma(yk[2][1], z4, yk[2][0] * z0); t2 = yk[2][0] * z2;
+            t0 = __shfl_xor_sync(0xffffffffu, t0, 2); t1 = __shfl_xor_sync(0xffffffffu, t1, 2); t2 = __shfl_xor_sync(0xffffffffu, t2, 2);
+            const double V0 = fma(yk[0][2], z3, fma(yk[0][1], z1, t0)) + r0;
+            const double V1 = fma(yk[0][1], z4, fma(yk[0][0], z0, t1)) + r1;
+            const double V2 = fma(yk[0][0], z2, t2) + r2;
+            const int k = dd * (dd + 1) / 2 + c;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[a][k] = fma(xa[2][a], V2, fma(xa[1][a], V1, fma(xa[0][a], V0, acc[a][k])));
+        }
+    }
+}
+
+#ifndef KL_SW_MINB
+#define KL_SW_MINB 6
+#endif
+template <bool HASB>
+__global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_begin, int e2_end, int seg_len) {
+    constexpr int P = 3, NQ2 = 16, NB = 48, W = 7, NST = 49, S3 = 147;
+    __shared__ __align__(128) PointData s_pd[2][NQ2];
+    __shared__ __align__(16) double s_b1[2][NB];        // [q1][m][a] of the element
+    __shared__ unsigned long long s_bar[2];
+    const int tid = threadIdx.x;
+    const int nrows = e2_end - e2_begin;
+    const int row = blockIdx.x % nrows, seg = blockIdx.x / nrows;     // consecutive CTAs take consecutive element rows of one segment column
+    const int e2 = e2_begin + row;
+    const int e1_begin = seg * seg_len, e1_end = min(d.nel1, e1_begin + seg_len);
+    const int q2 = tid & 3, jcls = (tid >> 2) & 3, b2 = tid >> 4, i2 = q2;
+    const int j0 = __ldg(&d.span2[e2]) - P;
+
+    auto issue = [&](int e1, int s) {
+        mbar_expect_tx(&s_bar[s], (unsigned)(NQ2 * sizeof(PointData) + NB * sizeof(double)));
+        tma_bulk_g2s(&s_pd[s][0], d.pd + ((size_t)e1 + (size_t)d.nel1 * e2) * NQ2, (unsigned)(NQ2 * sizeof(PointData)), &s_bar[s]);
+        tma_bulk_g2s(&s_b1[s][0], d.bas1 + (size_t)e1 * NB, (unsigned)(NB * sizeof(double)), &s_bar[s]);
+    };
+    if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+    __syncthreads();
+    if (tid == 0) {
+        issue(e1_begin, 0);
+        if (e1_begin + 1 < e1_end) issue(e1_begin + 1, 1);
+    }
+    // second-direction factors of this thread: of its column function (b2) and of the four row positions, ordered by
+    // reduce-scatter slot (slot s <-> i2 = lane ^ s); constant along the walk
+    const double* g2 = d.bas2 + (size_t)e2 * NB;
+    double yj[3], yk[4][3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        yj[m] = __ldg(&g2[(q2 * 3 + m) * 4 + b2]);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) yk[s][m] = __ldg(&g2[(q2 * 3 + m) * 4 + (q2 ^ s)]);
+    }
+    double acc[4][6];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[a][k] = 0.0;
+    int i0 = __ldg(&d.span1[e1_begin]) - P;
+    int b = (jcls - i0) & 3;          // local index of this thread's column function in the current element
+    bool live = false;                // the accumulators hold contributions of the current column function
+    double* __restrict__ val = d.values;
+
+    for (int e1 = e1_begin; e1 < e1_end; ++e1) {
+        const int le = e1 - e1_begin, s = le & 1;
+        const int i0n = (e1 + 1 < e1_end) ? __ldg(&d.span1[e1 + 1]) - P : i0 + P + 1;
+        mbar_wait(&s_bar[s], (le >> 1) & 1);
+#pragma unroll 1
+        for (int q1 = 0; q1 < 4; ++q1) {
+            const double* xb = &s_b1[s][q1 * 12];
+            double xa[3][4];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const double2 u = *reinterpret_cast<const double2*>(xb + 4 * m), v = *reinterpret_cast<const double2*>(xb + 4 * m + 2);
+                xa[m][0] = u.x; xa[m][1] = u.y; xa[m][2] = v.x; xa[m][3] = v.y;
+            }
+            const double x0 = xb[b], x1 = xb[4 + b], x2 = xb[8 + b];
+            sw_point<HASB>(s_pd[s][q1 * 4 + q2], x1 * yj[0], x0 * yj[1], x2 * yj[0], x0 * yj[2], x1 * yj[1], yk, xa, acc);
+        }
+        live = true;
+        __syncthreads();               // every thread is done with buffer s
+        if (tid == 0 && e1 + 2 < e1_end) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(e1 + 2, s);
+        }
+        // ---- window step: row functions I1 < i0n and column functions J1 < i0n have received their last contribution of this row
+        for (int st = i0; st < i0n; ++st) {
+            const int J1 = st + b, J2 = j0 + b2, I2 = j0 + i2;
+            const int Jc = J1 + d.n1 * J2;
+            if (live) {
+                const int4 cbJ = __ldg(reinterpret_cast<const int4*>(d.colbase) + Jc);
+                const int baseJ[3] = {cbJ.x, cbJ.y, cbJ.z};
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    if ((a != 0 && b != 0) || st + a > i0 + P) continue;     // slots beyond the element's support are empty
+                    const int I1 = st + a, Ic = I1 + d.n1 * I2;
+                    const int st_ij = (a - b + P) + W * (i2 - b2 + P), st_ji = NST - 1 - st_ij;
+                    const int4 cbI = __ldg(reinterpret_cast<const int4*>(d.colbase) + Ic);
+                    const int baseI[3] = {cbI.x, cbI.y, cbI.z};
+#pragma unroll
+                    for (int dd = 0; dd < 3; ++dd)
+#pragma unroll
+                        for (int c = 0; c <= dd; ++c) {
+                            const double v = acc[a][dd * (dd + 1) / 2 + c];
+                            const int p1 = cbJ.w ? baseJ[dd] + c * NST + st_ij : __ldg(&d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c]);
+                            if (p1 >= 0) atomicAdd(&val[p1], v);            // entry (row (I,c), col (J,dd))
+                            if (c < dd) {
+                                const int p2 = cbI.w ? baseI[c] + dd * NST + st_ji : __ldg(&d.pos[(size_t)(Ic * 3 + c) * S3 + st_ji * 3 + dd]);
+                                if (p2 >= 0) atomicAdd(&val[p2], v);        // entry (row (J,dd), col (I,c))
+                            }
+                        }
+                }
+            }
+            // shift the window by one function
+            const bool wrap = (b == 0);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                acc[0][k] = wrap ? 0.0 : acc[1][k];
+                acc[1][k] = wrap ? 0.0 : acc[2][k];
+                acc[2][k] = wrap ? 0.0 : acc[3][k];
+                acc[3][k] = 0.0;
+            }
+            if (wrap) live = false;
+            b = (b - 1) & 3;
+        }
+        i0 = i0n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // follower-pressure tangent  -p R_i dn_jd[c] = +p R_i n_d g_j[c]  (unsymmetric, full i x j loop; cheap)
 template <int P>
 __global__ void __launch_bounds__(256) k_pressure_tangent(KLDev d, int e2_begin, int e2_end) {
@@ -807,7 +1014,17 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     // the membrane-bending coupling block B vanishes identically for the linear (SvK) law and for membranes
     const bool hasB = ctx->d.mat.material != KL_MAT_SVK && ctx->d.mat.bending;
     KL_CUDA(cudaEventRecord(ctx->ev[4], s));
-    if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
+    if (P == 3 && !ctx->jac_shared) {
+        // sliding-window kernel: segments of element rows, sized for >= ~8 waves of resident CTAs
+        int seg = ctx->jac_seg;
+        if (seg <= 0) {
+            const long long slots = (long long)ctx->n_sm * KL_SW_MINB * 8;
+            seg = (int)std::min<long long>(64, std::max<long long>(8, ((long long)nel + slots - 1) / slots));
+        }
+        const int nseg = (ctx->d.nel1 + seg - 1) / seg;
+        if (hasB) k_jacobian_sw<true><<<(e2e - e2b) * nseg, 64, 0, s>>>(ctx->d, e2b, e2e, seg);
+        else k_jacobian_sw<false><<<(e2e - e2b) * nseg, 64, 0, s>>>(ctx->d, e2b, e2e, seg);
+    } else if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     else k_jacobian<P, false><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     KL_CUDA(cudaEventRecord(ctx->ev[5], s));
     ctx->launches++;

@@ -364,6 +364,9 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     m.pressure = P->pressure;
     ctx->e2_begin = 0; ctx->e2_end = d.nel2;
     d.ablate = getenv("KL_ABLATE") ? atoi(getenv("KL_ABLATE")) : 0;
+    KL_CUDA_CTX(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+    ctx->jac_shared = getenv("KL_JAC_SHARED") ? atoi(getenv("KL_JAC_SHARED")) : 0;
+    ctx->jac_seg = getenv("KL_SW_SEG") ? atoi(getenv("KL_SW_SEG")) : 0;
     if ((rc = kl_build_pattern(ctx))) { kl_destroy(ctx); return rc; }
     if ((rc = build_fext(ctx, P))) { kl_destroy(ctx); return rc; }
     if ((rc = build_d2h_plan(ctx, P))) { kl_destroy(ctx); return rc; }

@@ -84,6 +84,8 @@ struct kl_ctx {
     int launches = 0;
     unsigned attr_done = 0;          // per-context (= per-device) cudaFuncSetAttribute bookkeeping, bit per kernel family
     int n_sm = 0;
+    int jac_shared = 0;              // env KL_JAC_SHARED=1: the shared-memory tile kernel k_jacobian instead of k_jacobian_sw (A/B, P = 3)
+    int jac_seg = 0;                 // env KL_SW_SEG: elements per segment of k_jacobian_sw (0 = automatic)
     int n_strips_d2h = 16;           // pipelined D2H granularity (measured 8 / 16 / 32: e2e 23.32 / 23.05 / 23.07 ms per step)
     struct D2HStrip { int e2_begin, e2_end; std::vector<std::pair<size_t, size_t>> ranges; };   // value ranges complete after the strip
     std::vector<D2HStrip> d2h_plan;
