@@ -745,7 +745,7 @@ __device__ __forceinline__ void sw_point(const PointData& pd, double N1, double 
     const double Ha1 = pd.Ha1, Ha2 = pd.Ha2, Hn = pd.Hn;
     const double eta = Ha1 * N1 + Ha2 * N2;
     const double p1 = pd.N[0] * N1 + pd.N[2] * N2, p2 = pd.N[1] * N2 + pd.N[2] * N1;
-    const double ga1 = pd.acon[0] * N1 + pd.acon[2] * N2, ga2 = pd.acon[2] * N1 + pd.acon[1] * N2;
+    const double hg1 = Hn * (pd.acon[0] * N1 + pd.acon[2] * N2), hg2 = Hn * (pd.acon[2] * N1 + pd.acon[1] * N2);
     const double q[3] = {pd.q[0], pd.q[1], pd.q[2]};
 #pragma unroll
     for (int dd = 0; dd < 3; ++dd) {
@@ -757,8 +757,9 @@ __device__ __forceinline__ void sw_point(const PointData& pd, double N1, double 
             mu[v] = -(n[dd] * Dh[v]);
             if (HASB) mu[v] += BE1[v] * a1[dd] + BE2[v] * a2[dd];
         }
-        const double s1 = G1[0] * mu[0] + G1[1] * mu[1] + 2.0 * G1[2] * mu[2] + Nhat * c1[dd] - Ha1 * g[dd] + Hn * n[dd] * ga1;
-        const double s2 = G2[0] * mu[0] + G2[1] * mu[1] + 2.0 * G2[2] * mu[2] + Nhat * c2[dd] - Ha2 * g[dd] + Hn * n[dd] * ga2;
+        const double mu2 = mu[2] + mu[2];
+        const double s1 = fma(G1[0], mu[0], fma(G1[1], mu[1], fma(G1[2], mu2, fma(Nhat, c1[dd], fma(hg1, n[dd], -(Ha1 * g[dd]))))));
+        const double s2 = fma(G2[0], mu[0], fma(G2[1], mu[1], fma(G2[2], mu2, fma(Nhat, c2[dd], fma(hg2, n[dd], -(Ha2 * g[dd]))))));
         const double en = eta * n[dd];
 #pragma unroll
         for (int c = 0; c <= dd; ++c) {
@@ -775,16 +776,16 @@ __device__ __forceinline__ void sw_point(const PointData& pd, double N1, double 
             const double ng = n[dd] * g[c];
             const double z2 = Mt0 * ng - n[c] * mu[0];     // multiplies N_i,11
             const double z3 = Mt1 * ng - n[c] * mu[1];     // N_i,22
-            const double z4 = Mt2 * ng - 2.0 * n[c] * mu[2];   // N_i,12
+            const double z4 = Mt2 * ng - n[c] * mu2;           // N_i,12
             // second-direction contraction for the four row positions (slot s = i2 ^ lane) and reduce-scatter over the q2 lanes:
             //   w0 multiplies N_{i1}(q1), w1 N'_{i1}(q1), w2 N''_{i1}(q1)
             double r0, r1, r2, t0, t1, t2;
             r0 = fma(yk[3][2], z3, yk[3][1] * z1); r1 = fma(yk[3][1], z4, yk[3][0] * z0); r2 = yk[3][0] * z2;
-            r0 = __shfl_xor_sync(0xffffffffu, r0, 2); r1 = __shfl_xor_sync(0xffffffffu, r1, 2); r2 = __shfl_xor_sync(0xffffffffu, r2, 2);
+            r0 = __shfl_xor_sync(0xffffffffu, r0, 16); r1 = __shfl_xor_sync(0xffffffffu, r1, 16); r2 = __shfl_xor_sync(0xffffffffu, r2, 16);
             r0 = fma(yk[1][2], z3, fma(yk[1][1], z1, r0)); r1 = fma(yk[1][1], z4, fma(yk[1][0], z0, r1)); r2 = fma(yk[1][0], z2, r2);
-            r0 = __shfl_xor_sync(0xffffffffu, r0, 1); r1 = __shfl_xor_sync(0xffffffffu, r1, 1); r2 = __shfl_xor_sync(0xffffffffu, r2, 1);
+            r0 = __shfl_xor_sync(0xffffffffu, r0, 8); r1 = __shfl_xor_sync(0xffffffffu, r1, 8); r2 = __shfl_xor_sync(0xffffffffu, r2, 8);
             t0 = fma(yk[2][2], z3, yk[2][1] * z1); t1 = fma(yk[2][1], z4, yk[2][0] * z0); t2 = yk[2][0] * z2;
-            t0 = __shfl_xor_sync(0xffffffffu, t0, 2); t1 = __shfl_xor_sync(0xffffffffu, t1, 2); t2 = __shfl_xor_sync(0xffffffffu, t2, 2);
+            t0 = __shfl_xor_sync(0xffffffffu, t0, 16); t1 = __shfl_xor_sync(0xffffffffu, t1, 16); t2 = __shfl_xor_sync(0xffffffffu, t2, 16);
             const double V0 = fma(yk[0][2], z3, fma(yk[0][1], z1, t0)) + r0;
             const double V1 = fma(yk[0][1], z4, fma(yk[0][0], z0, t1)) + r1;
             const double V2 = fma(yk[0][0], z2, t2) + r2;
@@ -798,24 +799,65 @@ __device__ __forceinline__ void sw_point(const PointData& pd, double N1, double 
 #ifndef KL_SW_MINB
 #define KL_SW_MINB 6
 #endif
+// flush one window slot: the 3x3 component block (c <= d computed; c < d also written transposed) of node pair (I, J).
+// cbJ / cbI = colbase of the two control points; regular columns are addressed arithmetically.
+__device__ __forceinline__ void sw_flush_slot(const KLDev& d, double* __restrict__ val, const double (&v)[6], const int4 cbJ, const int4 cbI,
+                                              int Ic, int Jc, int st_ij) {
+    constexpr int NST = 49, S3 = 147;
+    const int st_ji = NST - 1 - st_ij;
+    if (cbJ.w & cbI.w) {
+        double* pj0 = val + (cbJ.x + st_ij);
+        double* pj1 = val + (cbJ.y + st_ij);
+        double* pj2 = val + (cbJ.z + st_ij);
+        double* pi0 = val + (cbI.x + st_ji);
+        double* pi1 = val + (cbI.y + st_ji);
+        atomicAdd(pj0, v[0]);                                              // (c,d) = (0,0)
+        atomicAdd(pj1, v[1]); atomicAdd(pi0 + NST, v[1]);                  // (0,1) and its transpose: row (J,1), col (I,0)
+        atomicAdd(pj1 + NST, v[2]);                                        // (1,1)
+        atomicAdd(pj2, v[3]); atomicAdd(pi0 + 2 * NST, v[3]);              // (0,2)
+        atomicAdd(pj2 + NST, v[4]); atomicAdd(pi1 + 2 * NST, v[4]);        // (1,2)
+        atomicAdd(pj2 + 2 * NST, v[5]);                                    // (2,2)
+    } else {
+#pragma unroll
+        for (int dd = 0; dd < 3; ++dd)
+#pragma unroll
+            for (int c = 0; c <= dd; ++c) {
+                const double x = v[dd * (dd + 1) / 2 + c];
+                const int p1 = __ldg(&d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c]);
+                if (p1 >= 0) atomicAdd(&val[p1], x);            // entry (row (I,c), col (J,dd))
+                if (c < dd) {
+                    const int p2 = __ldg(&d.pos[(size_t)(Ic * 3 + c) * S3 + st_ji * 3 + dd]);
+                    if (p2 >= 0) atomicAdd(&val[p2], x);        // entry (row (J,dd), col (I,c))
+                }
+            }
+    }
+}
+
 template <bool HASB>
 __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_begin, int e2_end, int seg_len) {
-    constexpr int P = 3, NQ2 = 16, NB = 48, W = 7, NST = 49, S3 = 147;
+    constexpr int P = 3, NQ2 = 16, NB = 48, W = 7;
     __shared__ __align__(128) PointData s_pd[2][NQ2];
     __shared__ __align__(16) double s_b1[2][NB];        // [q1][m][a] of the element
+    __shared__ __align__(16) int4 s_cb[2][4][4];        // colbase of the element's control points [row i2][a]
     __shared__ unsigned long long s_bar[2];
     const int tid = threadIdx.x;
     const int nrows = e2_end - e2_begin;
     const int row = blockIdx.x % nrows, seg = blockIdx.x / nrows;     // consecutive CTAs take consecutive element rows of one segment column
     const int e2 = e2_begin + row;
     const int e1_begin = seg * seg_len, e1_end = min(d.nel1, e1_begin + seg_len);
-    const int q2 = tid & 3, jcls = (tid >> 2) & 3, b2 = tid >> 4, i2 = q2;
+    // lane map: the 8 lanes of a quarter-warp share one quadrature point (q2 = lane >> 3): a 128-bit shared-memory load whose address is
+    // uniform per quarter-warp costs 2 cycles instead of 4 (tools/micro/lds_shfl.cu); column function j = (lane & 7) + 8 * warp
+    const int q2 = (tid >> 3) & 3, jj = (tid & 7) + 8 * (tid >> 5), jcls = jj & 3, b2 = jj >> 2, i2 = q2;
     const int j0 = __ldg(&d.span2[e2]) - P;
 
     auto issue = [&](int e1, int s) {
-        mbar_expect_tx(&s_bar[s], (unsigned)(NQ2 * sizeof(PointData) + NB * sizeof(double)));
+        const int i0e = __ldg(&d.span1[e1]) - P;
+        mbar_expect_tx(&s_bar[s], (unsigned)(NQ2 * sizeof(PointData) + NB * sizeof(double) + 16 * sizeof(int4)));
         tma_bulk_g2s(&s_pd[s][0], d.pd + ((size_t)e1 + (size_t)d.nel1 * e2) * NQ2, (unsigned)(NQ2 * sizeof(PointData)), &s_bar[s]);
         tma_bulk_g2s(&s_b1[s][0], d.bas1 + (size_t)e1 * NB, (unsigned)(NB * sizeof(double)), &s_bar[s]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            tma_bulk_g2s(&s_cb[s][r][0], reinterpret_cast<const int4*>(d.colbase) + (i0e + d.n1 * (j0 + r)), (unsigned)(4 * sizeof(int4)), &s_bar[s]);
     };
     if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
     __syncthreads();
@@ -842,6 +884,7 @@ __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_
     int b = (jcls - i0) & 3;          // local index of this thread's column function in the current element
     bool live = false;                // the accumulators hold contributions of the current column function
     double* __restrict__ val = d.values;
+    const int I2 = j0 + i2, J2 = j0 + b2;
 
     for (int e1 = e1_begin; e1 < e1_end; ++e1) {
         const int le = e1 - e1_begin, s = le & 1;
@@ -860,6 +903,11 @@ __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_
             sw_point<HASB>(s_pd[s][q1 * 4 + q2], x1 * yj[0], x0 * yj[1], x2 * yj[0], x0 * yj[2], x1 * yj[1], yk, xa, acc);
         }
         live = true;
+        // scatter addressing of this element: column function J and the four row functions of row i2
+        int4 cbJ = s_cb[s][b2][b];
+        int4 cbI[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) cbI[a] = s_cb[s][i2][a];
         __syncthreads();               // every thread is done with buffer s
         if (tid == 0 && e1 + 2 < e1_end) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -867,30 +915,14 @@ __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_
         }
         // ---- window step: row functions I1 < i0n and column functions J1 < i0n have received their last contribution of this row
         for (int st = i0; st < i0n; ++st) {
-            const int J1 = st + b, J2 = j0 + b2, I2 = j0 + i2;
-            const int Jc = J1 + d.n1 * J2;
             if (live) {
-                const int4 cbJ = __ldg(reinterpret_cast<const int4*>(d.colbase) + Jc);
-                const int baseJ[3] = {cbJ.x, cbJ.y, cbJ.z};
+                const int Jc = (st + b) + d.n1 * J2, Ic0 = st + d.n1 * I2;
+                const int st0 = (P - b) + W * (i2 - b2 + P);
+                sw_flush_slot(d, val, acc[0], cbJ, cbI[0], Ic0, Jc, st0);
+                if (b == 0) {        // the column function leaves the support: all its pairs are complete
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    if ((a != 0 && b != 0) || st + a > i0 + P) continue;     // slots beyond the element's support are empty
-                    const int I1 = st + a, Ic = I1 + d.n1 * I2;
-                    const int st_ij = (a - b + P) + W * (i2 - b2 + P), st_ji = NST - 1 - st_ij;
-                    const int4 cbI = __ldg(reinterpret_cast<const int4*>(d.colbase) + Ic);
-                    const int baseI[3] = {cbI.x, cbI.y, cbI.z};
-#pragma unroll
-                    for (int dd = 0; dd < 3; ++dd)
-#pragma unroll
-                        for (int c = 0; c <= dd; ++c) {
-                            const double v = acc[a][dd * (dd + 1) / 2 + c];
-                            const int p1 = cbJ.w ? baseJ[dd] + c * NST + st_ij : __ldg(&d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c]);
-                            if (p1 >= 0) atomicAdd(&val[p1], v);            // entry (row (I,c), col (J,dd))
-                            if (c < dd) {
-                                const int p2 = cbI.w ? baseI[c] + dd * NST + st_ji : __ldg(&d.pos[(size_t)(Ic * 3 + c) * S3 + st_ji * 3 + dd]);
-                                if (p2 >= 0) atomicAdd(&val[p2], v);        // entry (row (J,dd), col (I,c))
-                            }
-                        }
+                    for (int a = 1; a < 4; ++a)
+                        if (st + a <= i0 + P) sw_flush_slot(d, val, acc[a], cbJ, cbI[a], Ic0 + a, Jc, st0 + a);
                 }
             }
             // shift the window by one function
@@ -902,6 +934,7 @@ __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_
                 acc[2][k] = wrap ? 0.0 : acc[3][k];
                 acc[3][k] = 0.0;
             }
+            cbI[0] = cbI[1]; cbI[1] = cbI[2]; cbI[2] = cbI[3];
             if (wrap) live = false;
             b = (b - 1) & 3;
         }
