@@ -3,20 +3,25 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--nel 576] [--material svk|nh|mr|nh_c|mr_c]
 
-A "step" is one pass of the hot path over one displacement state: one Jacobian assembly K(x) plus one
-residual assembly R(x) of the named workload (the two closures every Newton / arc-length iteration calls,
-reference: src/gsStaticSolvers/gsStaticNewton.hpp:160-191).  value = quadrature points processed per second
-by all ranks (each step integrates every quadrature point of the mesh in both assemblies; the unit counts
-a point once per step).
+A "step" is one pass of the hot path over one displacement state: one residual assembly R(x) followed by one Jacobian
+assembly K(x) at the same state — the two closures every Newton / arc-length iteration calls, in the order the reference
+calls them (src/gsStaticSolvers/gsStaticNewton.hpp:160-191).  value = quadrature points processed per second by all
+ranks (each step integrates every quadrature point of the mesh in both assemblies; the unit counts a point once per step).
 
-  value : inputs resident in HBM, device-side calls (kl_jacobian_device + kl_residual_device), CUDA events
-  e2e   : the reference-facing host-pointer calls (kl_jacobian + kl_residual) with pinned HOST buffers; the
-          H2D copy of x and the D2H copy of all matrix values and the residual are inside the timed region
-  N>1   : one process per GPU; every rank assembles its own replica at its own displacement state (the way
-          gsAPALM workers own one arc-length interval each, benchmarks/benchmark_Frustrum_APALM.cpp:391-458);
-          no data-path collective; weak scaling.
-  --impl reference : the CPU path (oracle port, OpenMP over all host cores) on a bounded sample of the same
-          workload — the real gismo/gsKLShell assembler cannot be built in this image.
+  value : inputs resident in HBM; the two SEPARATE device calls kl_residual_device + kl_jacobian_device that the
+          Residual_t / Jacobian_t closures map to (the library detects the repeated state on the device and reuses the
+          per-point records; `--fused-call` times the single-call entry kl_assemble_device instead); CUDA events
+  e2e   : the reference-facing host-pointer calls (kl_residual + kl_jacobian) with pinned HOST buffers; the H2D copy of x
+          and the D2H copy of ALL matrix values and the residual are inside the timed region.  Two more host-buffer legs
+          are reported next to it: e2e_lower (lower-triangular view for LDLT consumers, half the bytes) and
+          e2e_device_solve (values stay in HBM, the CGDiagonal solve runs there; only vectors cross PCIe)
+  N>1   : one process per GPU; every rank assembles its own replica at its own displacement state (the way gsAPALM
+          workers own one arc-length interval each, benchmarks/benchmark_Frustrum_APALM.cpp:391-458); no data-path
+          collective; weak scaling.  The same run also times ONE matrix split into element-row strips with the NCCL halo
+          exchange (strong scaling) and reports it as the `strong` sub-record, with its parity check against the
+          single-GPU assembly of the same state.
+  --impl reference : the CPU path (oracle port, OpenMP over all host cores) on the SAME workload — the real
+          gismo/gsKLShell assembler cannot be built in this image.
 """
 from __future__ import annotations
 
@@ -62,18 +67,15 @@ def emit(obj):
     out.flush()
 
 
-def flops_per_qp(p, material):
-    """FP64 operations of the Jacobian kernel per quadrature point for the algorithm of DESIGN.md §5 (FMA = 2 flops):
-    phase 3 (upper-triangle tiles, sum-factorised): tiles * [ (p+1)*45 + 27*(p+1) ] FMA per fixed-q1 column
-    phase 2 (Z_j = T.d_j):  478 flops per (basis function, point) for the linear law (B = 0), 555 with the
-                             membrane-bending coupling block (hyperelastic laws)
-    p = 3 linear law: 5760 + 16*478 = 13408, which is what ncu counts as executed
-    (sm__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on, profiles/r1_r1i_summary.txt)."""
-    nloc = (p + 1) ** 2
-    tiles = (p + 1) * (p + 1) * (p + 2) // 2
-    ph3 = 2 * tiles * ((p + 1) * 45 + 27 * (p + 1)) / (p + 1)     # per point: one column has p+1 points
-    ph2 = (478 if material == "svk" else 555) * nloc
-    return int(ph3 + ph2)
+def flops_per_qp(p, hasB):
+    """FP64 operations the degree-3 Jacobian kernel k_jacobian_sw executes per quadrature point: per (basis
+    function, point) thread 286 DFMA + 124 DMUL + 25 DADD = 721 flops for the linear law (membrane-bending block B = 0) and
+    324 + 135 + 28 -> 811 flops with B (hyperelastic laws), counted in the SASS of the kernel and equal to what ncu reports
+    as executed (sm__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on, profiles/r2_sw1_jacobian_summary.txt); times the
+    16 basis functions of an element.  This is the kernel's own operation count (FMA = 2), not an estimate of another
+    algorithm: the shared-memory kernel of round 1 executed 13 408 flops per point for the same result."""
+    assert p == 3
+    return 16 * (811 if hasB else 721)
 
 
 def bind_to_gpu_numa_node(index):
@@ -101,7 +103,7 @@ class ClockSampler:
         self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
 
     def _nvml(self):
-        """In-process NVML polling (about 200 samples per second): several samples fall inside a 70 ms timed region."""
+        """In-process NVML polling (about 200 samples per second): several samples fall inside a 50 ms timed region."""
         import pynvml
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
@@ -149,40 +151,131 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def workload_name(args):
+    return (f"benchmark_Roof shallow Scordelis-Lo roof (configs[1]), degree 3, {args.nel}x{args.nel} elements, "
+            f"material={args.material}, t=6.35, N/S edges fixed, x = {args.scale}*h*U(-1,1)")
+
+
 def run_reference(args):
-    """CPU arm: oracle port with OpenMP on all host cores, bounded sample (coarser mesh of the same workload)."""
+    """CPU arm: oracle port with OpenMP on all host cores on the SAME mesh, state and warm-up count as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle.binding import Oracle
-    nel = args.ref_nel
+    nel = args.ref_nel or args.nel
     pr = make_problem(nel, args.material)
     orc = Oracle(pr, threads=os.cpu_count())     # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
     cores = orc.threads
     x = W.displacement_state(orc.n_dofs, args.scale * 508.0 / nel)
     vals, r = np.zeros(orc.nnz), np.zeros(orc.n_dofs)
-    for _ in range(min(args.warmup, 1)):
+    warm = max(args.warmup, 0)
+    for _ in range(warm):
         orc.jacobian_residual(x, vals, r)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         orc.jacobian_residual(x, vals, r)
     dt = (time.perf_counter() - t0) / args.steps
     v = orc.n_qp / dt
-    sample = f"roof {nel}x{nel} elements ({orc.n_dofs} DOFs, {orc.n_qp} quadrature points) per step, same material/BCs"
+    sample = (f"roof {nel}x{nel} elements ({orc.n_dofs} DOFs, {orc.n_qp} quadrature points) per step, same material/BCs/state as "
+              f"the GPU arm" + ("" if nel == args.nel else f" (coarser than the GPU arm's {args.nel}x{args.nel}: --ref-nel)"))
     emit(({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "reference_kind": "oracle port of the gsKLShell algorithm (OpenMP); "
-                   "the real gismo+gsKLShell assembler is not buildable here"},
+        "config": {"workload": workload_name(args) if nel == args.nel else workload_name(args).replace(f"{args.nel}x{args.nel}", f"{nel}x{nel}"),
+                   "n_dofs": orc.n_dofs, "nnz": orc.nnz, "quad_points": orc.n_qp,
+                   "reference_kind": "oracle port of the gsKLShell algorithm (OpenMP); the real gismo+gsKLShell assembler is not "
+                                     "buildable here"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_name(args):
-    return (f"benchmark_Roof shallow Scordelis-Lo roof (configs[1]), degree 3, {args.nel}x{args.nel} elements, "
-            f"material={args.material}, t=6.35, N/S edges fixed, x = {args.scale}*h*U(-1,1)")
+# ------------------------------------------------------------------------------------------------
+def time_device_steps(torch, step, steps, barrier=None):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if barrier:
+        barrier()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if barrier:
+        barrier()
+    else:
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def config_records(torch, capi, args, local, hbm_peak, fp64_peak):
+    """one sub-record per BASELINE.json config at benchmark size (Jacobian ms, step ms, roofline fractions),
+    each with its parity against the oracle on a coarse twin of the same problem."""
+    from gsstructuralanalysis_b200.ops import ShellAssembler
+    from oracle.binding import Oracle
+    cases = [
+        ("S1 plate (configs[0] scaled): tutorial paraboloid, corner-pinned, NH incompressible", lambda n: W.tutorial_paraboloid(n, 3, KL_MAT_NH, False), 576, 2e-3),
+        ("S1 plate, St.Venant-Kirchhoff", lambda n: W.tutorial_paraboloid(n, 3, KL_MAT_SVK, False), 576, 2e-3),
+        ("S2 roof r=10 (configs[1], 3.16M DOFs), SvK", lambda n: W.roof(n, 3), 1024, 2e-3),
+        ("S3 balloon (configs[2]): NURBS eighth sphere, NH incompressible, 4 thickness points, follower pressure", lambda n: W.balloon(n), 576, 2e-3),
+        ("S3 cylinder (configs[2]): NH incompressible, Neumann edge traction", lambda n: W.cylinder(n), 576, 2e-3),
+        ("S4 tension sheet (configs[3]): Mooney-Rivlin, non-uniform knots", lambda n: W.tension_sheet(n), 576, 1e-5),
+        ("S5 frustrum (configs[4]): Mooney-Rivlin, Neumann edge load", lambda n: W.frustrum(n), 576, 2e-3),
+    ]
+    out = []
+    stream = torch.cuda.current_stream().cuda_stream
+    for name, mk, nel, amp in cases:
+        try:
+            pr = mk(nel)
+            asm = ShellAssembler(pr, device=local)
+            L = max(np.ptp(pr.surface.cp[:, 0]), np.ptp(pr.surface.cp[:, 1]), np.ptp(pr.surface.cp[:, 2]))
+            # smooth state + seeded noise small enough for thick / degenerate parametrisations (see workloads.smooth_state)
+            hloc = L / nel
+            r = torch.empty(asm.n_dofs, dtype=torch.float64, device="cuda")
+            x = None
+
+            def step():
+                asm.residual_device(x.data_ptr(), r.data_ptr(), 1.0, -1.0, stream)
+                asm.jacobian_device(x.data_ptr(), stream)
+            # the largest smooth amplitude that is a valid configuration on this mesh (the degenerate pole of the balloon limits it)
+            for rel in (1e-3, 1e-4, 1e-5, 0.0):
+                x = torch.from_numpy(W.smooth_state(pr, rel * L, noise=amp * min(hloc, hloc * hloc / pr.thickness) * 0.1 * (rel > 0))).cuda()
+                for _ in range(3):
+                    step()
+                if asm.check(stream) == 0:
+                    break
+            else:
+                raise RuntimeError(capi.lib().kl_last_error().decode())
+            ms_step = time_device_steps(torch, step, 5)
+            jm, pm = C.c_float(), C.c_float()
+            asm.residual_device(x.data_ptr(), r.data_ptr(), 1.0, -1.0, stream)
+            capi.check(asm.L.kl_points_kernel_ms(asm.h, C.byref(pm)))
+            asm.jacobian_device(x.data_ptr(), stream)
+            capi.check(asm.L.kl_jacobian_kernel_ms(asm.h, C.byref(jm)))
+            hasB = pr.material != KL_MAT_SVK and pr.bending
+            fl = flops_per_qp(3, hasB) * asm.n_qp
+            ncp = pr.surface.n[0] * pr.surface.n[1]
+            by = 8 * asm.nnz + 48 * ncp
+            rec = {"workload": name, "elements": f"{nel}x{nel}", "state": f"smooth, amplitude {rel:g}*L + seeded noise", "n_dofs": asm.n_dofs, "nnz": asm.nnz, "quad_points": asm.n_qp,
+                   "jacobian_ms": jm.value, "points_residual_ms": pm.value, "step_ms": ms_step, "quad_pts_per_s": asm.n_qp / (ms_step * 1e-3),
+                   "fp64_frac": fl / (jm.value * 1e-3) / 1e12 / fp64_peak, "hbm_frac": by / (jm.value * 1e-3) / 1e9 / hbm_peak}
+            asm.close()
+            # parity on a coarse twin (the oracle finishes in a fraction of a second there)
+            prs = mk(12)
+            a2, o2 = ShellAssembler(prs, device=local), Oracle(prs)
+            Ls = max(np.ptp(prs.surface.cp[:, 0]), np.ptp(prs.surface.cp[:, 1]), np.ptp(prs.surface.cp[:, 2]))
+            hs = Ls / 12
+            xs = W.smooth_state(prs, 1e-3 * Ls, noise=amp * min(hs, hs * hs / prs.thickness) * 0.1)
+            ok, K = a2.jacobian(xs)
+            ok2, rr = a2.residual(xs)
+            Ko, ro = o2.jacobian_values(xs), o2.residual(xs)
+            rec["max_rel_diff_vs_oracle_12x12"] = {"K": float(np.abs(K.values - Ko).max() / np.abs(Ko).max()),
+                                                   "R": float(np.abs(rr - ro).max() / max(np.abs(ro).max(), np.abs(o2.force()).max(), 1e-300))}
+            a2.close(); o2.close()
+            out.append(rec)
+        except Exception as exc:       # a config that cannot run is reported, never silently dropped
+            out.append({"workload": name, "error": f"{type(exc).__name__}: {exc}"})
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -192,14 +285,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--nel", type=int, default=576)
-    ap.add_argument("--ref-nel", type=int, default=96)
+    ap.add_argument("--ref-nel", type=int, default=0, help="CPU arms: mesh of the sample (0 = the GPU arm's mesh, the default)")
     ap.add_argument("--material", default="svk", choices=list(MATS))
     ap.add_argument("--scale", type=float, default=0.002, help="displacement amplitude as a fraction of the element size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--separate-calls", action="store_true", help="device leg: kl_jacobian_device + kl_residual_device back to back instead of kl_assemble_device")
-    ap.add_argument("--mode", default="replicas", choices=["replicas", "strips"],
-                    help="N>1: independent replicas (weak scaling, default) or ONE matrix split into element-row strips with the halo exchange (strong scaling)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config sub-records (BASELINE.md table)")
+    ap.add_argument("--no-strips", action="store_true", help="N>1: skip the strong-scaling strips sub-record")
+    ap.add_argument("--fused-call", action="store_true", help="device leg: the single-call entry kl_assemble_device instead of the two closure calls")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything libraries print (NCCL banner, ...) is diverted to stderr
     global _REAL_STDOUT
@@ -234,6 +327,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     pr = make_problem(args.nel, args.material)
     t_setup = time.perf_counter()
     asm = ShellAssembler(pr, device=local)
@@ -246,95 +345,156 @@ def main():
     r_dev = torch.empty(n, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
 
-    strips = args.mode == "strips" and world > 1
-    if strips:
-        from gsstructuralanalysis_b200.parallel import plan_strips, exchange_halo, DevicePointerView
-        n1_, n2_ = pr.surface.n
-        plan = plan_strips(n1_, n2_, 3, n2_ - 3, pr.dof_map, pr.n_free, world, rank)
-        asm.set_strip(plan.e2_begin, plan.e2_end)
-        vals_view = DevicePointerView(asm.values_device_ptr(), nnz).tensor()
-        outer_h, _ = asm.pattern()
-        x_host = W.displacement_state(n, args.scale * h, seed=20240607)      # one state, one matrix
-        x_dev = torch.from_numpy(x_host).cuda()
-
     def step_device():
-        if not strips and not args.separate_calls:
-            # one Jacobian + one residual at the same state through the fused entry (internal force integrated by the point kernel)
+        if args.fused_call:
             asm.assemble_device(x_dev.data_ptr(), r_dev.data_ptr(), 1.0, -1.0, stream)
             return
+        # the Newton order of the reference: residual first, then the Jacobian at the same state (two closure calls)
+        asm.residual_device(x_dev.data_ptr(), r_dev.data_ptr(), 1.0, -1.0, stream)
         asm.jacobian_device(x_dev.data_ptr(), stream)
-        if strips:
-            # partial internal force of the strip; the owner adds F_ext after the exchange (not timed: one axpy)
-            asm.residual_device(x_dev.data_ptr(), r_dev.data_ptr(), 0.0, 1.0, stream)
-            exchange_halo(plan, outer_h, vals_view, r_dev, dist)
-        else:
-            asm.residual_device(x_dev.data_ptr(), r_dev.data_ptr(), 1.0, -1.0, stream)
 
     launches0 = asm.kernel_launches()
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_device()
     if asm.check(stream) != 0:
         raise SystemExit("assembly failed: " + capi.lib().kl_last_error().decode())
-    launches_per_step = (asm.kernel_launches() - launches0) // max(args.warmup, 3)
+    launches_per_step = (asm.kernel_launches() - launches0) // warm
 
     # ---- timed region: K steps, device resident, CUDA events, max over ranks
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    jac_ms = []
+    jac_ms, pts_ms = [], []
     with ClockSampler(local) as clk:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            step_device()
-        e1.record()
-        barrier()
-        total_ms = e0.elapsed_time(e1)
+        ms_per_step = allmax(time_device_steps(torch, step_device, args.steps, barrier))
         # dominant kernel alone (events recorded around the launch inside the library), same stream
         for _ in range(min(args.steps, 5)):
-            asm.jacobian_device(x_dev.data_ptr(), stream)
             ms = C.c_float()
+            asm.residual_device(x_dev.data_ptr(), r_dev.data_ptr(), 1.0, -1.0, stream)
+            capi.check(asm.L.kl_points_kernel_ms(asm.h, C.byref(ms)))
+            pts_ms.append(ms.value)
+            asm.jacobian_device(x_dev.data_ptr(), stream)
             capi.check(asm.L.kl_jacobian_kernel_ms(asm.h, C.byref(ms)))
             jac_ms.append(ms.value)
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = (1 if strips else world) * nqp / (ms_per_step * 1e-3)
+    value = world * nqp / (ms_per_step * 1e-3)
     jac_kernel_ms = float(np.mean(jac_ms))
 
     # ---- e2e: host-pointer closures with pinned host buffers, copies inside the timed region
-    e2e = None
-    if not args.no_e2e and not strips:
-        vals_pinned = torch.empty(nnz, dtype=torch.float64).pin_memory()
-        vals_np = vals_pinned.numpy()
-        asm._values = vals_np
+    e2e = e2e_lower = e2e_dev = None
+    if not args.no_e2e:
         xin = torch.from_numpy(x_host).pin_memory().numpy()
         r_pinned = torch.empty(n, dtype=torch.float64).pin_memory().numpy()     # the solver's result vector, reused every call
-        for _ in range(2):
-            ok, _ = asm.jacobian(xin)
-            ok2, _ = asm.residual(xin, out=r_pinned)
-            assert ok and ok2
-        barrier()
-        t0 = time.perf_counter()
         ksteps = max(2, min(args.steps, 5))
-        for _ in range(ksteps):
-            ok, K = asm.jacobian(xin)
-            tj = asm.last_timing()
-            ok2, r = asm.residual(xin, out=r_pinned)
-            assert ok and ok2
-        barrier()
-        dt = (time.perf_counter() - t0) / ksteps
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        e2e = {"value": world * nqp / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 8 * nnz + 8 * n,
-               "ms_per_step": dt * 1e3, "jacobian_breakdown_ms": tj, "steps": ksteps}
 
-    # ---- device-resident linear solve on the matrix just assembled (not part of `value`):
-    #      a bounded number of Jacobi-PCG iterations, timed by CUDA events inside the library
+        def timed_host(fn):
+            for _ in range(2):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ksteps):
+                fn()
+            barrier()
+            return allmax((time.perf_counter() - t0) / ksteps)
+
+        vals_pinned = torch.empty(nnz, dtype=torch.float64).pin_memory()
+        asm._values = vals_pinned.numpy()
+        tj = {}
+
+        def host_step():
+            ok2, _ = asm.residual(xin, out=r_pinned)
+            ok, _ = asm.jacobian(xin)
+            tj.update(asm.last_timing())
+            assert ok and ok2
+        dt = timed_host(host_step)
+        e2e = {"value": world * nqp / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 8 * nnz + 8 * n,
+               "ms_per_step": dt * 1e3, "jacobian_breakdown_ms": dict(tj), "steps": ksteps,
+               "what": "kl_residual + kl_jacobian, all matrix values copied to the caller's pinned array every step"}
+        asm._values = None
+        del vals_pinned
+        # lower-triangular view: what a SimplicialLDLT consumer reads (benchmark_Roof.cpp:359-360)
+        asm.pattern_lower()
+        low_pinned = torch.empty(asm.nnz_lower, dtype=torch.float64).pin_memory().numpy()
+
+        def host_step_lower():
+            ok2, _ = asm.residual(xin, out=r_pinned)
+            ok, _ = asm.jacobian_lower(xin, out=low_pinned)
+            assert ok and ok2
+        dt = timed_host(host_step_lower)
+        e2e_lower = {"value": world * nqp / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 8 * asm.nnz_lower + 8 * n,
+                     "ms_per_step": dt * 1e3, "steps": ksteps, "what": "kl_residual + kl_jacobian_lower (row >= col entries only)"}
+        del low_pinned
+        # values stay in HBM, the linear solve runs there (gsSparseSolver-shaped adapter): only vectors cross PCIe
+        f_host = torch.from_numpy(asm.force()).pin_memory().numpy()
+        cg_iters = 50
+
+        def host_step_dev():
+            ok2, _ = asm.residual(xin, out=r_pinned)
+            ok, _ = asm.jacobian(xin, fetch=False)
+            assert ok and ok2
+        dt_asm = timed_host(host_step_dev)
+
+        def host_step_solve():
+            host_step_dev()
+            asm.cg_solve(f_host, tol=1e-30, max_iter=cg_iters)
+        dt = timed_host(host_step_solve)
+        e2e_dev = {"value": world * nqp / dt_asm, "unit": UNIT, "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 8 * n,
+                   "ms_per_step": dt_asm * 1e3, "steps": ksteps,
+                   "what": "kl_residual + kl_jacobian(values_host = NULL): the matrix stays on the device for the device CG",
+                   "with_solve": {"ms_per_step": dt * 1e3, "cg_iterations_per_step": cg_iters, "h2d_bytes_per_step": 3 * 8 * n,
+                                  "d2h_bytes_per_step": 2 * 8 * n, "value": world * nqp / dt,
+                                  "what": "the same plus one kl_cg_solve (CGDiagonal, capped at 50 iterations) per step"}}
+
+    # ---- strong scaling: ONE matrix in element-row strips + halo exchange (the path with a real exchange step)
+    strong = None
+    if world > 1 and not args.no_strips:
+        from gsstructuralanalysis_b200.parallel import plan_strips, exchange_halo, DevicePointerView, function_supports, value_ranges
+        x1 = torch.from_numpy(W.displacement_state(n, args.scale * h, seed=20240607)).cuda()      # one state, one matrix
+        vals_view = DevicePointerView(asm.values_device_ptr(), nnz).tensor()
+        outer_h, _ = asm.pattern()
+        # single-GPU assembly of the same state on this rank: the parity reference of the strips path
+        asm.jacobian_device(x1.data_ptr(), stream)
+        asm.residual_device(x1.data_ptr(), r_dev.data_ptr(), 0.0, 1.0, stream)
+        torch.cuda.synchronize()
+        K_full, R_full = vals_view.clone(), r_dev.clone()
+        n1_, n2_ = pr.surface.n
+        plan = plan_strips(n1_, n2_, 3, function_supports(pr.surface.U[1], 3)[2], pr.dof_map, pr.n_free, world, rank, knots2=pr.surface.U[1])
+        asm.set_strip(plan.e2_begin, plan.e2_end)
+        ex_ms = []
+
+        def strip_step(timed=False):
+            asm.jacobian_device(x1.data_ptr(), stream)
+            asm.residual_device(x1.data_ptr(), r_dev.data_ptr(), 0.0, 1.0, stream)     # partial internal force of the strip
+            if timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            nb = exchange_halo(plan, outer_h, vals_view, r_dev, dist)
+            if timed:
+                b.record(); torch.cuda.synchronize(); ex_ms.append(a.elapsed_time(b))
+            return nb
+        for _ in range(3):
+            halo_bytes = strip_step()
+        ms_strong = allmax(time_device_steps(torch, strip_step, args.steps, barrier))
+        for _ in range(3):
+            strip_step(True)
+        # parity of the owned columns against the single-GPU assembly (1e-12 of the largest entry)
+        sK, sR = float(K_full.abs().max()), float(R_full.abs().max())
+        errK = max([float((vals_view[a:b] - K_full[a:b]).abs().max()) for a, b in value_ranges(plan.owned_cols, outer_h) if b > a] + [0.0]) / sK
+        errR = max([float((r_dev[c0:c1] - R_full[c0:c1]).abs().max()) for c0, c1 in plan.owned_cols if c1 > c0] + [0.0]) / sR
+        errK, errR = allmax(errK), allmax(errR)
+        # per-rank fixed cost: an empty strip (launch overheads, memsets of nothing, state upload)
+        asm.set_strip(0, 0)
+        ms_fixed = allmax(time_device_steps(torch, lambda: (asm.jacobian_device(x1.data_ptr(), stream),
+                                                            asm.residual_device(x1.data_ptr(), r_dev.data_ptr(), 0.0, 1.0, stream)), 5, barrier))
+        asm.set_strip(0, asm.n_elements // (pr.surface.n[0] - 3))
+        strong = {"scaling": "strong", "ms_per_step": ms_strong, "value": nqp / (ms_strong * 1e-3), "unit": UNIT,
+                  "exchange_ms": allmax(float(np.mean(ex_ms))), "halo_bytes_received_max": int(allmax(float(halo_bytes))),
+                  "nccl_op": "batched ncclSend/ncclRecv to the neighbour strip (batch_isend_irecv), one fused add of the received ranges",
+                  "per_rank_fixed_ms": ms_fixed, "speedup_vs_1gpu_step": None,
+                  "parity_vs_single_gpu": {"max_rel_K": errK, "max_rel_R": errR, "ok": bool(errK <= 1e-12 and errR <= 1e-12)},
+                  "what": "ONE matrix of the same workload: every rank assembles its element-row strip, interface columns go to their owner"}
+        del K_full, R_full
+
+    # ---- device-resident linear solve on the matrix just assembled (not part of `value`)
     solver = None
-    if rank == 0 and not strips:
+    if rank == 0:
         try:
             asm.jacobian_device(x_dev.data_ptr(), stream)
             torch.cuda.synchronize()
@@ -356,7 +516,8 @@ def main():
     peak = C.c_double()
     pms = C.c_float()
     capi.check(asm.L.kl_measure_fp64_peak(local, C.byref(peak), C.byref(pms)))
-    fpq = flops_per_qp(3, args.material)
+    hasB = pr.material != KL_MAT_SVK and pr.bending
+    fpq = flops_per_qp(3, hasB)
     ncp = pr.surface.n[0] * pr.surface.n[1]
     bytes_alg = 8 * nnz + 2 * 24 * ncp
     hbm_peak = 6453.1
@@ -368,27 +529,36 @@ def main():
     achieved_tf = fpq * nqp / (jac_kernel_ms * 1e-3) / 1e12
     traffic = None      # dram__bytes_read+write of the kernel from the committed ncu --set full capture of this workload
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tj_ = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if args.nel == 576 and args.material == "svk":
-            traffic = tj["traffic"]
+            traffic = tj_["traffic"]
     except Exception:
         pass
-    roofline = {"kernel": "k_jacobian<3>", "bound": "fp64", "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
+    roofline = {"kernel": "k_jacobian_sw", "bound": "fp64", "achieved": achieved_tf, "peak": peak.value, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak.value, "traffic": traffic, "kernel_ms": jac_kernel_ms, "flops_per_qp": fpq,
-                "note": "FP64 flops are the binding roofline of the fused assembly (13.4 kflop vs 224 B per point); ncu shows the "
-                        "kernel limited by the L1/LSU pipe (87 % of peak) with the FP64 pipe 38 % busy, and its time follows the number "
-                        "of resident CTAs (profiles/r1_s2_jacobian_summary.txt, profiles/r1_ablation.txt) - DESIGN.md sections 5 and 8",
+                "share_of_step": jac_kernel_ms / ms_per_step,
+                "note": "FP64 flops are the binding roofline of the fused assembly (11.5 kflop executed vs 224 B per point); flops_per_qp is "
+                        "the kernel's own executed count (ncu: dfma/dmul/dadd), so frac equals the share of peak DFMA-equivalent issue; ncu: "
+                        "FP64 pipe 58 % busy, L1/LSU data pipe 69 % (shuffles + per-point record loads) - profiles/r2_sw1_jacobian_summary.txt, DESIGN.md section 5",
                 "hbm": {"algorithmic_bytes": bytes_alg, "bytes_per_qp": bytes_alg / nqp,
                         "achieved": bytes_alg / (jac_kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_alg / (jac_kernel_ms * 1e-3) / 1e9 / hbm_peak},
                 "peak_source": peak_src}
+    if strong:
+        strong["speedup_vs_1gpu_step"] = None      # the driver computes efficiencies from the per-N lines
 
-    # ---- CPU baseline on a bounded sample (oracle port; the checker timed, never shipped)
+    configs = None
+    if world == 1 and not args.no_configs:
+        asm.close()
+        torch.cuda.empty_cache()
+        configs = config_records(torch, capi, args, local, hbm_peak, peak.value)
+
+    # ---- CPU baseline on a bounded sample of the SAME workload (oracle port; the checker timed, never shipped)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         from oracle.binding import Oracle
         os.sched_setaffinity(0, all_cpus)      # the CPU baseline gets every host core back
-        nel_s = args.ref_nel
+        nel_s = args.ref_nel or args.nel
         prs = make_problem(nel_s, args.material)
         orc = Oracle(prs, threads=os.cpu_count())
         xs = W.displacement_state(orc.n_dofs, args.scale * 508.0 / nel_s)
@@ -396,33 +566,36 @@ def main():
         orc.jacobian_residual(xs, vals, rr)
         t0 = time.perf_counter()
         reps = 0
-        while reps < 3 or time.perf_counter() - t0 < 10.0:
+        while reps < 2 or time.perf_counter() - t0 < 10.0:
             orc.jacobian_residual(xs, vals, rr)
             reps += 1
             if time.perf_counter() - t0 > 30.0:
                 break
         dtc = (time.perf_counter() - t0) / reps
-        cpu = {"value": orc.n_qp / dtc, "unit": UNIT, "cores": orc.threads, "kind": "port",
-               "sample": f"roof {nel_s}x{nel_s} elements ({orc.n_qp} quadrature points) x {reps} J+R steps, OpenMP oracle"}
+        cpu = {"value": orc.n_qp / dtc, "unit": UNIT, "cores": orc.threads, "kind": "port", "ms_per_step": dtc * 1e3,
+               "sample": f"roof {nel_s}x{nel_s} elements ({orc.n_qp} quadrature points, the GPU arm's mesh and state) x {reps} J+R steps "
+                         f"after one warm-up, OpenMP oracle"}
 
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strips else "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "n_dofs": n, "nnz": nnz, "elements": asm.n_elements, "quad_points": nqp,
+        "config": {"workload": workload_name(args), "n_dofs": n, "nnz": nnz, "elements": nqp // 16, "quad_points": nqp,
                    "l2": "matrix values (8*nnz bytes = %.2f GB) exceed the 126 MB L2 every step" % (8 * nnz / 1e9),
-                   "multi_gpu": ("one matrix in element-row strips, point-to-point halo exchange of the interface columns" if strips else
-                                 "one replica per GPU at its own displacement state (APALM interval style), no collective"),
+                   "multi_gpu": "one replica per GPU at its own displacement state (APALM interval style), no collective; `strong` = one matrix in strips",
                    "setup_s": t_setup, "cpu_affinity": numa,
-                   "step": ("kl_jacobian_device + kl_residual_device" if (strips or args.separate_calls) else
-                            "kl_assemble_device: one Jacobian + one residual at the same state, internal force integrated by the point kernel")},
+                   "step": ("kl_assemble_device: one Jacobian + one residual at the same state in one call" if args.fused_call else
+                            "kl_residual_device then kl_jacobian_device at the same state: the two calls behind the Residual_t / Jacobian_t closures"),
+                   "state_amplitude": f"{args.scale}*h; BASELINE.md's 1e-2*L amplitude is covered by the parity tests (tests/test_gpu_parity.py)"},
         "clocks": clk.summary(),
-        "e2e": e2e,
+        "e2e": e2e, "e2e_lower": e2e_lower, "e2e_device_solve": e2e_dev,
         "gpu_launches": launches_per_step * args.steps,
-        "jacobian_ms": jac_kernel_ms,
+        "jacobian_ms": jac_kernel_ms, "points_residual_ms": float(np.mean(pts_ms)),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "linear_solve": solver,
+        "strong": strong,
+        "configs": configs,
     }
     emit(out)
     if world > 1:

@@ -14,40 +14,10 @@
 #include <iostream>
 
 #include "../include/gsStructuralAnalysisOps_b200.h"
+#include "problem_file.h"
 
 using namespace gismo;
 
-struct ProblemFile {
-    kl_problem P{};
-    std::vector<double> U1, U2, cp, w, fixed, pl_uv, pl_val;
-    std::vector<int32_t> map;
-    bool load(const char* path) {
-        std::ifstream f(path, std::ios::binary);
-        char magic[4];
-        int32_t h[16];
-        double d[8];
-        if (!f.read(magic, 4) || std::string(magic, 4) != "KLP1") return false;
-        f.read((char*)h, sizeof(h));
-        f.read((char*)d, sizeof(d));
-        const int ncp = h[4], has_w = h[5], npl = h[15];
-        auto rd = [&](std::vector<double>& v, size_t n) { v.resize(n); f.read((char*)v.data(), sizeof(double) * n); };
-        rd(U1, h[2]); rd(U2, h[3]); rd(cp, 3 * (size_t)ncp);
-        if (has_w) rd(w, ncp);
-        map.resize(3 * (size_t)ncp);
-        f.read((char*)map.data(), sizeof(int32_t) * map.size());
-        rd(fixed, h[7]);
-        if (npl) { rd(pl_uv, 2 * (size_t)npl); rd(pl_val, 3 * (size_t)npl); }
-        P.degree[0] = h[0]; P.degree[1] = h[1]; P.n_knots[0] = h[2]; P.n_knots[1] = h[3];
-        P.knots[0] = U1.data(); P.knots[1] = U2.data(); P.cp = cp.data(); P.weights = has_w ? w.data() : nullptr;
-        P.dof_map = map.data(); P.n_free = h[6]; P.n_fixed = h[7]; P.fixed_values = h[7] ? fixed.data() : nullptr;
-        P.material = h[8]; P.compressible = h[9]; P.num_gauss_thickness = h[10]; P.bending = h[11]; P.metric_z2 = h[12];
-        P.quA = h[13]; P.quB = h[14]; P.n_point_loads = npl;
-        P.E = d[0]; P.nu = d[1]; P.thickness = d[2]; P.mr_ratio = d[3];
-        P.body_force[0] = d[4]; P.body_force[1] = d[5]; P.body_force[2] = d[6]; P.pressure = d[7];
-        P.point_load_uv = npl ? pl_uv.data() : nullptr; P.point_load_val = npl ? pl_val.data() : nullptr;
-        return (bool)f;
-    }
-};
 
 // Jacobi-preconditioned CG ("CGDiagonal")
 static int pcg(const gsSparseMatrix<>& A, const gsVector<>& b, gsVector<>& x, double tol, int maxit) {

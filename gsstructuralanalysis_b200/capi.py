@@ -21,7 +21,9 @@ SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern
            "kl_check", "kl_values_device", "kl_set_strip", "kl_last_timing", "kl_last_error", "kl_kernel_launches",
            "kl_jacobian_kernel_ms", "kl_points_kernel_ms", "kl_measure_fp64_peak", "kl_mass",
            "kl_assemble_device", "kl_cg_solve", "kl_cg_solve_device", "kl_spmv", "kl_cg_last_timing", "kl_newton_solve",
-           "kl_stress_dim", "kl_eval_stress", "kl_principal_stretches", "kl_boundary_force"]
+           "kl_stress_dim", "kl_eval_stress", "kl_principal_stretches", "kl_boundary_force",
+           "kl_pin_values", "kl_unpin_values", "kl_fetch_values", "kl_set_values", "kl_pattern_lower_host", "kl_jacobian_lower",
+           "kl_al_residual_device"]
 
 # stress_type of constructStress (include/kl_shell.h)
 STRESS_TYPES = {"displacement": 0, "membrane_force": 1, "flexural_moment": 2, "membrane": 3, "flexural": 4,
@@ -67,6 +69,12 @@ def lib():
     L.kl_pattern_host.argtypes = [vp, c_int_p, c_int_p]
     L.kl_pattern_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.kl_jacobian.argtypes = [vp, c_double_p, c_double_p]
+    L.kl_jacobian_lower.argtypes = [vp, c_double_p, c_double_p]
+    L.kl_pattern_lower_host.argtypes = [vp, c_int_p, c_int_p, C.POINTER(C.c_int64)]
+    L.kl_pin_values.argtypes = [vp, c_double_p, C.c_int64]
+    L.kl_unpin_values.argtypes = [vp, c_double_p]
+    L.kl_fetch_values.argtypes = [vp, c_double_p]
+    L.kl_set_values.argtypes = [vp, c_double_p]
     L.kl_residual.argtypes = [vp, c_double_p, c_double_p]
     L.kl_al_residual.argtypes = [vp, c_double_p, C.c_double, c_double_p]
     L.kl_force.argtypes = [vp, c_double_p]

@@ -19,15 +19,30 @@
 size_t kl_pointdata_bytes(void) { return sizeof(PointData); }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void k_construct_solution(KLDev d, const double* __restrict__ x) {
+__global__ void k_construct_solution(KLDev d, const double* __restrict__ x, const int* __restrict__ skip, int i_begin, int i_count) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= 3 * d.ncp) return;
-    const int c = k / d.ncp, i = k - c * d.ncp;
-    const int g = d.map[k];
+    if (k >= 3 * i_count || (skip && *skip)) return;
+    const int c = k / i_count, i = i_begin + (k - c * i_count);
+    const int g = d.map[c * d.ncp + i];
     double v;
-    if (g < d.nfree) v = x ? x[g] : 0.0;
+    if (!x) v = 0.0;                 // x == NULL: the undeformed configuration (assemble() of the linear system), eliminated DoFs included
+    else if (g < d.nfree) v = x[g];
     else v = d.fixed ? d.fixed[g - d.nfree] : 0.0;
     d.disp[3 * i + c] = v;
+}
+
+// same-state detection: *same stays non-zero iff x is bit-identical to the state the per-point records were computed for;
+// the reference's Newton / arc-length loops call Residual(x) and then Jacobian(x) at one state
+// (src/gsStaticSolvers/gsStaticNewton.hpp:160-191), and the closures are separate std::functions
+__global__ void k_state_compare(const double* __restrict__ x, const double* __restrict__ xs, int n, int* __restrict__ same) {
+    bool diff = false;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        diff |= __double_as_longlong(x ? x[k] : 0.0) != __double_as_longlong(xs[k]);
+    if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) *same = 0;
+}
+__global__ void k_state_store(const double* __restrict__ x, double* __restrict__ xs, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) xs[k] = x ? x[k] : 0.0;
 }
 
 __global__ void k_axpby(double* __restrict__ r, const double* __restrict__ f, double a, double b, int n) {
@@ -51,8 +66,9 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 // WITH_RES: also integrate the internal force F_int - F_pressure into r from the staged records (RED), which makes the separate
 // k_residual pass unnecessary when Jacobian and residual are wanted at the same state (kl_assemble_device).
 template <int P, bool WITH_RES>
-__global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_points(KLDev d, int e2_begin, int e2_end, double* __restrict__ r) {
+__global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_points(KLDev d, int e2_begin, int e2_end, double* __restrict__ r, const int* __restrict__ skip) {
     using Cfg = PointCfg<P>;
+    if (skip && *skip) return;     // the records of this state are already in d.pd (same-state fusion)
     constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;
     extern __shared__ __align__(16) unsigned char smem_pts[];
     ElemStage<P>* stage = reinterpret_cast<ElemStage<P>*>(smem_pts);
@@ -545,6 +561,13 @@ __device__ __forceinline__ void tile_chunk(const BasisStage<P>& E, const double 
     }
 }
 
+// set-up only (d.lift != nullptr): an entry whose row is free and whose column is eliminated goes, times the Dirichlet value of the
+// column, into the lifting vector  K_L(free, eliminated) g  (gsExprAssembler eliminates the column into the rhs)
+__device__ __forceinline__ void lift_entry(const KLDev& d, int cp_row, int c_row, int cp_col, int c_col, double v) {
+    const int row = d.map[c_row * d.ncp + cp_row], col = d.map[c_col * d.ncp + cp_col];
+    if (row < d.nfree && col >= d.nfree && d.fixed) atomicAdd(&d.lift[row], v * d.fixed[col - d.nfree]);
+}
+
 // ---- scatter of one tile (upper triangle i <= j plus the transposed entries).  Regular columns are addressed
 //      arithmetically (outer[col] + c*nst + stencil slot); irregular ones (boundary, eliminated or matched DoFs in
 //      the stencil) go through the position table.  cb = colbase of the element's control points.
@@ -599,6 +622,10 @@ __device__ __forceinline__ void tile_scatter(const KLDev& d, const int4* cb, int
             const double v = acc[a][k];
             if (p1[k] >= 0) atomicAdd(&val[p1[k]], v);   // entry (row (I,c), col (J,dd))
             if (p2[k] >= 0) atomicAdd(&val[p2[k]], v);   // entry (row (J,dd), col (I,c))
+            if (d.lift) {
+                lift_entry(d, Ic, k / 3, Jc, k % 3, v);
+                if (i != tj) lift_entry(d, Jc, k % 3, Ic, k / 3, v);
+            }
         }
     }
 }
@@ -825,9 +852,11 @@ __device__ __forceinline__ void sw_flush_slot(const KLDev& d, double* __restrict
                 const double x = v[dd * (dd + 1) / 2 + c];
                 const int p1 = __ldg(&d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c]);
                 if (p1 >= 0) atomicAdd(&val[p1], x);            // entry (row (I,c), col (J,dd))
+                if (d.lift) lift_entry(d, Ic, c, Jc, dd, x);
                 if (c < dd) {
                     const int p2 = __ldg(&d.pos[(size_t)(Ic * 3 + c) * S3 + st_ji * 3 + dd]);
                     if (p2 >= 0) atomicAdd(&val[p2], x);        // entry (row (J,dd), col (I,c))
+                    if (d.lift) lift_entry(d, Jc, dd, Ic, c, x);
                 }
             }
     }
@@ -890,7 +919,11 @@ __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_
         const int le = e1 - e1_begin, s = le & 1;
         const int i0n = (e1 + 1 < e1_end) ? __ldg(&d.span1[e1 + 1]) - P : i0 + P + 1;
         mbar_wait(&s_bar[s], (le >> 1) & 1);
-#pragma unroll 1
+#ifndef KL_SW_UNROLL
+#define KL_SW_UNROLL 1
+#endif
+        constexpr int UNR = KL_SW_UNROLL;
+#pragma unroll UNR
         for (int q1 = 0; q1 < 4; ++q1) {
             const double* xb = &s_b1[s][q1 * 12];
             double xa[3][4];
@@ -987,10 +1020,29 @@ __global__ void __launch_bounds__(256) k_pressure_tangent(KLDev d, int e2_begin,
 }
 
 // ------------------------------------------------------------------------------------------------
-int kl_launch_construct(kl_ctx* ctx, const double* x_dev, cudaStream_t s) {
-    const int n = 3 * ctx->d.ncp;
-    k_construct_solution<<<(n + 255) / 256, 256, 0, s>>>(ctx->d, x_dev);
+int kl_launch_construct(kl_ctx* ctx, const double* x_dev, cudaStream_t s, const int* skip) {
+    const int i_begin = ctx->cp_row_begin * ctx->d.n1, i_count = (ctx->cp_row_end - ctx->cp_row_begin) * ctx->d.n1;
+    const int n = 3 * i_count;
+    if (n <= 0) return 0;
+    k_construct_solution<<<(n + 255) / 256, 256, 0, s>>>(ctx->d, x_dev, skip, i_begin, i_count);
     ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int kl_launch_state_compare(kl_ctx* ctx, const double* x_dev, cudaStream_t s) {
+    const int n = ctx->d.nfree;
+    const bool comparable = ctx->pd_valid && ((x_dev == nullptr) == (ctx->state_null != 0));
+    ctx->state_null = x_dev == nullptr;
+    KL_CUDA(cudaMemsetAsync(ctx->d_same, comparable ? 1 : 0, sizeof(int), s));
+    if (comparable) {
+        k_state_compare<<<std::max(1, std::min((n + 255) / 256, 4 * ctx->n_sm)), 256, 0, s>>>(x_dev, ctx->d_xstate, n, ctx->d_same);
+        ctx->launches++;
+    }
+    if (n > 0 && x_dev != ctx->d_xstate) {
+        k_state_store<<<(n + 255) / 256, 256, 0, s>>>(x_dev, ctx->d_xstate, n);
+        ctx->launches++;
+    }
     KL_CUDA(cudaGetLastError());
     return 0;
 }
@@ -1004,7 +1056,7 @@ int kl_launch_axpby(kl_ctx* ctx, double* r, const double* fext, double a_r, doub
 }
 
 template <int P>
-static int launch_points(kl_ctx* ctx, int e2b, int e2e, double* r, cudaStream_t s) {
+static int launch_points(kl_ctx* ctx, int e2b, int e2e, double* r, cudaStream_t s, const int* skip) {
     using Cfg = PointCfg<P>;
     const int nel = ctx->d.nel1 * (e2e - e2b);
     if (nel <= 0) return 0;
@@ -1014,17 +1066,17 @@ static int launch_points(kl_ctx* ctx, int e2b, int e2e, double* r, cudaStream_t 
         KL_CUDA(cudaFuncSetAttribute(k_points<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->attr_done |= 1u;
     }
-    if (r) k_points<P, true><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e, r);
-    else k_points<P, false><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e, nullptr);
+    if (r) k_points<P, true><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e, r, skip);
+    else k_points<P, false><<<(nel + Cfg::EPG - 1) / Cfg::EPG, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e, nullptr, skip);
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
     return 0;
 }
-int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s, double* r_dev) {
+int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s, double* r_dev, const int* skip) {
     switch (ctx->d.p) {
-        case 2: return launch_points<2>(ctx, e2_begin, e2_end, r_dev, s);
-        case 3: return launch_points<3>(ctx, e2_begin, e2_end, r_dev, s);
-        case 4: return launch_points<4>(ctx, e2_begin, e2_end, r_dev, s);
+        case 2: return launch_points<2>(ctx, e2_begin, e2_end, r_dev, s, skip);
+        case 3: return launch_points<3>(ctx, e2_begin, e2_end, r_dev, s, skip);
+        case 4: return launch_points<4>(ctx, e2_begin, e2_end, r_dev, s, skip);
     }
     kl_set_error("unsupported degree");
     return KL_E_ARG;

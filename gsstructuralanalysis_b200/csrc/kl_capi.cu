@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include "kl_internal.h"
 
 static thread_local std::string g_err;
@@ -241,7 +242,96 @@ static int build_fext(kl_ctx* ctx, const kl_problem* P) {
         for (int i = 0; i < d.nfree; ++i) fdev[i] += f[i];
         KL_CUDA(cudaMemcpy(ctx->d_fext, fdev.data(), sizeof(double) * d.nfree, cudaMemcpyHostToDevice));
     }
+    if (P->n_neumann > 0) {
+        // Neumann sides: F[i,c] += int_side N_i t_c |dX/dxi| dxi over the UNDEFORMED edge, Gauss rule of the assembly per boundary
+        // element.  On a side of an open knot vector only the edge row of functions is non-zero and the edge curve depends on the
+        // edge control points alone (rational: quotient rule on the 1-D NURBS curve).
+        if (!P->neumann_side || !P->neumann_val) { kl_set_error("kl_create: null Neumann array"); return KL_E_ARG; }
+        std::vector<double> f(std::max(d.nfree, 1), 0.0), fdev(std::max(d.nfree, 1));
+        const int p = d.p, nq = d.nq;
+        double xg[16], wg[16];
+        gauss_rule(nq, xg, wg);
+        for (int k = 0; k < P->n_neumann; ++k) {
+            const int side = P->neumann_side[k];
+            if (side < KL_WEST || side > KL_NORTH) { kl_set_error("kl_create: bad Neumann side"); return KL_E_ARG; }
+            const int dir = (side == KL_WEST || side == KL_EAST) ? 1 : 0;      // the parametric direction that runs along the side
+            const std::vector<double>& U = ctx->U[dir];
+            const std::vector<int>& span = ctx->span[dir];
+            const int fixed_idx = (side == KL_WEST || side == KL_SOUTH) ? 0 : ((dir == 1 ? d.n1 : d.n2) - 1);
+            auto cpi_of = [&](int i) { return dir == 0 ? i + d.n1 * fixed_idx : fixed_idx + d.n1 * i; };
+            for (size_t e = 0; e < span.size(); ++e) {
+                const int s = span[e];
+                const double ua = U[s], ub = U[s + 1];
+                for (int q = 0; q < nq; ++q) {
+                    const double u = 0.5 * (ua + ub) + 0.5 * (ub - ua) * xg[q];
+                    double ders[3][KL_MAXP + 1];
+                    bspline_span_ders(U, p, s, u, ders);
+                    double X[3] = {0, 0, 0}, dX[3] = {0, 0, 0}, W0 = 0, W1 = 0;
+                    for (int a = 0; a <= p; ++a) {
+                        const int ci = cpi_of(s - p + a);
+                        const double w = P->weights ? P->weights[ci] : 1.0;
+                        W0 += ders[0][a] * w; W1 += ders[1][a] * w;
+                        for (int c = 0; c < 3; ++c) { X[c] += ders[0][a] * w * P->cp[3 * ci + c]; dX[c] += ders[1][a] * w * P->cp[3 * ci + c]; }
+                    }
+                    double t2 = 0;
+                    for (int c = 0; c < 3; ++c) { const double tc = (dX[c] - W1 * X[c] / W0) / W0; t2 += tc * tc; }
+                    const double wJ = 0.5 * (ub - ua) * wg[q] * std::sqrt(t2);
+                    for (int a = 0; a <= p; ++a) {
+                        const int ci = cpi_of(s - p + a);
+                        for (int c = 0; c < 3; ++c) {
+                            const int g = P->dof_map[c * d.ncp + ci];
+                            if (g < d.nfree) f[g] += wJ * ders[0][a] * P->neumann_val[3 * k + c];
+                        }
+                    }
+                }
+            }
+        }
+        KL_CUDA(cudaMemcpy(fdev.data(), ctx->d_fext, sizeof(double) * d.nfree, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < d.nfree; ++i) fdev[i] += f[i];
+        KL_CUDA(cudaMemcpy(ctx->d_fext, fdev.data(), sizeof(double) * d.nfree, cudaMemcpyHostToDevice));
+    }
     return 0;
+}
+
+// Force = assemble().rhs(): dead loads + the follower pressure on the undeformed surface - the lifting of non-zero Dirichlet values
+static int build_force(kl_ctx* ctx, const kl_problem* P) {
+    KLDev& d = ctx->d;
+    const size_t vb = sizeof(double) * std::max(d.nfree, 1);
+    KL_CUDA(cudaMalloc((void**)&ctx->d_force, vb));
+    ctx->owned.push_back(ctx->d_force);
+    KL_CUDA(cudaMemcpy(ctx->d_force, ctx->d_fext, vb, cudaMemcpyDeviceToDevice));
+    bool lifting = false;
+    if (P->fixed_values) for (int k = 0; k < P->n_fixed; ++k) lifting |= P->fixed_values[k] != 0.0;
+    if (d.mat.pressure == 0.0 && !lifting) return 0;
+    cudaStream_t s = 0;
+    int rc;
+    // the undeformed configuration: every displacement coefficient zero, the eliminated ones included
+    KL_CUDA(cudaMemsetAsync(d.disp, 0, sizeof(double) * 3 * d.ncp, s));
+    if (d.mat.pressure != 0.0) {
+        KL_CUDA(cudaMemsetAsync(ctx->d_r, 0, vb, s));
+        if ((rc = kl_launch_residual(ctx, ctx->d_r, s))) return rc;                          // F_int(0) - P(0) = -P(0)
+        if ((rc = kl_launch_axpby(ctx, ctx->d_force, ctx->d_r, 1.0, -1.0, d.nfree, s))) return rc;
+    }
+    if (lifting) {
+        double* lift;
+        KL_CUDA(cudaMalloc((void**)&lift, vb));
+        KL_CUDA(cudaMemsetAsync(lift, 0, vb, s));
+        if ((rc = kl_launch_points(ctx, 0, d.nel2, s))) return rc;
+        KL_CUDA(cudaMemsetAsync(d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
+        const double pr = d.mat.pressure;
+        d.lift = lift;
+        d.mat.pressure = 0.0;                   // K_L of the lifting is the material + geometric stiffness at u = 0
+        rc = kl_launch_jacobian(ctx, 0, d.nel2, s);
+        d.lift = nullptr;
+        d.mat.pressure = pr;
+        if (rc) { cudaFree(lift); return rc; }
+        if ((rc = kl_launch_axpby(ctx, ctx->d_force, lift, 1.0, -1.0, d.nfree, s))) { cudaFree(lift); return rc; }
+        KL_CUDA(cudaStreamSynchronize(s));
+        cudaFree(lift);
+        KL_CUDA(cudaMemsetAsync(d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
+    }
+    KL_CUDA(cudaStreamSynchronize(s));
+    return kl_check(ctx, s);
 }
 
 // Pipelined copy-out plan: the element rows are cut into strips; a column of K is final once every element in the
@@ -253,7 +343,8 @@ static int build_d2h_plan(kl_ctx* ctx, const kl_problem* P) {
     int S = ctx->n_strips_d2h;
     if (const char* e = getenv("KL_D2H_STRIPS")) S = atoi(e);
     S = std::max(1, std::min(S, nel2 / std::max(1, 2 * d.p)));
-    std::vector<int> outer((size_t)nf + 1);
+    std::vector<int>& outer = ctx->h_outer;
+    outer.resize((size_t)nf + 1);
     KL_CUDA(cudaMemcpy(outer.data(), d.outer, sizeof(int) * ((size_t)nf + 1), cudaMemcpyDeviceToHost));
     std::vector<int> last_row(nf, -1);
     for (int c = 0; c < 3; ++c)
@@ -279,9 +370,13 @@ static int build_d2h_plan(kl_ctx* ctx, const kl_problem* P) {
         auto& r = ctx->d2h_plan[s].ranges;
         const size_t a = (size_t)outer[g], b = (size_t)outer[g + 1];
         if (!r.empty() && r.back().second == a) r.back().second = b; else r.emplace_back(a, b);
+        auto& c = ctx->d2h_plan[s].cols;
+        if (!c.empty() && c.back().second == g) c.back().second = g + 1; else c.emplace_back(g, g + 1);
     }
     ctx->strip_ev.resize(S);
     for (auto& e : ctx->strip_ev) KL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->copy_ev.resize(S);
+    for (auto& e : ctx->copy_ev) KL_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return 0;
 }
 
@@ -344,6 +439,10 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     KL_CUDA_CTX(cudaMemset(d.flag, 0, sizeof(int)));
     KL_CUDA_CTX(cudaMalloc((void**)&ctx->d_x, sizeof(double) * std::max(d.nfree, 1))); ctx->owned.push_back(ctx->d_x);
     KL_CUDA_CTX(cudaMalloc((void**)&ctx->d_r, sizeof(double) * std::max(d.nfree, 1))); ctx->owned.push_back(ctx->d_r);
+    KL_CUDA_CTX(cudaMalloc((void**)&ctx->d_xstate, sizeof(double) * std::max(d.nfree, 1))); ctx->owned.push_back(ctx->d_xstate);
+    KL_CUDA_CTX(cudaMalloc((void**)&ctx->d_same, sizeof(int))); ctx->owned.push_back(ctx->d_same);
+    KL_CUDA_CTX(cudaMemset(ctx->d_same, 0, sizeof(int)));
+    ctx->spec_allowed = getenv("KL_SPECULATE") ? atoi(getenv("KL_SPECULATE")) : 1;
     KL_CUDA_CTX(cudaMallocHost((void**)&ctx->h_pinned_x, sizeof(double) * std::max(d.nfree, 1)));
     KL_CUDA_CTX(cudaMallocHost((void**)&ctx->h_pinned_r, sizeof(double) * std::max(d.nfree, 1)));
     // material constants
@@ -363,6 +462,8 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     gauss_rule(m.ngauss, m.zg, m.wg);
     m.pressure = P->pressure;
     ctx->e2_begin = 0; ctx->e2_end = d.nel2;
+    ctx->cp_row_begin = 0; ctx->cp_row_end = d.n2;
+    ctx->h_map.assign(P->dof_map, P->dof_map + (size_t)3 * d.ncp);
     d.ablate = getenv("KL_ABLATE") ? atoi(getenv("KL_ABLATE")) : 0;
     KL_CUDA_CTX(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
     ctx->jac_shared = getenv("KL_JAC_SHARED") ? atoi(getenv("KL_JAC_SHARED")) : 0;
@@ -372,7 +473,8 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     if ((rc = build_d2h_plan(ctx, P))) { kl_destroy(ctx); return rc; }
     KL_CUDA_CTX(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     KL_CUDA_CTX(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (auto& e : ctx->ev) KL_CUDA(cudaEventCreate(&e));
+    for (auto& e : ctx->ev) KL_CUDA_CTX(cudaEventCreate(&e));
+    if ((rc = build_force(ctx, P))) { kl_destroy(ctx); return rc; }
     *out = ctx;
     return KL_OK;
 #undef KL_CUDA_CTX
@@ -383,7 +485,8 @@ extern "C" void kl_destroy(kl_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     kl_solve_free(ctx);
-    if (ctx->registered) cudaHostUnregister(ctx->registered);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (auto& e : ctx->copy_ev) if (e) cudaEventDestroy(e);
     for (void* p : ctx->owned) cudaFree(p);
     if (ctx->h_pinned_x) cudaFreeHost(ctx->h_pinned_x);
     if (ctx->h_pinned_r) cudaFreeHost(ctx->h_pinned_r);
@@ -423,6 +526,26 @@ extern "C" int kl_kernel_launches(const kl_ctx* ctx) { return ctx ? ctx->launche
 extern "C" int kl_set_strip(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end) {
     if (!ctx || e2_begin < 0 || e2_end > ctx->d.nel2 || e2_begin > e2_end) { kl_set_error("kl_set_strip: bad range"); return KL_E_ARG; }
     ctx->e2_begin = e2_begin; ctx->e2_end = e2_end;
+    ctx->pd_valid = 0;
+    // the strip reads the control-point rows of its elements and contributes only to their columns: zero just those value ranges
+    const KLDev& d = ctx->d;
+    ctx->zero_ranges.clear();
+    if (e2_begin == 0 && e2_end == d.nel2) { ctx->cp_row_begin = 0; ctx->cp_row_end = d.n2; return KL_OK; }
+    if (e2_end == e2_begin) { ctx->cp_row_begin = ctx->cp_row_end = 0; ctx->zero_ranges.emplace_back(0, 0); return KL_OK; }
+    ctx->cp_row_begin = ctx->span[1][e2_begin] - d.p;
+    ctx->cp_row_end = ctx->span[1][e2_end - 1] + 1;
+    std::vector<char> touched((size_t)d.nfree, 0);
+    for (int c = 0; c < 3; ++c)
+        for (int i = ctx->cp_row_begin * d.n1; i < ctx->cp_row_end * d.n1; ++i) {
+            const int g = ctx->h_map[(size_t)c * d.ncp + i];
+            if (g < d.nfree) touched[g] = 1;
+        }
+    for (int g = 0; g < d.nfree; ++g) {
+        if (!touched[g]) continue;
+        const size_t a = (size_t)ctx->h_outer[g], b = (size_t)ctx->h_outer[g + 1];
+        if (!ctx->zero_ranges.empty() && ctx->zero_ranges.back().second == a) ctx->zero_ranges.back().second = b;
+        else ctx->zero_ranges.emplace_back(a, b);
+    }
     return KL_OK;
 }
 
@@ -444,26 +567,67 @@ extern "C" int kl_check(kl_ctx* ctx, void* stream) {
 }
 
 // ---- device-resident entry points -----------------------------------------------------------------
+// Same-state fusion.  The reference's solvers ask for Residual(x) and then Jacobian(x) at ONE state through two separate
+// std::functions (gsStaticNewton.hpp:160-191, gsALMBase.hpp:214-258).  A residual call therefore runs the per-point kernel
+// with the material tangent and leaves the records of the whole mesh in d.pd (speculation); a Jacobian call first compares
+// its x with the state of those records ON THE DEVICE and lets constructSolution + the point kernel return at once when they
+// match.  Nothing is synchronised and a miss costs one extra launch.  Speculation switches itself off while the caller only
+// asks for residuals (explicit dynamics, dynamic relaxation, line searches) and on again at the next Jacobian call.
+static int zero_values(kl_ctx* ctx, cudaStream_t s) {
+    if (ctx->zero_ranges.empty()) { KL_CUDA(cudaMemsetAsync(ctx->d.values, 0, sizeof(double) * (size_t)ctx->nnz, s)); return 0; }
+    for (const auto& r : ctx->zero_ranges)
+        if (r.second > r.first) KL_CUDA(cudaMemsetAsync(ctx->d.values + r.first, 0, sizeof(double) * (r.second - r.first), s));
+    return 0;
+}
+static int points_and_jacobian(kl_ctx* ctx, const double* x_dev, cudaStream_t s, int e2b, int e2e, bool launch_jac) {
+    int rc;
+    if ((rc = kl_launch_state_compare(ctx, x_dev, s))) return rc;
+    if ((rc = kl_launch_construct(ctx, x_dev, s, ctx->d_same))) return rc;
+    KL_CUDA(cudaEventRecord(ctx->ev[6], s));
+    if ((rc = kl_launch_points(ctx, e2b, e2e, s, nullptr, ctx->d_same))) return rc;
+    KL_CUDA(cudaEventRecord(ctx->ev[7], s));
+    ctx->pd_valid = (e2b == 0 && e2e == ctx->d.nel2);
+    ctx->last_call = 2;
+    ctx->spec_on = 1;
+    if ((rc = zero_values(ctx, s))) return rc;
+    return launch_jac ? kl_launch_jacobian(ctx, e2b, e2e, s) : 0;
+}
+
 extern "C" int kl_jacobian_device(kl_ctx* ctx, const double* x_dev, void* stream) {
     if (!ctx) return KL_E_ARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc;
-    if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
-    KL_CUDA(cudaEventRecord(ctx->ev[6], s));
-    if ((rc = kl_launch_points(ctx, ctx->e2_begin, ctx->e2_end, s))) return rc;
-    KL_CUDA(cudaEventRecord(ctx->ev[7], s));
-    KL_CUDA(cudaMemsetAsync(ctx->d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
-    return kl_launch_jacobian(ctx, ctx->e2_begin, ctx->e2_end, s);
+    return points_and_jacobian(ctx, x_dev, (cudaStream_t)stream, ctx->e2_begin, ctx->e2_end, true);
 }
 
 extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, void* stream) {
     if (!ctx || !r_dev) return KL_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
+    const bool whole = ctx->e2_begin == 0 && ctx->e2_end == ctx->d.nel2;
+    if (ctx->last_call == 1) ctx->spec_on = 0;          // two residuals in a row: the caller is not running a Newton-type loop
     if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
     KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, s));
-    if ((rc = kl_launch_residual(ctx, r_dev, s))) return rc;
+    if (ctx->spec_on && ctx->spec_allowed && whole) {
+        // per-point records with the tangent + internal force from the staged records; remember the state they belong to
+        const int n = ctx->d.nfree;
+        ctx->pd_valid = 0;
+        if ((rc = kl_launch_state_compare(ctx, x_dev, s))) return rc;      // pd_valid == 0: only stores the state
+        KL_CUDA(cudaEventRecord(ctx->ev[6], s));
+        if ((rc = kl_launch_points(ctx, ctx->e2_begin, ctx->e2_end, s, r_dev))) return rc;
+        KL_CUDA(cudaEventRecord(ctx->ev[7], s));
+        ctx->pd_valid = 1;
+        ctx->last_call = 1;
+        (void)n;
+    } else {
+        if ((rc = kl_launch_residual(ctx, r_dev, s))) return rc;
+        ctx->last_call = 0;
+    }
     return kl_launch_axpby(ctx, r_dev, ctx->d_fext, sign_fint, lam_fext, ctx->d.nfree, s);
+}
+
+extern "C" int kl_al_residual_device(kl_ctx* ctx, const double* x_dev, double lam, double* r_dev, void* stream) {
+    // Force - lam*Force - rhs(x) with rhs(x) = F_dead - (F_int(x) - P(x))
+    if (int rc = kl_residual_device(ctx, x_dev, -1.0, 1.0, r_dev, stream)) return rc;
+    return kl_launch_axpby(ctx, r_dev, ctx->d_force, 1.0, 1.0 - lam, ctx->d.nfree, (cudaStream_t)stream);
 }
 
 extern "C" int kl_assemble_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, void* stream) {
@@ -472,30 +636,20 @@ extern "C" int kl_assemble_device(kl_ctx* ctx, const double* x_dev, double lam_f
     int rc;
     if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
     KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, s));
+    ctx->pd_valid = 0;
+    if ((rc = kl_launch_state_compare(ctx, x_dev, s))) return rc;
     KL_CUDA(cudaEventRecord(ctx->ev[6], s));
     // the point kernel integrates the internal force from the records it has just staged: no separate residual pass
     if ((rc = kl_launch_points(ctx, ctx->e2_begin, ctx->e2_end, s, r_dev))) return rc;
     KL_CUDA(cudaEventRecord(ctx->ev[7], s));
+    ctx->pd_valid = (ctx->e2_begin == 0 && ctx->e2_end == ctx->d.nel2);
+    ctx->last_call = 2;
     if ((rc = kl_launch_axpby(ctx, r_dev, ctx->d_fext, sign_fint, lam_fext, ctx->d.nfree, s))) return rc;
-    KL_CUDA(cudaMemsetAsync(ctx->d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
+    if ((rc = zero_values(ctx, s))) return rc;
     return kl_launch_jacobian(ctx, ctx->e2_begin, ctx->e2_end, s);
 }
 
 // ---- host-pointer entry points (what the Jacobian_t / Residual_t closures call) -------------------
-static int ensure_registered(kl_ctx* ctx, void* p, size_t bytes) {
-    if (ctx->registered == p && ctx->registered_bytes >= bytes) return 1;
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return 1;   // already pinned
-    cudaGetLastError();
-    if (ctx->registered) { cudaHostUnregister(ctx->registered); ctx->registered = nullptr; }
-    if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess) {
-        ctx->registered = p; ctx->registered_bytes = bytes;
-        return 1;
-    }
-    cudaGetLastError();
-    return 0;
-}
-
 // page-locked (cudaMallocHost / cudaHostRegister'ed) caller memory is copied from / to directly; pageable memory goes through
 // the context's pinned staging buffers
 static bool host_is_pinned(const void* p) {
@@ -510,7 +664,7 @@ static const double* stage_x(kl_ctx* ctx, const double* x_host, int n) {
     return ctx->h_pinned_x;
 }
 
-static int run_residual(kl_ctx* ctx, const double* x_host, double lam_fext, double sign_fint, double* r_host) {
+static int run_residual(kl_ctx* ctx, const double* x_host, double lam_fext, double sign_fint, double* r_host, bool al = false) {
     if (!ctx || !r_host) { kl_set_error("null argument"); return KL_E_ARG; }
     KL_CUDA(cudaSetDevice(ctx->device));
     const int n = ctx->d.nfree;
@@ -522,7 +676,7 @@ static int run_residual(kl_ctx* ctx, const double* x_host, double lam_fext, doub
         xd = ctx->d_x;
     }
     KL_CUDA(cudaEventRecord(ctx->ev[1], s));
-    int rc = kl_residual_device(ctx, xd, lam_fext, sign_fint, ctx->d_r, s);
+    int rc = al ? kl_al_residual_device(ctx, xd, lam_fext, ctx->d_r, s) : kl_residual_device(ctx, xd, lam_fext, sign_fint, ctx->d_r, s);
     if (rc) return rc;
     KL_CUDA(cudaEventRecord(ctx->ev[2], s));
     const bool direct = host_is_pinned(r_host);
@@ -537,7 +691,7 @@ static int run_residual(kl_ctx* ctx, const double* x_host, double lam_fext, doub
 }
 
 extern "C" int kl_residual(kl_ctx* ctx, const double* x_host, double* r_host) { return run_residual(ctx, x_host, 1.0, -1.0, r_host); }
-extern "C" int kl_al_residual(kl_ctx* ctx, const double* x_host, double lam, double* r_host) { return run_residual(ctx, x_host, -lam, 1.0, r_host); }
+extern "C" int kl_al_residual(kl_ctx* ctx, const double* x_host, double lam, double* r_host) { return run_residual(ctx, x_host, lam, 1.0, r_host, true); }
 
 extern "C" int kl_mass(kl_ctx* ctx, double density, double* values_host, double* lumped_host) {
     if (!ctx || (!values_host && !lumped_host)) { kl_set_error("kl_mass: null argument"); return KL_E_ARG; }
@@ -557,11 +711,68 @@ extern "C" int kl_mass(kl_ctx* ctx, double density, double* values_host, double*
 extern "C" int kl_force(kl_ctx* ctx, double* f_host) {
     if (!ctx || !f_host) return KL_E_ARG;
     KL_CUDA(cudaSetDevice(ctx->device));
-    KL_CUDA(cudaMemcpy(f_host, ctx->d_fext, sizeof(double) * ctx->d.nfree, cudaMemcpyDeviceToHost));
+    KL_CUDA(cudaMemcpy(f_host, ctx->d_force, sizeof(double) * ctx->d.nfree, cudaMemcpyDeviceToHost));
     return KL_OK;
 }
 
-extern "C" int kl_jacobian(kl_ctx* ctx, const double* x_host, double* values_host) {
+// ---- copy-out of the matrix values -------------------------------------------------------------------
+// The library never page-locks memory it does not own (a solver that builds a fresh gsSparseMatrix per call, as
+// gsStaticNewton::_computeJacobian does, would leave a stale registration behind when it frees the matrix).  Page-locked
+// caller memory (cudaMallocHost, or kl_pin_values by the owner of a long-lived matrix) is written by the DMA engine directly;
+// pageable memory is served through a context-owned page-locked staging buffer and copied out by a few host threads while
+// the next strip is still in flight.
+static int staging_get(kl_ctx* ctx, size_t bytes) {
+    if (ctx->h_stage_bytes >= bytes) return 0;
+    if (ctx->h_stage) { cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_bytes = 0; }
+    KL_CUDA(cudaMallocHost((void**)&ctx->h_stage, bytes));
+    ctx->h_stage_bytes = bytes;
+    return 0;
+}
+
+struct CopyRange { size_t dst, src, n; int ev; };   // element offsets; ev = index of the event that completes the range
+
+// device `src_dev` -> host `dst_host` in the given ranges, each waiting for strip event ev on the compute stream
+static int copy_out(kl_ctx* ctx, const double* src_dev, double* dst_host, const std::vector<CopyRange>& ranges, size_t total) {
+    const bool direct = host_is_pinned(dst_host);
+    double* land = dst_host;
+    if (!direct) {
+        if (int rc = staging_get(ctx, sizeof(double) * total)) return rc;
+        land = ctx->h_stage;
+    }
+    int last_ev = -1;
+    std::vector<cudaEvent_t>& cev = ctx->copy_ev;
+    for (const auto& r : ranges) {
+        if (r.ev != last_ev) {
+            if (last_ev >= 0 && !direct) KL_CUDA(cudaEventRecord(cev[last_ev], ctx->copy_stream));
+            if (r.ev >= 0) KL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->strip_ev[r.ev], 0));
+            last_ev = r.ev;
+        }
+        KL_CUDA(cudaMemcpyAsync(land + r.dst, src_dev + r.src, sizeof(double) * r.n, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    if (last_ev >= 0 && !direct) KL_CUDA(cudaEventRecord(cev[last_ev], ctx->copy_stream));
+    KL_CUDA(cudaEventRecord(ctx->ev[3], ctx->copy_stream));
+    if (direct) { KL_CUDA(cudaStreamSynchronize(ctx->copy_stream)); return 0; }
+    // pageable destination: helper threads copy each strip out of the staging buffer as soon as its event has fired
+    const int NT = 4;
+    const int dev = ctx->device;
+    auto worker = [&](int t) {
+        cudaSetDevice(dev);
+        int cur = -2;
+        for (const auto& r : ranges) {
+            if (r.ev != cur) { if (r.ev >= 0) cudaEventSynchronize(cev[r.ev]); else cudaStreamSynchronize(ctx->copy_stream); cur = r.ev; }
+            const size_t a = r.n * t / NT, b = r.n * (t + 1) / NT;
+            std::memcpy(dst_host + r.dst + a, land + r.dst + a, sizeof(double) * (b - a));
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < NT; ++t) th.emplace_back(worker, t);
+    worker(0);
+    for (auto& x : th) x.join();
+    KL_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return 0;
+}
+
+static int jacobian_host(kl_ctx* ctx, const double* x_host, double* values_host, bool lower) {
     if (!ctx) { kl_set_error("null context"); return KL_E_ARG; }
     KL_CUDA(cudaSetDevice(ctx->device));
     const int n = ctx->d.nfree;
@@ -575,40 +786,92 @@ extern "C" int kl_jacobian(kl_ctx* ctx, const double* x_host, double* values_hos
     KL_CUDA(cudaEventRecord(ctx->ev[1], s));
     int rc;
     const bool whole = ctx->e2_begin == 0 && ctx->e2_end == ctx->d.nel2;
+    if (lower && (rc = kl_lower_tables(ctx))) return rc;
     if (!values_host || !whole || ctx->d2h_plan.size() < 2) {
         if ((rc = kl_jacobian_device(ctx, xd, s))) return rc;
+        if (values_host && lower && (rc = kl_launch_pack_lower(ctx, 0, n, s))) return rc;
         KL_CUDA(cudaEventRecord(ctx->ev[2], s));
         if (values_host) {
-            const size_t bytes = sizeof(double) * (size_t)ctx->nnz;
-            ensure_registered(ctx, values_host, bytes);   // pageable memory still works, only slower
-            KL_CUDA(cudaMemcpyAsync(values_host, ctx->d.values, bytes, cudaMemcpyDeviceToHost, s));
+            KL_CUDA(cudaEventRecord(ctx->strip_ev[0], s));
+            std::vector<CopyRange> one{{0, 0, (size_t)(lower ? ctx->nnz_lower : ctx->nnz), 0}};
+            if ((rc = copy_out(ctx, lower ? ctx->d_values_lower : ctx->d.values, values_host, one, one[0].n))) return rc;
+        } else {
+            KL_CUDA(cudaEventRecord(ctx->ev[3], s));
         }
-        KL_CUDA(cudaEventRecord(ctx->ev[3], s));
     } else {
         // strips of element rows on the compute stream; the value ranges a strip completes are copied out on the copy
         // stream while the next strip is assembled (only `double` values ever cross PCIe)
-        ensure_registered(ctx, values_host, sizeof(double) * (size_t)ctx->nnz);
-        if ((rc = kl_launch_construct(ctx, xd, s))) return rc;
-        if ((rc = kl_launch_points(ctx, 0, ctx->d.nel2, s))) return rc;
-        KL_CUDA(cudaMemsetAsync(ctx->d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
+        if ((rc = points_and_jacobian(ctx, xd, s, 0, ctx->d.nel2, false))) return rc;
+        std::vector<CopyRange> ranges;
         for (size_t k = 0; k < ctx->d2h_plan.size(); ++k) {
             const auto& st = ctx->d2h_plan[k];
             if ((rc = kl_launch_jacobian(ctx, st.e2_begin, st.e2_end, s))) return rc;
+            if (lower) {
+                // columns completed by this strip, packed to their lower-triangular part (a contiguous range of the packed array)
+                for (const auto& c : st.cols) {
+                    if ((rc = kl_launch_pack_lower(ctx, c.first, c.second, s))) return rc;
+                    const size_t a = (size_t)ctx->h_outer_lower[c.first], b = (size_t)ctx->h_outer_lower[c.second];
+                    ranges.push_back({a, a, b - a, (int)k});
+                }
+            } else {
+                for (const auto& r : st.ranges) ranges.push_back({r.first, r.first, r.second - r.first, (int)k});
+            }
             KL_CUDA(cudaEventRecord(ctx->strip_ev[k], s));
-            KL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->strip_ev[k], 0));
-            for (const auto& r : st.ranges)
-                KL_CUDA(cudaMemcpyAsync(values_host + r.first, ctx->d.values + r.first, sizeof(double) * (r.second - r.first),
-                                        cudaMemcpyDeviceToHost, ctx->copy_stream));
         }
         KL_CUDA(cudaEventRecord(ctx->ev[2], s));
-        KL_CUDA(cudaEventRecord(ctx->ev[3], ctx->copy_stream));
-        KL_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        if ((rc = copy_out(ctx, lower ? ctx->d_values_lower : ctx->d.values, values_host, ranges, (size_t)(lower ? ctx->nnz_lower : ctx->nnz)))) return rc;
     }
     rc = kl_check(ctx, s);
     cudaEventElapsedTime(&ctx->ms_h2d, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->ms_kernel, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->ms_d2h, ctx->ev[2], ctx->ev[3]);   // copy-out time NOT hidden behind the assembly
     return rc;
+}
+
+extern "C" int kl_jacobian(kl_ctx* ctx, const double* x_host, double* values_host) { return jacobian_host(ctx, x_host, values_host, false); }
+extern "C" int kl_jacobian_lower(kl_ctx* ctx, const double* x_host, double* values_lower_host) {
+    if (ctx && ctx->d.mat.pressure != 0.0) { kl_set_error("kl_jacobian_lower: the follower-pressure tangent is unsymmetric"); return KL_E_ARG; }
+    return jacobian_host(ctx, x_host, values_lower_host, true);
+}
+
+extern "C" int kl_pin_values(kl_ctx* ctx, double* values_host, int64_t count) {
+    if (!ctx || !values_host || count <= 0) return KL_E_ARG;
+    KL_CUDA(cudaSetDevice(ctx->device));
+    if (host_is_pinned(values_host)) return KL_OK;
+    KL_CUDA(cudaHostRegister(values_host, sizeof(double) * (size_t)count, cudaHostRegisterDefault));
+    return KL_OK;
+}
+extern "C" int kl_unpin_values(kl_ctx* ctx, double* values_host) {
+    if (!ctx || !values_host) return KL_E_ARG;
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KL_CUDA(cudaHostUnregister(values_host));
+    return KL_OK;
+}
+
+extern "C" int kl_fetch_values(kl_ctx* ctx, double* values_host) {
+    if (!ctx || !values_host) return KL_E_ARG;
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KL_CUDA(cudaStreamSynchronize(ctx->stream));
+    KL_CUDA(cudaEventRecord(ctx->strip_ev[0], ctx->stream));
+    std::vector<CopyRange> one{{0, 0, (size_t)ctx->nnz, 0}};
+    return copy_out(ctx, ctx->d.values, values_host, one, (size_t)ctx->nnz);
+}
+extern "C" int kl_set_values(kl_ctx* ctx, const double* values_host) {
+    if (!ctx || !values_host) return KL_E_ARG;
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KL_CUDA(cudaMemcpyAsync(ctx->d.values, values_host, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyHostToDevice, ctx->stream));
+    KL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KL_OK;
+}
+
+extern "C" int kl_pattern_lower_host(kl_ctx* ctx, int32_t* outer_lower, int32_t* inner_lower, int64_t* nnz_lower) {
+    if (!ctx) return KL_E_ARG;
+    KL_CUDA(cudaSetDevice(ctx->device));
+    if (int rc = kl_lower_tables(ctx)) return rc;
+    if (nnz_lower) *nnz_lower = ctx->nnz_lower;
+    if (outer_lower) KL_CUDA(cudaMemcpy(outer_lower, ctx->d_outer_lower, sizeof(int) * ((size_t)ctx->d.nfree + 1), cudaMemcpyDeviceToHost));
+    if (inner_lower) KL_CUDA(cudaMemcpy(inner_lower, ctx->d_inner_lower, sizeof(int) * (size_t)ctx->nnz_lower, cudaMemcpyDeviceToHost));
+    return KL_OK;
 }
 
 extern "C" int kl_last_timing(const kl_ctx* ctx, float* ms_kernel, float* ms_h2d, float* ms_d2h) {

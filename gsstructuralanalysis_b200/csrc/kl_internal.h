@@ -53,6 +53,7 @@ struct KLDev {
     int nst;               // (2p+1)^2
     const int* colbase;    // [ncp][4]: outer[map[d][J]] for d=0..2 (-1 if eliminated), [3] = 1 if the column block of J is regular
     int* flag;             // device error flag
+    double* lift;          // set-up only: accumulates K(free row, eliminated column) * fixed value (lifting of non-zero Dirichlet values)
     PointData* pd;         // [elements][nq*nq] per-point records written by k_points
     int ablate;            // profiling only (env KL_ABLATE): 1 skip scatter, 2 skip phase 3, 4 skip phase 2
     KLMaterial mat;
@@ -68,15 +69,26 @@ struct kl_ctx {
     int nfixed = 0;
     int64_t nnz = 0;
     int e2_begin = 0, e2_end = 0;    // strip of element rows assembled by this context
+    std::vector<int> h_map;          // host copy of the DoF map [3*ncp]
+    std::vector<int> h_outer;        // host copy of outer [nfree+1]
+    std::vector<std::pair<size_t, size_t>> zero_ranges;   // value ranges the strip contributes to (zeroed per call); empty = whole array
+    int cp_row_begin = 0, cp_row_end = 0;                 // control-point rows the strip reads (constructSolution range)
     // owned device buffers
     std::vector<void*> owned;
     double* d_x = nullptr;           // [nfree]
     double* d_r = nullptr;           // [nfree]
-    double* d_fext = nullptr;        // [nfree]
+    double* d_fext = nullptr;        // [nfree] dead loads: body force, point loads, Neumann tractions
+    double* d_force = nullptr;       // [nfree] Force = assemble().rhs(): dead loads + follower pressure on the undeformed surface - Dirichlet lifting
     double* h_pinned_x = nullptr;    // pinned staging for x / r
     double* h_pinned_r = nullptr;
-    void* registered = nullptr;      // user value buffer currently cudaHostRegister'ed
-    size_t registered_bytes = 0;
+    double* h_stage = nullptr;       // context-owned page-locked staging for copy-outs into pageable caller memory (lazy)
+    size_t h_stage_bytes = 0;
+    // lower-triangular view (row >= col) for LDLT consumers: built on the first kl_pattern_lower_host / kl_jacobian_lower
+    int64_t nnz_lower = 0;
+    int* d_outer_lower = nullptr;    // [nfree+1]
+    int* d_inner_lower = nullptr;    // [nnz_lower]
+    double* d_values_lower = nullptr;// [nnz_lower] packed values
+    std::vector<int> h_outer_lower;
     cudaStream_t stream = nullptr;   // own stream for the host-pointer entry points
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev[8]{};
@@ -84,12 +96,21 @@ struct kl_ctx {
     int launches = 0;
     unsigned attr_done = 0;          // per-context (= per-device) cudaFuncSetAttribute bookkeeping, bit per kernel family
     int n_sm = 0;
+    // state cache (same-state fusion behind the separate Residual_t / Jacobian_t closures): d_xstate = the solution vector the per-point
+    // records in d.pd were computed for; a Jacobian call at a bit-identical state skips constructSolution + the point kernel
+    double* d_xstate = nullptr;      // [nfree]
+    int* d_same = nullptr;           // device word: != 0 when the current call's x equals d_xstate
+    int pd_valid = 0;                // d.pd / d_xstate hold a whole-mesh evaluation (tangent included)
+    int state_null = 0;              // that state was x == NULL (undeformed configuration, Dirichlet values not applied)
+    int spec_on = 1;                 // residual calls also write the per-point records (speculating on a Jacobian at the same state)
+    int last_call = 0;               // 1 residual (speculative), 2 jacobian, 0 other
+    int spec_allowed = 1;            // env KL_SPECULATE=0 disables the speculation (A/B)
     int jac_shared = 0;              // env KL_JAC_SHARED=1: the shared-memory tile kernel k_jacobian instead of k_jacobian_sw (A/B, P = 3)
     int jac_seg = 0;                 // env KL_SW_SEG: elements per segment of k_jacobian_sw (0 = automatic)
     int n_strips_d2h = 16;           // pipelined D2H granularity (measured 8 / 16 / 32: e2e 23.32 / 23.05 / 23.07 ms per step)
-    struct D2HStrip { int e2_begin, e2_end; std::vector<std::pair<size_t, size_t>> ranges; };   // value ranges complete after the strip
+    struct D2HStrip { int e2_begin, e2_end; std::vector<std::pair<size_t, size_t>> ranges; std::vector<std::pair<int, int>> cols; };   // value ranges and column ranges complete after the strip
     std::vector<D2HStrip> d2h_plan;
-    std::vector<cudaEvent_t> strip_ev;
+    std::vector<cudaEvent_t> strip_ev, copy_ev;
     KLSolveWS* solve_ws = nullptr;   // created on the first kl_cg_solve / kl_newton_solve
 };
 
@@ -110,10 +131,13 @@ void gauss_rule(int n, double* x, double* w);
 void kl_solve_free(kl_ctx* ctx);
 // kl_pattern.cu
 int kl_build_pattern(kl_ctx* ctx);
+int kl_lower_tables(kl_ctx* ctx);                                   // lazily builds the lower-triangular pattern + per-strip packed ranges
+int kl_launch_pack_lower(kl_ctx* ctx, int col_begin, int col_end, cudaStream_t s);   // packed lower values of the columns [col_begin, col_end)
 // kl_assemble.cu
-int kl_launch_construct(kl_ctx* ctx, const double* x_dev, cudaStream_t s);
+int kl_launch_construct(kl_ctx* ctx, const double* x_dev, cudaStream_t s, const int* skip = nullptr);   // rows [cp_row_begin, cp_row_end)
+int kl_launch_state_compare(kl_ctx* ctx, const double* x_dev, cudaStream_t s);   // *d_same = (x == d_xstate), then d_xstate = x
 int kl_launch_jacobian(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s);
-int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s, double* r_dev = nullptr);   // r_dev: also r += F_int - F_pressure
+int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s, double* r_dev = nullptr, const int* skip = nullptr);   // r_dev: also r += F_int - F_pressure
 int kl_launch_residual(kl_ctx* ctx, double* r_dev, cudaStream_t s, bool full = false);   // r += F_int - F_pressure (atomic); full: r = [3][ncp], internal force at every control point
 size_t kl_pointdata_bytes(void);
 int kl_launch_bodyforce(kl_ctx* ctx, double* f_dev, const double bf[3], cudaStream_t s);

@@ -192,3 +192,78 @@ int kl_build_pattern(kl_ctx* ctx) {
     d.outer = outer; d.inner = inner; d.pos = pos; d.values = values;
     return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Lower-triangular view (row >= col) of the symmetric stiffness matrix for consumers that only read one triangle
+// (gsSparseSolver<>::SimplicialLDLT of benchmarks/benchmark_Roof.cpp:359-360 factorises selfadjointView<Lower>): the same
+// compressed column layout with the upper entries dropped, i.e. the tail of every column (row indices ascend).  Half the
+// bytes cross PCIe.
+__global__ void k_lower_count(const int* __restrict__ outer, const int* __restrict__ inner, int n, int* __restrict__ cnt) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int lo = outer[j], hi = outer[j + 1];
+    const int end = hi;
+    while (lo < hi) {                       // first entry with row >= j
+        const int mid = (lo + hi) >> 1;
+        if (inner[mid] < j) lo = mid + 1; else hi = mid;
+    }
+    cnt[j] = end - lo;
+}
+// one warp per column: copy the tail (inner indices once, values every call)
+template <bool INNER>
+__global__ void k_lower_pack(const int* __restrict__ outer, const int* __restrict__ outer_lo, const int* __restrict__ inner,
+                             const double* __restrict__ val, int col_begin, int col_end, int* __restrict__ inner_lo, double* __restrict__ val_lo) {
+    const int lane = threadIdx.x & 31;
+    const int j = col_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= col_end) return;
+    const int a = outer_lo[j], b = outer_lo[j + 1];
+    const int src = outer[j + 1] - (b - a);
+    for (int k = lane; k < b - a; k += 32) {
+        if (INNER) inner_lo[a + k] = inner[src + k];
+        else val_lo[a + k] = val[src + k];
+    }
+}
+
+int kl_lower_tables(kl_ctx* ctx) {
+    if (ctx->d_outer_lower) return 0;
+    const KLDev& d = ctx->d;
+    const int n = d.nfree, T = 256;
+    int* cnt;
+    if (int rc = dev_alloc(ctx, &cnt, (size_t)n + 1)) return rc;
+    KL_CUDA(cudaMemset(cnt, 0, sizeof(int) * ((size_t)n + 1)));
+    k_lower_count<<<(n + T - 1) / T, T>>>(d.outer, d.inner, n, cnt);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    int* outer_lo;
+    if (int rc = dev_alloc(ctx, &outer_lo, (size_t)n + 1)) return rc;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    KL_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, outer_lo, n + 1));
+    KL_CUDA(cudaMalloc(&tmp, tmp_bytes));
+    KL_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, outer_lo, n + 1));
+    KL_CUDA(cudaDeviceSynchronize());
+    KL_CUDA(cudaFree(tmp));
+    ctx->h_outer_lower.resize((size_t)n + 1);
+    KL_CUDA(cudaMemcpy(ctx->h_outer_lower.data(), outer_lo, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToHost));
+    ctx->nnz_lower = ctx->h_outer_lower[n];
+    if (int rc = dev_alloc(ctx, &ctx->d_inner_lower, (size_t)ctx->nnz_lower)) return rc;
+    if (int rc = dev_alloc(ctx, &ctx->d_values_lower, (size_t)ctx->nnz_lower)) return rc;
+    if (n > 0) {
+        k_lower_pack<true><<<(n + 7) / 8, T>>>(d.outer, outer_lo, d.inner, nullptr, 0, n, ctx->d_inner_lower, nullptr);
+        ctx->launches++;
+        KL_CUDA(cudaGetLastError());
+    }
+    KL_CUDA(cudaDeviceSynchronize());
+    ctx->d_outer_lower = outer_lo;
+    return 0;
+}
+
+int kl_launch_pack_lower(kl_ctx* ctx, int col_begin, int col_end, cudaStream_t s) {
+    if (col_end <= col_begin) return 0;
+    k_lower_pack<false><<<(col_end - col_begin + 7) / 8, 256, 0, s>>>(ctx->d.outer, ctx->d_outer_lower, nullptr, ctx->d.values, col_begin, col_end,
+                                                                     nullptr, ctx->d_values_lower);
+    ctx->launches++;
+    KL_CUDA(cudaGetLastError());
+    return 0;
+}

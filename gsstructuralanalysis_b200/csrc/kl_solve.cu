@@ -701,7 +701,7 @@ extern "C" int kl_newton_solve(kl_ctx* ctx, double* U_host, const kl_newton_opti
     if (opt->linear_start) {
         // deltaU = DeltaU = K(0)^-1 F; U = 0; relative residual based on the linear solution (headstart)
         NW_ASM(kl_jacobian_device(ctx, nullptr, s));
-        KL_CUDA(cudaMemcpyAsync(w->b, ctx->d_fext, vb, cudaMemcpyDeviceToDevice, s));
+        KL_CUDA(cudaMemcpyAsync(w->b, ctx->d_force, vb, cudaMemcpyDeviceToDevice, s));   // K(0) DU = Force (lifting and undeformed pressure load included)
         NW_CG();
         KL_CUDA(cudaMemcpyAsync(w->nDU, w->x, vb, cudaMemcpyDeviceToDevice, s));
         KL_CUDA(cudaMemsetAsync(w->nU, 0, vb, s));

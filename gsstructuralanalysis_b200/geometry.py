@@ -222,6 +222,20 @@ def frustrum(R1=2.0, R2=1.0, h=1.0):
     return Surface((2, 1), (U1, U2), np.array(cp), np.array(w), "frustrum")
 
 
+def half_cylinder():
+    """filedata/surface/half_cylinder.xml of the reference (benchmarks/benchmark_Cylinder.cpp:70): NURBS, degree 2x2, knots
+    [0 0 0 1 1 1] x [0 0 0 0.5 1 1 1], 3 x 4 control points (first direction = axis, fastest), the active (uncommented)
+    geometry of the file."""
+    U1 = np.array([0, 0, 0, 1, 1, 1.0])
+    U2 = np.array([0, 0, 0, 0.5, 1, 1, 1.0])
+    w = np.array([1, 1, 1, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 1, 1, 1.0])
+    cp = np.array([[0.00, 0.00, -0.09], [0.075, 0.00, -0.09], [0.15, 0.00, -0.09],
+                   [0.00, 0.09, -0.09], [0.075, 0.09, -0.09], [0.15, 0.09, -0.09],
+                   [0.00, 0.09, 0.09], [0.075, 0.09, 0.09], [0.15, 0.09, 0.09],
+                   [0.00, 0.00, 0.09], [0.075, 0.00, 0.09], [0.15, 0.00, 0.09]])
+    return Surface((2, 2), (U1, U2), cp, w, "half_cylinder")
+
+
 def rectangle_with_clamping(L=0.14, B=0.07, p=3, nel1=8, nel2=8, clamp=1e-2):
     """Rectangle(L,B) with extra knots at `clamp` from the west/east edges
     (benchmarks/benchmark_TensionWrinkling.cpp:160-205,579-617) -> non-uniform knot vector."""

@@ -60,7 +60,7 @@ class ShellAssembler:
         return self._pattern
 
     def values_buffer(self):
-        """Host value array that the matrix view aliases (pinned on first use by the library)."""
+        """Host value array that the matrix view aliases (pageable unless the owner pins it with pin_values)."""
         if self._values is None:
             self._values = np.zeros(max(self.nnz, 1))
         return self._values
@@ -79,6 +79,46 @@ class ShellAssembler:
             return True, None
         outer, inner = self.pattern()
         return True, SparseView(self.n_dofs, outer, inner, v[:self.nnz])
+
+    def pattern_lower(self):
+        """(outer, inner) of the lower-triangular view (row >= col) handed to one-triangle consumers (SimplicialLDLT)."""
+        if getattr(self, "_pattern_lower", None) is None:
+            nl = C.c_int64()
+            capi.check(self.L.kl_pattern_lower_host(self.h, None, None, C.byref(nl)))
+            outer = np.zeros(self.n_dofs + 1, dtype=np.int32)
+            inner = np.zeros(max(nl.value, 1), dtype=np.int32)
+            capi.check(self.L.kl_pattern_lower_host(self.h, outer.ctypes.data_as(c_int_p), inner.ctypes.data_as(c_int_p), C.byref(nl)))
+            self.nnz_lower = nl.value
+            self._pattern_lower = (outer, inner[:nl.value])
+        return self._pattern_lower
+
+    def jacobian_lower(self, x, out=None):
+        """K(x), lower triangle only (half the PCIe bytes): SparseView on the lower pattern."""
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        outer, inner = self.pattern_lower()
+        v = np.zeros(max(self.nnz_lower, 1)) if out is None else out
+        rc = self.L.kl_jacobian_lower(self.h, _dp(x), _dp(v))
+        if rc != 0:
+            self.last_error = self.L.kl_last_error().decode()
+            return False, None
+        return True, SparseView(self.n_dofs, outer, inner, v[:self.nnz_lower])
+
+    def fetch_values(self, out=None):
+        """lazy fetch of the matrix the last jacobian(fetch=False) / jacobian_device call left on the GPU"""
+        v = np.zeros(max(self.nnz, 1)) if out is None else out
+        capi.check(self.L.kl_fetch_values(self.h, _dp(v)))
+        return v[:self.nnz]
+
+    def set_values(self, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        assert v.shape[0] >= self.nnz
+        capi.check(self.L.kl_set_values(self.h, _dp(v)))
+
+    def pin_values(self, arr):
+        capi.check(self.L.kl_pin_values(self.h, _dp(arr), arr.shape[0]))
+
+    def unpin_values(self, arr):
+        capi.check(self.L.kl_unpin_values(self.h, _dp(arr)))
 
     def residual(self, x, out=None):
         """constructSolution; assembleVector(def); v = rhs()   (= F_ext - F_int).  `out`: the caller's result vector (the

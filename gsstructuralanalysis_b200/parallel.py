@@ -4,16 +4,18 @@ Two ways the path shards:
   * replicas — every rank owns a whole assembler and assembles independent states (gsAPALM's workers,
     benchmarks/benchmark_Frustrum_APALM.cpp:391-458).  No communication; see bench.py.
   * strips   — ONE matrix split by element rows of the second parametric direction.  Rank g assembles the elements
-    of its strip into its (full-size) value array; the contributions that land in columns owned by the next rank
-    (the p rows of control points the strips share) are sent to their owner and added there.  This is the one real
-    exchange step of the path; it moves only `double` values of the interface columns (about 6 MB per interface at
-    1M DOF) with point-to-point sends (NCCL on GPUs, gloo in the CPU tests).
+    of its strip; the contributions that land in columns owned by the next rank (the control-point rows whose support
+    reaches into the next strip) are sent to their owner and added there.  This is the one real exchange step of the
+    path; it moves only `double` values of the interface columns (about 6 MB per interface at 1M DOF) with
+    point-to-point sends (NCCL on GPUs, gloo in the CPU tests).  DoFs that tie control points of several strips
+    together (a collapsed west/east side is ONE DoF for the whole side) are completed by a small all-reduce instead.
 
-The partition logic below is pure host arithmetic on the DoF map and is shared by the GPU path and the CPU tests.
+The partition logic below is pure host arithmetic on the knot vector and the DoF map and is shared by the GPU path and
+the CPU tests.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 import numpy as np
 
 
@@ -27,59 +29,83 @@ def _ranges(sorted_idx):
     return [(int(sorted_idx[a]), int(sorted_idx[b - 1]) + 1) for a, b in zip(starts, ends)]
 
 
+def function_supports(knots, p):
+    """(flo, fhi): first / last non-empty element of every 1-D B-spline function of an open knot vector, and the number
+    of non-empty elements (what kl_create builds as flo / fhi; repeated interior knots are fine)."""
+    U = np.asarray(knots, dtype=np.float64)
+    n = len(U) - p - 1
+    spans = [k for k in range(p, n) if U[k + 1] > U[k]]
+    flo = np.full(n, 1 << 30, dtype=np.int64)
+    fhi = np.full(n, -1, dtype=np.int64)
+    for e, k in enumerate(spans):
+        flo[k - p:k + 1] = np.minimum(flo[k - p:k + 1], e)
+        fhi[k - p:k + 1] = np.maximum(fhi[k - p:k + 1], e)
+    return flo, fhi, len(spans)
+
+
 @dataclass
 class StripPlan:
     rank: int
     world: int
     e2_begin: int                 # element rows assembled by this rank
     e2_end: int
-    owned_cols: list              # [(c0,c1)] column ranges this rank owns after the exchange
+    owned_cols: list              # [(c0,c1)] column ranges complete on this rank after the exchange
     send_cols: list               # column ranges whose partial sums go to rank+1
     recv_cols: list               # column ranges received from rank-1 (== that rank's send_cols)
+    shared_cols: list             # column ranges touched by several strips' OWN rows (matched DoFs): completed by all-reduce
+    _bufs: dict = field(default_factory=dict)     # receive / pack buffers, allocated once per (device, dtype)
 
 
-def plan_strips(n1, n2, p, nel2, dof_map, n_free, world, rank, fhi2=None):
-    """Element rows are split into `world` contiguous strips; control-point row i2 is owned by the strip that holds
-    its first element, so a strip only ever contributes to its own rows and to the first p rows of the next strip.
-    fhi2/flo2-free version for open knot vectors without interior repetitions: function i2 lives on elements
-    [i2-p, i2] clipped to [0, nel2)."""
-    assert nel2 >= world * p, "each strip needs at least p element rows"
+def plan_strips(n1, n2, p, nel2, dof_map, n_free, world, rank, knots2=None):
+    """Element rows are split into `world` contiguous strips.  Control-point row i2 is owned by the strip that holds the
+    LAST element of its support, so a strip contributes to its own rows and to rows owned by the next strip only (every
+    strip holds at least p element rows).  knots2: second-direction knot vector (default: uniform open, one element per
+    interior span, i.e. function i2 lives on elements [i2-p, i2])."""
+    if knots2 is None:
+        flo = np.maximum(np.arange(n2) - p, 0)
+        fhi = np.minimum(np.arange(n2), nel2 - 1)
+    else:
+        flo, fhi, ne = function_supports(knots2, p)
+        assert ne == nel2 and len(flo) == n2
+    if nel2 < world * p:
+        raise ValueError("each strip needs at least p element rows")
     bounds = [(nel2 * g) // world for g in range(world + 1)]
-    ncp = n1 * n2
     dm = np.asarray(dof_map).reshape(3, n2, n1)
+    strip_of_elem = np.zeros(nel2, dtype=np.int64)
+    for g in range(world):
+        strip_of_elem[bounds[g]:bounds[g + 1]] = g
+    owner_row = strip_of_elem[fhi]                          # owner strip of every control-point row
 
-    def first_elem(i2):
-        return max(i2 - p, 0)
-
-    def cols_of_rows(r0, r1):
-        if r1 <= r0:
+    def cols_of_rows(mask):
+        if not mask.any():
             return np.zeros(0, dtype=np.int64)
-        c = np.unique(dm[:, r0:r1, :].reshape(-1))
+        c = np.unique(dm[:, mask, :].reshape(-1))
         return c[c < n_free]
 
-    # owner of cp row i2: strip containing element min(i2, nel2-1)  (so rows [E_g, E_{g+1}) belong to g, the last strip
-    # also owns the trailing p rows)
-    def owner_rows(g):
-        r0 = bounds[g]
-        r1 = bounds[g + 1] if g + 1 < world else n2
-        return r0, r1
-
-    plans = []
+    owned_sets = [cols_of_rows(owner_row == g) for g in range(world)]
+    # a DoF that appears in the own rows of more than one strip (matched DoFs along direction 2)
+    allc = np.concatenate(owned_sets) if world > 1 else owned_sets[0]
+    uniq, cnt = np.unique(allc, return_counts=True)
+    shared = uniq[cnt > 1]
+    send_sets = []
     for g in range(world):
-        r0, r1 = owner_rows(g)
-        owned = cols_of_rows(r0, r1)
         if g + 1 < world:
-            s0, s1 = bounds[g + 1], min(bounds[g + 1] + p, n2)
-            send = cols_of_rows(s0, s1)
+            # rows owned by a later strip that this strip's elements reach
+            mask = (owner_row > g) & (flo < bounds[g + 1])
+            if (owner_row[mask] > g + 1).any():
+                raise ValueError("a control-point row of strip %d is supported two strips away: strips are too thin" % g)
+            send = np.setdiff1d(cols_of_rows(mask), shared)
+            # everything sent must be owned by the neighbour
+            if len(np.setdiff1d(send, owned_sets[g + 1])):
+                raise ValueError("interface column of strip %d is not owned by its neighbour (matched DoFs across strips)" % g)
         else:
             send = np.zeros(0, dtype=np.int64)
-        plans.append((owned, send))
-    # matched DoFs can tie rows of different strips together (collapsed sides): a column is owned by the LOWEST rank
-    # that lists it, and every other rank that touches it sends it there.  With the slab ordering this only ever
-    # involves neighbours for clamped sides; collapsed sides along direction 1 stay inside one strip.
-    owned, send = plans[rank]
-    recv = plans[rank - 1][1] if rank > 0 else np.zeros(0, dtype=np.int64)
-    return StripPlan(rank, world, bounds[rank], bounds[rank + 1], _ranges(owned), _ranges(send), _ranges(recv))
+        send_sets.append(send)
+    owned = np.setdiff1d(owned_sets[rank], shared)
+    owned = np.union1d(owned, shared)          # shared columns are complete on every rank after the all-reduce
+    recv = send_sets[rank - 1] if rank > 0 else np.zeros(0, dtype=np.int64)
+    return StripPlan(rank, world, bounds[rank], bounds[rank + 1], _ranges(owned), _ranges(send_sets[rank]), _ranges(recv),
+                     _ranges(shared))
 
 
 def value_ranges(col_ranges, outer):
@@ -87,34 +113,65 @@ def value_ranges(col_ranges, outer):
     return [(int(outer[c0]), int(outer[c1])) for c0, c1 in col_ranges]
 
 
-def exchange_halo(plan: StripPlan, outer, values, residual, dist, device_tensor_fn=None):
+def _buffers(plan, outer, values, residual):
+    """receive buffers (one flat tensor per neighbour message) are allocated once and reused by every exchange"""
+    import torch
+    key = (str(values.device), values.dtype, None if residual is None else residual.dtype)
+    b = plan._bufs.get(key)
+    if b is None:
+        vr, sr = value_ranges(plan.recv_cols, outer), value_ranges(plan.shared_cols, outer)
+        b = {
+            "recv_v": [torch.empty(b_ - a_, dtype=values.dtype, device=values.device) for a_, b_ in vr],
+            "recv_r": ([torch.empty(c1 - c0, dtype=residual.dtype, device=residual.device) for c0, c1 in plan.recv_cols]
+                       if residual is not None else []),
+            "shared": torch.empty(sum(b_ - a_ for a_, b_ in sr) + (sum(c1 - c0 for c0, c1 in plan.shared_cols) if residual is not None else 0),
+                                  dtype=values.dtype, device=values.device),
+            "vr": vr, "sr": sr, "send_vr": value_ranges(plan.send_cols, outer),
+        }
+        plan._bufs[key] = b
+    return b
+
+
+def exchange_halo(plan: StripPlan, outer, values, residual, dist):
     """Send the partial sums of the interface columns to rank+1 and add what rank-1 sent (one batched group of
-    point-to-point operations).  `values` / `residual` are torch tensors (CPU for gloo, CUDA views for nccl).
+    point-to-point operations, pre-allocated receive buffers, one fused add); columns shared by several strips are
+    summed with one all-reduce.  `values` / `residual` are torch tensors (CPU for gloo, CUDA views for nccl).
     After the call the entries of plan.owned_cols are complete on this rank.  Returns the bytes received."""
     import torch
-    ops, bufs = [], []
+    b = _buffers(plan, outer, values, residual)
+    ops = []
     if plan.rank + 1 < plan.world:
-        for (a, b) in value_ranges(plan.send_cols, outer):
-            ops.append(dist.P2POp(dist.isend, values[a:b], plan.rank + 1))
+        for (a, e) in b["send_vr"]:
+            ops.append(dist.P2POp(dist.isend, values[a:e], plan.rank + 1))
         if residual is not None:
             for (c0, c1) in plan.send_cols:
                 ops.append(dist.P2POp(dist.isend, residual[c0:c1], plan.rank + 1))
+    dst, src = [], []
     if plan.rank > 0:
-        for (a, b) in value_ranges(plan.recv_cols, outer):
-            t = torch.empty(b - a, dtype=values.dtype, device=values.device)
+        for (a, e), t in zip(b["vr"], b["recv_v"]):
             ops.append(dist.P2POp(dist.irecv, t, plan.rank - 1))
-            bufs.append((values, a, b, t))
+            dst.append(values[a:e]); src.append(t)
         if residual is not None:
-            for (c0, c1) in plan.recv_cols:
-                t = torch.empty(c1 - c0, dtype=residual.dtype, device=residual.device)
+            for (c0, c1), t in zip(plan.recv_cols, b["recv_r"]):
                 ops.append(dist.P2POp(dist.irecv, t, plan.rank - 1))
-                bufs.append((residual, c0, c1, t))
+                dst.append(residual[c0:c1]); src.append(t)
     if ops:
         for r in dist.batch_isend_irecv(ops):
             r.wait()
-    for (dst, a, b, t) in bufs:
-        dst[a:b] += t
-    return sum(t.numel() for (_, _, _, t) in bufs) * 8
+    if dst:
+        torch._foreach_add_(dst, src)           # one fused launch for all interface ranges
+    nbytes = sum(t.numel() for t in src) * 8
+    if plan.shared_cols and plan.world > 1:
+        flat, o = b["shared"], 0
+        parts = [values[a:e] for a, e in b["sr"]] + ([residual[c0:c1] for c0, c1 in plan.shared_cols] if residual is not None else [])
+        for t in parts:
+            flat[o:o + t.numel()].copy_(t); o += t.numel()
+        dist.all_reduce(flat)
+        o = 0
+        for t in parts:
+            t.copy_(flat[o:o + t.numel()]); o += t.numel()
+        nbytes += flat.numel() * 8
+    return nbytes
 
 
 class DevicePointerView:

@@ -51,6 +51,9 @@ class kl_problem(C.Structure):
         ("n_point_loads", C.c_int32),
         ("point_load_uv", c_double_p),
         ("point_load_val", c_double_p),
+        ("n_neumann", C.c_int32),
+        ("neumann_side", c_int_p),
+        ("neumann_val", c_double_p),
     ]
 
 
@@ -98,6 +101,7 @@ class ShellProblem:
     body_force: tuple = (0.0, 0.0, 0.0)
     pressure: float = 0.0
     point_loads: list = field(default_factory=list)   # [((u,v),(fx,fy,fz)), ...]
+    neumann: list = field(default_factory=list)       # [(side, (tx,ty,tz)), ...]  BCs.addCondition(side, condition_type::neumann, &neuData)
     # filled by number_dofs()
     dof_map: np.ndarray | None = None
     n_free: int = 0
@@ -151,11 +155,18 @@ class ShellProblem:
         if self.point_loads:
             P.point_load_uv = dp(np.array([pl[0] for pl in self.point_loads]).reshape(-1))
             P.point_load_val = dp(np.array([pl[1] for pl in self.point_loads]).reshape(-1))
+        P.n_neumann = len(self.neumann)
+        if self.neumann:
+            sides = np.ascontiguousarray([nm[0] for nm in self.neumann], dtype=np.int32)
+            keep.append(sides)
+            P.neumann_side = sides.ctypes.data_as(c_int_p)
+            P.neumann_val = dp(np.array([nm[1] for nm in self.neumann]).reshape(-1))
         return P, keep
 
     def save(self, path):
         """Binary dump read by examples/newton_shell.cpp (little endian):
-        'KLP1', 16 int32 header, 8 doubles, then the arrays in the order of kl_problem."""
+        'KLP1', 16 int32 header, 8 doubles, then the arrays in the order of kl_problem; Neumann sides follow at the end
+        (int32 count, sides, traction vectors) and are optional for readers of the older layout."""
         import struct
         s = self.surface
         assert self.dof_map is not None
@@ -177,3 +188,7 @@ class ShellProblem:
             if self.point_loads:
                 f.write(np.array([pl[0] for pl in self.point_loads], dtype="<f8").tobytes())
                 f.write(np.array([pl[1] for pl in self.point_loads], dtype="<f8").tobytes())
+            f.write(struct.pack("<i", len(self.neumann)))
+            if self.neumann:
+                f.write(np.array([nm[0] for nm in self.neumann], dtype="<i4").tobytes())
+                f.write(np.array([nm[1] for nm in self.neumann], dtype="<f8").tobytes())

@@ -69,17 +69,31 @@ def tension_sheet(nel=8, degree=3):
 
 
 def frustrum(nel=8, degree=3):
-    """configs[4]: benchmarks/benchmark_Frustrum_APALM.cpp — quarter frustrum R1=2,R2=1,h=1, MR mu=4.225,
-    ratio 7, t=0.1, bottom fixed, top collapsed in z, symmetry on the sides (:207-259,751-810)."""
+    """configs[4]: benchmarks/benchmark_Frustrum_APALM.cpp testCase 0 — quarter frustrum R1=2, R2=1, h=1, MR mu=4.225,
+    ratio 7, t=0.1 (:195-207); north: Neumann traction (0,0,-1), x/y dirichlet, z collapsed; south fixed; east x=0 symmetry
+    (dirichlet x, clamped y,z); west y=0 symmetry (clamped x, dirichlet y, clamped z) (:216-259)."""
     s = _uniform(G.frustrum(), degree, nel)
     mu = 4.225
     bc = BoundaryConditions()
+    bc.add_condition(NORTH, KL_BC_DIRICHLET, 0).add_condition(NORTH, KL_BC_DIRICHLET, 1).add_condition(NORTH, KL_BC_COLLAPSED, 2)
     bc.add_condition(SOUTH, KL_BC_DIRICHLET)
-    bc.add_condition(NORTH, KL_BC_COLLAPSED, 2)
-    bc.add_condition(WEST, KL_BC_DIRICHLET, 1).add_condition(WEST, KL_BC_CLAMPED, 0).add_condition(WEST, KL_BC_CLAMPED, 2)
     bc.add_condition(EAST, KL_BC_DIRICHLET, 0).add_condition(EAST, KL_BC_CLAMPED, 1).add_condition(EAST, KL_BC_CLAMPED, 2)
+    bc.add_condition(WEST, KL_BC_CLAMPED, 0).add_condition(WEST, KL_BC_DIRICHLET, 1).add_condition(WEST, KL_BC_CLAMPED, 2)
     return ShellProblem(s, bc, material=KL_MAT_MR, compressible=False, E=2 * mu * 1.5, nu=0.5, thickness=0.1, mr_ratio=7.0,
-                        point_loads=[((0.0, 1.0), (0.0, 0.0, -1.0))])
+                        neumann=[(NORTH, (0.0, 0.0, -1.0))])
+
+
+def cylinder(nel=8, degree=3, material=KL_MAT_NH):
+    """configs[2]: benchmarks/benchmark_Cylinder.cpp with -M 1 — half cylinder (filedata/surface/half_cylinder.xml), E=168e9,
+    nu=0.4, t=2e-3 (:97-100), incompressible Neo-Hookean; north: Neumann traction (0,0,-1), y dirichlet, z clamped; east:
+    x dirichlet, z clamped; south: fixed (+ clamped z) (:118-139)."""
+    s = _uniform(G.half_cylinder(), degree, nel)
+    bc = BoundaryConditions()
+    bc.add_condition(NORTH, KL_BC_DIRICHLET, 1).add_condition(NORTH, KL_BC_CLAMPED, 2)
+    bc.add_condition(EAST, KL_BC_DIRICHLET, 0).add_condition(EAST, KL_BC_CLAMPED, 2)
+    bc.add_condition(SOUTH, KL_BC_DIRICHLET)      # the additional clamped z on an eliminated side changes nothing
+    return ShellProblem(s, bc, material=material, compressible=False, E=168e9, nu=0.4, thickness=2e-3, mr_ratio=4.0,
+                        neumann=[(NORTH, (0.0, 0.0, -1.0))])
 
 
 def plate_1m(nel=576, degree=3, material=KL_MAT_SVK, compressible=False):
@@ -93,3 +107,40 @@ def displacement_state(n_dofs, scale, seed=20240607):
     the same generator feeds the oracle and the GPU path, so parity does not depend on it."""
     rng = np.random.default_rng(seed)
     return scale * rng.uniform(-1.0, 1.0, n_dofs)
+
+
+def dilation_state(prob, eps, noise=0.0, seed=20240607):
+    """Smooth synthetic state u = eps * X (a homogeneous dilation of the control net) on the free DoFs plus optional noise:
+    valid on degenerate parametrisations (the pole of the balloon) and on thick, finely meshed shells where seeded noise
+    of a fixed fraction of the element size would flip the through-thickness metric.  Coupled DoFs take the value of the
+    last control point mapped to them."""
+    n1, n2 = prob.surface.n
+    ncp = n1 * n2
+    x = np.zeros(prob.n_free)
+    dm = np.asarray(prob.dof_map).reshape(3, ncp)
+    for c in range(3):
+        free = dm[c] < prob.n_free
+        x[dm[c][free]] = eps * prob.surface.cp[free, c]
+    if noise:
+        x += noise * np.random.default_rng(seed).uniform(-1.0, 1.0, prob.n_free)
+    return x
+
+
+def smooth_state(prob, amp, noise=0.0, seed=20240607):
+    """Smooth synthetic state u_c = amp_c sin(pi xi) sin(pi eta) sampled at the Greville abscissae of the control points
+    (+ optional seeded noise): it vanishes on every side, so it is compatible with any homogeneous Dirichlet / symmetry
+    condition, with the degenerate pole of the balloon and with thick, finely meshed shells, where seeded noise of a fixed
+    fraction of the element size would flip the through-thickness metric.  amp: scalar or 3 components."""
+    s = prob.surface
+    g1, g2 = G.greville(s.p[0], s.U[0]), G.greville(s.p[1], s.U[1])
+    phi = np.outer(np.sin(np.pi * g2), np.sin(np.pi * g1)).reshape(-1)          # control point i = i1 + n1 * i2
+    a = np.broadcast_to(np.asarray(amp, dtype=np.float64), (3,)) * np.array([1.0, -0.7, 0.5])
+    ncp = phi.size
+    x = np.zeros(prob.n_free)
+    dm = np.asarray(prob.dof_map).reshape(3, ncp)
+    for c in range(3):
+        free = dm[c] < prob.n_free
+        x[dm[c][free]] = a[c] * phi[free]
+    if noise:
+        x += noise * np.random.default_rng(seed).uniform(-1.0, 1.0, prob.n_free)
+    return x

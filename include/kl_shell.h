@@ -95,6 +95,12 @@ typedef struct kl_problem {
     int32_t n_point_loads;
     const double* point_load_uv;   /* [n_point_loads*2] parametric positions              */
     const double* point_load_val;  /* [n_point_loads*3] load vectors                      */
+    /* BCs.addCondition(side, condition_type::neumann, &neuData) with a constant traction vector per unit UNDEFORMED edge
+     * length (gsConstantFunction neuData; benchmarks/benchmark_Frustrum_APALM.cpp:236-242,267, benchmark_Cylinder.cpp:118-129):
+     * F[i,c] += int_side N_i t_c |dX/dxi| dxi, a dead load                                                          */
+    int32_t n_neumann;
+    const int32_t* neumann_side;   /* [n_neumann] KL_WEST .. KL_NORTH                     */
+    const double* neumann_val;     /* [n_neumann*3] traction vectors                      */
 } kl_problem;
 
 typedef struct kl_ctx kl_ctx;
@@ -124,12 +130,31 @@ int kl_pattern_device(const kl_ctx* ctx, const int32_t** outer_dev, const int32_
  * values_host (nnz doubles) may be NULL: then the values stay on the device only. */
 int kl_jacobian(kl_ctx* ctx, const double* x_host, double* values_host);
 
+/* Copy-out rules of kl_jacobian / kl_jacobian_lower / kl_fetch_values: page-locked caller memory (cudaMallocHost, or
+ * kl_pin_values) is written by the DMA engine directly; pageable memory is served through a page-locked staging buffer the
+ * context owns and copied out by host threads.  The library never page-locks memory it does not own: a solver that builds
+ * a fresh gsSparseMatrix per call (gsStaticNewton::_computeJacobian, src/gsStaticSolvers/gsStaticNewton.hpp:205-212) may free
+ * it at any time.  The OWNER of a long-lived value array may pin it once with kl_pin_values and must unpin it before freeing. */
+int kl_pin_values(kl_ctx* ctx, double* values_host, int64_t count);
+int kl_unpin_values(kl_ctx* ctx, double* values_host);
+/* values of the matrix left on the device by the last kl_jacobian(.., NULL) / kl_jacobian_device / kl_mass call -> host (lazy
+ * fetch for consumers that need the host matrix after all), and the reverse (a host matrix for kl_cg_solve). */
+int kl_fetch_values(kl_ctx* ctx, double* values_host);
+int kl_set_values(kl_ctx* ctx, const double* values_host);
+
+/* Lower-triangular view (row >= col) of K for consumers that read one triangle only (SimplicialLDLT,
+ * benchmarks/benchmark_Roof.cpp:359-360; Eigen's selfadjointView<Lower>): the same compressed column layout without the
+ * upper entries.  kl_pattern_lower_host: outer_lower[n_dofs+1], inner_lower[nnz_lower] (either may be NULL to query
+ * nnz_lower first); kl_jacobian_lower writes nnz_lower values, half the bytes of kl_jacobian.  Refused with follower pressure. */
+int kl_pattern_lower_host(kl_ctx* ctx, int32_t* outer_lower, int32_t* inner_lower, int64_t* nnz_lower);
+int kl_jacobian_lower(kl_ctx* ctx, const double* x_host, double* values_lower_host);
+
 /* R(x) = F_ext - F_int(x): replaces constructSolution; assembleVector(def); v = rhs()
  * (tutorials/nonlinear_shell_static.cpp:129-136). */
 int kl_residual(kl_ctx* ctx, const double* x_host, double* r_host);
 
-/* Arc-length form  F_int(x) - lam*F_ext  ==  Force - lam*Force - rhs()
- * (benchmarks/benchmark_Roof.cpp:335-344). */
+/* Arc-length form  Force - lam*Force - rhs(x)  (benchmarks/benchmark_Roof.cpp:335-344); equal to F_int(x) - lam*F_ext for
+ * dead loads and homogeneous Dirichlet values. */
 int kl_al_residual(kl_ctx* ctx, const double* x_host, double lam, double* r_host);
 
 /* Mass matrix M_ij^{cd} = delta_cd * density * thickness * int N_i N_j dA on the SAME pattern as K (values of the
@@ -138,7 +163,11 @@ int kl_al_residual(kl_ctx* ctx, const double* x_host, double lam, double* r_host
  * (unittests/gsStaticSolver_test.cpp:249-253; Mass_t in gsStructuralAnalysisTypes.h:77).  Either output may be NULL. */
 int kl_mass(kl_ctx* ctx, double density, double* values_host, double* lumped_host);
 
-/* External force vector F (what assemble(); rhs() yields at u=0 for homogeneous BCs). */
+/* Force = assembler->assemble(); assembler->rhs(): the right-hand side of the LINEAR system at the undeformed geometry
+ * (tutorials/nonlinear_shell_static.cpp:141-143, benchmarks/benchmark_Balloon.cpp:262-263): body force, point loads and
+ * Neumann tractions, the follower pressure evaluated on the undeformed surface (p N_i n meas), and the lifting of non-zero
+ * Dirichlet values, -K_L(free, eliminated) g.  kl_al_residual uses the same vector:
+ *     Force - lam*Force - rhs(x),   rhs(x) = kl_residual(x)                       (benchmarks/benchmark_Balloon.cpp:285) */
 int kl_force(kl_ctx* ctx, double* f_host);
 
 /* Device-resident variants: x_dev / out pointers are device memory; work is enqueued on
@@ -148,6 +177,7 @@ int kl_force(kl_ctx* ctx, double* f_host);
 int kl_jacobian_device(kl_ctx* ctx, const double* x_dev, void* stream);
 int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint,
                        double* r_dev, void* stream);
+int kl_al_residual_device(kl_ctx* ctx, const double* x_dev, double lam, double* r_dev, void* stream);   /* Force - lam*Force - rhs(x) */
 int kl_check(kl_ctx* ctx, void* stream);          /* sync stream, map device flag to KL_E_* */
 double* kl_values_device(kl_ctx* ctx);            /* device K values, length nnz            */
 

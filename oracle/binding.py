@@ -39,6 +39,7 @@ def lib():
         L.klo_residual.argtypes = [C.c_void_p, c_double_p, c_double_p]
         L.klo_al_residual.argtypes = [C.c_void_p, c_double_p, C.c_double, c_double_p]
         L.klo_force.argtypes = [C.c_void_p, c_double_p]
+        L.klo_dead_force.argtypes = [C.c_void_p, c_double_p]
         L.klo_mass.argtypes = [C.c_void_p, C.c_double, c_double_p, c_double_p]
         L.klo_jacobian_residual.argtypes = [C.c_void_p, c_double_p, c_double_p, c_double_p]
         L.klo_build_dofmap.argtypes = [C.c_int, C.c_int, C.POINTER(kl_bc), c_int_p, c_int_p, c_int_p]
@@ -113,6 +114,20 @@ class Oracle:
         if rc:
             raise RuntimeError(f"oracle residual rc={rc}")
         return r
+
+    def internal_force(self, x):
+        """(F_int - P)(x) of the elements assembled by this oracle (the whole mesh, or its strip): dead loads - rhs(x)"""
+        f = np.zeros(self.n_dofs)
+        self.L.klo_dead_force(self.h, _dp(f))
+        return f - self.residual(x)
+
+    def diagonal(self, values):
+        """diagonal of a matrix stored on the oracle's pattern (0 where the pattern has no diagonal entry)"""
+        cols = np.repeat(np.arange(self.n_dofs), np.diff(self.outer))
+        d = np.zeros(self.n_dofs)
+        m = self.inner == cols
+        d[cols[m]] = values[m]
+        return d
 
     def al_residual(self, x, lam):
         x = np.ascontiguousarray(x, dtype=np.float64)

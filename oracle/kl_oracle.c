@@ -58,7 +58,10 @@ typedef struct klo {
     int* outer;
     int* inner;
     long nnz;
-    double* fext;         /* [nfree] */
+    double* fext;         /* [nfree] dead loads */
+    double* force;        /* [nfree] Force = assemble().rhs(): dead loads + pressure on the undeformed surface - Dirichlet lifting */
+    double* lift;         /* set-up only: K_L(free, eliminated) g */
+    int nneu; int* neu_side; double* neu_val;
     int nthreads;
     int e2_begin, e2_end;  /* element rows assembled (strip partition tests) */
 } klo;
@@ -461,7 +464,7 @@ static void eval_qp(const klo* o, int e1, int e2, double u, double v, const doub
 static void construct_disp(const klo* o, const double* x, double* disp) {
     for (int c = 0; c < 3; ++c) for (int i = 0; i < o->ncp; ++i) {
         int g = o->map[c * o->ncp + i];
-        disp[3 * i + c] = (g < o->nfree) ? (x ? x[g] : 0.0) : (o->fixed ? o->fixed[g - o->nfree] : 0.0);
+        disp[3 * i + c] = !x ? 0.0 : ((g < o->nfree) ? x[g] : (o->fixed ? o->fixed[g - o->nfree] : 0.0));   /* x == NULL: undeformed */
     }
 }
 
@@ -590,7 +593,13 @@ static int assemble_full(const klo* o, const double* x, double* Kval, double* fi
                 }
                 if (Ke) for (int s = 0; s < nd; ++s) {
                     int gs = o->map[(s % 3) * ncp + q.cpidx[s / 3]];
-                    if (gs >= nf) continue;
+                    if (gs >= nf) {      /* eliminated column: its Dirichlet value times the entry goes to the lifting vector (set-up) */
+                        if (o->lift && o->fixed) {
+#pragma omp atomic
+                            o->lift[gr] += Ke[(size_t)r * nd + s] * o->fixed[gs - nf];
+                        }
+                        continue;
+                    }
                     long pos = find_pos(o, gr, gs);
 #pragma omp atomic
                     Kval[pos] += Ke[(size_t)r * nd + s];
@@ -644,7 +653,61 @@ static void build_fext(klo* o) {
             if (g < o->nfree) o->fext[g] += q.R[l] * o->pl_val[3 * k + c];
         }
     }
+    /* Neumann sides (BCs.addCondition(side, condition_type::neumann, &neuData), benchmarks/benchmark_Frustrum_APALM.cpp:236-242,267;
+     * benchmark_Cylinder.cpp:118-129): F[i,c] += int_side N_i t_c |dX/dxi| dxi on the undeformed edge; the surface point evaluation
+     * on the side supplies basis values and the tangent (A1 along south/north, A2 along west/east). */
+    for (int k = 0; k < o->nneu; ++k) {
+        int side = o->neu_side[k];
+        int dir = (side == KL_WEST || side == KL_EAST) ? 1 : 0;
+        int nqs = dir == 0 ? nq1 : nq2;
+        const double* xq = dir == 0 ? xq1 : xq2;
+        const double* wq = dir == 0 ? wq1 : wq2;
+        double fixedpar = (side == KL_WEST || side == KL_SOUTH) ? o->U[1 - dir][o->p[1 - dir]] : o->U[1 - dir][o->n[1 - dir]];
+        int efix = (side == KL_WEST || side == KL_SOUTH) ? 0 : o->nel[1 - dir] - 1;
+        for (int e = 0; e < o->nel[dir]; ++e) {
+            double ua = o->U[dir][o->span[dir][e]], ub = o->U[dir][o->span[dir][e] + 1];
+            for (int qq = 0; qq < nqs; ++qq) {
+                double t = 0.5 * (ua + ub) + 0.5 * (ub - ua) * xq[qq];
+                double u = dir == 0 ? t : fixedpar, v = dir == 0 ? fixedpar : t;
+                eval_qp(o, dir == 0 ? e : efix, dir == 0 ? efix : e, u, v, disp, &q);
+                const double* tan = dir == 0 ? q.A1 : q.A2;
+                double wJ = 0.5 * (ub - ua) * wq[qq] * sqrt(dot3(tan, tan));
+                for (int l = 0; l < q.nloc; ++l) for (int c = 0; c < 3; ++c) {
+                    int g = o->map[c * o->ncp + q.cpidx[l]];
+                    if (g < o->nfree) o->fext[g] += wJ * q.R[l] * o->neu_val[3 * k + c];
+                }
+            }
+        }
+    }
     free(disp);
+}
+
+static int assemble_full(const klo* o, const double* x, double* Kval, double* fint, double* ffull);
+/* Force = assemble(); rhs() of the LINEAR system at the undeformed geometry (benchmarks/benchmark_Balloon.cpp:262-263):
+ * dead loads + follower pressure on the undeformed surface - lifting of non-zero Dirichlet values */
+static void build_force(klo* o) {
+    int n = o->nfree > 0 ? o->nfree : 1;
+    o->force = (double*)malloc(sizeof(double) * n);
+    memcpy(o->force, o->fext, sizeof(double) * n);
+    int lifting = 0;
+    if (o->fixed) for (int k = 0; k < o->nfixed; ++k) lifting |= o->fixed[k] != 0.0;
+    if (o->P.pressure != 0.0) {
+        double* r = (double*)calloc(n, sizeof(double));
+        assemble_full(o, NULL, NULL, r, NULL);           /* F_int(0) - P(0) = -P(0) at the undeformed configuration */
+        for (int i = 0; i < o->nfree; ++i) o->force[i] -= r[i];
+        free(r);
+    }
+    if (lifting) {
+        double* K = (double*)malloc(sizeof(double) * (o->nnz > 0 ? o->nnz : 1));
+        double pr = o->P.pressure;
+        o->P.pressure = 0.0;
+        o->lift = (double*)calloc(n, sizeof(double));
+        assemble_full(o, NULL, K, NULL, NULL);
+        for (int i = 0; i < o->nfree; ++i) o->force[i] -= o->lift[i];
+        free(o->lift); o->lift = NULL;
+        o->P.pressure = pr;
+        free(K);
+    }
 }
 
 /* ------------------------------------------------------------------------------------ */
@@ -672,6 +735,13 @@ klo* klo_create(const kl_problem* P) {
     o->npl = P->n_point_loads;
     o->pl_uv = dupd(P->point_load_uv, 2 * (size_t)o->npl);
     o->pl_val = dupd(P->point_load_val, 3 * (size_t)o->npl);
+    o->nneu = P->n_neumann;
+    o->neu_side = NULL; o->neu_val = NULL;
+    if (o->nneu > 0) {
+        o->neu_side = (int*)malloc(sizeof(int) * o->nneu);
+        memcpy(o->neu_side, P->neumann_side, sizeof(int) * o->nneu);
+        o->neu_val = dupd(P->neumann_val, 3 * (size_t)o->nneu);
+    }
     o->nthreads = 1;
 #ifdef _OPENMP
     o->nthreads = omp_get_max_threads();
@@ -679,6 +749,7 @@ klo* klo_create(const kl_problem* P) {
     o->e2_begin = 0; o->e2_end = o->nel[1];
     build_pattern(o);
     build_fext(o);
+    build_force(o);
     return o;
 }
 
@@ -686,7 +757,7 @@ void klo_destroy(klo* o) {
     if (!o) return;
     for (int d = 0; d < 2; ++d) { free(o->U[d]); free(o->span[d]); }
     free(o->cp); free(o->w); free(o->map); free(o->fixed); free(o->pl_uv); free(o->pl_val);
-    free(o->outer); free(o->inner); free(o->fext); free(o);
+    free(o->outer); free(o->inner); free(o->fext); free(o->force); free(o->neu_side); free(o->neu_val); free(o);
 }
 
 void klo_set_strip(klo* o, int b, int e) { o->e2_begin = b; o->e2_end = e; }
@@ -705,17 +776,19 @@ int klo_pattern(const klo* o, int* outer, int* inner) {
     return 0;
 }
 int klo_jacobian(const klo* o, const double* x, double* values) { return assemble(o, x, values, NULL); }
-int klo_force(const klo* o, double* f) { memcpy(f, o->fext, sizeof(double) * o->nfree); return 0; }
+/* dead loads only (body force, point loads, Neumann tractions): what rhs(x) = F_dead - (F_int - P)(x) is built from */
+int klo_dead_force(const klo* o, double* f) { memcpy(f, o->fext, sizeof(double) * o->nfree); return 0; }
+int klo_force(const klo* o, double* f) { memcpy(f, o->force, sizeof(double) * o->nfree); return 0; }
 /* r = F_ext - F_int (assembleVector; rhs()) */
 int klo_residual(const klo* o, const double* x, double* r) {
     int rc = assemble(o, x, NULL, r);
     for (int i = 0; i < o->nfree; ++i) r[i] = o->fext[i] - r[i];
     return rc;
 }
-/* r = F_int - lam F_ext (benchmarks/benchmark_Roof.cpp:335-344) */
+/* r = Force - lam*Force - rhs(x)  (benchmarks/benchmark_Roof.cpp:335-344, benchmark_Balloon.cpp:285) */
 int klo_al_residual(const klo* o, const double* x, double lam, double* r) {
     int rc = assemble(o, x, NULL, r);
-    for (int i = 0; i < o->nfree; ++i) r[i] = r[i] - lam * o->fext[i];
+    for (int i = 0; i < o->nfree; ++i) r[i] = (1.0 - lam) * o->force[i] - (o->fext[i] - r[i]);
     return rc;
 }
 /* both in one sweep (used by the CPU baseline timing: Jacobian + residual per "step") */

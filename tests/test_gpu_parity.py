@@ -39,16 +39,30 @@ def _compare(ShellAssembler, prob, scale, tag):
         assert ok, (tag, asm.last_error if not ok else "")
         Ko = orc.jacobian_values(x)
         errK = np.abs(K.values - Ko).max() / np.abs(Ko).max()
+        # per-entry checks next to the max-norm one: (a) every entry against the scale of ITS row and column,
+        # |dK_ij| <= tol sqrt(|K_ii| |K_jj|) — small coupling blocks (membrane-bending, rows of soft DoFs) are held to their own
+        # magnitude, not to the largest entry of the matrix; (b) plain relative error of every entry above 1e-10 max|K|
+        diag = np.abs(orc.diagonal(Ko))
+        cols = np.repeat(np.arange(asm.n_dofs), np.diff(outer))
+        sc = np.sqrt(diag[inner] * diag[cols])
+        ok_sc = sc > 0
+        errKe = (np.abs(K.values - Ko)[ok_sc] / sc[ok_sc]).max()
+        big = np.abs(Ko) >= 1e-10 * np.abs(Ko).max()
+        errKr = (np.abs(K.values - Ko)[big] / np.abs(Ko)[big]).max()
         ok, r = asm.residual(x)
         assert ok
         ro = orc.residual(x)
-        rs = max(np.abs(ro).max(), np.abs(fo).max(), 1e-300)
+        # scale of the residual check: one ulp of a control-point coordinate moves F_int by |K| ulp(X), so next to |R| and |F| the
+        # noise floor 1e-4 |K| |X| enters (it only matters for stiff, lightly loaded problems: the cylinder has E = 1.68e11, load 1)
+        rs = max(np.abs(ro).max(), np.abs(fo).max(), 1e-4 * np.abs(Ko).max() * np.abs(prob.surface.cp).max(), 1e-300)
         errR = np.abs(r - ro).max() / rs
         ok, ra = asm.al_residual(x, 0.37)
         rao = orc.al_residual(x, 0.37)
         errA = np.abs(ra - rao).max() / rs
-        print(f"{tag}: n={asm.n_dofs} nnz={asm.nnz} errK={errK:.2e} errR={errR:.2e} errAL={errA:.2e}")
+        print(f"{tag}: n={asm.n_dofs} nnz={asm.nnz} errK={errK:.2e} errK_entry={errKe:.2e} errK_rel(>1e-10)={errKr:.2e} errR={errR:.2e} errAL={errA:.2e}")
         assert errK <= RTOL, (tag, errK)
+        assert errKe <= 1e-10, (tag, errKe)      # measured 1e-13 .. 1e-11 (thin sheets: t^3 bending entries next to membrane ones)
+        assert errKr <= 1e-6, (tag, errKr)      # 1e-16 absolute on an entry of relative size 1e-10: the FP64 limit of this check
         assert errR <= RTOL, (tag, errR)
         assert errA <= RTOL, (tag, errA)
     asm.close()
@@ -85,7 +99,47 @@ def test_tension_sheet_nonuniform_knots(gpu):
 
 
 def test_frustrum(gpu):
-    _compare(gpu, W.frustrum(6), 2e-3, "frustrum")
+    _compare(gpu, W.frustrum(6), 2e-3, "frustrum")          # Neumann traction on the collapsed north side
+
+
+def test_cylinder_neumann(gpu):
+    _compare(gpu, W.cylinder(6), 1e-5, "cylinder")
+
+
+@pytest.mark.parametrize("side", [0, 1, 2, 3])
+def test_neumann_every_side_nurbs(gpu, side):
+    from gsstructuralanalysis_b200 import geometry as G
+    from gsstructuralanalysis_b200.problem import ShellProblem, BoundaryConditions
+    pr = ShellProblem(W._uniform(G.frustrum(), 3, 5), BoundaryConditions().add_corner_value(0), material=KL_MAT_NH,
+                      E=3.0, nu=0.5, thickness=0.1, neumann=[(side, (0.3, -0.2, 1.0))])
+    _compare(gpu, pr, 1e-3, f"neumann-side{side}")
+
+
+def test_force_with_pressure_and_prescribed_displacements(gpu):
+    """Force = assemble().rhs(): follower pressure on the undeformed surface and the lifting -K_L(free, eliminated) g."""
+    pr = W.balloon(6)
+    from gsstructuralanalysis_b200 import capi
+    pr.number_dofs(capi.lib().kl_build_dofmap)
+    # prescribed values of a smooth field (a small shear of the control net; the symmetry planes make a dilation vanish there): seeded noise on the coincident pole points would tear
+    # the degenerate elements apart and turn the comparison into a conditioning test
+    dm = np.asarray(pr.dof_map).reshape(3, -1)
+    pr.fixed_values = np.zeros(pr.n_fixed)
+    for c in range(3):
+        el = dm[c] >= pr.n_free
+        pr.fixed_values[dm[c][el] - pr.n_free] = 1e-3 * (pr.surface.cp[el, (c + 1) % 3] + 0.5 * pr.surface.cp[el, (c + 2) % 3])
+    assert np.abs(pr.fixed_values).max() > 0
+    _compare(gpu, pr, 2e-2, "balloon-lifting")
+
+
+@pytest.mark.parametrize("name", ["roof", "plate", "frustrum", "balloon"])
+def test_benchmark_amplitude_state(gpu, name):
+    """the timed displacement state x = 1e-2 L U(-1,1) (L = size of the geometry) on a mesh coarse enough
+    that it is a valid configuration (the amplitude is tied to L, not to the element size; the tension sheet's 1e-2-wide clamping
+    elements cannot take it and stay with test_tension_sheet_nonuniform_knots)."""
+    pr = {"roof": lambda: W.roof(4), "plate": lambda: W.tutorial_paraboloid(4, 3, KL_MAT_MR, True),
+          "frustrum": lambda: W.frustrum(3), "balloon": lambda: W.balloon(3)}[name]()
+    L = max(np.ptp(pr.surface.cp[:, k]) for k in range(3))
+    _compare(gpu, pr, 1e-2 * L, f"amplitude-{name}")
 
 
 def test_membrane_only(gpu):

@@ -10,6 +10,19 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _cases():
+    from gsstructuralanalysis_b200 import workloads as W
+    return {"roof": lambda: W.roof(9), "paraboloid": lambda: W.tutorial_paraboloid(8), "balloon": lambda: W.balloon(8),
+            "tension": lambda: W.tension_sheet(8)}        # tension: the collapsed east side is ONE DoF shared by every strip
+
+
+def _plan(pr, world, rank):
+    from gsstructuralanalysis_b200.parallel import plan_strips, function_supports
+    n1, n2 = pr.surface.n
+    nel2 = function_supports(pr.surface.U[1], 3)[2]
+    return plan_strips(n1, n2, 3, nel2, pr.dof_map, pr.n_free, world, rank, knots2=pr.surface.U[1])
+
+
 def _worker(rank, world, port, case, q):
     sys.path.insert(0, ROOT)
     import torch
@@ -20,16 +33,17 @@ def _worker(rank, world, port, case, q):
     from gsstructuralanalysis_b200 import workloads as W
     from gsstructuralanalysis_b200.parallel import plan_strips, exchange_halo, value_ranges
     from oracle.binding import Oracle
-    pr = {"roof": lambda: W.roof(9), "paraboloid": lambda: W.tutorial_paraboloid(8), "balloon": lambda: W.balloon(8)}[case]()
+    CASES = _cases()
+    pr = CASES[case]()
     full = Oracle(pr)
-    x = W.displacement_state(full.n_dofs, 1e-3)
-    Kfull, Rint_full = full.jacobian_values(x), full.force() - full.residual(x)
+    x = W.displacement_state(full.n_dofs, 1e-5 if case == "tension" else 1e-3)
+    Kfull, Rint_full = full.jacobian_values(x), full.internal_force(x)
     n1, n2 = pr.surface.n
-    plan = plan_strips(n1, n2, 3, n2 - 3, pr.dof_map, pr.n_free, world, rank)
+    plan = _plan(pr, world, rank)
     part = Oracle(pr)
     part.set_strip(plan.e2_begin, plan.e2_end)
     Kp = torch.from_numpy(part.jacobian_values(x))
-    Rp = torch.from_numpy(part.force() - part.residual(x))      # partial internal force
+    Rp = torch.from_numpy(part.internal_force(x))      # partial internal force
     moved = exchange_halo(plan, full.outer, Kp, Rp, dist)
     ok = True
     for (a, b) in value_ranges(plan.owned_cols, full.outer):
@@ -42,12 +56,12 @@ def _worker(rank, world, port, case, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["roof", "paraboloid", "balloon"])
+@pytest.mark.parametrize("case", ["roof", "paraboloid", "balloon", "tension"])
 def test_strip_partition_world2(case):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 500) + {"roof": 0, "paraboloid": 1, "balloon": 2}[case]
+    port = 29500 + (os.getpid() % 500) + {"roof": 0, "paraboloid": 1, "balloon": 2, "tension": 3}[case]
     procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
     for p in procs:
         p.start()
@@ -55,11 +69,12 @@ def test_strip_partition_world2(case):
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] for r in res), res
-    from gsstructuralanalysis_b200 import workloads as W
     from oracle.binding import Oracle
-    pr = {"roof": lambda: W.roof(9), "paraboloid": lambda: W.tutorial_paraboloid(8), "balloon": lambda: W.balloon(8)}[case]()
+    pr = _cases()[case]()
     n = Oracle(pr).n_dofs
-    assert sum(r[2] for r in res) == n          # every column owned exactly once
+    nshared = sum(c1 - c0 for c0, c1 in _plan(pr, 2, 0).shared_cols)
+    assert sum(r[2] for r in res) == n + nshared          # every column owned exactly once (shared ones complete on every rank)
+    assert (nshared > 0) == (case == "tension")
     assert max(r[3] for r in res) > 0           # something crossed the interface
 
 
@@ -79,3 +94,12 @@ def test_plan_ranges_cover_all_columns():
             if r > 0:
                 assert pl.recv_cols == plan_strips(n1, n2, 3, n2 - 3, pr.dof_map, pr.n_free, world, r - 1).send_cols
         assert (seen == 1).all()
+    with pytest.raises(ValueError):         # strips thinner than p element rows would need non-neighbour exchanges
+        plan_strips(n1, n2, 3, n2 - 3, pr.dof_map, pr.n_free, 8, 0)
+
+
+def test_function_supports_with_repeated_knots():
+    from gsstructuralanalysis_b200.parallel import function_supports
+    U = [0, 0, 0, 0, 0.25, 0.5, 0.5, 0.75, 1, 1, 1, 1]      # degree 3, double knot at 0.5: 4 elements, 8 functions
+    flo, fhi, ne = function_supports(U, 3)
+    assert ne == 4 and list(flo) == [0, 0, 0, 0, 1, 2, 2, 3] and list(fhi) == [0, 1, 1, 2, 3, 3, 3, 3]
