@@ -23,7 +23,7 @@ SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern
            "kl_assemble_device", "kl_cg_solve", "kl_cg_solve_device", "kl_spmv", "kl_cg_last_timing", "kl_newton_solve",
            "kl_stress_dim", "kl_eval_stress", "kl_principal_stretches", "kl_boundary_force",
            "kl_pin_values", "kl_unpin_values", "kl_fetch_values", "kl_set_values", "kl_pattern_lower_host", "kl_jacobian_lower",
-           "kl_al_residual_device"]
+           "kl_al_residual_device", "kl_alm_step"]
 
 # stress_type of constructStress (include/kl_shell.h)
 STRESS_TYPES = {"displacement": 0, "membrane_force": 1, "flexural_moment": 2, "membrane": 3, "flexural": 4,
@@ -41,6 +41,16 @@ class kl_newton_info(C.Structure):
     _fields_ = [("status", C.c_int32), ("iterations", C.c_int32), ("cg_iterations", C.c_int64),
                 ("residual", C.c_double), ("residual_ini", C.c_double), ("dU_norm", C.c_double), ("DU_norm", C.c_double),
                 ("ms_assembly", C.c_float), ("ms_solve", C.c_float)]
+
+
+class kl_alm_options(C.Structure):
+    _fields_ = [("tolU", C.c_double), ("tolF", C.c_double), ("max_it", C.c_int32), ("phi", C.c_double), ("relaxation", C.c_double),
+                ("cg_tol", C.c_double), ("cg_max_iter", C.c_int32)]
+
+
+class kl_alm_info(C.Structure):
+    _fields_ = [("status", C.c_int32), ("iterations", C.c_int32), ("cg_iterations", C.c_int64), ("residueF", C.c_double),
+                ("residueU", C.c_double), ("phi", C.c_double), ("DeltaL", C.c_double), ("ms_assembly", C.c_float), ("ms_solve", C.c_float)]
 
 
 _LIB = None
@@ -97,6 +107,8 @@ def lib():
     L.kl_spmv.argtypes = [vp, c_double_p, c_double_p]
     L.kl_cg_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.kl_newton_solve.argtypes = [vp, c_double_p, C.POINTER(kl_newton_options), C.POINTER(kl_newton_info)]
+    L.kl_alm_step.argtypes = [vp, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.POINTER(kl_alm_options), C.POINTER(kl_alm_info)]
+    L.kl_al_residual_device.argtypes = [vp, vp, C.c_double, vp, vp]
     L.kl_stress_dim.argtypes = [C.c_int32]
     L.kl_eval_stress.argtypes = [vp, c_double_p, C.c_int32, C.c_int32, c_double_p, C.c_double, c_double_p]
     L.kl_principal_stretches.argtypes = [vp, c_double_p, C.c_int32, c_double_p, C.c_double, c_double_p]

@@ -581,12 +581,13 @@ static int zero_values(kl_ctx* ctx, cudaStream_t s) {
 }
 static int points_and_jacobian(kl_ctx* ctx, const double* x_dev, cudaStream_t s, int e2b, int e2e, bool launch_jac) {
     int rc;
+    if (ctx->pd_valid && (ctx->pd_e2b != e2b || ctx->pd_e2e != e2e)) ctx->pd_valid = 0;     // records of another set of element rows
     if ((rc = kl_launch_state_compare(ctx, x_dev, s))) return rc;
     if ((rc = kl_launch_construct(ctx, x_dev, s, ctx->d_same))) return rc;
     KL_CUDA(cudaEventRecord(ctx->ev[6], s));
     if ((rc = kl_launch_points(ctx, e2b, e2e, s, nullptr, ctx->d_same))) return rc;
     KL_CUDA(cudaEventRecord(ctx->ev[7], s));
-    ctx->pd_valid = (e2b == 0 && e2e == ctx->d.nel2);
+    ctx->pd_valid = 1; ctx->pd_e2b = e2b; ctx->pd_e2e = e2e;
     ctx->last_call = 2;
     ctx->spec_on = 1;
     if ((rc = zero_values(ctx, s))) return rc;
@@ -602,11 +603,10 @@ extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_f
     if (!ctx || !r_dev) return KL_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
-    const bool whole = ctx->e2_begin == 0 && ctx->e2_end == ctx->d.nel2;
     if (ctx->last_call == 1) ctx->spec_on = 0;          // two residuals in a row: the caller is not running a Newton-type loop
     if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
     KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, s));
-    if (ctx->spec_on && ctx->spec_allowed && whole) {
+    if (ctx->spec_on && ctx->spec_allowed) {
         // per-point records with the tangent + internal force from the staged records; remember the state they belong to
         const int n = ctx->d.nfree;
         ctx->pd_valid = 0;
@@ -614,7 +614,7 @@ extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_f
         KL_CUDA(cudaEventRecord(ctx->ev[6], s));
         if ((rc = kl_launch_points(ctx, ctx->e2_begin, ctx->e2_end, s, r_dev))) return rc;
         KL_CUDA(cudaEventRecord(ctx->ev[7], s));
-        ctx->pd_valid = 1;
+        ctx->pd_valid = 1; ctx->pd_e2b = ctx->e2_begin; ctx->pd_e2e = ctx->e2_end;
         ctx->last_call = 1;
         (void)n;
     } else {
@@ -642,7 +642,7 @@ extern "C" int kl_assemble_device(kl_ctx* ctx, const double* x_dev, double lam_f
     // the point kernel integrates the internal force from the records it has just staged: no separate residual pass
     if ((rc = kl_launch_points(ctx, ctx->e2_begin, ctx->e2_end, s, r_dev))) return rc;
     KL_CUDA(cudaEventRecord(ctx->ev[7], s));
-    ctx->pd_valid = (ctx->e2_begin == 0 && ctx->e2_end == ctx->d.nel2);
+    ctx->pd_valid = 1; ctx->pd_e2b = ctx->e2_begin; ctx->pd_e2e = ctx->e2_end;
     ctx->last_call = 2;
     if ((rc = kl_launch_axpby(ctx, r_dev, ctx->d_fext, sign_fint, lam_fext, ctx->d.nfree, s))) return rc;
     if ((rc = zero_values(ctx, s))) return rc;

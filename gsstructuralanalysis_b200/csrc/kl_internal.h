@@ -100,7 +100,8 @@ struct kl_ctx {
     // records in d.pd were computed for; a Jacobian call at a bit-identical state skips constructSolution + the point kernel
     double* d_xstate = nullptr;      // [nfree]
     int* d_same = nullptr;           // device word: != 0 when the current call's x equals d_xstate
-    int pd_valid = 0;                // d.pd / d_xstate hold a whole-mesh evaluation (tangent included)
+    int pd_valid = 0;                // d.pd / d_xstate hold an evaluation (tangent included) of the element rows [pd_e2b, pd_e2e)
+    int pd_e2b = 0, pd_e2e = 0;
     int state_null = 0;              // that state was x == NULL (undeformed configuration, Dirichlet values not applied)
     int spec_on = 1;                 // residual calls also write the per-point records (speculating on a Jacobian at the same state)
     int last_call = 0;               // 1 residual (speculative), 2 jacobian, 0 other

@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(CG_THREADS) k_cg_dir(const CGState* __restrict
 }
 
 // Newton helpers: out = a + s*b; partial of |v|^2
-__global__ void __launch_bounds__(CG_THREADS) k_vec_axpy_out(double* __restrict__ out, const double* __restrict__ a, const double* __restrict__ b, double s, int n) {
+__global__ void __launch_bounds__(CG_THREADS) k_vec_axpy_out(double* out, const double* a, const double* __restrict__ b, double s, int n) {   // out may alias a
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = fma(s, b[i], a[i]);
 }
 __global__ void __launch_bounds__(CG_THREADS) k_vec_norm2(const double* __restrict__ v, int n, double* __restrict__ part) {
@@ -414,9 +414,42 @@ __global__ void __launch_bounds__(CG_THREADS) k_vec_norm_final(const double* __r
     if (threadIdx.x == 0) *out = sqrt(s);
 }
 
+// the seven inner products of one Crisfield corrector iteration in one pass (gsALMCrisfield::computeLambdasSimple / computeLambdaDOT,
+// src/gsALMSolvers/gsALMCrisfield.hpp:206-226,404-425): part[k][block], k = Ut.Ut, Ut.DU, Ubar.Ut, DU.DU, DU.Ubar, Ubar.Ubar, DUold.Ut
+__global__ void __launch_bounds__(CG_THREADS) k_alm_dots(const double* __restrict__ Ut, const double* __restrict__ Ubar, const double* __restrict__ DU,
+                                                         const double* __restrict__ DUold, int n, double* __restrict__ part) {
+    __shared__ double sm[CG_THREADS / 32];
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double ut = Ut[i], ub = Ubar[i], du = DU[i], dold = DUold[i];
+        a[0] = fma(ut, ut, a[0]); a[1] = fma(ut, du, a[1]); a[2] = fma(ub, ut, a[2]); a[3] = fma(du, du, a[3]);
+        a[4] = fma(du, ub, a[4]); a[5] = fma(ub, ub, a[5]); a[6] = fma(dold, ut, a[6]);
+    }
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const double t = block_sum(a[k], sm);
+        if (threadIdx.x == 0) part[k * gridDim.x + blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(CG_THREADS) k_alm_dots_final(const double* __restrict__ part, int nb, double* __restrict__ out) {
+    __shared__ double sm[CG_THREADS / 32];
+    for (int k = 0; k < 7; ++k) {
+        const double s = sum_partials(part + k * nb, nb, sm);
+        if (threadIdx.x == 0) out[k] = s;
+        __syncthreads();
+    }
+}
+// out = a*x + b*y (y may be null)
+__global__ void __launch_bounds__(CG_THREADS) k_vec_lin2(double* out, const double* x, double a, const double* y, double b, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = y ? fma(a, x[i], b * y[i]) : a * x[i];
+}
+
 }  // namespace
 
 struct KLSolveWS {
+    double *aU = nullptr, *aDU = nullptr, *adU = nullptr, *aUt = nullptr, *aUbar = nullptr, *aR = nullptr, *aDUold = nullptr, *aX = nullptr;   // arc-length vectors (lazy)
+    double* dots = nullptr;       // device [8], pinned twin dots_host
+    double* dots_host = nullptr;
     int n = 0, nb = 0, nb_spmv = 0;
     double *p = nullptr, *tmp = nullptr, *z = nullptr, *r = nullptr, *x = nullptr, *invdiag = nullptr, *part = nullptr, *b = nullptr;
     int *colinfo = nullptr, *runbase = nullptr;   // index-free SpMV of regular columns
@@ -448,7 +481,7 @@ static int ws_get(kl_ctx* ctx, KLSolveWS** out) {
     const size_t vb = sizeof(double) * (size_t)(n > 0 ? n : 1);
     double** vecs[] = {&w->p, &w->tmp, &w->z, &w->r, &w->x, &w->invdiag, &w->b, &w->nU, &w->nDU, &w->ndU, &w->nR, &w->nX};
     for (double** v : vecs) KL_CUDA(cudaMalloc((void**)v, vb));
-    const int npart = 2 * (w->nb > w->nb_spmv ? w->nb : w->nb_spmv);
+    const int npart = 8 * (w->nb > w->nb_spmv ? w->nb : w->nb_spmv);
     KL_CUDA(cudaMalloc((void**)&w->part, sizeof(double) * npart));
     KL_CUDA(cudaMalloc((void**)&w->st, sizeof(CGState)));
     KL_CUDA(cudaMalloc((void**)&w->scal, sizeof(double) * 4));
@@ -476,7 +509,9 @@ static int ws_get(kl_ctx* ctx, KLSolveWS** out) {
 void kl_solve_free(kl_ctx* ctx) {
     KLSolveWS* w = ctx->solve_ws;
     if (!w) return;
-    double* vecs[] = {w->p, w->tmp, w->z, w->r, w->x, w->invdiag, w->b, w->nU, w->nDU, w->ndU, w->nR, w->nX, w->part, w->scal};
+    double* vecs[] = {w->p, w->tmp, w->z, w->r, w->x, w->invdiag, w->b, w->nU, w->nDU, w->ndU, w->nR, w->nX, w->part, w->scal,
+                      w->aU, w->aDU, w->adU, w->aUt, w->aUbar, w->aR, w->aDUold, w->aX, w->dots};
+    if (w->dots_host) cudaFreeHost(w->dots_host);
     for (double* v : vecs) if (v) cudaFree(v);
     if (w->st) cudaFree(w->st);
     if (w->colinfo) cudaFree(w->colinfo);
@@ -561,6 +596,10 @@ static int cg_run(kl_ctx* ctx, KLSolveWS* w, double tol, int max_iter, int* iter
         KL_CUDA(cudaMemcpyAsync(w->st_host, w->st, sizeof(CGState), cudaMemcpyDeviceToHost, s));
         KL_CUDA(cudaStreamSynchronize(s));
         if (w->st_host->done) break;
+        {   // an indefinite or unassembled matrix makes pAp <= 0 / NaN: the stop test |r|^2 < threshold can then never fire
+            const CGState& c = *w->st_host;
+            if (batches > 0 && (!(c.rn2 == c.rn2) || !(c.pAp == c.pAp) || c.pAp <= 0.0 || !std::isfinite(c.rn2))) break;
+        }
         if (use_graph) KL_CUDA(cudaGraphLaunch(w->graph, s));
         else
             for (int k = 0; k < CG_BATCH; ++k)
@@ -573,8 +612,8 @@ static int cg_run(kl_ctx* ctx, KLSolveWS* w, double tol, int max_iter, int* iter
     ctx->launches += (int)(batches * CG_BATCH * 5);
     if (iters) *iters = st.iters;
     if (rel_err) *rel_err = st.rhsNorm2 > 0.0 ? std::sqrt(st.rn2 / st.rhsNorm2) : 0.0;
-    if (!(st.rn2 == st.rn2) || !(st.pAp == st.pAp)) {
-        kl_set_error("kl_cg_solve: non-finite value in the iteration (matrix not assembled or not positive definite?)");
+    if (!(st.rn2 == st.rn2) || !(st.pAp == st.pAp) || !std::isfinite(st.rn2) || (!st.done && st.pAp <= 0.0)) {
+        kl_set_error("kl_cg_solve: non-finite value or p.Ap <= 0 in the iteration (matrix not assembled or not positive definite?)");
         return KL_E_NONFINITE;
     }
     cudaEventElapsedTime(&w->ms_total, w->e0, w->e1);
@@ -752,4 +791,229 @@ extern "C" int kl_newton_solve(kl_ctx* ctx, double* U_host, const kl_newton_opti
     return KL_OK;
 #undef NW_ASM
 #undef NW_CG
+}
+
+
+// ---- Crisfield arc-length step (gsALMBase<T>::_step, src/gsALMSolvers/gsALMBase.hpp:354-416, with gsALMCrisfield<T>,
+//      src/gsALMSolvers/gsALMCrisfield.hpp:66-226,328-425), device resident: per corrector iteration one Jacobian, two CGDiagonal
+//      solves with the same matrix (deltaUt = K^-1 F, deltaUbar = -K^-1 R), one arc-length residual and the constraint update; only
+//      the solution vectors cross PCIe, once per step.  Options follow gsALMBase::defaultOptions (:25-52) / gsALMCrisfield (:26-27):
+//      AngleMethod = 0 (previous step), no quasi-Newton, no stability computation.
+static int alm_ws(kl_ctx* ctx, KLSolveWS* w) {
+    if (w->aU) return KL_OK;
+    const size_t vb = sizeof(double) * (size_t)(w->n > 0 ? w->n : 1);
+    double** vecs[] = {&w->aU, &w->aDU, &w->adU, &w->aUt, &w->aUbar, &w->aR, &w->aDUold, &w->aX};
+    for (double** v : vecs) KL_CUDA(cudaMalloc((void**)v, vb));
+    KL_CUDA(cudaMalloc((void**)&w->dots, sizeof(double) * 8));
+    KL_CUDA(cudaMallocHost((void**)&w->dots_host, sizeof(double) * 8));
+    (void)ctx;
+    return KL_OK;
+}
+
+static inline int sgn(double v) { return (v > 0) - (v < 0); }
+
+extern "C" int kl_alm_step(kl_ctx* ctx, double* U_host, double* L_io, double* DUold_host, double* DLold_io, double arc_length,
+                           const kl_alm_options* opt, kl_alm_info* info) {
+    if (!ctx || !U_host || !L_io || !DLold_io || !opt || !info) { kl_set_error("kl_alm_step: null argument"); return KL_E_ARG; }
+    KL_CUDA(cudaSetDevice(ctx->device));
+    KLSolveWS* w = nullptr;
+    int rc = ws_get(ctx, &w);
+    if (rc) return rc;
+    if ((rc = alm_ws(ctx, w))) return rc;
+    cudaStream_t s = ctx->stream;
+    const int n = w->n;
+    const size_t vb = sizeof(double) * (size_t)n;
+    std::memset(info, 0, sizeof(*info));
+    float ms_asm = 0.f, ms_sol = 0.f, ms = 0.f;
+    cudaEvent_t ea = ctx->ev[0], eb = ctx->ev[1];
+    int it_cg = 0;
+    double err_cg = 0.0;
+    const double* F = ctx->d_force;
+#define AL_FAIL(code) do { info->status = (code); info->ms_assembly = ms_asm; info->ms_solve = ms_sol; return KL_OK; } while (0)
+#define AL_ASM(call)                                                                                   \
+    do {                                                                                               \
+        KL_CUDA(cudaEventRecord(ea, s));                                                               \
+        int rc_ = (call);                                                                              \
+        if (rc_ == KL_OK) rc_ = kl_check(ctx, s);                                                      \
+        KL_CUDA(cudaEventRecord(eb, s));                                                               \
+        KL_CUDA(cudaStreamSynchronize(s));                                                             \
+        cudaEventElapsedTime(&ms, ea, eb); ms_asm += ms;                                               \
+        if (rc_ == KL_E_CUDA || rc_ == KL_E_ARG) return rc_;                                           \
+        if (rc_ != KL_OK) AL_FAIL(2);                                                                  \
+    } while (0)
+#define AL_SOLVE(rhs_expr, out)                                                                        \
+    do {                                                                                               \
+        rhs_expr;                                                                                      \
+        int rc_ = cg_run(ctx, w, opt->cg_tol, opt->cg_max_iter, &it_cg, &err_cg, s);                   \
+        ms_sol += w->ms_total; info->cg_iterations += it_cg;                                           \
+        if (rc_ == KL_E_CUDA || rc_ == KL_E_ARG) return rc_;                                           \
+        if (rc_ != KL_OK) AL_FAIL(3);                                                                  \
+        KL_CUDA(cudaMemcpyAsync((out), w->x, vb, cudaMemcpyDeviceToDevice, s));                        \
+    } while (0)
+    auto dots = [&](double* d7) -> int {
+        k_alm_dots<<<w->nb, CG_THREADS, 0, s>>>(w->aUt, w->aUbar, w->aDU, w->aDUold, n, w->part);
+        k_alm_dots_final<<<1, CG_THREADS, 0, s>>>(w->part, w->nb, w->dots);
+        KL_CUDA(cudaGetLastError());
+        ctx->launches += 2;
+        KL_CUDA(cudaMemcpyAsync(w->dots_host, w->dots, sizeof(double) * 7, cudaMemcpyDeviceToHost, s));
+        KL_CUDA(cudaStreamSynchronize(s));
+        for (int k = 0; k < 7; ++k) d7[k] = w->dots_host[k];
+        return KL_OK;
+    };
+    auto lin2 = [&](double* out, const double* x, double a, const double* y, double b) {
+        k_vec_lin2<<<w->nb, CG_THREADS, 0, s>>>(out, x, a, y, b, n);
+        ctx->launches++;
+    };
+
+    // state in: m_U, m_L, m_DeltaUold, m_DeltaLold (setSolution / setPrevious, gsALMBase.h:185-194)
+    double L = *L_io, DLold = *DLold_io;
+    std::memcpy(ctx->h_pinned_x, U_host, vb);
+    KL_CUDA(cudaMemcpyAsync(w->aU, ctx->h_pinned_x, vb, cudaMemcpyHostToDevice, s));
+    KL_CUDA(cudaStreamSynchronize(s));
+    if (DUold_host) {
+        std::memcpy(ctx->h_pinned_x, DUold_host, vb);
+        KL_CUDA(cudaMemcpyAsync(w->aDUold, ctx->h_pinned_x, vb, cudaMemcpyHostToDevice, s));
+        KL_CUDA(cudaStreamSynchronize(s));
+    } else {
+        KL_CUDA(cudaMemsetAsync(w->aDUold, 0, vb, s));
+    }
+    double nF = 0, nU = 0, nDUold = 0;
+    if ((rc = dev_norm(ctx, w, F, &nF, s))) return rc;
+    if ((rc = dev_norm(ctx, w, w->aU, &nU, s))) return rc;
+    if ((rc = dev_norm(ctx, w, w->aDUold, &nDUold, s))) return rc;
+    const double FF = nF * nF;
+    const bool phi_user = opt->phi >= 0.0;
+    double phi = phi_user ? opt->phi : 0.0;
+    const double relax = opt->relaxation != 0.0 ? opt->relaxation : 1.0;
+    const int maxit = opt->max_it > 0 ? opt->max_it : 100;
+    // initiateStep
+    KL_CUDA(cudaMemsetAsync(w->aDU, 0, vb, s));
+    KL_CUDA(cudaMemsetAsync(w->aUbar, 0, vb, s));
+    KL_CUDA(cudaMemsetAsync(w->adU, 0, vb, s));
+    double DL = 0.0, dL = 0.0, eta = 1.0, d7[7];
+    // predictor (gsALMCrisfield.hpp:111-164)
+    AL_ASM(kl_jacobian_device(ctx, w->aU, s));
+    AL_SOLVE(KL_CUDA(cudaMemcpyAsync(w->b, F, vb, cudaMemcpyDeviceToDevice, s)), w->aUt);
+    if ((rc = dots(d7))) return rc;
+    if (nDUold * nDUold == 0.0 && DLold * DLold == 0.0) {       // no information about a previous step
+        dL = arc_length / std::sqrt(2.0 * d7[0]);
+        if (!phi_user) phi = std::sqrt(d7[0] / FF);
+    } else {
+        if (!phi_user) phi = std::sqrt(nU * nU / (L * L * FF));
+        const double A0 = phi * phi * FF;                       // computeLambdaMU (:386-401)
+        const int dir = sgn(d7[6] + A0 * DLold);
+        const double denum = std::sqrt(d7[0] + A0);
+        dL = dir * (denum == 0.0 ? arc_length : arc_length / denum);
+    }
+    lin2(w->adU, w->aUt, dL, nullptr, 0.0);                     // deltaU = deltaL * deltaUt (deltaUbar = 0 here)
+    lin2(w->aDU, w->aDU, 1.0, w->adU, 1.0);
+    DL += dL;
+    const double A0 = phi * phi * FF;
+    // residual and its reference norms (gsALMBase.hpp:151-171)
+    lin2(w->aX, w->aU, 1.0, w->aDU, 1.0);
+    AL_ASM(kl_al_residual_device(ctx, w->aX, L + DL, w->aR, s));
+    double nR = 0, ndU = 0, nDU = 0;
+    if ((rc = dev_norm(ctx, w, w->aR, &nR, s))) return rc;
+    if ((rc = dev_norm(ctx, w, w->aDU, &nDU, s))) return rc;
+    const double basisF = std::fabs(L + DL) * nF, basisU = nDU;
+    info->residueF = nR / basisF; info->residueU = 1.0;
+    info->status = 1;
+    int it = 1;
+    for (; it < maxit; ++it) {
+        // quasiNewtonIteration: new tangent, deltaUt (:67-72)
+        AL_ASM(kl_jacobian_device(ctx, w->aX, s));
+        AL_SOLVE(KL_CUDA(cudaMemcpyAsync(w->b, F, vb, cudaMemcpyDeviceToDevice, s)), w->aUt);
+        // iteration: deltaUbar = K^-1 (-R), constraint (:75-99)
+        AL_SOLVE(lin2(w->b, w->aR, -1.0, nullptr, 0.0), w->aUbar);
+        if ((rc = dots(d7))) return rc;
+        eta = 1.0;
+        const double lamold = dL;
+        const double a0 = d7[0] + A0, b0 = 2.0 * (d7[1] + DL * A0), b1 = 2.0 * d7[2];
+        const double c0 = d7[3] + DL * DL * A0 - arc_length * arc_length, c1 = 2.0 * d7[4], c2 = d7[5];
+        double al1 = a0, al2 = b0 + eta * b1, al3 = c0 + eta * c1 + eta * eta * c2;
+        double disc = al2 * al2 - 4.0 * al1 * al3;
+        double dLs[2] = {0, 0};
+        bool complex_root = false;
+        if (disc >= 0.0) {
+            dLs[0] = (-al2 + std::sqrt(disc)) / (2.0 * al1);
+            dLs[1] = (-al2 - std::sqrt(disc)) / (2.0 * al1);
+        } else {
+            // computeLambdasModified (Lam 1992) -> eta; computeLambdasEta (Zhou 1995)
+            const double m1 = b1 * b1 - 4.0 * a0 * c2, m2 = 2.0 * b0 * b1 - 4.0 * a0 * c1, m3 = b0 * b0 - 4.0 * a0 * c0;
+            disc = m2 * m2 - 4.0 * m1 * m3;
+            if (disc >= 0.0) {
+                const double e1 = (-m2 + std::sqrt(disc)) / (2.0 * m1), e2 = (-m2 - std::sqrt(disc)) / (2.0 * m1);
+                const double eta1 = std::min(e1, e2), eta2 = std::max(e1, e2), xi = 0.05 * std::fabs(eta2 - eta1);
+                if (eta2 < 1.0) eta = eta2 - xi;
+                else if (eta2 > 1.0 && -m2 / m1 < 1.0) eta = eta2 + xi;
+                else if (eta1 < 1.0 && -m2 / m1 > 1.0) eta = eta1 - xi;
+                else if (eta1 > 1.0) eta = eta1 + xi;
+            }
+            if (disc >= 0.0 && eta > 0.05) {
+                al2 = b0 + eta * b1;
+                dLs[0] = dLs[1] = -al2 / (2.0 * al1);
+            } else {
+                eta = 1.0;
+                complex_root = true;
+            }
+        }
+        if (!complex_root) {
+            // computeLambdaDOT (Ritto-Correa 2008)
+            const double t = d7[6] + phi * phi * DLold;
+            const double DOT1 = dLs[0] * t, DOT2 = dLs[1] * t;
+            dL = (DOT1 < DOT2) ? dLs[1] : dLs[0];
+            lin2(w->adU, w->aUbar, eta, w->aUt, dL);
+        } else {
+            // computeLambdasComplex (Lam 1992, eq. 13-17): Fint = K (U + DeltaU), scaled back onto the constraint
+            lin2(w->adU, w->aDU, 1.0, w->aUbar, 1.0);                      // DeltaUcr
+            lin2(w->p, w->aU, 1.0, w->aDU, 1.0);
+            if ((rc = launch_spmv<false>(ctx, w, w->p, w->tmp, nullptr, nullptr, s))) return rc;
+            ctx->launches++;
+            double nCr = 0, FintF = 0;
+            // Fint.F via |Fint + F|^2 - |Fint|^2 - |F|^2
+            double nA = 0, nB = 0;
+            if ((rc = dev_norm(ctx, w, w->tmp, &nA, s))) return rc;
+            lin2(w->tmp, w->tmp, 1.0, F, 1.0);
+            if ((rc = dev_norm(ctx, w, w->tmp, &nB, s))) return rc;
+            FintF = 0.5 * (nB * nB - nA * nA - FF);
+            if ((rc = dev_norm(ctx, w, w->adU, &nCr, s))) return rc;
+            const double DLcr = FintF / FF - L;
+            const double mu = arc_length / std::sqrt(nCr * nCr + A0 * DLcr * DLcr);
+            dL = mu * DLcr - DL;
+            lin2(w->adU, w->adU, mu, w->aDU, -1.0);
+        }
+        // relaxation against an oscillating load factor
+        if ((lamold * dL < 0) && (std::fabs(dL) <= std::fabs(lamold)) && relax != 1.0) {
+            lin2(w->adU, w->aUt, relax * dL, w->aUbar, relax * eta);
+            dL = relax * dL;
+        }
+        lin2(w->aDU, w->aDU, 1.0, w->adU, 1.0);
+        DL += dL;
+        lin2(w->aX, w->aU, 1.0, w->aDU, 1.0);
+        AL_ASM(kl_al_residual_device(ctx, w->aX, L + DL, w->aR, s));
+        if ((rc = dev_norm(ctx, w, w->aR, &nR, s))) return rc;
+        if ((rc = dev_norm(ctx, w, w->adU, &ndU, s))) return rc;
+        info->residueF = nR / basisF; info->residueU = ndU / basisU;
+        if (info->residueF < opt->tolF && info->residueU < opt->tolU) { info->status = 0; break; }
+    }
+    info->iterations = it;
+    info->phi = phi; info->DeltaL = DL;
+    info->ms_assembly = ms_asm; info->ms_solve = ms_sol;
+    if (info->status != 0) return KL_OK;                         // NotConverged: the caller's state is untouched (it bisects)
+    // iterationFinish: U += DeltaU, L += DeltaL, DeltaUold = DeltaU (AngleMethod = step)
+    KL_CUDA(cudaMemcpyAsync(ctx->h_pinned_r, w->aX, vb, cudaMemcpyDeviceToHost, s));
+    KL_CUDA(cudaStreamSynchronize(s));
+    std::memcpy(U_host, ctx->h_pinned_r, vb);
+    if (DUold_host) {
+        KL_CUDA(cudaMemcpyAsync(ctx->h_pinned_r, w->aDU, vb, cudaMemcpyDeviceToHost, s));
+        KL_CUDA(cudaStreamSynchronize(s));
+        std::memcpy(DUold_host, ctx->h_pinned_r, vb);
+    }
+    *L_io = L + DL;
+    *DLold_io = DL;
+    KL_CUDA(cudaGetLastError());
+    return KL_OK;
+#undef AL_FAIL
+#undef AL_ASM
+#undef AL_SOLVE
 }

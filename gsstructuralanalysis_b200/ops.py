@@ -212,6 +212,17 @@ class ShellAssembler:
         capi.check(self.L.kl_newton_solve(self.h, _dp(U), C.byref(opt), C.byref(info)))
         return U, {k: getattr(info, k) for k, _ in capi.kl_newton_info._fields_}
 
+    def alm_step(self, U, L, DUold=None, DLold=0.0, arc_length=1e-2, tolU=1e-6, tolF=1e-3, max_it=100, phi=-1.0, relaxation=1.0,
+                 cg_tol=0.0, cg_max_iter=0):
+        """gsALMCrisfield::step(), device resident: returns (status, U, L, DeltaU, DeltaL, info); the inputs are not modified."""
+        U = np.array(U, dtype=np.float64)
+        DU = np.zeros(self.n_dofs) if DUold is None else np.array(DUold, dtype=np.float64)
+        Lc, DLc = C.c_double(L), C.c_double(DLold)
+        opt = capi.kl_alm_options(tolU, tolF, max_it, phi, relaxation, cg_tol, cg_max_iter)
+        info = capi.kl_alm_info()
+        capi.check(self.L.kl_alm_step(self.h, _dp(U), C.byref(Lc), _dp(DU), C.byref(DLc), float(arc_length), C.byref(opt), C.byref(info)))
+        return info.status, U, Lc.value, DU, DLc.value, {k: getattr(info, k) for k, _ in capi.kl_alm_info._fields_}
+
     # -- stress / stretch recovery (SURVEY 8f rank 4) --------------------------------------------
     def eval_stress(self, x, stress_type, uv, z=0.0):
         """constructStress(mp_def, field, stress_type::X) evaluated at the parametric points uv [n,2]: array [n, dim]

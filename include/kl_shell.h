@@ -232,6 +232,32 @@ typedef struct kl_newton_info {
 } kl_newton_info;
 int kl_newton_solve(kl_ctx* ctx, double* U_host_inout, const kl_newton_options* opt, kl_newton_info* info);
 
+/* gsALMBase<T>::step() with gsALMCrisfield<T> (src/gsALMSolvers/gsALMBase.hpp:354-416, gsALMCrisfield.hpp:66-226,328-425) and the
+ * CGDiagonal solver benchmarks/benchmark_Frustrum_APALM.cpp:435 selects, everything device resident: per corrector iteration one
+ * Jacobian, two solves with that matrix (deltaUt = K^-1 Force, deltaUbar = -K^-1 R), one arc-length residual, the quadratic
+ * constraint (real, modified and complex-root branches) and the root choice of Ritto-Correa.  Options as in
+ * gsALMBase::defaultOptions (:25-52): AngleMethod 0, no quasi-Newton, no stability computation.
+ * State in/out (host): U, L = m_U, m_L; DeltaUold (may be NULL = 0), DeltaLold = the previous step (setPrevious: U - Uprev).
+ * status 0: converged, state advanced; 1: NotConverged / 2: AssemblyError / 3: SolverError: state untouched, the caller
+ * halves arc_length and retries (gsAPALM.hpp:975-983). */
+typedef struct kl_alm_options {
+    double tolU, tolF;          /* "TolU" (1e-6), "TolF" (1e-3)                                       */
+    int32_t max_it;             /* "MaxIter" (100)                                                    */
+    double phi;                 /* "Scaling": >= 0 fixed, < 0 automatic (gsALMCrisfield.hpp:26)        */
+    double relaxation;          /* "Relaxation" (1)                                                   */
+    double cg_tol;              /* <= 0: Eigen default DBL_EPSILON                                    */
+    int32_t cg_max_iter;        /* <= 0: Eigen default 2 n                                            */
+} kl_alm_options;
+typedef struct kl_alm_info {
+    int32_t status;             /* gsStatus                                                           */
+    int32_t iterations;         /* m_numIterations                                                    */
+    int64_t cg_iterations;
+    double residueF, residueU, phi, DeltaL;
+    float ms_assembly, ms_solve;
+} kl_alm_info;
+int kl_alm_step(kl_ctx* ctx, double* U_host_inout, double* L_inout, double* DeltaUold_host_inout, double* DeltaLold_inout,
+                double arc_length, const kl_alm_options* opt, kl_alm_info* info);
+
 /* ---- stress / stretch recovery -----------------------------------------------
  * Replaces assembler->constructStress(mp_def, field, stress_type::X) followed by field evaluation
  * (benchmarks/benchmark_Balloon.cpp:381-408, benchmark_TensionWrinkling.cpp:505-540, benchmark_Pillow.cpp:431,484-505),

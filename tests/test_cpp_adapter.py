@@ -63,32 +63,34 @@ def _parse(line):
 
 
 def test_apalm_queue_semantics_cpu():
-    """gsAPALMData pop/submit rules (src/gsALMSolvers/gsAPALMData.hpp:215-252,391-409) with fake workers: every level-1
-    interval is 25 % off and gets refined once into 2 children, deeper levels are exact."""
+    """gsAPALMData pop / submit / storage rules (src/gsALMSolvers/gsAPALMData.hpp:215-252,291-433) with fake workers: on level 1
+    the lower error of an interval is 25 % and its two computed sub-intervals are queued on level 2, which is exact."""
     _build_apalm()
     for workers in (1, 3, 8):
         r = subprocess.run([APALM, "--fake", str(workers), "8"], capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stdout + r.stderr
         d = _parse(r.stdout.strip().splitlines()[-1])
-        assert int(d["jobs"]) == 8 + 16 and int(d["points"]) == 24 and int(d["maxLevel"]) == 2 and int(d["failed"]) == 0
+        assert int(d["jobs"]) == 8 + 16 and int(d["points"]) == 48 and int(d["maxLevel"]) == 2 and int(d["failed"]) == 0
         per = [int(v) for v in r.stdout.strip().split("per_worker=")[1].split()]
         assert len(per) == workers and sum(per) == 24 and min(per) >= 1
 
 
 @pytest.mark.gpu
-def test_apalm_intervals_one_per_gpu(tmp_path):
+def test_apalm_traversal_on_the_gpus(tmp_path):
+    """benchmark_Frustrum_APALM in small: serial level-0 chain of Crisfield steps, then the correction jobs on every GPU of the box."""
     import torch
     _build_apalm()
     from gsstructuralanalysis_b200 import workloads as W, capi
-    pr = W.frustrum(24)
+    pr = W.frustrum(12)
     pr.number_dofs(capi.lib().kl_build_dofmap)
     path = os.path.join(str(tmp_path), "f.klp")
     pr.save(path)
     n = torch.cuda.device_count()
-    r = subprocess.run([APALM, path, str(n), str(4 * n), "3"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([APALM, path, str(n), "6", "0.05", "2", "1e-3", "2"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     d = _parse(r.stdout.strip().splitlines()[-1])
-    assert int(d["jobs"]) == 4 * n and int(d["failed"]) == 0
+    assert int(d["jobs"]) >= 6 and int(d["failed"]) == 0 and int(d["points"]) >= 7 + 2 * 6
+    assert float(d["lambda_end"]) > 0 and float(d["t_chain_s"]) > 0 and float(d["sum_job_s"]) > 0
 
 
 SOLID_EXE = os.path.join(ROOT, "examples", "solid_newton")
