@@ -207,6 +207,34 @@ def time_device_steps(torch, step, steps, barrier=None):
     return e0.elapsed_time(e1) / steps
 
 
+def run_apalm(n_gpus, args):
+    """benchmark_Frustrum_APALM on this box: serial chain of coarse Crisfield steps, then the correction jobs on n_gpus workers."""
+    from gsstructuralanalysis_b200 import build as kbuild, capi
+    exe = kbuild.build_examples()
+    pr = W.frustrum(args.apalm_nel)
+    pr.number_dofs(capi.lib().kl_build_dofmap)
+    path = os.path.join("/tmp", "kl_apalm_%d.klp" % os.getpid())
+    pr.save(path)
+    cmd = [exe, path, str(n_gpus), str(args.apalm_steps), "0.05", "2", "1e-3", "2", "1e-12"]
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    wall = time.perf_counter() - t0
+    os.remove(path)
+    line = [l for l in r.stdout.splitlines() if l.startswith("APALM ")]
+    if r.returncode != 0 or not line:
+        return {"error": (r.stdout + r.stderr)[-400:]}
+    d = dict(tok.split("=") for tok in line[-1].split() if "=" in tok and not tok.startswith("per_worker"))
+    out = {k: (float(v) if "." in v else int(v)) for k, v in d.items()}
+    out["jobs_per_worker"] = [int(v) for v in line[-1].split("per_worker=")[1].split()]
+    out["process_wall_s"] = wall
+    out["workload"] = (f"benchmark_Frustrum_APALM testCase 0 (configs[4]): frustrum {args.apalm_nel}x{args.apalm_nel} elements, degree 3, Mooney-Rivlin, "
+                       f"Neumann top edge, gsALMCrisfield (CGDiagonal on the device, Scaling 0), {args.apalm_steps} level-0 steps of dL = 0.05, "
+                       "SubIntervals 2, tolerance 1e-3, MaxLevel 2")
+    out["what"] = ("t_chain_s: sequential level-0 chain on one GPU; sum_job_s: the correction jobs one after the other; t_parallel_s: the same jobs on "
+                   "n_gpus worker threads (one GPU + one assembler replica each); speedup_total = (t_chain + sum_job) / (t_chain + t_parallel)")
+    return out
+
+
 def config_records(torch, capi, args, local, hbm_peak, fp64_peak):
     """one sub-record per BASELINE.json config at benchmark size (Jacobian ms, step ms, roofline fractions),
     each with its parity against the oracle on a coarse twin of the same problem."""
@@ -292,6 +320,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config sub-records (BASELINE.md table)")
     ap.add_argument("--no-strips", action="store_true", help="N>1: skip the strong-scaling strips sub-record")
+    ap.add_argument("--no-apalm", action="store_true", help="skip the gsAPALM traversal sub-record")
+    ap.add_argument("--apalm-nel", type=int, default=64)
+    ap.add_argument("--apalm-steps", type=int, default=16)
     ap.add_argument("--fused-call", action="store_true", help="device leg: the single-call entry kl_assemble_device instead of the two closure calls")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: everything libraries print (NCCL banner, ...) is diverted to stderr
@@ -445,7 +476,8 @@ def main():
     # ---- strong scaling: ONE matrix in element-row strips + halo exchange (the path with a real exchange step)
     strong = None
     if world > 1 and not args.no_strips:
-        from gsstructuralanalysis_b200.parallel import plan_strips, exchange_halo, DevicePointerView, function_supports, value_ranges
+        from gsstructuralanalysis_b200.parallel import (plan_strips, exchange_halo, assemble_strip_overlapped, DevicePointerView,
+                                                        function_supports, value_ranges)
         x1 = torch.from_numpy(W.displacement_state(n, args.scale * h, seed=20240607)).cuda()      # one state, one matrix
         vals_view = DevicePointerView(asm.values_device_ptr(), nnz).tensor()
         outer_h, _ = asm.pattern()
@@ -460,6 +492,9 @@ def main():
         ex_ms = []
 
         def strip_step(timed=False):
+            if not timed:
+                # interface rows first, halo exchange in flight while the rest of the strip is assembled
+                return assemble_strip_overlapped(asm, plan, outer_h, vals_view, r_dev, x1.data_ptr(), dist, stream)
             asm.residual_device(x1.data_ptr(), r_dev.data_ptr(), 0.0, 1.0, stream)     # partial internal force of the strip
             asm.jacobian_device(x1.data_ptr(), stream)
             if timed:
@@ -486,11 +521,33 @@ def main():
         asm.set_strip(0, asm.n_elements // (pr.surface.n[0] - 3))
         strong = {"scaling": "strong", "ms_per_step": ms_strong, "value": nqp / (ms_strong * 1e-3), "unit": UNIT,
                   "exchange_ms": allmax(float(np.mean(ex_ms))), "halo_bytes_received_max": int(allmax(float(halo_bytes))),
-                  "nccl_op": "batched ncclSend/ncclRecv to the neighbour strip (batch_isend_irecv), one fused add of the received ranges",
+                  "nccl_op": "batched ncclSend/ncclRecv to the neighbour strip (batch_isend_irecv) posted after the interface rows and overlapped with the "
+                              "rest of the strip, one fused add of the received ranges; exchange_ms = the same exchange timed without overlap",
                   "per_rank_fixed_ms": ms_fixed, "speedup_vs_1gpu_step": None,
                   "parity_vs_single_gpu": {"max_rel_K": errK, "max_rel_R": errR, "ok": bool(errK <= 1e-12 and errR <= 1e-12)},
                   "what": "ONE matrix of the same workload: every rank assembles its element-row strip, interface columns go to their owner"}
         del K_full, R_full
+
+    # ---- gsAPALM traversal of the frustrum (configs[4]): level-0 chain + correction jobs, one worker thread per GPU of this box
+    #      (examples/apalm_dispatch.cpp over include/gsAPALM_b200.h); the other ranks keep their GPUs idle meanwhile
+    apalm = None
+    if not args.no_apalm:
+        flag = os.path.join("/tmp", "kl_apalm_done_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid()))
+        if rank == 0:
+            try:
+                apalm = run_apalm(world, args)
+            except Exception as exc:
+                apalm = {"error": f"{type(exc).__name__}: {exc}"}
+            if world > 1:
+                open(flag, "w").close()
+        else:
+            t_wait = time.time()
+            while not os.path.exists(flag) and time.time() - t_wait < 900:
+                time.sleep(0.2)
+        if world > 1:
+            dist.barrier()
+            if rank == 0 and os.path.exists(flag):
+                os.remove(flag)
 
     # ---- device-resident linear solve on the matrix just assembled (not part of `value`)
     solver = None
@@ -595,6 +652,7 @@ def main():
         "cpu_baseline": cpu,
         "linear_solve": solver,
         "strong": strong,
+        "apalm": apalm,
         "configs": configs,
     }
     emit(out)

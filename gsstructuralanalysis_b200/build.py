@@ -47,5 +47,17 @@ def build(force=False, verbose=False, out=None, extra=()):
     return out
 
 
+def build_examples(force=False):
+    """host-side C++ drivers over the C ABI (g++; they link the in-tree libkl_shell.so)"""
+    root = os.path.dirname(HERE)
+    exe = os.path.join(root, "examples", "apalm_dispatch")
+    src = os.path.join(root, "examples", "apalm_dispatch.cpp")
+    deps = [src, os.path.join(root, "examples", "problem_file.h"), os.path.join(root, "include", "gsAPALM_b200.h"),
+            os.path.join(root, "include", "kl_shell.h")]
+    if force or not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-pthread", "-o", exe, src, "-L" + HERE, "-l:libkl_shell.so", "-Wl,-rpath," + HERE])
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -23,7 +23,7 @@ SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern
            "kl_assemble_device", "kl_cg_solve", "kl_cg_solve_device", "kl_spmv", "kl_cg_last_timing", "kl_newton_solve",
            "kl_stress_dim", "kl_eval_stress", "kl_principal_stretches", "kl_boundary_force",
            "kl_pin_values", "kl_unpin_values", "kl_fetch_values", "kl_set_values", "kl_pattern_lower_host", "kl_jacobian_lower",
-           "kl_al_residual_device", "kl_alm_step"]
+           "kl_al_residual_device", "kl_alm_step", "kl_strip_begin_device", "kl_jacobian_rows_device"]
 
 # stress_type of constructStress (include/kl_shell.h)
 STRESS_TYPES = {"displacement": 0, "membrane_force": 1, "flexural_moment": 2, "membrane": 3, "flexural": 4,
@@ -109,6 +109,8 @@ def lib():
     L.kl_newton_solve.argtypes = [vp, c_double_p, C.POINTER(kl_newton_options), C.POINTER(kl_newton_info)]
     L.kl_alm_step.argtypes = [vp, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double, C.POINTER(kl_alm_options), C.POINTER(kl_alm_info)]
     L.kl_al_residual_device.argtypes = [vp, vp, C.c_double, vp, vp]
+    L.kl_strip_begin_device.argtypes = [vp, vp, C.c_double, C.c_double, vp, C.c_int32, vp]
+    L.kl_jacobian_rows_device.argtypes = [vp, C.c_int32, C.c_int32, vp]
     L.kl_stress_dim.argtypes = [C.c_int32]
     L.kl_eval_stress.argtypes = [vp, c_double_p, C.c_int32, C.c_int32, c_double_p, C.c_double, c_double_p]
     L.kl_principal_stretches.argtypes = [vp, c_double_p, C.c_int32, c_double_p, C.c_double, c_double_p]

@@ -624,6 +624,29 @@ extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_f
     return kl_launch_axpby(ctx, r_dev, ctx->d_fext, sign_fint, lam_fext, ctx->d.nfree, s);
 }
 
+// Strip assembly in two phases so that the halo exchange overlaps the bulk of the work: phase 0 evaluates the points of
+// the whole strip (records + internal force), zeroes the strip's value ranges and assembles the LAST `tail_rows` element rows, whose
+// contributions reach the next strip; the caller starts the exchange and calls kl_jacobian_rows_device for the remaining rows.
+extern "C" int kl_strip_begin_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, int32_t tail_rows, void* stream) {
+    if (!ctx || !r_dev || tail_rows < 0) return KL_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc;
+    const int spec = ctx->spec_on, last = ctx->last_call;
+    ctx->spec_on = 1; ctx->last_call = 0;                     // the per-point records of the strip are needed by the Jacobian rows
+    rc = kl_residual_device(ctx, x_dev, lam_fext, sign_fint, r_dev, stream);
+    ctx->spec_on = spec; ctx->last_call = last;
+    if (rc) return rc;
+    if (!ctx->spec_allowed) { kl_set_error("kl_strip_begin_device needs the per-point records (KL_SPECULATE=0 is set)"); return KL_E_ARG; }
+    if ((rc = zero_values(ctx, s))) return rc;
+    const int b = std::max(ctx->e2_begin, ctx->e2_end - tail_rows);
+    return kl_launch_jacobian(ctx, b, ctx->e2_end, s);
+}
+extern "C" int kl_jacobian_rows_device(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end, void* stream) {
+    if (!ctx || e2_begin < ctx->e2_begin || e2_end > ctx->e2_end) { kl_set_error("kl_jacobian_rows_device: rows outside the strip"); return KL_E_ARG; }
+    if (!ctx->pd_valid || ctx->pd_e2b != ctx->e2_begin || ctx->pd_e2e != ctx->e2_end) { kl_set_error("kl_jacobian_rows_device: no per-point records of this strip"); return KL_E_ARG; }
+    return kl_launch_jacobian(ctx, e2_begin, e2_end, (cudaStream_t)stream);
+}
+
 extern "C" int kl_al_residual_device(kl_ctx* ctx, const double* x_dev, double lam, double* r_dev, void* stream) {
     // Force - lam*Force - rhs(x) with rhs(x) = F_dead - (F_int(x) - P(x))
     if (int rc = kl_residual_device(ctx, x_dev, -1.0, 1.0, r_dev, stream)) return rc;

@@ -175,6 +175,13 @@ class ShellAssembler:
         capi.check(self.L.kl_assemble_device(self.h, C.c_void_p(x_dev_ptr), lam_fext, sign_fint, C.c_void_p(r_dev_ptr),
                                              C.c_void_p(stream)))
 
+    def strip_begin_device(self, x_dev_ptr, r_dev_ptr, lam_fext, sign_fint, tail_rows, stream=0):
+        capi.check(self.L.kl_strip_begin_device(self.h, C.c_void_p(x_dev_ptr), lam_fext, sign_fint, C.c_void_p(r_dev_ptr), int(tail_rows),
+                                                C.c_void_p(stream)))
+
+    def jacobian_rows_device(self, e2_begin, e2_end, stream=0):
+        capi.check(self.L.kl_jacobian_rows_device(self.h, int(e2_begin), int(e2_end), C.c_void_p(stream)))
+
     def check(self, stream=0):
         return self.L.kl_check(self.h, C.c_void_p(stream))
 

@@ -53,6 +53,7 @@ class StripPlan:
     send_cols: list               # column ranges whose partial sums go to rank+1
     recv_cols: list               # column ranges received from rank-1 (== that rank's send_cols)
     shared_cols: list             # column ranges touched by several strips' OWN rows (matched DoFs): completed by all-reduce
+    tail_rows: int = 0            # the last element rows of the strip that reach control-point rows of the next strip
     _bufs: dict = field(default_factory=dict)     # receive / pack buffers, allocated once per (device, dtype)
 
 
@@ -87,7 +88,7 @@ def plan_strips(n1, n2, p, nel2, dof_map, n_free, world, rank, knots2=None):
     allc = np.concatenate(owned_sets) if world > 1 else owned_sets[0]
     uniq, cnt = np.unique(allc, return_counts=True)
     shared = uniq[cnt > 1]
-    send_sets = []
+    send_sets, tails = [], []
     for g in range(world):
         if g + 1 < world:
             # rows owned by a later strip that this strip's elements reach
@@ -98,14 +99,16 @@ def plan_strips(n1, n2, p, nel2, dof_map, n_free, world, rank, knots2=None):
             # everything sent must be owned by the neighbour
             if len(np.setdiff1d(send, owned_sets[g + 1])):
                 raise ValueError("interface column of strip %d is not owned by its neighbour (matched DoFs across strips)" % g)
+            tails.append(int(bounds[g + 1] - flo[mask].min()) if mask.any() else 0)
         else:
             send = np.zeros(0, dtype=np.int64)
+            tails.append(0)
         send_sets.append(send)
     owned = np.setdiff1d(owned_sets[rank], shared)
     owned = np.union1d(owned, shared)          # shared columns are complete on every rank after the all-reduce
     recv = send_sets[rank - 1] if rank > 0 else np.zeros(0, dtype=np.int64)
     return StripPlan(rank, world, bounds[rank], bounds[rank + 1], _ranges(owned), _ranges(send_sets[rank]), _ranges(recv),
-                     _ranges(shared))
+                     _ranges(shared), tails[rank])
 
 
 def value_ranges(col_ranges, outer):
@@ -132,21 +135,28 @@ def _buffers(plan, outer, values, residual):
     return b
 
 
-def exchange_halo(plan: StripPlan, outer, values, residual, dist):
-    """Send the partial sums of the interface columns to rank+1 and add what rank-1 sent (one batched group of
-    point-to-point operations, pre-allocated receive buffers, one fused add); columns shared by several strips are
-    summed with one all-reduce.  `values` / `residual` are torch tensors (CPU for gloo, CUDA views for nccl).
-    After the call the entries of plan.owned_cols are complete on this rank.  Returns the bytes received."""
-    import torch
+def assemble_strip_overlapped(asm, plan: StripPlan, outer, values, residual, x_dev_ptr, dist, stream=0):
+    """One Jacobian + internal-force assembly of this rank's strip with the halo exchange overlapped: the last element rows
+    (plan.tail_rows: the only ones that touch the next strip's columns) are assembled first, their partial sums start travelling, the rest of
+    the strip is assembled meanwhile, and the received ranges are added at the end.  Returns the bytes received."""
+    tail = min(plan.tail_rows, plan.e2_end - plan.e2_begin)
+    asm.strip_begin_device(x_dev_ptr, residual.data_ptr(), 0.0, 1.0, tail, stream)
+    pending = exchange_halo_begin(plan, outer, values, residual, dist)
+    if plan.e2_end - tail > plan.e2_begin:
+        asm.jacobian_rows_device(plan.e2_begin, plan.e2_end - tail, stream)
+    return exchange_halo_end(plan, outer, values, residual, dist, pending)
+
+
+def exchange_halo_begin(plan: StripPlan, outer, values, residual, dist):
+    """post the sends of the interface columns and the receives from the previous strip (asynchronous)"""
     b = _buffers(plan, outer, values, residual)
-    ops = []
+    ops, dst, src = [], [], []
     if plan.rank + 1 < plan.world:
         for (a, e) in b["send_vr"]:
             ops.append(dist.P2POp(dist.isend, values[a:e], plan.rank + 1))
         if residual is not None:
             for (c0, c1) in plan.send_cols:
                 ops.append(dist.P2POp(dist.isend, residual[c0:c1], plan.rank + 1))
-    dst, src = [], []
     if plan.rank > 0:
         for (a, e), t in zip(b["vr"], b["recv_v"]):
             ops.append(dist.P2POp(dist.irecv, t, plan.rank - 1))
@@ -155,23 +165,42 @@ def exchange_halo(plan: StripPlan, outer, values, residual, dist):
             for (c0, c1), t in zip(plan.recv_cols, b["recv_r"]):
                 ops.append(dist.P2POp(dist.irecv, t, plan.rank - 1))
                 dst.append(residual[c0:c1]); src.append(t)
-    if ops:
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    return reqs, dst, src
+
+
+def exchange_halo_end(plan: StripPlan, outer, values, residual, dist, pending):
+    import torch
+    reqs, dst, src = pending
+    for r in reqs:
+        r.wait()
     if dst:
-        torch._foreach_add_(dst, src)           # one fused launch for all interface ranges
+        torch._foreach_add_(dst, src)
     nbytes = sum(t.numel() for t in src) * 8
-    if plan.shared_cols and plan.world > 1:
-        flat, o = b["shared"], 0
-        parts = [values[a:e] for a, e in b["sr"]] + ([residual[c0:c1] for c0, c1 in plan.shared_cols] if residual is not None else [])
-        for t in parts:
-            flat[o:o + t.numel()].copy_(t); o += t.numel()
-        dist.all_reduce(flat)
-        o = 0
-        for t in parts:
-            t.copy_(flat[o:o + t.numel()]); o += t.numel()
-        nbytes += flat.numel() * 8
-    return nbytes
+    return nbytes + _allreduce_shared(plan, outer, values, residual, dist)
+
+
+def _allreduce_shared(plan, outer, values, residual, dist):
+    if not (plan.shared_cols and plan.world > 1):
+        return 0
+    b = _buffers(plan, outer, values, residual)
+    flat, o = b["shared"], 0
+    parts = [values[a:e] for a, e in b["sr"]] + ([residual[c0:c1] for c0, c1 in plan.shared_cols] if residual is not None else [])
+    for t in parts:
+        flat[o:o + t.numel()].copy_(t); o += t.numel()
+    dist.all_reduce(flat)
+    o = 0
+    for t in parts:
+        t.copy_(flat[o:o + t.numel()]); o += t.numel()
+    return flat.numel() * 8
+
+
+def exchange_halo(plan: StripPlan, outer, values, residual, dist):
+    """Send the partial sums of the interface columns to rank+1 and add what rank-1 sent (one batched group of
+    point-to-point operations, pre-allocated receive buffers, one fused add); columns shared by several strips are
+    summed with one all-reduce.  `values` / `residual` are torch tensors (CPU for gloo, CUDA views for nccl).
+    After the call the entries of plan.owned_cols are complete on this rank.  Returns the bytes received."""
+    return exchange_halo_end(plan, outer, values, residual, dist, exchange_halo_begin(plan, outer, values, residual, dist))
 
 
 class DevicePointerView:

@@ -186,6 +186,13 @@ double* kl_values_device(kl_ctx* ctx);            /* device K values, length nnz
  * completed by the halo reduce in the host layer. */
 int kl_set_strip(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end);
 
+/* Two-phase strip assembly for overlapping the halo exchange with the bulk of the strip: kl_strip_begin_device = residual of the
+ * strip (r = lam_fext*F_dead + sign_fint*(F_int - P)) + zeroing of the strip's value ranges + Jacobian of its LAST tail_rows element
+ * rows (the ones that reach into the next strip); kl_jacobian_rows_device = Jacobian of further rows of the strip from the same
+ * per-point records.  Work is enqueued on `stream`, not synchronised. */
+int kl_strip_begin_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, int32_t tail_rows, void* stream);
+int kl_jacobian_rows_device(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end, void* stream);
+
 /* Kernel-only timing of the last call in ms (CUDA events on the launch stream). */
 int kl_last_timing(const kl_ctx* ctx, float* ms_kernel, float* ms_h2d, float* ms_d2h);
 /* One Newton iteration's worth of assembly at ONE state: K(x) into the device values (as kl_jacobian_device) and

@@ -43,6 +43,7 @@ def main():
     asm.jacobian_device(xd.data_ptr(), stream)
     asm.residual_device(xd.data_ptr(), rd.data_ptr(), 0.0, 1.0, stream)     # partial F_int of the strip
     assert asm.check(stream) == 0
+    overlapped = os.environ.get("KL_OVERLAP", "1") == "1" and torch.cuda.device_count() >= world
     vals = DevicePointerView(asm.values_device_ptr(), asm.nnz).tensor()
     outer, _ = asm.pattern()
     torch.cuda.synchronize()
@@ -51,7 +52,12 @@ def main():
     if shared_gpu:
         vals_dev, rd_dev = vals, rd
         vals, rd = vals_dev.cpu(), rd_dev.cpu()
-    moved = exchange_halo(plan, outer, vals, rd, dist)      # first call also warms NCCL up
+    if overlapped:        # two-phase assembly, exchange in flight while the bulk of the strip is assembled
+        from gsstructuralanalysis_b200.parallel import assemble_strip_overlapped
+        moved = assemble_strip_overlapped(asm, plan, outer, vals, rd, xd.data_ptr(), dist, stream)
+        assert asm.check(stream) == 0
+    else:
+        moved = exchange_halo(plan, outer, vals, rd, dist)      # first call also warms NCCL up
     t_asm, t_x = [], []
     for _ in range(0 if shared_gpu else reps - 1):
         dist.barrier(); torch.cuda.synchronize()
