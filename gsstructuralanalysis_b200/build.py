@@ -9,11 +9,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkl_shell.so")
-SOURCES = ["kl_capi.cu", "kl_pattern.cu", "kl_assemble.cu", "kl_solve.cu", "kl_stress.cu", "ks_solid.cu"]
+SOURCES = ["kl_capi.cu", "kl_pattern.cu", "kl_assemble.cu", "kl_solve.cu", "kl_stress.cu", "kl_multipatch.cu", "ks_solid.cu"]
 HEADERS = ["kl_internal.h", "kl_device.cuh", os.path.join("..", "..", "include", "kl_shell.h"),
            os.path.join("..", "..", "include", "ks_solid.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -37,13 +37,33 @@ def build(force=False, verbose=False, out=None, extra=()):
     if out is None and not force and not needs_build():
         return OUT
     out = out or OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    # one object per translation unit, compiled concurrently and reused while neither the source nor a header is newer
+    from concurrent.futures import ThreadPoolExecutor
+    variant = out != OUT or bool(extra)
+    objdir = os.path.join(CSRC, "build", "variant_" + str(abs(hash((out, tuple(extra))))) if variant else "product")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    nvcc = _nvcc()
+
+    def compile_one(f):
+        src, obj = os.path.join(CSRC, f), os.path.join(objdir, f + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, ""
+        cmd = [nvcc] + NVCC_FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed on " + f)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+        res = list(ex.map(compile_one, SOURCES))
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + [o for o, _ in res], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed")
+        raise RuntimeError("nvcc link failed")
     if verbose:
-        print(r.stderr)
+        print("".join(log for _, log in res))
     return out
 
 

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from .problem import kl_problem, kl_bc, c_double_p, c_int_p
+from .problem import kl_problem, kl_bc, kl_interface, c_double_p, c_int_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("KL_LIB") or os.path.join(_HERE, "libkl_shell.so")   # KL_LIB: A/B builds of the same sources
@@ -23,7 +23,9 @@ SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern
            "kl_assemble_device", "kl_cg_solve", "kl_cg_solve_device", "kl_spmv", "kl_cg_last_timing", "kl_newton_solve",
            "kl_stress_dim", "kl_eval_stress", "kl_principal_stretches", "kl_boundary_force",
            "kl_pin_values", "kl_unpin_values", "kl_fetch_values", "kl_set_values", "kl_pattern_lower_host", "kl_jacobian_lower",
-           "kl_al_residual_device", "kl_alm_step", "kl_strip_begin_device", "kl_jacobian_rows_device"]
+           "kl_al_residual_device", "kl_alm_step", "kl_strip_begin_device", "kl_jacobian_rows_device",
+           "kl_mp_build_dofmap", "kl_mp_create", "kl_mp_destroy", "kl_mp_context", "kl_mp_patch", "kl_mp_num_patches",
+           "kl_mp_set_active", "kl_mp_interface_dofs"]
 
 # stress_type of constructStress (include/kl_shell.h)
 STRESS_TYPES = {"displacement": 0, "membrane_force": 1, "flexural_moment": 2, "membrane": 3, "flexural": 4,
@@ -115,6 +117,17 @@ def lib():
     L.kl_eval_stress.argtypes = [vp, c_double_p, C.c_int32, C.c_int32, c_double_p, C.c_double, c_double_p]
     L.kl_principal_stretches.argtypes = [vp, c_double_p, C.c_int32, c_double_p, C.c_double, c_double_p]
     L.kl_boundary_force.argtypes = [vp, c_double_p, C.c_int32, c_double_p]
+    L.kl_mp_build_dofmap.argtypes = [C.c_int32, c_int_p, c_int_p, C.POINTER(kl_bc), C.c_int32, C.POINTER(kl_interface), c_int_p, c_int_p, c_int_p]
+    L.kl_mp_create.argtypes = [C.c_int32, C.POINTER(kl_problem), C.c_int, C.POINTER(vp)]
+    L.kl_mp_destroy.argtypes = [vp]
+    L.kl_mp_destroy.restype = None
+    L.kl_mp_context.argtypes = [vp]
+    L.kl_mp_context.restype = vp
+    L.kl_mp_patch.argtypes = [vp, C.c_int32]
+    L.kl_mp_patch.restype = vp
+    L.kl_mp_num_patches.argtypes = [vp]
+    L.kl_mp_set_active.argtypes = [vp, c_int_p]
+    L.kl_mp_interface_dofs.argtypes = [vp, c_int_p, c_int_p]
     _LIB = L
     return L
 

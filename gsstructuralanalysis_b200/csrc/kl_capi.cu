@@ -23,82 +23,116 @@ extern "C" const char* kl_last_error(void) { return g_err.c_str(); }
 // A matched group is eliminated as a whole when any member is.  Numbering is component-major:
 // plain free DoFs in tensor order, then matched groups by first appearance; eliminated DoFs follow
 // after ALL free ones (global_to_bindex = index - freeSize).
-extern "C" int kl_build_dofmap(int32_t n1, int32_t n2, const kl_bc* bc, int32_t* dof_map, int32_t* n_free, int32_t* n_fixed) {
-    if (n1 < 2 || n2 < 2 || !bc || !dof_map || !n_free || !n_fixed) { kl_set_error("kl_build_dofmap: bad argument"); return KL_E_ARG; }
-    const int ncp = n1 * n2;
-    std::vector<int> label(ncp), state(ncp);   // state: 0 plain, 1 matched, 2 eliminated
+// Several patches: the DoF universe of a component is the concatenation of the patches (patch-major, gsDofMapper offsets);
+// interfaces add match pairs between the two sides (gsMultiBasis::matchInterface -> gsDofMapper::matchDofs), k-th function of
+// side 0 with the k-th (or, reversed, the (len-1-k)-th) function of side 1.
+static int side_dof(int n1, int n2, int s, int k, int layer) {
+    switch (s) {
+        case KL_WEST: return layer + n1 * k;
+        case KL_EAST: return (n1 - 1 - layer) + n1 * k;
+        case KL_SOUTH: return k + n1 * layer;
+        default: return k + n1 * (n2 - 1 - layer);
+    }
+}
+static int build_dofmap_mp(int np, const int32_t* n1, const int32_t* n2, const kl_bc* bc, int nif, const kl_interface* ifs,
+                           int32_t* dof_map, int32_t* n_free, int32_t* n_fixed) {
+    std::vector<int> off(np + 1, 0);
+    for (int q = 0; q < np; ++q) {
+        if (n1[q] < 2 || n2[q] < 2) { kl_set_error("kl_build_dofmap: a patch needs at least 2 x 2 control points"); return KL_E_ARG; }
+        off[q + 1] = off[q] + n1[q] * n2[q];
+    }
+    const int N = off[np];
+    for (int k = 0; k < nif; ++k) {
+        const kl_interface& f = ifs[k];
+        for (int e = 0; e < 2; ++e)
+            if (f.patch[e] < 0 || f.patch[e] >= np || f.side[e] < KL_WEST || f.side[e] > KL_NORTH) { kl_set_error("kl_mp_build_dofmap: bad interface"); return KL_E_ARG; }
+        const int l0 = f.side[0] <= KL_EAST ? n2[f.patch[0]] : n1[f.patch[0]], l1 = f.side[1] <= KL_EAST ? n2[f.patch[1]] : n1[f.patch[1]];
+        if (l0 != l1) { kl_set_error("kl_mp_build_dofmap: the two sides of an interface have different numbers of functions (non-conforming)"); return KL_E_ARG; }
+    }
+    std::vector<int> parent(N), state(N);   // state: 0 plain, 1 matched, 2 eliminated
+    std::vector<std::vector<int>> elim_slot(3, std::vector<int>(N, -1));
     std::vector<std::pair<int, int>> pairs;
-    std::vector<std::vector<int>> elim_slot(3, std::vector<int>(ncp, -1));
     int free_total = 0, elim_total = 0;
-    auto side_dof = [&](int s, int k, int layer) {
-        switch (s) {
-            case KL_WEST: return layer + n1 * k;
-            case KL_EAST: return (n1 - 1 - layer) + n1 * k;
-            case KL_SOUTH: return k + n1 * layer;
-            default: return k + n1 * (n2 - 1 - layer);
-        }
-    };
+    auto find = [&](int i) { while (parent[i] != i) { parent[i] = parent[parent[i]]; i = parent[i]; } return i; };
     for (int c = 0; c < 3; ++c) {
         pairs.clear();
-        for (int i = 0; i < ncp; ++i) { label[i] = i; state[i] = 0; }
-        for (int s = 0; s < 4; ++s) {
-            const int kind = bc->side[s][c];
-            const int len = (s == KL_WEST || s == KL_EAST) ? n2 : n1;
-            for (int k = 0; k < len; ++k) {
-                const int b0 = side_dof(s, k, 0);
-                if (kind == KL_BC_DIRICHLET) state[b0] = 2;
-                else if (kind == KL_BC_CLAMPED) pairs.emplace_back(b0, side_dof(s, k, 1));
-                else if (kind == KL_BC_COLLAPSED && k > 0) pairs.emplace_back(side_dof(s, 0, 0), b0);
-            }
-        }
-        const int corners[4] = {0, n1 - 1, n1 * (n2 - 1), n1 * n2 - 1};
-        for (int k = 0; k < 4; ++k) if (bc->corner[k][c]) state[corners[k]] = 2;
-        // min-label propagation over the match pairs
-        for (auto& pr : pairs) { if (state[pr.first] != 2) state[pr.first] = 1; if (state[pr.second] != 2) state[pr.second] = 1; }
-        bool changed = !pairs.empty();
-        while (changed) {
-            changed = false;
-            for (auto& pr : pairs) {
-                const int m = std::min(label[pr.first], label[pr.second]);
-                if (label[pr.first] != m) { label[pr.first] = m; changed = true; }
-                if (label[pr.second] != m) { label[pr.second] = m; changed = true; }
-            }
-        }
-        // elimination spreads over matched groups
-        std::vector<char> group_elim(ncp, 0);
-        for (auto& pr : pairs) if (state[pr.first] == 2 || state[pr.second] == 2) group_elim[label[pr.first]] = 1;
-        bool again = true;
-        while (again) {
-            again = false;
-            for (auto& pr : pairs) {
-                const int g = label[pr.first];
-                if (group_elim[g]) {
-                    if (state[pr.first] != 2) { state[pr.first] = 2; again = true; }
-                    if (state[pr.second] != 2) { state[pr.second] = 2; again = true; }
+        for (int i = 0; i < N; ++i) { parent[i] = i; state[i] = 0; }
+        for (int q = 0; q < np; ++q) {
+            const int m1 = n1[q], m2 = n2[q], o = off[q];
+            for (int s = 0; s < 4; ++s) {
+                const int kind = bc[q].side[s][c];
+                const int len = (s == KL_WEST || s == KL_EAST) ? m2 : m1;
+                for (int k = 0; k < len; ++k) {
+                    const int b0 = o + side_dof(m1, m2, s, k, 0);
+                    if (kind == KL_BC_DIRICHLET) state[b0] = 2;
+                    else if (kind == KL_BC_CLAMPED) pairs.emplace_back(b0, o + side_dof(m1, m2, s, k, 1));
+                    else if (kind == KL_BC_COLLAPSED && k > 0) pairs.emplace_back(o + side_dof(m1, m2, s, 0, 0), b0);
                 }
             }
+            const int corners[4] = {0, m1 - 1, m1 * (m2 - 1), m1 * m2 - 1};
+            for (int k = 0; k < 4; ++k) if (bc[q].corner[k][c]) state[o + corners[k]] = 2;
         }
+        for (int k = 0; k < nif; ++k) {
+            const kl_interface& f = ifs[k];
+            const int qa = f.patch[0], qb = f.patch[1];
+            const int len = f.side[0] <= KL_EAST ? n2[qa] : n1[qa];
+            for (int i = 0; i < len; ++i)
+                pairs.emplace_back(off[qa] + side_dof(n1[qa], n2[qa], f.side[0], i, 0),
+                                   off[qb] + side_dof(n1[qb], n2[qb], f.side[1], f.reversed ? len - 1 - i : i, 0));
+        }
+        // matched groups (root = smallest member) and the spread of an elimination over a group
+        for (auto& pr : pairs) {
+            if (state[pr.first] != 2) state[pr.first] = 1;
+            if (state[pr.second] != 2) state[pr.second] = 1;
+            const int a = find(pr.first), b = find(pr.second);
+            if (a != b) { if (a < b) parent[b] = a; else parent[a] = b; }
+        }
+        std::vector<char> group_elim(N, 0);
+        for (auto& pr : pairs) if (state[pr.first] == 2 || state[pr.second] == 2) group_elim[find(pr.first)] = 1;
+        for (auto& pr : pairs) if (group_elim[find(pr.first)]) state[pr.first] = state[pr.second] = 2;
+        // numbering: plain free DoFs in (patch, tensor) order, then matched groups by first appearance
         int cnt = 0;
-        for (int i = 0; i < ncp; ++i) if (state[i] == 0) dof_map[c * ncp + i] = free_total + cnt++;
-        std::vector<int> gid(ncp, -1);
-        for (int i = 0; i < ncp; ++i) if (state[i] == 1) {
-            int& g = gid[label[i]];
+        std::vector<int> val(N, -1), gid(N, -1);
+        for (int i = 0; i < N; ++i) if (state[i] == 0) val[i] = free_total + cnt++;
+        for (int i = 0; i < N; ++i) if (state[i] == 1) {
+            int& g = gid[find(i)];
             if (g < 0) g = free_total + cnt++;
-            dof_map[c * ncp + i] = g;
+            val[i] = g;
         }
         free_total += cnt;
         std::fill(gid.begin(), gid.end(), -1);
-        for (int i = 0; i < ncp; ++i) if (state[i] == 2) {
-            int& g = gid[label[i]];
+        for (int i = 0; i < N; ++i) if (state[i] == 2) {
+            int& g = gid[find(i)];
             if (g < 0) g = elim_total++;
             elim_slot[c][i] = g;
         }
+        for (int q = 0; q < np; ++q) {
+            const int ncp = n1[q] * n2[q];
+            for (int i = 0; i < ncp; ++i) dof_map[(size_t)3 * off[q] + (size_t)c * ncp + i] = val[off[q] + i];
+        }
     }
     for (int c = 0; c < 3; ++c)
-        for (int i = 0; i < ncp; ++i) if (elim_slot[c][i] >= 0) dof_map[c * ncp + i] = free_total + elim_slot[c][i];
+        for (int q = 0; q < np; ++q) {
+            const int ncp = n1[q] * n2[q];
+            for (int i = 0; i < ncp; ++i)
+                if (elim_slot[c][off[q] + i] >= 0) dof_map[(size_t)3 * off[q] + (size_t)c * ncp + i] = free_total + elim_slot[c][off[q] + i];
+        }
     *n_free = free_total;
     *n_fixed = elim_total;
     return KL_OK;
+}
+
+extern "C" int kl_build_dofmap(int32_t n1, int32_t n2, const kl_bc* bc, int32_t* dof_map, int32_t* n_free, int32_t* n_fixed) {
+    if (n1 < 2 || n2 < 2 || !bc || !dof_map || !n_free || !n_fixed) { kl_set_error("kl_build_dofmap: bad argument"); return KL_E_ARG; }
+    return build_dofmap_mp(1, &n1, &n2, bc, 0, nullptr, dof_map, n_free, n_fixed);
+}
+extern "C" int kl_mp_build_dofmap(int32_t n_patches, const int32_t* n1, const int32_t* n2, const kl_bc* bc, int32_t n_interfaces,
+                                  const kl_interface* ifs, int32_t* dof_map, int32_t* n_free, int32_t* n_fixed) {
+    if (n_patches < 1 || !n1 || !n2 || !bc || !dof_map || !n_free || !n_fixed || n_interfaces < 0 || (n_interfaces > 0 && !ifs)) {
+        kl_set_error("kl_mp_build_dofmap: bad argument");
+        return KL_E_ARG;
+    }
+    return build_dofmap_mp(n_patches, n1, n2, bc, n_interfaces, ifs, dof_map, n_free, n_fixed);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -381,7 +415,8 @@ static int build_d2h_plan(kl_ctx* ctx, const kl_problem* P) {
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
+// everything of a context that does not depend on the sparse pattern
+int kl_ctx_create_base(const kl_problem* P, int device, kl_ctx** out) {
     if (!P || !out) { kl_set_error("kl_create: null argument"); return KL_E_ARG; }
     *out = nullptr;
     int ndev = 0;
@@ -468,16 +503,30 @@ extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
     KL_CUDA_CTX(cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
     ctx->jac_shared = getenv("KL_JAC_SHARED") ? atoi(getenv("KL_JAC_SHARED")) : 0;
     ctx->jac_seg = getenv("KL_SW_SEG") ? atoi(getenv("KL_SW_SEG")) : 0;
-    if ((rc = kl_build_pattern(ctx))) { kl_destroy(ctx); return rc; }
-    if ((rc = build_fext(ctx, P))) { kl_destroy(ctx); return rc; }
-    if ((rc = build_d2h_plan(ctx, P))) { kl_destroy(ctx); return rc; }
     KL_CUDA_CTX(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     KL_CUDA_CTX(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (auto& e : ctx->ev) KL_CUDA_CTX(cudaEventCreate(&e));
-    if ((rc = build_force(ctx, P))) { kl_destroy(ctx); return rc; }
     *out = ctx;
     return KL_OK;
 #undef KL_CUDA_CTX
+}
+
+// the pattern-dependent rest: load vectors, copy-out plan (not for members of a kl_mp: their columns are shared with other patches)
+int kl_ctx_finish(kl_ctx* ctx, const kl_problem* P) {
+    int rc;
+    if ((rc = build_fext(ctx, P))) return rc;
+    if (!ctx->mp_member && (rc = build_d2h_plan(ctx, P))) return rc;
+    return build_force(ctx, P);
+}
+
+extern "C" int kl_create(const kl_problem* P, int device, kl_ctx** out) {
+    if (out) *out = nullptr;
+    kl_ctx* ctx = nullptr;
+    int rc = kl_ctx_create_base(P, device, &ctx);
+    if (rc) return rc;
+    if ((rc = kl_build_pattern(ctx)) || (rc = kl_ctx_finish(ctx, P))) { kl_destroy(ctx); return rc; }
+    *out = ctx;
+    return KL_OK;
 }
 
 extern "C" void kl_destroy(kl_ctx* ctx) {
@@ -501,9 +550,9 @@ extern "C" int kl_sizes(const kl_ctx* ctx, int32_t* n_dofs, int64_t* nnz, int64_
     if (!ctx) return KL_E_ARG;
     if (n_dofs) *n_dofs = ctx->d.nfree;
     if (nnz) *nnz = ctx->nnz;
-    const int64_t ne = (int64_t)ctx->d.nel1 * ctx->d.nel2;
+    const int64_t ne = ctx->mp ? ctx->mp->n_elements : (int64_t)ctx->d.nel1 * ctx->d.nel2;
     if (n_elements) *n_elements = ne;
-    if (n_qp) *n_qp = ne * ctx->d.nq * ctx->d.nq;
+    if (n_qp) *n_qp = ctx->mp ? ctx->mp->n_qp : ne * ctx->d.nq * ctx->d.nq;
     return KL_OK;
 }
 
@@ -521,9 +570,10 @@ extern "C" int kl_pattern_device(const kl_ctx* ctx, const int32_t** outer_dev, c
     return KL_OK;
 }
 extern "C" double* kl_values_device(kl_ctx* ctx) { return ctx ? ctx->d.values : nullptr; }
-extern "C" int kl_kernel_launches(const kl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int kl_kernel_launches(const kl_ctx* ctx) { return ctx ? ctx->launches + (ctx->mp ? kl_mp_launches(ctx->mp) : 0) : 0; }
 
 extern "C" int kl_set_strip(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end) {
+    if (ctx && ctx->mp_member) { kl_set_error("kl_set_strip: a patch of a kl_mp is partitioned by patches (kl_mp_set_active), not by strips"); return KL_E_ARG; }
     if (!ctx || e2_begin < 0 || e2_end > ctx->d.nel2 || e2_begin > e2_end) { kl_set_error("kl_set_strip: bad range"); return KL_E_ARG; }
     ctx->e2_begin = e2_begin; ctx->e2_end = e2_end;
     ctx->pd_valid = 0;
@@ -551,6 +601,10 @@ extern "C" int kl_set_strip(kl_ctx* ctx, int32_t e2_begin, int32_t e2_end) {
 
 extern "C" int kl_check(kl_ctx* ctx, void* stream) {
     if (!ctx) return KL_E_ARG;
+    if (ctx->mp) {
+        KL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        return kl_mp_check(ctx->mp, (cudaStream_t)stream);
+    }
     int flag = 0;
     KL_CUDA(cudaMemcpyAsync(&flag, ctx->d.flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     KL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -596,19 +650,18 @@ static int points_and_jacobian(kl_ctx* ctx, const double* x_dev, cudaStream_t s,
 
 extern "C" int kl_jacobian_device(kl_ctx* ctx, const double* x_dev, void* stream) {
     if (!ctx) return KL_E_ARG;
+    if (ctx->mp) return kl_mp_jacobian_device(ctx->mp, x_dev, (cudaStream_t)stream);
     return points_and_jacobian(ctx, x_dev, (cudaStream_t)stream, ctx->e2_begin, ctx->e2_end, true);
 }
 
-extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, void* stream) {
-    if (!ctx || !r_dev) return KL_E_ARG;
-    cudaStream_t s = (cudaStream_t)stream;
+// r += F_int(x) - P(x) over the element rows of the context (no zeroing, no load vector): shared by the single-patch entry point
+// below and by the multi-patch assembler, which sums the patches into one vector
+int kl_residual_accumulate(kl_ctx* ctx, const double* x_dev, double* r_dev, cudaStream_t s) {
     int rc;
     if (ctx->last_call == 1) ctx->spec_on = 0;          // two residuals in a row: the caller is not running a Newton-type loop
     if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
-    KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, s));
     if (ctx->spec_on && ctx->spec_allowed) {
         // per-point records with the tangent + internal force from the staged records; remember the state they belong to
-        const int n = ctx->d.nfree;
         ctx->pd_valid = 0;
         if ((rc = kl_launch_state_compare(ctx, x_dev, s))) return rc;      // pd_valid == 0: only stores the state
         KL_CUDA(cudaEventRecord(ctx->ev[6], s));
@@ -616,11 +669,19 @@ extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_f
         KL_CUDA(cudaEventRecord(ctx->ev[7], s));
         ctx->pd_valid = 1; ctx->pd_e2b = ctx->e2_begin; ctx->pd_e2e = ctx->e2_end;
         ctx->last_call = 1;
-        (void)n;
     } else {
         if ((rc = kl_launch_residual(ctx, r_dev, s))) return rc;
         ctx->last_call = 0;
     }
+    return 0;
+}
+
+extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, void* stream) {
+    if (!ctx || !r_dev) return KL_E_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ctx->mp) return kl_mp_residual_device(ctx->mp, x_dev, lam_fext, sign_fint, r_dev, s);
+    KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, s));
+    if (int rc = kl_residual_accumulate(ctx, x_dev, r_dev, s)) return rc;
     return kl_launch_axpby(ctx, r_dev, ctx->d_fext, sign_fint, lam_fext, ctx->d.nfree, s);
 }
 
@@ -629,6 +690,7 @@ extern "C" int kl_residual_device(kl_ctx* ctx, const double* x_dev, double lam_f
 // contributions reach the next strip; the caller starts the exchange and calls kl_jacobian_rows_device for the remaining rows.
 extern "C" int kl_strip_begin_device(kl_ctx* ctx, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, int32_t tail_rows, void* stream) {
     if (!ctx || !r_dev || tail_rows < 0) return KL_E_ARG;
+    if (ctx->mp || ctx->mp_member) { kl_set_error("strips are not available on a multi-patch assembler"); return KL_E_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
     const int spec = ctx->spec_on, last = ctx->last_call;
@@ -657,6 +719,10 @@ extern "C" int kl_assemble_device(kl_ctx* ctx, const double* x_dev, double lam_f
     if (!ctx || !r_dev) return KL_E_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int rc;
+    if (ctx->mp) {      // the patches speculate on the Jacobian in their residual pass: the same fusion, patch by patch
+        if ((rc = kl_mp_residual_device(ctx->mp, x_dev, lam_fext, sign_fint, r_dev, s))) return rc;
+        return kl_mp_jacobian_device(ctx->mp, x_dev, s);
+    }
     if ((rc = kl_launch_construct(ctx, x_dev, s))) return rc;
     KL_CUDA(cudaMemsetAsync(r_dev, 0, sizeof(double) * ctx->d.nfree, s));
     ctx->pd_valid = 0;
@@ -723,7 +789,8 @@ extern "C" int kl_mass(kl_ctx* ctx, double density, double* values_host, double*
     // the mass matrix shares the value array of K on the device (it is a set-up quantity; K is re-assembled every call)
     if (values_host) KL_CUDA(cudaMemsetAsync(ctx->d.values, 0, sizeof(double) * (size_t)ctx->nnz, s));
     if (lumped_host) KL_CUDA(cudaMemsetAsync(ctx->d_r, 0, sizeof(double) * ctx->d.nfree, s));
-    int rc = kl_launch_mass(ctx, density * ctx->d.mat.t, values_host ? ctx->d.values : nullptr, lumped_host ? ctx->d_r : nullptr, s);
+    int rc = ctx->mp ? kl_mp_mass_device(ctx->mp, density, values_host ? ctx->d.values : nullptr, lumped_host ? ctx->d_r : nullptr, s)
+                     : kl_launch_mass(ctx, density * ctx->d.mat.t, values_host ? ctx->d.values : nullptr, lumped_host ? ctx->d_r : nullptr, s);
     if (rc) return rc;
     if (values_host) KL_CUDA(cudaMemcpyAsync(values_host, ctx->d.values, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost, s));
     if (lumped_host) KL_CUDA(cudaMemcpyAsync(lumped_host, ctx->d_r, sizeof(double) * ctx->d.nfree, cudaMemcpyDeviceToHost, s));

@@ -16,6 +16,7 @@
 
 struct PointData;
 struct KLSolveWS;   // kl_solve.cu: workspace of the device-resident CG / Newton loop
+struct kl_mp;
 
 struct KLMaterial {
     int material, compressible, ngauss, bending, metric_z2;
@@ -66,6 +67,7 @@ struct kl_ctx {
     std::vector<double> U[2];
     std::vector<int> span[2];
     std::vector<int> flo[2], fhi[2]; // element range of each 1-D function
+    int* d_flohi[4] = {nullptr, nullptr, nullptr, nullptr};   // device copies (pattern build): lo1, hi1, lo2, hi2
     int nfixed = 0;
     int64_t nnz = 0;
     int e2_begin = 0, e2_end = 0;    // strip of element rows assembled by this context
@@ -113,6 +115,21 @@ struct kl_ctx {
     std::vector<D2HStrip> d2h_plan;
     std::vector<cudaEvent_t> strip_ev, copy_ev;
     KLSolveWS* solve_ws = nullptr;   // created on the first kl_cg_solve / kl_newton_solve
+    // multi-patch (kl_multipatch.cu): a patch context assembles into the matrix / vectors of its kl_mp (d.outer / d.inner / d.values are
+    // shared, d.nfree is the global count); the kl_mp's own "matrix context" has no geometry at all (d.ncp == 0)
+    int mp_member = 0;
+    struct kl_mp* mp = nullptr;      // set on the matrix context of a kl_mp: the assembly entry points dispatch to the patches
+};
+
+// Several C0-coupled patches with one gsDofMapper numbering and one sparse matrix (include/kl_shell.h: kl_mp_*)
+struct kl_mp {
+    int device = 0;
+    std::vector<kl_ctx*> patch;      // geometry, tables, scatter maps and per-point records of every patch
+    std::vector<int> active;         // patch -> GPU partition: only active patches are assembled by this process
+    kl_ctx* g = nullptr;             // matrix context: global pattern / values / vectors / streams (no geometry); accepted by kl_cg_solve,
+                                     // kl_spmv, kl_fetch_values, kl_set_values, kl_pattern_host, kl_sizes
+    int64_t n_elements = 0, n_qp = 0;
+    std::vector<int> coupled_cols;   // global DoFs shared by more than one patch (interface columns), ascending
 };
 
 void kl_set_error(const std::string& s);
@@ -128,10 +145,24 @@ void kl_set_error(const std::string& s);
 // kl_capi.cu: host-side 1-D basis / quadrature helpers shared with ks_solid.cu
 void bspline_span_ders(const std::vector<double>& U, int p, int k, double u, double out[3][KL_MAXP + 1]);
 void gauss_rule(int n, double* x, double* w);
+int kl_ctx_create_base(const kl_problem* P, int device, kl_ctx** out);   // everything that does not depend on the sparse pattern
+int kl_ctx_finish(kl_ctx* ctx, const kl_problem* P);                      // load vectors (+ copy-out plan of a stand-alone patch)
+int kl_residual_accumulate(kl_ctx* ctx, const double* x_dev, double* r_dev, cudaStream_t s);   // r += F_int(x) - P(x) of the context's elements
+// kl_multipatch.cu: what the matrix context of a kl_mp dispatches to
+int kl_mp_jacobian_device(kl_mp* mp, const double* x_dev, cudaStream_t s);
+int kl_mp_residual_device(kl_mp* mp, const double* x_dev, double lam_fext, double sign_fint, double* r_dev, cudaStream_t s);
+int kl_mp_mass_device(kl_mp* mp, double density, double* values, double* lumped, cudaStream_t s);
+int kl_mp_check(kl_mp* mp, cudaStream_t s);
+int kl_mp_launches(const kl_mp* mp);
 // kl_solve.cu
 void kl_solve_free(kl_ctx* ctx);
 // kl_pattern.cu
-int kl_build_pattern(kl_ctx* ctx);
+int kl_build_pattern(kl_ctx* ctx);                                  // single patch: keys + compress + tables + value array
+long long kl_pattern_key_count(const kl_ctx* ctx);
+int kl_pattern_gen_keys(kl_ctx* ctx, unsigned long long* keys_dev);                 // 9 * nst * ncp keys (col << 32 | row) of one patch
+int kl_pattern_compress(kl_ctx* owner, unsigned long long* keys, unsigned long long* keys_alt, long long total, int nfree,
+                        int** outer, int** inner, long long* nnz);                  // sort + unique -> compressed pattern owned by `owner`
+int kl_pattern_tables(kl_ctx* ctx);                                 // scatter table + colbase of one patch against d.outer / d.inner
 int kl_lower_tables(kl_ctx* ctx);                                   // lazily builds the lower-triangular pattern + per-strip packed ranges
 int kl_launch_pack_lower(kl_ctx* ctx, int col_begin, int col_end, cudaStream_t s);   // packed lower values of the columns [col_begin, col_end)
 // kl_assemble.cu

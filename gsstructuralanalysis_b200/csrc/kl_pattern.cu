@@ -110,86 +110,126 @@ static int dev_alloc(kl_ctx* ctx, T** p, size_t n) {
     return 0;
 }
 
-int kl_build_pattern(kl_ctx* ctx) {
+static int pat_args(kl_ctx* ctx, PatArgs* out) {
     KLDev& d = ctx->d;
     PatArgs a{};
     a.p = d.p; a.n1 = d.n1; a.n2 = d.n2; a.ncp = d.ncp; a.nfree = d.nfree; a.nst = d.nst;
     a.map = d.map;
-    int *lo1, *hi1, *lo2, *hi2;
-    if (int rc = dev_alloc(ctx, &lo1, d.n1)) return rc;
-    if (int rc = dev_alloc(ctx, &hi1, d.n1)) return rc;
-    if (int rc = dev_alloc(ctx, &lo2, d.n2)) return rc;
-    if (int rc = dev_alloc(ctx, &hi2, d.n2)) return rc;
-    KL_CUDA(cudaMemcpy(lo1, ctx->flo[0].data(), sizeof(int) * d.n1, cudaMemcpyHostToDevice));
-    KL_CUDA(cudaMemcpy(hi1, ctx->fhi[0].data(), sizeof(int) * d.n1, cudaMemcpyHostToDevice));
-    KL_CUDA(cudaMemcpy(lo2, ctx->flo[1].data(), sizeof(int) * d.n2, cudaMemcpyHostToDevice));
-    KL_CUDA(cudaMemcpy(hi2, ctx->fhi[1].data(), sizeof(int) * d.n2, cudaMemcpyHostToDevice));
-    a.lo1 = lo1; a.hi1 = hi1; a.lo2 = lo2; a.hi2 = hi2;
+    if (!ctx->d_flohi[0]) {
+        const std::vector<int>* src[4] = {&ctx->flo[0], &ctx->fhi[0], &ctx->flo[1], &ctx->fhi[1]};
+        for (int k = 0; k < 4; ++k) {
+            if (int rc = dev_alloc(ctx, &ctx->d_flohi[k], src[k]->size())) return rc;
+            KL_CUDA(cudaMemcpy(ctx->d_flohi[k], src[k]->data(), sizeof(int) * src[k]->size(), cudaMemcpyHostToDevice));
+        }
+    }
+    a.lo1 = ctx->d_flohi[0]; a.hi1 = ctx->d_flohi[1]; a.lo2 = ctx->d_flohi[2]; a.hi2 = ctx->d_flohi[3];
+    *out = a;
+    return 0;
+}
 
-    const long long total = 9LL * d.nst * d.ncp;
+long long kl_pattern_key_count(const kl_ctx* ctx) { return 9LL * ctx->d.nst * ctx->d.ncp; }
+
+int kl_pattern_gen_keys(kl_ctx* ctx, unsigned long long* keys) {
+    PatArgs a;
+    if (int rc = pat_args(ctx, &a)) return rc;
+    const long long total = kl_pattern_key_count(ctx);
     if (total >= (1LL << 31)) { kl_set_error("kl_create: 9 * (2p+1)^2 * n_cp exceeds int32 (index_t); the mesh is too large for one context"); return KL_E_ARG; }
-    unsigned long long *keys = nullptr, *keys_alt = nullptr, *ukeys = nullptr;
-    long long* d_num = nullptr;
-    KL_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * total));
-    KL_CUDA(cudaMalloc(&keys_alt, sizeof(unsigned long long) * total));
-    KL_CUDA(cudaMalloc(&d_num, sizeof(long long)));
     const int T = 256;
     k_gen_keys<<<(unsigned)((total + T - 1) / T), T>>>(a, keys, total);
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// keys (possibly of several patches) -> compressed pattern; keys / keys_alt are scratch of `total` entries each
+int kl_pattern_compress(kl_ctx* owner, unsigned long long* keys, unsigned long long* keys_alt, long long total, int nfree,
+                        int** outer_out, int** inner_out, long long* nnz_out) {
+    const int T = 256;
+    long long* d_num = nullptr;
+    KL_CUDA(cudaMalloc(&d_num, sizeof(long long)));
     // radix sort (all 64 bits: the sentinel must end up last)
     cub::DoubleBuffer<unsigned long long> db(keys, keys_alt);
     void* tmp = nullptr;
     size_t tmp_bytes = 0;
-    KL_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, (int)total));
+    KL_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, total));
     KL_CUDA(cudaMalloc(&tmp, tmp_bytes));
-    KL_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, (int)total));
+    KL_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, total));
     KL_CUDA(cudaFree(tmp));
     unsigned long long* sorted = db.Current();
-    ukeys = (sorted == keys) ? keys_alt : keys;
+    unsigned long long* ukeys = (sorted == keys) ? keys_alt : keys;
     tmp = nullptr; tmp_bytes = 0;
-    KL_CUDA(cub::DeviceSelect::Unique(tmp, tmp_bytes, sorted, ukeys, d_num, (int)total));
+    KL_CUDA(cub::DeviceSelect::Unique(tmp, tmp_bytes, sorted, ukeys, d_num, total));
     KL_CUDA(cudaMalloc(&tmp, tmp_bytes));
-    KL_CUDA(cub::DeviceSelect::Unique(tmp, tmp_bytes, sorted, ukeys, d_num, (int)total));
+    KL_CUDA(cub::DeviceSelect::Unique(tmp, tmp_bytes, sorted, ukeys, d_num, total));
     KL_CUDA(cudaFree(tmp));
     long long nuniq = 0;
     KL_CUDA(cudaMemcpy(&nuniq, d_num, sizeof(long long), cudaMemcpyDeviceToHost));
+    KL_CUDA(cudaFree(d_num));
     // drop the sentinel if present (it is the largest key)
     if (nuniq > 0) {
         unsigned long long last = 0;
         KL_CUDA(cudaMemcpy(&last, ukeys + (nuniq - 1), sizeof(last), cudaMemcpyDeviceToHost));
         if (last == ~0ULL) --nuniq;
     }
-    ctx->nnz = nuniq;
     if (nuniq >= (1LL << 31)) { kl_set_error("nnz exceeds int32 (index_t)"); return KL_E_ARG; }
-    int *outer, *inner, *pos;
-    if (int rc = dev_alloc(ctx, &outer, (size_t)d.nfree + 1)) return rc;
-    if (int rc = dev_alloc(ctx, &inner, (size_t)nuniq)) return rc;
+    int *outer, *inner;
+    if (int rc = dev_alloc(owner, &outer, (size_t)nfree + 1)) return rc;
+    if (int rc = dev_alloc(owner, &inner, (size_t)nuniq)) return rc;
     {
-        const long long n = std::max<long long>(nuniq, (long long)d.nfree + 1);
-        k_outer_inner<<<(unsigned)((n + T - 1) / T), T>>>(ukeys, nuniq, d.nfree, outer, inner);
-        ctx->launches++;
+        const long long n = std::max<long long>(nuniq, (long long)nfree + 1);
+        k_outer_inner<<<(unsigned)((n + T - 1) / T), T>>>(ukeys, nuniq, nfree, outer, inner);
+        owner->launches++;
         KL_CUDA(cudaGetLastError());
     }
     KL_CUDA(cudaDeviceSynchronize());
-    KL_CUDA(cudaFree(keys));
-    KL_CUDA(cudaFree(keys_alt));
-    KL_CUDA(cudaFree(d_num));
+    *outer_out = outer; *inner_out = inner; *nnz_out = nuniq;
+    return 0;
+}
+
+int kl_pattern_tables(kl_ctx* ctx) {
+    KLDev& d = ctx->d;
+    PatArgs a;
+    if (int rc = pat_args(ctx, &a)) return rc;
+    const long long total = kl_pattern_key_count(ctx);
+    const int T = 256;
+    int* pos;
     if (int rc = dev_alloc(ctx, &pos, (size_t)total)) return rc;
-    k_pos_table<<<(unsigned)((total + T - 1) / T), T>>>(a, outer, inner, pos, total);
+    k_pos_table<<<(unsigned)((total + T - 1) / T), T>>>(a, d.outer, d.inner, pos, total);
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
     int* colbase;
     if (int rc = dev_alloc(ctx, &colbase, (size_t)4 * d.ncp)) return rc;
-    k_colbase<<<(d.ncp + T - 1) / T, T>>>(a, outer, pos, colbase);
+    k_colbase<<<(d.ncp + T - 1) / T, T>>>(a, d.outer, pos, colbase);
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
-    d.colbase = colbase;
-    double* values;
-    if (int rc = dev_alloc(ctx, &values, (size_t)nuniq)) return rc;
-    KL_CUDA(cudaMemset(values, 0, sizeof(double) * (nuniq ? nuniq : 1)));
     KL_CUDA(cudaDeviceSynchronize());
-    d.outer = outer; d.inner = inner; d.pos = pos; d.values = values;
+    d.colbase = colbase;
+    d.pos = pos;
+    return 0;
+}
+
+int kl_build_pattern(kl_ctx* ctx) {
+    KLDev& d = ctx->d;
+    const long long total = kl_pattern_key_count(ctx);
+    if (total >= (1LL << 31)) { kl_set_error("kl_create: 9 * (2p+1)^2 * n_cp exceeds int32 (index_t); the mesh is too large for one context"); return KL_E_ARG; }
+    unsigned long long *keys = nullptr, *keys_alt = nullptr;
+    KL_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * total));
+    KL_CUDA(cudaMalloc(&keys_alt, sizeof(unsigned long long) * total));
+    int rc = kl_pattern_gen_keys(ctx, keys);
+    int *outer = nullptr, *inner = nullptr;
+    long long nnz = 0;
+    if (!rc) rc = kl_pattern_compress(ctx, keys, keys_alt, total, d.nfree, &outer, &inner, &nnz);
+    cudaFree(keys);
+    cudaFree(keys_alt);
+    if (rc) return rc;
+    ctx->nnz = nnz;
+    d.outer = outer; d.inner = inner;
+    if ((rc = kl_pattern_tables(ctx))) return rc;
+    double* values;
+    if ((rc = dev_alloc(ctx, &values, (size_t)nnz))) return rc;
+    KL_CUDA(cudaMemset(values, 0, sizeof(double) * (nnz ? nnz : 1)));
+    KL_CUDA(cudaDeviceSynchronize());
+    d.values = values;
     return 0;
 }
 

@@ -488,7 +488,7 @@ static int ws_get(kl_ctx* ctx, KLSolveWS** out) {
     KL_CUDA(cudaMallocHost((void**)&w->st_host, sizeof(CGState)));
     KL_CUDA(cudaMallocHost((void**)&w->scal_host, sizeof(double) * 4));
     static const bool no_fast = getenv("KL_SPMV_GENERIC") != nullptr;
-    if (!no_fast && n > 0) {
+    if (!no_fast && n > 0 && ctx->d.ncp > 0) {      // the matrix context of a kl_mp has no single tensor grid: generic SpMV
         const int W = 2 * ctx->d.p + 1;
         KL_CUDA(cudaMalloc((void**)&w->colinfo, sizeof(int) * (size_t)n));
         KL_CUDA(cudaMalloc((void**)&w->runbase, sizeof(int) * (size_t)ctx->d.ncp * 3 * W));

@@ -294,6 +294,7 @@ static int upload_state(kl_ctx* ctx, const double* x_host, cudaStream_t s) {
 extern "C" int kl_eval_stress(kl_ctx* ctx, const double* x_host, int32_t type, int32_t n_pts, const double* uv_host, double z,
                               double* out_host) {
     if (!ctx || n_pts < 0 || (n_pts > 0 && (!uv_host || !out_host))) { kl_set_error("kl_eval_stress: bad argument"); return KL_E_ARG; }
+    if (ctx->mp) { kl_set_error("kl_eval_stress: fields are evaluated per patch: pass kl_mp_patch(mp, q), not the matrix context"); return KL_E_ARG; }
     const int dim = stress_dim(type);
     if (!dim) { kl_set_error("kl_eval_stress: unknown stress type"); return KL_E_ARG; }
     if (n_pts == 0) return KL_OK;
@@ -332,6 +333,7 @@ extern "C" int kl_principal_stretches(kl_ctx* ctx, const double* x_host, int32_t
 
 extern "C" int kl_boundary_force(kl_ctx* ctx, const double* x_host, int32_t side, double* out3_host) {
     if (!ctx || !out3_host || side < 0 || side > 3) { kl_set_error("kl_boundary_force: bad argument"); return KL_E_ARG; }
+    if (ctx->mp) { kl_set_error("kl_boundary_force: patch sides belong to a patch: pass kl_mp_patch(mp, q), not the matrix context"); return KL_E_ARG; }
     KL_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const int ncp = ctx->d.ncp, n1 = ctx->d.n1, n2 = ctx->d.n2;

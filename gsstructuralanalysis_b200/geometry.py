@@ -141,6 +141,88 @@ class Surface:
         return self.respace(self.p, (open_uniform_knots(self.p[0], nel1), open_uniform_knots(self.p[1], nel2)))
 
 
+    def insert_knot(self, direction, u, multiplicity):
+        """Raise the multiplicity of the knot u in one direction to `multiplicity` by Boehm's knot insertion on the homogeneous
+        control net (exact, the surface does not change): multiplicity = p gives a C0 line, p + 1 separates the two sides."""
+        p = self.p[direction]
+        U = np.asarray(self.U[direction], dtype=np.float64).copy()
+        n1, n2 = self.n
+        H = self.homogeneous().reshape(n2, n1, 4)
+        H = H.transpose(1, 0, 2).copy() if direction == 0 else H.copy()     # insertion axis first
+        have = int(np.sum(np.abs(U - u) < 1e-14))
+        for _ in range(max(0, multiplicity - have)):
+            k = int(np.searchsorted(U, u, side="right")) - 1               # U[k] <= u < U[k+1]
+            n = H.shape[0]
+            Q = np.empty((n + 1,) + H.shape[1:])
+            for i in range(n + 1):
+                if i <= k - p:
+                    Q[i] = H[i]
+                elif i >= k + 1:
+                    Q[i] = H[i - 1]
+                else:
+                    a = (u - U[i]) / (U[i + p] - U[i])
+                    Q[i] = a * H[i] + (1.0 - a) * H[i - 1]
+            H = Q
+            U = np.insert(U, k + 1, float(u))
+        H = H.transpose(1, 0, 2) if direction == 0 else H
+        C = np.ascontiguousarray(H).reshape(-1, 4)
+        UU = (U, np.asarray(self.U[1])) if direction == 0 else (np.asarray(self.U[0]), U)
+        if self.w is None:
+            return Surface(self.p, UU, C[:, :3].copy(), None, self.name)
+        w = C[:, 3].copy()
+        return Surface(self.p, UU, C[:, :3] / w[:, None], w, self.name)
+
+    def split(self, direction, u):
+        """The two patches left / right (below / above) of the parameter line u: same parametrisation, each with an open knot
+        vector; their facing sides carry identical control points (a conforming C0 interface)."""
+        s = self.insert_knot(direction, u, self.p[direction] + 1)
+        p = s.p[direction]
+        U = s.U[direction]
+        k = int(np.searchsorted(U, u, side="left"))          # first of the p + 1 copies of u
+        n1, n2 = s.n
+        cp = s.cp.reshape(n2, n1, 3)
+        w = None if s.w is None else s.w.reshape(n2, n1)
+        Ua, Ub = U[:k + p + 1], U[k:]
+        na = len(Ua) - p - 1
+        parts = []
+        for lo, hi, Ud in ((0, na, Ua), (na, (n1 if direction == 0 else n2), Ub)):
+            if direction == 0:
+                c, ww, UU = cp[:, lo:hi], (None if w is None else w[:, lo:hi]), (Ud, s.U[1])
+            else:
+                c, ww, UU = cp[lo:hi, :], (None if w is None else w[lo:hi, :]), (s.U[0], Ud)
+            parts.append(Surface(s.p, (np.array(UU[0]), np.array(UU[1])), np.ascontiguousarray(c).reshape(-1, 3).copy(),
+                                 None if ww is None else np.ascontiguousarray(ww).reshape(-1).copy(), self.name))
+        return parts[0], parts[1]
+
+
+def split_grid(surface, cuts1, cuts2):
+    """Cut a surface into a grid of conforming patches along the parameter lines cuts1 (first direction) x cuts2 (second):
+    returns (patches, interfaces) with patches ordered first direction fastest and interfaces as
+    (patch0, side0, patch1, side1, reversed) tuples in G+Smo side numbering (west 0, east 1, south 2, north 3)."""
+    cols = [surface]
+    for u in sorted(cuts1):
+        a, b = cols[-1].split(0, u)
+        cols[-1:] = [a, b]
+    rows = []
+    for c in cols:
+        col = [c]
+        for v in sorted(cuts2):
+            a, b = col[-1].split(1, v)
+            col[-1:] = [a, b]
+        rows.append(col)
+    m1, m2 = len(cols), len(cuts2) + 1
+    patches = [rows[i][j] for j in range(m2) for i in range(m1)]
+    interfaces = []
+    for j in range(m2):
+        for i in range(m1):
+            q = i + m1 * j
+            if i + 1 < m1:
+                interfaces.append((q, 1, q + 1, 0, 0))          # east of q meets west of its right neighbour
+            if j + 1 < m2:
+                interfaces.append((q, 3, q + m1, 2, 0))         # north of q meets south of the patch above
+    return patches, interfaces
+
+
 # --------------------------------------------------------------------------------------
 # benchmark geometries
 # --------------------------------------------------------------------------------------

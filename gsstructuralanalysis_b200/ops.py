@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .problem import ShellProblem, c_double_p, c_int_p
+from .problem import ShellProblem, MultiPatchProblem, c_double_p, c_int_p
 
 
 def _dp(a):
@@ -32,8 +32,13 @@ class SparseView:
 
 
 class ShellAssembler:
-    def __init__(self, prob: ShellProblem, device: int = -1):
+    def __init__(self, prob: ShellProblem, device: int = -1, _handle=None):
         self.L = capi.lib()
+        self._owns = _handle is None
+        if _handle is not None:          # non-owning view (the matrix context or one patch of a MultiPatchAssembler)
+            self.prob, self.h = prob, C.c_void_p(_handle)
+            self._init_sizes()
+            return
         if prob.dof_map is None:
             prob.number_dofs(self.L.kl_build_dofmap)
         self.prob = prob
@@ -41,6 +46,9 @@ class ShellAssembler:
         h = C.c_void_p()
         capi.check(self.L.kl_create(C.byref(P), device, C.byref(h)))
         self.h = h
+        self._init_sizes()
+
+    def _init_sizes(self):
         nd, nnz, ne, nq = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64()
         capi.check(self.L.kl_sizes(self.h, C.byref(nd), C.byref(nnz), C.byref(ne), C.byref(nq)))
         self.n_dofs, self.nnz, self.n_elements, self.n_qp = nd.value, nnz.value, ne.value, nq.value
@@ -271,7 +279,8 @@ class ShellAssembler:
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.kl_destroy(self.h)
+            if self._owns:
+                self.L.kl_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -279,3 +288,44 @@ class ShellAssembler:
             self.close()
         except Exception:
             pass
+
+
+class MultiPatchAssembler(ShellAssembler):
+    """gsThinShellAssembler on a gsMultiPatch with C0-matched interfaces (include/kl_shell.h: kl_mp_*): one DoF numbering, one
+    matrix.  Every matrix / vector level method of ShellAssembler works on the whole multi-patch; patch(q) is the view of ONE
+    patch for the geometry-level calls (eval_stress, computePrincipalStretches, boundaryForce) with the global solution vector."""
+
+    def __init__(self, mprob: MultiPatchProblem, device: int = -1):
+        L = capi.lib()
+        if any(p.dof_map is None for p in mprob.patches):
+            mprob.number_dofs(L.kl_mp_build_dofmap)
+        self.mprob = mprob
+        arr, self._keep = mprob.to_c()
+        mp = C.c_void_p()
+        capi.check(L.kl_mp_create(len(mprob.patches), arr, device, C.byref(mp)))
+        self.mp = mp
+        super().__init__(None, _handle=L.kl_mp_context(mp))
+
+    def patch(self, q):
+        return ShellAssembler(self.mprob.patches[q], _handle=self.L.kl_mp_patch(self.mp, q))
+
+    def set_active(self, active=None):
+        """patch -> GPU partition: assemble only the patches with active[q] != 0 (None = all)"""
+        if active is None:
+            capi.check(self.L.kl_mp_set_active(self.mp, None))
+        else:
+            a = np.ascontiguousarray(active, dtype=np.int32)
+            capi.check(self.L.kl_mp_set_active(self.mp, a.ctypes.data_as(c_int_p)))
+
+    def interface_dofs(self):
+        n = C.c_int32()
+        capi.check(self.L.kl_mp_interface_dofs(self.mp, C.byref(n), None))
+        d = np.zeros(max(n.value, 1), dtype=np.int32)
+        capi.check(self.L.kl_mp_interface_dofs(self.mp, C.byref(n), d.ctypes.data_as(c_int_p)))
+        return d[:n.value]
+
+    def close(self):
+        if getattr(self, "mp", None):
+            self.L.kl_mp_destroy(self.mp)
+            self.mp = None
+            self.h = None

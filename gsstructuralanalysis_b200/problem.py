@@ -24,6 +24,10 @@ class kl_bc(C.Structure):
     _fields_ = [("side", (C.c_int32 * 3) * 4), ("corner", (C.c_int32 * 3) * 4)]
 
 
+class kl_interface(C.Structure):
+    _fields_ = [("patch", C.c_int32 * 2), ("side", C.c_int32 * 2), ("reversed", C.c_int32)]
+
+
 class kl_problem(C.Structure):
     _fields_ = [
         ("degree", C.c_int32 * 2),
@@ -192,3 +196,53 @@ class ShellProblem:
             if self.neumann:
                 f.write(np.array([nm[0] for nm in self.neumann], dtype="<i4").tobytes())
                 f.write(np.array([nm[1] for nm in self.neumann], dtype="<f8").tobytes())
+
+
+@dataclass
+class MultiPatchProblem:
+    """Several conforming patches glued C0 along whole sides: a gsMultiPatch with computeTopology() / addInterface()
+    (benchmarks/benchmark_Wrinkling.cpp:446-522) + one ShellProblem (material, loads, boundary conditions) per patch.
+    interfaces: [(patch0, side0, patch1, side1, reversed), ...]."""
+    patches: list
+    interfaces: list = field(default_factory=list)
+    n_free: int = 0
+    n_fixed: int = 0
+
+    def number_dofs(self, build_dofmap_mp_fn):
+        """build_dofmap_mp_fn: the C symbol kl_mp_build_dofmap (product) or a callable with the same signature (oracle)."""
+        npatch = len(self.patches)
+        n1 = np.ascontiguousarray([p.surface.n[0] for p in self.patches], dtype=np.int32)
+        n2 = np.ascontiguousarray([p.surface.n[1] for p in self.patches], dtype=np.int32)
+        bcs = (kl_bc * npatch)(*[p.bc.to_c() for p in self.patches])
+        ifs = (kl_interface * max(len(self.interfaces), 1))()
+        for k, (pa, sa, pb, sb, rev) in enumerate(self.interfaces):
+            ifs[k].patch[0], ifs[k].patch[1], ifs[k].side[0], ifs[k].side[1], ifs[k].reversed = pa, pb, sa, sb, int(rev)
+        total = int(3 * np.sum(n1.astype(np.int64) * n2))
+        m = np.zeros(total, dtype=np.int32)
+        nf, nx = C.c_int32(0), C.c_int32(0)
+        rc = build_dofmap_mp_fn(npatch, n1.ctypes.data_as(c_int_p), n2.ctypes.data_as(c_int_p), bcs, len(self.interfaces), ifs,
+                                m.ctypes.data_as(c_int_p), C.byref(nf), C.byref(nx))
+        if rc != 0:
+            raise RuntimeError(f"build_dofmap_mp failed rc={rc}")
+        self.set_dof_maps(m, nf.value, nx.value)
+        return self
+
+    def set_dof_maps(self, m, n_free, n_fixed, fixed_values=None):
+        self.n_free, self.n_fixed = int(n_free), int(n_fixed)
+        fv = np.zeros(self.n_fixed) if fixed_values is None else np.ascontiguousarray(fixed_values, dtype=np.float64)
+        off = 0
+        for p in self.patches:
+            ncp = p.surface.n[0] * p.surface.n[1]
+            p.dof_map = np.ascontiguousarray(m[off:off + 3 * ncp], dtype=np.int32)
+            p.n_free, p.n_fixed, p.fixed_values = self.n_free, self.n_fixed, fv
+            off += 3 * ncp
+        return self
+
+    def to_c(self):
+        arr = (kl_problem * len(self.patches))()
+        keep = []
+        for k, p in enumerate(self.patches):
+            P, kp = p.to_c()
+            arr[k] = P
+            keep.append((P, kp))
+        return arr, keep

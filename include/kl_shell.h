@@ -310,6 +310,36 @@ int kl_principal_stretches(kl_ctx* ctx, const double* x_host, int32_t n_pts, con
  * out3: (Fx, Fy, Fz). */
 int kl_boundary_force(kl_ctx* ctx, const double* x_host, int32_t side, double* out3_host);
 
+/* ---- multi-patch: several conforming patches glued C0 along whole sides ---------------------------------------------
+ * Replaces a gsMultiPatch with computeTopology() / addInterface() handed to gsThinShellAssembler(mp, dbasis, bc, force, mm)
+ * (benchmarks/benchmark_Wrinkling.cpp:446-522, benchmark_cylinder_DC.cpp:146): the interfaces are matched inside the common
+ * gsDofMapper (gsMultiBasis::matchInterface -> gsDofMapper::matchDofs) and the element loop pushes every patch into
+ * ONE matrix.  kl_interface: side[0] of patch[0] is glued to side[1] of patch[1]; the k-th function along side 0 meets the k-th
+ * (reversed != 0: the (len-1-k)-th) function along side 1; both sides must carry the same number of functions (conforming).
+ * kl_mp_build_dofmap numbers all patches at once (patch-major within a component, otherwise as kl_build_dofmap); dof_map is
+ * the concatenation of the per-patch maps: patch q starts at 3 * sum_{r<q} n1[r]*n2[r] and holds [c * ncp_q + i]. */
+typedef struct kl_interface { int32_t patch[2]; int32_t side[2]; int32_t reversed; } kl_interface;
+int kl_mp_build_dofmap(int32_t n_patches, const int32_t* n1, const int32_t* n2, const kl_bc* bc, int32_t n_interfaces,
+                       const kl_interface* interfaces, int32_t* dof_map, int32_t* n_free, int32_t* n_fixed);
+/* One kl_problem per patch; every dof_map holds GLOBAL indices, n_free / n_fixed / fixed_values are the global ones (identical in
+ * every patch).  Material, loads, degree and knots may differ from patch to patch. */
+typedef struct kl_mp kl_mp;
+int kl_mp_create(int32_t n_patches, const kl_problem* patches, int device, kl_mp** out);
+void kl_mp_destroy(kl_mp* mp);
+/* The assembler handle of the whole multi-patch: a kl_ctx accepted by every matrix / vector level entry point of this header
+ * (kl_sizes, kl_pattern_*, kl_jacobian[_device|_lower], kl_residual[_device], kl_al_residual[_device], kl_assemble_device,
+ * kl_force, kl_mass, kl_check, kl_fetch_values / kl_set_values / kl_pin_values, kl_cg_solve, kl_spmv, kl_newton_solve, kl_alm_step).
+ * It is owned by the kl_mp (do not kl_destroy it).  Geometry-level calls (kl_eval_stress, kl_principal_stretches,
+ * kl_boundary_force) take the context of ONE patch, kl_mp_patch(mp, q), with the global solution vector. */
+kl_ctx* kl_mp_context(kl_mp* mp);
+kl_ctx* kl_mp_patch(kl_mp* mp, int32_t q);
+int32_t kl_mp_num_patches(const kl_mp* mp);
+/* Patch -> GPU partition: active[q] != 0 for the patches THIS process assembles (NULL = all).  The process then
+ * produces partial sums: its patches' share of K, of F_int and of the load vectors; the columns of the interface DoFs
+ * (kl_mp_interface_dofs: count, then the ascending list) and the vectors are completed by the reduce of the host layer. */
+int kl_mp_set_active(kl_mp* mp, const int32_t* active);
+int kl_mp_interface_dofs(const kl_mp* mp, int32_t* count, int32_t* dofs);
+
 /* Duration in ms of the last Jacobian kernel launch itself (CUDA events on its stream; syncs). */
 int kl_jacobian_kernel_ms(kl_ctx* ctx, float* ms);
 /* Same for the per-quadrature-point kernel (geometry + material) that precedes it. */
