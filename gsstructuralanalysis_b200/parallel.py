@@ -10,6 +10,11 @@ Two ways the path shards:
     point-to-point sends (NCCL on GPUs, gloo in the CPU tests).  DoFs that tie control points of several strips
     together (a collapsed west/east side is ONE DoF for the whole side) are completed by a small all-reduce instead.
 
+  * patches  — a multi-patch (kl_mp_*) split by PATCHES: rank g assembles the patches assigned to it (kl_mp_set_active).  Only the
+    columns of interface DoFs (functions glued across patches owned by different ranks) receive contributions from more than one
+    rank; every such column is owned by the lowest rank that touches it, the other ranks send their partial column (and residual
+    entry) to the owner, which adds them: the same grouped point-to-point exchange as for strips (plan_patches / exchange_patches).
+
 The partition logic below is pure host arithmetic on the knot vector and the DoF map and is shared by the GPU path and
 the CPU tests.
 """
@@ -201,6 +206,76 @@ def exchange_halo(plan: StripPlan, outer, values, residual, dist):
     summed with one all-reduce.  `values` / `residual` are torch tensors (CPU for gloo, CUDA views for nccl).
     After the call the entries of plan.owned_cols are complete on this rank.  Returns the bytes received."""
     return exchange_halo_end(plan, outer, values, residual, dist, exchange_halo_begin(plan, outer, values, residual, dist))
+
+
+@dataclass
+class PatchPlan:
+    rank: int
+    world: int
+    active: list                  # active[q] = 1 for the patches this rank assembles
+    owned_cols: list              # [(c0,c1)] column ranges complete on this rank after the exchange
+    send: dict                    # owner rank -> column ranges whose partial sums this rank sends there
+    recv: dict                    # sender rank -> column ranges this rank receives and adds
+    _bufs: dict = field(default_factory=dict)
+
+
+def plan_patches(dof_maps, n_free, patch_rank, world, rank):
+    """dof_maps: the GLOBAL dof map of every patch; patch_rank[q]: the rank that assembles patch q.  A DoF touched by the patches of
+    several ranks is owned by the lowest of them."""
+    touch = np.zeros((world, n_free), dtype=bool)
+    for q, m in enumerate(dof_maps):
+        g = np.unique(np.asarray(m))
+        touch[patch_rank[q], g[g < n_free]] = True
+    owner = np.argmax(touch, axis=0)                     # first (lowest) rank that touches the DoF
+    untouched = ~touch.any(axis=0)
+    owner[untouched] = 0
+    send, recv = {}, {}
+    for r in range(world):
+        if r == rank:
+            continue
+        mine_to_r = np.nonzero(touch[rank] & (owner == r))[0]
+        if len(mine_to_r):
+            send[r] = _ranges(mine_to_r)
+        r_to_me = np.nonzero(touch[r] & (owner == rank))[0]
+        if len(r_to_me):
+            recv[r] = _ranges(r_to_me)
+    owned = np.nonzero(owner == rank)[0]
+    return PatchPlan(rank, world, [1 if patch_rank[q] == rank else 0 for q in range(len(dof_maps))], _ranges(owned), send, recv)
+
+
+def exchange_patches(plan: PatchPlan, outer, values, residual, dist):
+    """Complete the interface columns on their owners: one batched group of point-to-point operations (NCCL / gloo), pre-allocated
+    receive buffers, one fused add.  Returns the bytes received."""
+    import torch
+    key = (str(values.device), values.dtype)
+    b = plan._bufs.get(key)
+    if b is None:
+        b = {r: ([torch.empty(e - a, dtype=values.dtype, device=values.device) for a, e in value_ranges(cr, outer)],
+                 [torch.empty(c1 - c0, dtype=values.dtype, device=values.device) for c0, c1 in cr] if residual is not None else [])
+             for r, cr in plan.recv.items()}
+        plan._bufs[key] = b
+    ops, dst, src = [], [], []
+    for r in sorted(set(plan.send) | set(plan.recv)):      # the same peer order on both sides of every pair
+        if r in plan.send:
+            for a, e in value_ranges(plan.send[r], outer):
+                ops.append(dist.P2POp(dist.isend, values[a:e], r))
+            if residual is not None:
+                for c0, c1 in plan.send[r]:
+                    ops.append(dist.P2POp(dist.isend, residual[c0:c1], r))
+        if r in plan.recv:
+            bv, br = b[r]
+            for (a, e), t in zip(value_ranges(plan.recv[r], outer), bv):
+                ops.append(dist.P2POp(dist.irecv, t, r))
+                dst.append(values[a:e]); src.append(t)
+            if residual is not None:
+                for (c0, c1), t in zip(plan.recv[r], br):
+                    ops.append(dist.P2POp(dist.irecv, t, r))
+                    dst.append(residual[c0:c1]); src.append(t)
+    for req in (dist.batch_isend_irecv(ops) if ops else []):
+        req.wait()
+    if dst:
+        torch._foreach_add_(dst, src)
+    return sum(t.numel() for t in src) * 8
 
 
 class DevicePointerView:

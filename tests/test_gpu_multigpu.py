@@ -18,3 +18,13 @@ def test_strips_two_ranks(case):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, KL_CASE=case))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "ok=True" in r.stdout
+
+
+def test_patches_two_ranks():
+    """Two ranks, one multi-patch matrix split by patches (kl_mp_set_active) with the interface exchange: NCCL on a 2-GPU box,
+    gloo with both ranks on GPU 0 otherwise (never skipped)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(ROOT, "tests", "multigpu_patches.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ok=True" in r.stdout
