@@ -87,6 +87,63 @@ int main(int argc, char** argv) {
                 diff, info.ms_assembly, info.ms_solve);
     if (dstatus != gsStatus::Success || diff > 1e-6 * U.norm()) return 1;
 
+    // Third pass: the loop of gsStaticNewton::_solveNonlinear (src/gsStaticSolvers/gsStaticNewton.hpp:142-193) written against the
+    // solver interface it uses — jacMat = computeJacobian(U); m_solver->compute(jacMat); deltaU = m_solver->solve(R) (:205-240) — with
+    // the assembler in Device copy-out mode and gsSparseSolverB200 as m_solver: K never leaves the GPU.
+    {
+        assembler->setCopyOut(gsB200CopyOut::Device);
+        gsSparseSolver<real_t>::uPtr m_solver(new gsSparseSolverB200<real_t>(*assembler));
+        static_cast<gsSparseSolverB200<real_t>*>(m_solver.get())->setTolerance(1e-12);
+        static_cast<gsSparseSolverB200<real_t>*>(m_solver.get())->setMaxIterations(20 * n);
+        gsVector<> U3(n), R3(n);
+        U3.setZero(n);
+        if (!Residual(U3, R3)) return 1;
+        gsStatus st3 = gsStatus::NotConverged;
+        gsSparseMatrix<> jacMat;
+        for (int it = 0; it < maxIt; ++it) {
+            if (!Jacobian(U3, jacMat)) { st3 = gsStatus::AssemblyError; break; }
+            m_solver->compute(jacMat);
+            if (m_solver->info() != 0) { st3 = gsStatus::SolverError; break; }
+            gsVector<> d3 = m_solver->solve(R3);
+            if (!m_solver->succeed()) { st3 = gsStatus::SolverError; break; }
+            U3 += d3;
+            if (!Residual(U3, R3)) { st3 = gsStatus::AssemblyError; break; }
+            if (d3.norm() / U3.norm() < 1e-6 && R3.norm() / R0 < 1e-9) { st3 = gsStatus::Success; break; }
+        }
+        double d3max = 0;
+        for (index_t i = 0; i < n; ++i) d3max = std::max(d3max, std::fabs(U3[i] - U[i]));
+        // a host matrix handed to the same solver is uploaded (compute) and gives the same solution; the placeholder can be fetched
+        gsSparseMatrix<> Kfetched;
+        bool ok3 = assembler->fetch(Kfetched);
+        assembler->setCopyOut(gsB200CopyOut::Full);
+        gsSparseMatrix<> Kfull;
+        ok3 = ok3 && Jacobian(U3, Kfull);
+        double dk = 0, kmax = 0;
+        for (index_t k = 0; k < Kfull.nonZeros(); ++k) { dk = std::max(dk, std::fabs(Kfull.valuePtr()[k] - Kfetched.valuePtr()[k])); kmax = std::max(kmax, std::fabs(Kfull.valuePtr()[k])); }
+        m_solver->compute(Kfull);
+        gsVector<> xs = m_solver->solve(R);
+        ok3 = ok3 && m_solver->succeed();
+        // lower-triangular copy-out: the entries with row >= col of the same matrix
+        assembler->setCopyOut(gsB200CopyOut::Lower);
+        gsSparseMatrix<> Klow;
+        ok3 = ok3 && Jacobian(U3, Klow);
+        double dl = 0;
+        index_t nlow = 0;
+        for (index_t j = 0; j < n && ok3; ++j) {
+            index_t kl = Klow.outerIndexPtr()[j];
+            for (index_t k = Kfull.outerIndexPtr()[j]; k < Kfull.outerIndexPtr()[j + 1]; ++k) {
+                if (Kfull.innerIndexPtr()[k] < j) continue;
+                if (kl >= Klow.outerIndexPtr()[j + 1] || Klow.innerIndexPtr()[kl] != Kfull.innerIndexPtr()[k]) { ok3 = false; break; }
+                dl = std::max(dl, std::fabs(Klow.valuePtr()[kl] - Kfull.valuePtr()[k]));
+                ++kl; ++nlow;
+            }
+        }
+        assembler->setCopyOut(gsB200CopyOut::Full);
+        std::printf("SPARSE_SOLVER_B200 %s max|U3 - U| = %.3e  fetched-vs-full %.3e  lower-vs-full %.3e (%d of %d entries)\n",
+                    st3 == gsStatus::Success ? "Success" : "NotConverged", d3max, dk / kmax, dl / kmax, (int)nlow, (int)Klow.nonZeros());
+        if (st3 != gsStatus::Success || !ok3 || d3max > 1e-6 * U.norm() || dk > 1e-12 * kmax || dl > 1e-12 * kmax || nlow != Klow.nonZeros()) return 1;
+    }
+
     // Post-processing of the converged state as the reference's drivers do it (unittests/gsStaticSolver_test.cpp:313-324,
     // benchmarks/benchmark_Balloon.cpp:381-408): principal stretches, boundary reaction, membrane Cauchy stress.
     const std::vector<real_t> pt = {0.5, 0.5};

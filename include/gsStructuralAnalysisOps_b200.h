@@ -104,6 +104,23 @@ private:
     std::vector<T> m_val;
 };
 
+/// Stand-in for the abstract gsSparseSolver<T> (upstream gismo/src/gsMatrix/gsSparseSolver.h, not in /root/reference
+/// [UPSTREAM-RECALLED]): what the reference's solvers hold as `typename gsSparseSolver<T>::uPtr m_solver` and drive with
+/// compute(jacMat) / info() / solve(F) (src/gsStaticSolvers/gsStaticBase.h:85,164-166,260, gsStaticNewton.hpp:214-240,
+/// src/gsALMSolvers/gsALMBase.hpp:73,186-205).  info() follows Eigen::ComputationInfo: 0 Success, 1 NumericalIssue,
+/// 2 NoConvergence, 3 InvalidInput.
+template <class T = real_t>
+class gsSparseSolver {
+public:
+    typedef std::unique_ptr<gsSparseSolver> uPtr;
+    virtual ~gsSparseSolver() {}
+    virtual gsSparseSolver& compute(const gsSparseMatrix<T>& matrix) = 0;
+    virtual gsVector<T> solve(const gsVector<T>& rhs) const = 0;
+    virtual int info() const = 0;
+    virtual bool succeed() const = 0;
+    virtual std::string detail() const = 0;
+};
+
 /// src/gsStructuralAnalysisTools/gsStructuralAnalysisTypes.h:22-30
 enum struct gsStatus { Success, NotConverged, AssemblyError, SolverError, NotStarted, OtherError };
 
@@ -131,6 +148,15 @@ struct gsStructuralAnalysisOps {
 
 namespace gismo {
 
+/** How the Jacobian_t closure hands K to the solver.
+      Full   : every value into m (what `m = assembler.matrix()` does; 8 nnz bytes over PCIe per call)
+      Lower  : m is the lower-triangular view (row >= col) — all that SimplicialLDLT / selfadjointView<Lower> read
+               (benchmarks/benchmark_Roof.cpp:359-360); half the bytes
+      Device : K stays on the GPU; m receives the pattern and a tag only.  The consumer is gsSparseSolverB200 (below), which
+               recognises the tag in compute(m) and solves on the device; any other consumer calls fetch(m) first. */
+enum class gsB200CopyOut { Full, Lower, Device };
+template <class T = real_t> class gsSparseSolverB200;
+
 /** Owns one device context and hands out cheap-to-copy operator handles (the reference stores its closures by
     value inside the solvers: src/gsStaticSolvers/gsStaticNewton.h:232-235), so the handles share the context through
     a shared_ptr.  One object per GPU / solver thread; calls on one object are serialised by the caller, as in the
@@ -146,6 +172,24 @@ public:
         if (rc != KL_OK) throw std::runtime_error(std::string("kl_create: ") + kl_last_error());
         m_s = std::make_shared<Shared>();
         m_s->ctx = c;
+        init();
+    }
+    /** Multi-patch: one kl_problem per patch, all numbered by ONE mapper (kl_mp_build_dofmap) — the reference's
+        gsThinShellAssembler(mp, dbasis, bc, force, materialMatrix) on a gsMultiPatch with computeTopology()
+        (benchmarks/benchmark_Wrinkling.cpp:446-522).  Every operator below then acts on the whole multi-patch. */
+    gsThinShellAssemblerB200(const std::vector<kl_problem>& patches, int device = -1) {
+        kl_mp* mp = nullptr;
+        const int rc = kl_mp_create((int32_t)patches.size(), patches.data(), device, &mp);
+        if (rc != KL_OK) throw std::runtime_error(std::string("kl_mp_create: ") + kl_last_error());
+        m_s = std::make_shared<Shared>();
+        m_s->mp = mp;
+        m_s->ctx = kl_mp_context(mp);
+        init();
+    }
+
+private:
+    void init() {
+        kl_ctx* c = m_s->ctx;
         int64_t nnz = 0, ne = 0, nq = 0;
         kl_sizes(c, &m_s->ndofs, &nnz, &ne, &nq);
         m_s->nnz = nnz;
@@ -153,6 +197,31 @@ public:
         m_s->inner.resize((size_t)nnz);
         if (kl_pattern_host(c, m_s->outer.data(), m_s->inner.data()) != KL_OK)
             throw std::runtime_error(std::string("kl_pattern_host: ") + kl_last_error());
+    }
+
+public:
+    /// geometry-level calls of a multi-patch (computePrincipalStretches, boundaryForce, evalStress) address one patch
+    void selectPatch(int32_t q) {
+        if (!m_s->mp || !kl_mp_patch(m_s->mp, q)) throw std::runtime_error("selectPatch: not a multi-patch assembler / no such patch");
+        m_s->geo = kl_mp_patch(m_s->mp, q);
+    }
+    void setCopyOut(gsB200CopyOut mode) {
+        if (mode == gsB200CopyOut::Lower && m_s->outer_lower.empty()) {
+            int64_t nl = 0;
+            if (kl_pattern_lower_host(m_s->ctx, nullptr, nullptr, &nl) != KL_OK) throw std::runtime_error(kl_last_error());
+            m_s->outer_lower.resize((size_t)m_s->ndofs + 1);
+            m_s->inner_lower.resize((size_t)nl);
+            m_s->nnz_lower = nl;
+            if (kl_pattern_lower_host(m_s->ctx, m_s->outer_lower.data(), m_s->inner_lower.data(), &nl) != KL_OK)
+                throw std::runtime_error(kl_last_error());
+        }
+        m_s->mode = mode;
+    }
+    gsB200CopyOut copyOut() const { return m_s->mode; }
+    /// Device mode: bring the values of the matrix behind the placeholder m to the host after all (lazy fetch)
+    bool fetch(gsSparseMatrix<T>& m) const {
+        adoptPattern(m, m_s->ndofs, m_s->nnz, m_s->outer.data(), m_s->inner.data());
+        return kl_fetch_values(m_s->ctx, m.valuePtr()) == KL_OK;
     }
 
     index_t numDofs() const { return m_s->ndofs; }
@@ -163,7 +232,16 @@ public:
     Ops::Jacobian_t jacobian() const {
         auto s = m_s;
         return [s](gsVector<T> const& x, gsSparseMatrix<T>& m) {
+            if (s->mode == gsB200CopyOut::Lower) {
+                adoptPattern(m, s->ndofs, s->nnz_lower, s->outer_lower.data(), s->inner_lower.data());
+                return kl_jacobian_lower(s->ctx, x.data(), m.valuePtr()) == KL_OK;
+            }
             adoptPattern(m, s->ndofs, s->nnz, s->outer.data(), s->inner.data());
+            if (s->mode == gsB200CopyOut::Device) {
+                if (kl_jacobian(s->ctx, x.data(), nullptr) != KL_OK) return false;
+                if (s->nnz > 0) m.valuePtr()[0] = s->newTag();      // placeholder: pattern + tag, the values live on the GPU
+                return true;
+            }
             return kl_jacobian(s->ctx, x.data(), m.valuePtr()) == KL_OK;
         };
     }
@@ -279,18 +357,18 @@ public:
     bool computePrincipalStretches(const std::vector<T>& uv, gsVector<T> const& solVector, T z, std::vector<T>& lambdas) const {
         const int32_t n = (int32_t)(uv.size() / 2);
         lambdas.assign((size_t)3 * n, T(0));
-        return kl_principal_stretches(m_s->ctx, solVector.data(), n, uv.data(), z, lambdas.data()) == KL_OK;
+        return kl_principal_stretches(m_s->geoCtx(), solVector.data(), n, uv.data(), z, lambdas.data()) == KL_OK;
     }
     /** assembler->boundaryForce(mp_def, patchSide(0, side)) (unittests/gsStaticSolver_test.cpp:321); side = KL_WEST.. */
     bool boundaryForce(gsVector<T> const& solVector, int side, T force[3]) const {
-        return kl_boundary_force(m_s->ctx, solVector.data(), side, force) == KL_OK;
+        return kl_boundary_force(m_s->geoCtx(), solVector.data(), side, force) == KL_OK;
     }
     /** assembler->constructStress(mp_def, field, stress_type::X) evaluated at parametric points
         (benchmarks/benchmark_Balloon.cpp:381-408): `type` = KL_STRESS_*, result kl_stress_dim(type) values per point. */
     bool evalStress(gsVector<T> const& solVector, int type, const std::vector<T>& uv, std::vector<T>& result, T z = 0) const {
         const int32_t n = (int32_t)(uv.size() / 2);
         result.assign((size_t)kl_stress_dim(type) * n, T(0));
-        return kl_eval_stress(m_s->ctx, solVector.data(), type, n, uv.data(), z, result.data()) == KL_OK;
+        return kl_eval_stress(m_s->geoCtx(), solVector.data(), type, n, uv.data(), z, result.data()) == KL_OK;
     }
     /// gsStaticBase::defaultOptions (gsStaticBase.h:66-75) + gsStaticNewton::defaultOptions (gsStaticNewton.hpp:20-25)
     static kl_newton_options defaultNewtonOptions() {
@@ -313,14 +391,78 @@ private:
 #endif
     }
 
+    template <class U> friend class gsSparseSolverB200;
     struct Shared {
         kl_ctx* ctx = nullptr;
+        kl_mp* mp = nullptr;             // multi-patch: owns ctx (= kl_mp_context)
+        kl_ctx* geo = nullptr;           // patch addressed by the geometry-level calls (multi-patch)
         int32_t ndofs = 0;
-        int64_t nnz = 0;
-        std::vector<int32_t> outer, inner;
-        ~Shared() { if (ctx) kl_destroy(ctx); }
+        int64_t nnz = 0, nnz_lower = 0;
+        std::vector<int32_t> outer, inner, outer_lower, inner_lower;
+        gsB200CopyOut mode = gsB200CopyOut::Full;
+        uint64_t generation = 0;         // Device mode: which Jacobian call the device matrix belongs to
+        kl_ctx* geoCtx() const { return geo ? geo : ctx; }
+        /// the tag written into values[0] of a Device-mode placeholder: a quiet NaN whose payload is the generation
+        T newTag() { ++generation; return tagOf(generation); }
+        static T tagOf(uint64_t g) {
+            const uint64_t bits = 0x7ff8000000000000ULL | (0x0000b20000000000ULL) | (g & 0xffffffffffULL);
+            T v; std::memcpy(&v, &bits, sizeof(v)); return v;
+        }
+        bool isCurrentPlaceholder(const gsSparseMatrix<T>& m) const {
+            if (mode != gsB200CopyOut::Device || generation == 0 || (int64_t)m.nonZeros() != nnz || nnz == 0) return false;
+            const T want = tagOf(generation);
+            return std::memcmp(m.valuePtr(), &want, sizeof(T)) == 0;
+        }
+        ~Shared() { if (mp) kl_mp_destroy(mp); else if (ctx) kl_destroy(ctx); }
     };
     std::shared_ptr<Shared> m_s;   // shared by every handle handed out, so handles may outlive this object
+};
+
+/** gsSparseSolver-shaped front of the device-resident CGDiagonal (kl_cg_solve), for the solvers' `m_solver`
+    (src/gsStaticSolvers/gsStaticBase.h:85,164-166,260; src/gsALMSolvers/gsALMBase.hpp:73,186-205).
+      compute(m): m is the Device-mode placeholder of the assembler's current matrix -> nothing moves;
+                  m is any other matrix on the assembler's full pattern (Full mode, or a matrix the solver has modified,
+                  e.g. K - shift*M) -> its values are uploaded once (8 nnz bytes H2D);
+                  anything else -> info() = InvalidInput.
+      solve(b)  : Jacobi-preconditioned CG with Eigen's conventions on the GPU; only b and x cross PCIe.
+    The matrix must be symmetric positive definite, as for gsSparseSolver<>::CGDiagonal. */
+template <class T>
+class gsSparseSolverB200 : public gsSparseSolver<T> {
+public:
+    explicit gsSparseSolverB200(const gsThinShellAssemblerB200& assembler) : m_s(assembler.m_s) {}
+    void setTolerance(T tol) { m_tol = tol; }              ///< Eigen default: machine epsilon
+    void setMaxIterations(index_t it) { m_maxit = it; }   ///< Eigen default: 2 n
+    gsSparseSolverB200& compute(const gsSparseMatrix<T>& m) override {
+        m_info = 0;
+        if (m_s->isCurrentPlaceholder(m)) return *this;
+        if ((index_t)m.rows() != (index_t)m_s->ndofs || (int64_t)m.nonZeros() != m_s->nnz) { m_info = 3; return *this; }
+        if (kl_set_values(m_s->ctx, m.valuePtr()) != KL_OK) m_info = 1;
+        return *this;
+    }
+    gsVector<T> solve(const gsVector<T>& rhs) const override {
+        gsVector<T> x;
+        x.resize(m_s->ndofs);
+        int32_t it = 0;
+        double err = 0;
+        const int rc = kl_cg_solve(m_s->ctx, rhs.data(), x.data(), m_tol, m_maxit, &it, &err);
+        m_iterations = it; m_error = err;
+        const double tol = m_tol > 0 ? m_tol : 2.220446049250313e-16;
+        m_info = rc != KL_OK ? 1 : (err <= tol ? 0 : 2);
+        return x;
+    }
+    int info() const override { return m_info; }
+    bool succeed() const override { return m_info == 0; }
+    std::string detail() const override { return "CGDiagonal on the B200 (libkl_shell kl_cg_solve)"; }
+    index_t iterations() const { return m_iterations; }
+    T error() const { return m_error; }
+
+private:
+    std::shared_ptr<gsThinShellAssemblerB200::Shared> m_s;
+    T m_tol = 0;
+    index_t m_maxit = 0;
+    mutable int m_info = 0;
+    mutable index_t m_iterations = 0;
+    mutable T m_error = 0;
 };
 
 /** gsElasticityAssembler<real_t> behind the solid closures (tutorials/nonlinear_solid_static.cpp:101-114,

@@ -44,6 +44,7 @@ def test_cpp_newton_converges_on_gpu(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "STATUS Success" in r.stdout, r.stdout
     assert "DEVICE_NEWTON Success" in r.stdout, r.stdout
+    assert "SPARSE_SOLVER_B200 Success" in r.stdout, r.stdout    # gsSparseSolver-shaped device CG, Device / Lower copy-out modes
     assert "STRETCHES" in r.stdout, r.stdout      # computePrincipalStretches / boundaryForce / evalStress of the adapter
 
 
