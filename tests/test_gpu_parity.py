@@ -195,6 +195,38 @@ def test_gpu_scordelis_lo_known_answer(gpu):
     assert abs(-uz - 0.3006) / 0.3006 < 5e-3       # filedata/pde/kirchhoff_shell_scordelis.xml:104-107 gives 0.30024
 
 
+@pytest.mark.parametrize("material,lam", [(KL_MAT_NH, 1.1), (KL_MAT_NH, 1.6), (KL_MAT_MR, 1.6)])
+def test_gpu_inflated_sphere_closed_form(gpu, material, lam):
+    """Thin hyperelastic sphere under follower pressure, solved with the GPU closures: r = lam R, stretches (lam, lam, lam^-2) for
+    the closed-form pressure 2 t/R (lam^-1 - lam^-7)(c1 + c2 lam^2) lam^2 (nominal pressure, benchmarks/benchmark_Balloon.cpp:359)."""
+    from tests import kat_problems as kp
+    from gsstructuralanalysis_b200 import capi
+    pr, x0, p = kp.sphere_inflation(capi.lib().kl_build_dofmap, material, lam, t=1e-3, nel=8)
+    asm, x, its = kp.sphere_inflation_solve(lambda q: gpu(q), pr, x0)
+    r_mean, r_spread, st = kp.sphere_inflation_measure(asm, pr, x)
+    assert abs(r_mean - lam) <= 5e-6 * lam, (r_mean, lam)
+    assert r_spread <= 2e-5
+    assert abs(st[0] - lam) <= 1e-4 * lam and abs(st[1] - lam) <= 1e-4 * lam and abs(st[2] - lam ** -2) <= 1e-4, st
+
+
+def test_gpu_plate_patch_test(gpu):
+    """constant strain on a non-uniform degree-3 mesh: zero internal force at interior control points, side reactions = t P N L"""
+    from tests import kat_problems as kp
+    from gsstructuralanalysis_b200 import capi
+    pr, x, S, Fm = kp.plate_patch_test(capi.lib().kl_build_dofmap)
+    asm = gpu(pr)
+    ok, r = asm.residual(x)
+    assert ok
+    n1, n2 = pr.surface.n
+    dm = np.asarray(pr.dof_map).reshape(3, n2, n1)
+    f = -r[dm]
+    P = Fm @ S
+    scale = pr.thickness * np.abs(P).max()
+    assert np.abs(f[:, 1:-1, 1:-1]).max() <= 1e-12 * scale
+    assert np.abs(f[:2, :, -1].sum(axis=1) - pr.thickness * 1.0 * P[:, 0]).max() <= 1e-12 * scale
+    assert np.abs(f[:2, -1, :].sum(axis=1) - pr.thickness * 2.0 * P[:, 1]).max() <= 1e-12 * scale
+
+
 def test_pipelined_copy_out_path(gpu):
     """nel >= 12 switches kl_jacobian to the strip-pipelined D2H path (kl_capi.cu: build_d2h_plan)."""
     _compare(gpu, W.roof(16), 0.3, "roof16-pipelined")

@@ -32,3 +32,45 @@ def test_scordelis_lo_linear_deflection():
     # reference value 0.30024 (kirchhoff_shell_scordelis.xml:104-107); converged KL value 0.3006
     assert abs(-uz - 0.3006) / 0.3006 < 5e-3, uz
     assert abs(-uz - 0.30024) / 0.30024 < 1e-2, uz
+
+
+# ---- closed forms that need no reference build -----------------------------------------------------------------------
+@pytest.mark.parametrize("material", [KL_MAT_NH, KL_MAT_MR])
+@pytest.mark.parametrize("lam", [1.1, 1.6])
+def test_inflated_sphere_closed_form(material, lam):
+    """p_true = 2 t/R (lam^-1 - lam^-7)(c1 + c2 lam^2), set as the nominal pressure p_true lam^2 (the reference's own convention,
+    benchmarks/benchmark_Balloon.cpp:359): the discrete equilibrium is the sphere of radius lam R with stretches (lam, lam, lam^-2)."""
+    pr, x0, p = kp.sphere_inflation(olib().klo_build_dofmap, material, lam, t=1e-3, nel=8)
+    orc, x, its = kp.sphere_inflation_solve(lambda q: OracleOps(q), pr, x0)
+    r_mean, r_spread, st = kp.sphere_inflation_measure(orc.o, pr, x)
+    assert abs(r_mean - lam) <= 5e-6 * lam, (r_mean, lam)            # measured 5e-7 (h^4: 2e-8 at 16 elements)
+    assert r_spread <= 2e-5, r_spread                               # it stays a sphere
+    assert abs(st[0] - lam) <= 1e-4 * lam and abs(st[1] - lam) <= 1e-4 * lam and abs(st[2] - lam ** -2) <= 1e-4, st
+    # and the pressure is not a free parameter of the check: 1 % more pressure moves the radius measurably
+    pr2, x02, _ = kp.sphere_inflation(olib().klo_build_dofmap, material, lam, t=1e-3, nel=8)
+    pr2.pressure = 1.01 * p
+    orc2, x2, _ = kp.sphere_inflation_solve(lambda q: OracleOps(q), pr2, x02)
+    assert abs(kp.sphere_inflation_measure(orc2.o, pr2, x2)[0] - lam) > 1e-3 * lam
+
+
+def test_plate_patch_test_nonuniform_mesh():
+    pr, x, S, Fm = kp.plate_patch_test(olib().klo_build_dofmap)
+    orc = Oracle(pr)
+    fint = -orc.residual(x)
+    n1, n2 = pr.surface.n
+    dm = np.asarray(pr.dof_map).reshape(3, n2, n1)
+    f = fint[dm]                                                # [c, i2, i1]
+    t, Wd, Ld = pr.thickness, 1.0, 2.0
+    P = Fm @ S                                                  # first Piola-Kirchhoff stress (in-plane block)
+    scale = t * np.abs(P).max()
+    assert np.abs(f[:, 1:-1, 1:-1]).max() <= 1e-12 * scale      # interior equilibrium of the constant stress field
+    assert np.abs(f[2]).max() <= 1e-12 * scale                  # no out-of-plane force
+    east = f[:2, :, -1].sum(axis=1)
+    north = f[:2, -1, :].sum(axis=1)
+    assert np.abs(east - t * Wd * P[:, 0]).max() <= 1e-12 * scale
+    assert np.abs(north - t * Ld * P[:, 1]).max() <= 1e-12 * scale
+    # the tangent at that state annihilates nothing it should not: K = K^T and K (rigid translation) = 0
+    K = orc.jacobian(x)
+    assert abs(K - K.T).max() <= 1e-12 * abs(K).max()
+    tr = np.zeros(orc.n_dofs); tr[dm[0].reshape(-1)] = 1.0
+    assert np.abs(K @ tr).max() <= 1e-10 * abs(K).max()
