@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkl_shell.so")
-SOURCES = ["kl_capi.cu", "kl_pattern.cu", "kl_assemble.cu", "kl_solve.cu", "kl_stress.cu", "kl_multipatch.cu", "ks_solid.cu"]
+SOURCES = ["kl_capi.cu", "kl_pattern.cu", "kl_assemble.cu", "kl_solve.cu", "kl_stress.cu", "kl_multipatch.cu", "kl_stability.cu", "ks_solid.cu"]
 HEADERS = ["kl_internal.h", "kl_device.cuh", os.path.join("..", "..", "include", "kl_shell.h"),
            os.path.join("..", "..", "include", "ks_solid.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

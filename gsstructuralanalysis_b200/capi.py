@@ -25,7 +25,7 @@ SYMBOLS = ["kl_build_dofmap", "kl_create", "kl_destroy", "kl_sizes", "kl_pattern
            "kl_pin_values", "kl_unpin_values", "kl_fetch_values", "kl_set_values", "kl_pattern_lower_host", "kl_jacobian_lower",
            "kl_al_residual_device", "kl_alm_step", "kl_strip_begin_device", "kl_jacobian_rows_device",
            "kl_mp_build_dofmap", "kl_mp_create", "kl_mp_destroy", "kl_mp_context", "kl_mp_patch", "kl_mp_num_patches",
-           "kl_mp_set_active", "kl_mp_interface_dofs"]
+           "kl_mp_set_active", "kl_mp_interface_dofs", "kl_stability"]
 
 # stress_type of constructStress (include/kl_shell.h)
 STRESS_TYPES = {"displacement": 0, "membrane_force": 1, "flexural_moment": 2, "membrane": 3, "flexural": 4,
@@ -117,6 +117,7 @@ def lib():
     L.kl_eval_stress.argtypes = [vp, c_double_p, C.c_int32, C.c_int32, c_double_p, C.c_double, c_double_p]
     L.kl_principal_stretches.argtypes = [vp, c_double_p, C.c_int32, c_double_p, C.c_double, c_double_p]
     L.kl_boundary_force.argtypes = [vp, c_double_p, C.c_int32, c_double_p]
+    L.kl_stability.argtypes = [vp, c_double_p, c_int_p, c_double_p]
     L.kl_mp_build_dofmap.argtypes = [C.c_int32, c_int_p, c_int_p, C.POINTER(kl_bc), C.c_int32, C.POINTER(kl_interface), c_int_p, c_int_p, c_int_p]
     L.kl_mp_create.argtypes = [C.c_int32, C.POINTER(kl_problem), C.c_int, C.POINTER(vp)]
     L.kl_mp_destroy.argtypes = [vp]

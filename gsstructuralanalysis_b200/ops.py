@@ -238,6 +238,14 @@ class ShellAssembler:
         capi.check(self.L.kl_alm_step(self.h, _dp(U), C.byref(Lc), _dp(DU), C.byref(DLc), float(arc_length), C.byref(opt), C.byref(info)))
         return info.status, U, Lc.value, DU, DLc.value, {k: getattr(info, k) for k, _ in capi.kl_alm_info._fields_}
 
+    def stability(self, return_D=False):
+        """gsALMBase::_computeStability, "Determinant" method, on the matrix of the last jacobian() call (device LDL^T):
+        (indicator = min D, negatives = number of negative pivots[, D per DoF])."""
+        ind, neg = C.c_double(), C.c_int32()
+        D = np.zeros(self.n_dofs) if return_D else None
+        capi.check(self.L.kl_stability(self.h, C.byref(ind), C.byref(neg), _dp(D) if return_D else None))
+        return (ind.value, neg.value, D) if return_D else (ind.value, neg.value)
+
     # -- stress / stretch recovery (SURVEY 8f rank 4) --------------------------------------------
     def eval_stress(self, x, stress_type, uv, z=0.0):
         """constructStress(mp_def, field, stress_type::X) evaluated at the parametric points uv [n,2]: array [n, dim]

@@ -265,6 +265,17 @@ typedef struct kl_alm_info {
 int kl_alm_step(kl_ctx* ctx, double* U_host_inout, double* L_inout, double* DeltaUold_host_inout, double* DeltaLold_inout,
                 double arc_length, const kl_alm_options* opt, kl_alm_info* info);
 
+/* ---- stability indicator of the arc-length solvers ---------------------------------------------------------
+ * gsALMBase<T>::_computeStability / gsStaticBase<T>::_computeStabilityDet with the "Determinant" method
+ * (src/gsALMSolvers/gsALMBase.hpp:546-611, src/gsStaticSolvers/gsStaticBase.h:161-179): m_stabilityVec = SimplicialLDLT::vectorD(),
+ * m_negatives = countNegatives(vectorD), m_indicator = min(vectorD), stability = sign(m_indicator).  The matrix is the one the last
+ * kl_jacobian / kl_jacobian_device call left on the device; it is factorised there (banded L D L^T without pivoting in a
+ * node-major ordering, 8 n (bw + 33) bytes of scratch).  negatives and the SIGN of the indicator do not depend on the ordering
+ * (Sylvester's law of inertia) and therefore agree with the reference; the value of the indicator is the smallest pivot of this
+ * ordering, as Eigen's is of its AMD ordering.  vectorD_host (n_dofs entries, the pivot of every DoF) may be NULL.
+ * Refused for unsymmetric tangents (follower pressure) and on a multi-patch. */
+int kl_stability(kl_ctx* ctx, double* indicator, int32_t* negatives, double* vectorD_host);
+
 /* ---- stress / stretch recovery -----------------------------------------------
  * Replaces assembler->constructStress(mp_def, field, stress_type::X) followed by field evaluation
  * (benchmarks/benchmark_Balloon.cpp:381-408, benchmark_TensionWrinkling.cpp:505-540, benchmark_Pillow.cpp:431,484-505),
