@@ -67,6 +67,18 @@ public:
     }
     const std::vector<double>& solutionU() const { return m_U; }
     double solutionL() const { return m_L; }
+    /** gsALMBase::computeStability(jacobian = true) with the "Determinant" method (gsALMBase.hpp:546-611): K(m_U) is assembled and
+        factorised (L D L^T) on the device, m_indicator = min D, m_negatives = #(D < 0).  Returns false on assembly / factorisation
+        failure (the reference throws 2 / 3). */
+    bool computeStability() {
+        m_stabilityPrev = stability();
+        if (kl_jacobian(m_ctx, m_U.data(), nullptr) != KL_OK) return false;
+        return kl_stability(m_ctx, &m_indicator, &m_negatives, nullptr) == KL_OK;
+    }
+    double indicator() const { return m_indicator; }
+    int negatives() const { return m_negatives; }
+    int stability() const { return m_indicator < 0 ? 1 : -1; }                                   // gsALMBase.hpp:617-621
+    bool stabilityChange() const { return stability() * m_stabilityPrev < 0; }                   // gsALMBase.hpp:623-627
     /// gsALMCrisfield::distance: sqrt(DeltaU.DeltaU + phi^2 F.F DeltaL^2); the benchmark sets Scaling = 0 (:440)
     double distance(const std::vector<double>& DU, double DL) const {
         double s = 0;
@@ -88,6 +100,9 @@ private:
     kl_alm_info m_info{};
     std::vector<double> m_U, m_DeltaUold;
     double m_L = 0, m_DeltaLold = 0, m_arcLength = 1e-2, m_phi = 0, m_A0 = 0;
+    double m_indicator = 0;
+    int m_stabilityPrev = -1;
+    int32_t m_negatives = 0;
     long m_steps = 0, m_iterations = 0, m_cgIterations = 0;
     double m_msAssembly = 0, m_msSolve = 0;
 };
