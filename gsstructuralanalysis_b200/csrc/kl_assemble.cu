@@ -1100,11 +1100,13 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     const bool hasB = ctx->d.mat.material != KL_MAT_SVK && ctx->d.mat.bending;
     KL_CUDA(cudaEventRecord(ctx->ev[4], s));
     if (P == 3 && !ctx->jac_shared) {
-        // sliding-window kernel: segments of element rows, sized for >= ~8 waves of resident CTAs
+        // sliding-window kernel: segments of element rows, sized for about 24 waves of resident CTAs, 8 .. 24 elements long
+        // (measured at 576 x 576 elements, profiles/r2_ablation.txt: 8 / 12 / 16 / 24 / 32 / 48 / 64 elements per segment give
+        // 3.58 / 3.52 / 3.50 / 3.51 / 3.54 / 3.60 / 3.65 ms: short segments keep the tail small, below 10 the window restarts cost more)
         int seg = ctx->jac_seg;
         if (seg <= 0) {
-            const long long slots = (long long)ctx->n_sm * KL_SW_MINB * 8;
-            seg = (int)std::min<long long>(64, std::max<long long>(8, ((long long)nel + slots - 1) / slots));
+            const long long slots = (long long)ctx->n_sm * KL_SW_MINB * 24;
+            seg = (int)std::min<long long>(24, std::max<long long>(8, ((long long)nel + slots - 1) / slots));
         }
         const int nseg = (ctx->d.nel1 + seg - 1) / seg;
         if (hasB) k_jacobian_sw<true><<<(e2e - e2b) * nseg, 64, 0, s>>>(ctx->d, e2b, e2e, seg);

@@ -59,6 +59,8 @@ class StripPlan:
     recv_cols: list               # column ranges received from rank-1 (== that rank's send_cols)
     shared_cols: list             # column ranges touched by several strips' OWN rows (matched DoFs): completed by all-reduce
     tail_rows: int = 0            # the last element rows of the strip that reach control-point rows of the next strip
+    compute_begin: int = 0        # halo-compute: assembling the element rows [compute_begin, e2_end) completes every owned column on this
+                                  # rank WITHOUT any exchange (p redundant element rows per interface); -1 when shared columns forbid it
     _bufs: dict = field(default_factory=dict)     # receive / pack buffers, allocated once per (device, dtype)
 
 
@@ -112,8 +114,14 @@ def plan_strips(n1, n2, p, nel2, dof_map, n_free, world, rank, knots2=None):
     owned = np.setdiff1d(owned_sets[rank], shared)
     owned = np.union1d(owned, shared)          # shared columns are complete on every rank after the all-reduce
     recv = send_sets[rank - 1] if rank > 0 else np.zeros(0, dtype=np.int64)
+    # halo-compute: the owner also integrates the element rows of the previous strip that its own control-point rows
+    # reach into, so nothing has to be sent; elements of the overlap are assembled twice, which would double-count shared columns
+    mine = owner_row == rank
+    compute_begin = int(flo[mine].min()) if mine.any() else bounds[rank]
+    if len(shared):
+        compute_begin = -1
     return StripPlan(rank, world, bounds[rank], bounds[rank + 1], _ranges(owned), _ranges(send_sets[rank]), _ranges(recv),
-                     _ranges(shared), tails[rank])
+                     _ranges(shared), tails[rank], compute_begin)
 
 
 def value_ranges(col_ranges, outer):

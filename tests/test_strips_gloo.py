@@ -50,6 +50,16 @@ def _worker(rank, world, port, case, q):
         ok &= bool(np.abs(Kp.numpy()[a:b] - Kfull[a:b]).max() <= 1e-13 * np.abs(Kfull).max())
     for (c0, c1) in plan.owned_cols:
         ok &= bool(np.abs(Rp.numpy()[c0:c1] - Rint_full[c0:c1]).max() <= 1e-13 * max(np.abs(Rint_full).max(), 1e-300))
+    # halo-compute: the owner integrates the overlapping element rows itself and nothing is exchanged
+    if plan.compute_begin >= 0:
+        part.set_strip(plan.compute_begin, plan.e2_end)
+        Kh, Rh = part.jacobian_values(x), part.internal_force(x)
+        for (a, b) in value_ranges(plan.owned_cols, full.outer):
+            ok &= bool(np.abs(Kh[a:b] - Kfull[a:b]).max() <= 1e-13 * np.abs(Kfull).max())
+        for (c0, c1) in plan.owned_cols:
+            ok &= bool(np.abs(Rh[c0:c1] - Rint_full[c0:c1]).max() <= 1e-13 * max(np.abs(Rint_full).max(), 1e-300))
+    else:
+        ok &= case == "tension"          # only the collapsed side forbids it
     owned = sum(c1 - c0 for c0, c1 in plan.owned_cols)
     q.put((rank, ok, owned, moved))
     dist.barrier()
