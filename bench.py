@@ -306,6 +306,84 @@ def config_records(torch, capi, args, local, hbm_peak, fp64_peak):
     return out
 
 
+def multipatch_record(torch, dist, args, local, rank, world, barrier, allmax):
+    """configs[3] as BASELINE.json frames it ("multipatch row-partitioned assembly at 1/2/4/8 GPUs"): the tension sheet cut into 8 conforming
+    patches along the second direction, glued C0 by one DoF mapper (kl_mp_*).  N = 1: all patches on one GPU next to the uncut single
+    patch; N > 1: patch -> GPU partition (kl_mp_set_active) + the interface exchange of parallel.exchange_patches."""
+    from gsstructuralanalysis_b200.ops import ShellAssembler, MultiPatchAssembler
+    from gsstructuralanalysis_b200.parallel import plan_patches, exchange_patches, DevicePointerView, value_ranges
+    npatch, nel = 8, args.nel
+    base = W.tension_sheet(nel)
+    single, multi, cps = W.cut(base, [], [k / npatch for k in range(1, npatch)])
+    stream = torch.cuda.current_stream().cuda_stream
+    asm = MultiPatchAssembler(multi, device=local)
+    n, nnz, nqp = asm.n_dofs, asm.nnz, asm.n_qp
+    Lx = float(np.ptp(base.surface.cp[:, 0]))
+    hloc = Lx / nel
+    # one smooth state for every rank, expressed through the uncut patch and permuted to the multi-patch numbering
+    single.number_dofs(asm.L.kl_build_dofmap)
+    perm = W.dof_permutation(single, multi, cps)
+    xs = W.smooth_state(single, 1e-3 * Lx, noise=1e-5 * min(hloc, hloc * hloc / base.thickness) * 0.1)
+    x = torch.from_numpy(np.ascontiguousarray(xs[perm])).cuda()
+    r = torch.zeros(n, dtype=torch.float64, device="cuda")
+    vals = DevicePointerView(asm.values_device_ptr(), nnz).tensor()
+    outer_h, _ = asm.pattern()
+
+    def whole():
+        asm.residual_device(x.data_ptr(), r.data_ptr(), 1.0, -1.0, stream)
+        asm.jacobian_device(x.data_ptr(), stream)
+    for _ in range(3):
+        whole()
+    if asm.check(stream) != 0:
+        raise RuntimeError("multipatch: " + asm.L.kl_last_error().decode())
+    ms_whole = time_device_steps(torch, whole, args.steps)
+    rec = {"workload": f"S4 tension sheet (configs[3]) {nel}x{nel} elements cut into {npatch} conforming patches of {nel}x{nel // npatch} elements, Mooney-Rivlin",
+           "n_dofs": n, "nnz": nnz, "quad_points": nqp, "patches": npatch, "interface_dofs": int(len(asm.interface_dofs())),
+           "one_gpu_all_patches_ms": ms_whole, "one_gpu_quad_pts_per_s": nqp / (ms_whole * 1e-3)}
+    K_full, R_full = vals.clone(), r.clone()
+    if rank == 0:
+        # the uncut patch (same function space) on this GPU: what gluing costs, and the identity that pins it
+        one = ShellAssembler(single, device=local)
+        x1 = torch.from_numpy(np.ascontiguousarray(xs)).cuda()
+        r1 = torch.zeros(n, dtype=torch.float64, device="cuda")
+
+        def uncut():
+            one.residual_device(x1.data_ptr(), r1.data_ptr(), 1.0, -1.0, stream)
+            one.jacobian_device(x1.data_ptr(), stream)
+        for _ in range(3):
+            uncut()
+        rec["uncut_single_patch_ms"] = time_device_steps(torch, uncut, args.steps)
+        torch.cuda.synchronize()
+        pt = torch.from_numpy(perm).cuda()
+        rec["max_rel_diff_vs_uncut_patch"] = {"R": float((R_full - r1[pt]).abs().max() / max(float(r1.abs().max()), 1e-300))}
+        one.close()
+        del x1, r1
+    if world > 1:
+        patch_rank = [q * world // npatch for q in range(npatch)]
+        plan = plan_patches([p.dof_map for p in multi.patches], multi.n_free, patch_rank, world, rank)
+        asm.set_active(plan.active)
+
+        def part():
+            asm.residual_device(x.data_ptr(), r.data_ptr(), 1.0, -1.0, stream)
+            asm.jacobian_device(x.data_ptr(), stream)
+            return exchange_patches(plan, outer_h, vals, r, dist)
+        for _ in range(3):
+            moved = part()
+        ms_part = allmax(time_device_steps(torch, part, args.steps, barrier))
+        sK, sR = float(K_full.abs().max()), float(R_full.abs().max())
+        eK = max([float((vals[a:b] - K_full[a:b]).abs().max()) for a, b in value_ranges(plan.owned_cols, outer_h) if b > a] + [0.0]) / sK
+        eR = max([float((r[c0:c1] - R_full[c0:c1]).abs().max()) for c0, c1 in plan.owned_cols if c1 > c0] + [0.0]) / sR
+        eK, eR = allmax(eK), allmax(eR)
+        rec["strong"] = {"scaling": "strong", "ms_per_step": ms_part, "value": nqp / (ms_part * 1e-3), "unit": UNIT, "patch_rank": patch_rank,
+                         "interface_bytes_received_max": int(allmax(float(moved))),
+                         "nccl_op": "batched ncclSend/ncclRecv of the interface columns to their owner rank (batch_isend_irecv), one fused add",
+                         "parity_vs_all_patches_on_one_gpu": {"max_rel_K": eK, "max_rel_R": eR, "ok": bool(eK <= 1e-12 and eR <= 1e-12)}}
+    asm.close()
+    del K_full, R_full, vals
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -321,6 +399,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config sub-records (BASELINE.md table)")
     ap.add_argument("--no-strips", action="store_true", help="N>1: skip the strong-scaling strips sub-record")
     ap.add_argument("--no-apalm", action="store_true", help="skip the gsAPALM traversal sub-record")
+    ap.add_argument("--no-multipatch", action="store_true", help="skip the multi-patch sub-record")
     ap.add_argument("--apalm-nel", type=int, default=64)
     ap.add_argument("--apalm-steps", type=int, default=16)
     ap.add_argument("--fused-call", action="store_true", help="device leg: the single-call entry kl_assemble_device instead of the two closure calls")
@@ -548,6 +627,16 @@ def main():
                           "(halo-reduce, the headline of this record); halo_compute = the same partition with redundant interface elements instead of the exchange"}
         del K_full, R_full
 
+    # ---- multi-patch (configs[3] as framed): 8 glued patches, patch -> GPU partition with the interface exchange when N > 1
+    multipatch = None
+    if not args.no_multipatch:
+        try:
+            multipatch = multipatch_record(torch, dist if world > 1 else None, args, local, rank, world, barrier, allmax)
+        except Exception as exc:
+            if world > 1:
+                raise          # a rank that drops out of a collective would hang the others
+            multipatch = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- gsAPALM traversal of the frustrum (configs[4]): level-0 chain + correction jobs, one worker thread per GPU of this box
     #      (examples/apalm_dispatch.cpp over include/gsAPALM_b200.h); the other ranks keep their GPUs idle meanwhile
     apalm = None
@@ -672,6 +761,7 @@ def main():
         "cpu_baseline": cpu,
         "linear_solve": solver,
         "strong": strong,
+        "multipatch": multipatch,
         "apalm": apalm,
         "configs": configs,
     }

@@ -262,7 +262,7 @@ def exchange_patches(plan: PatchPlan, outer, values, residual, dist):
                  [torch.empty(c1 - c0, dtype=values.dtype, device=values.device) for c0, c1 in cr] if residual is not None else [])
              for r, cr in plan.recv.items()}
         plan._bufs[key] = b
-    ops, dst, src = [], [], []
+    ops, adds = [], []
     for r in sorted(set(plan.send) | set(plan.recv)):      # the same peer order on both sides of every pair
         if r in plan.send:
             for a, e in value_ranges(plan.send[r], outer):
@@ -272,6 +272,7 @@ def exchange_patches(plan: PatchPlan, outer, values, residual, dist):
                     ops.append(dist.P2POp(dist.isend, residual[c0:c1], r))
         if r in plan.recv:
             bv, br = b[r]
+            dst, src = [], []
             for (a, e), t in zip(value_ranges(plan.recv[r], outer), bv):
                 ops.append(dist.P2POp(dist.irecv, t, r))
                 dst.append(values[a:e]); src.append(t)
@@ -279,11 +280,14 @@ def exchange_patches(plan: PatchPlan, outer, values, residual, dist):
                 for (c0, c1), t in zip(plan.recv[r], br):
                     ops.append(dist.P2POp(dist.irecv, t, r))
                     dst.append(residual[c0:c1]); src.append(t)
+            adds.append((dst, src))
     for req in (dist.batch_isend_irecv(ops) if ops else []):
         req.wait()
-    if dst:
+    # one fused add PER SENDER: the ranges of one sender are disjoint, but several senders may contribute to the same column (a DoF
+    # shared by more than two ranks, e.g. a collapsed side) and a fused multi-tensor add must not see the same destination twice
+    for dst, src in adds:
         torch._foreach_add_(dst, src)
-    return sum(t.numel() for t in src) * 8
+    return sum(t.numel() for _, src in adds for t in src) * 8
 
 
 class DevicePointerView:

@@ -15,7 +15,9 @@ def _problem(case):
     from tests.mp_problems import cut
     from oracle.multipatch import build_dofmap_mp
     base, cuts, ranks = {"roof_2x2": (lambda: W.roof(6), ([0.5], [0.5]), [0, 1, 1, 0]),
-                         "balloon_3x1": (lambda: W.balloon(6), ([1.0 / 3, 2.0 / 3], []), [0, 1, 0])}[case]
+                         "balloon_3x1": (lambda: W.balloon(6), ([1.0 / 3, 2.0 / 3], []), [0, 1, 0]),
+                         "roof_chain4": (lambda: W.roof(8), ([], [0.25, 0.5, 0.75]), [0, 1, 2, 3]),
+                         "tension_chain4": (lambda: W.tension_sheet(8), ([], [0.25, 0.5, 0.75]), [0, 1, 2, 3])}[case]
     _, multi, _ = cut(base(), *cuts)
     multi.number_dofs(build_dofmap_mp)
     return multi, ranks
@@ -32,7 +34,7 @@ def _worker(rank, world, port, case, q):
     from oracle.multipatch import MultiPatchOracle
     multi, ranks = _problem(case)
     orc = MultiPatchOracle(multi)
-    x = 1e-3 * np.random.default_rng(4).uniform(-1, 1, orc.n_dofs)
+    x = (1e-6 if case.startswith("tension") else 1e-3) * np.random.default_rng(4).uniform(-1, 1, orc.n_dofs)
     Kfull, Rfull = orc.jacobian_values(x), orc.residual(x)
     plan = plan_patches([p.dof_map for p in multi.patches], multi.n_free, ranks, world, rank)
     mine = [k for k, a in enumerate(plan.active) if a]
@@ -49,13 +51,14 @@ def _worker(rank, world, port, case, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case", ["roof_2x2", "balloon_3x1"])
-def test_patch_partition_world2(case):
+@pytest.mark.parametrize("case,world", [("roof_2x2", 2), ("balloon_3x1", 2), ("roof_chain4", 4), ("tension_chain4", 4)])
+def test_patch_partition(case, world):
+    """roof_chain4: a chain of patches, one per rank — every inner rank both sends (to the owner below) and receives (from above)"""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29100 + (os.getpid() % 500) + (0 if case == "roof_2x2" else 1)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, q)) for r in range(2)]
+    port = 29100 + (os.getpid() % 500) + {"roof_2x2": 0, "balloon_3x1": 1, "roof_chain4": 2, "tension_chain4": 3}[case]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
