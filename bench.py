@@ -616,15 +616,20 @@ def main():
         ms_fixed = allmax(time_device_steps(torch, lambda: (asm.residual_device(x1.data_ptr(), r_dev.data_ptr(), 0.0, 1.0, stream),
                                                             asm.jacobian_device(x1.data_ptr(), stream)), 5, barrier))
         asm.set_strip(0, asm.n_elements // (pr.surface.n[0] - 3))
-        strong = {"scaling": "strong", "ms_per_step": ms_strong, "value": nqp / (ms_strong * 1e-3), "unit": UNIT,
-                  "exchange_ms": allmax(float(np.mean(ex_ms))), "halo_bytes_received_max": int(allmax(float(halo_bytes))),
-                  "nccl_op": "batched ncclSend/ncclRecv to the neighbour strip (batch_isend_irecv) posted after the interface rows and overlapped with the "
-                              "rest of the strip, one fused add of the received ranges; exchange_ms = the same exchange timed without overlap",
-                  "per_rank_fixed_ms": ms_fixed, "speedup_vs_1gpu_step": None,
-                  "parity_vs_single_gpu": {"max_rel_K": errK, "max_rel_R": errR, "ok": bool(errK <= 1e-12 and errR <= 1e-12)},
-                  "halo_compute": halo_compute,
-                  "what": "ONE matrix of the same workload: every rank assembles its element-row strip, interface columns go to their owner "
-                          "(halo-reduce, the headline of this record); halo_compute = the same partition with redundant interface elements instead of the exchange"}
+        reduce_rec = {"ms_per_step": ms_strong, "value": nqp / (ms_strong * 1e-3), "exchange_ms": allmax(float(np.mean(ex_ms))),
+                      "halo_bytes_received_max": int(allmax(float(halo_bytes))),
+                      "nccl_op": "batched ncclSend/ncclRecv to the neighbour strip (batch_isend_irecv) posted after the interface rows and overlapped with the "
+                                 "rest of the strip, one fused add of the received ranges; exchange_ms = the same exchange timed without overlap",
+                      "parity_vs_single_gpu": {"max_rel_K": errK, "max_rel_R": errR, "ok": bool(errK <= 1e-12 and errR <= 1e-12)}}
+        best_hc = halo_compute is not None and halo_compute["ms_per_step"] < ms_strong
+        best = halo_compute if best_hc else reduce_rec
+        strong = {"scaling": "strong", "mode": "halo_compute" if best_hc else "halo_reduce", "ms_per_step": best["ms_per_step"],
+                  "value": best["value"], "unit": UNIT, "per_rank_fixed_ms": ms_fixed, "speedup_vs_1gpu_step": None,
+                  "parity_vs_single_gpu": best["parity_vs_single_gpu"], "halo_reduce": reduce_rec, "halo_compute": halo_compute,
+                  "what": "ONE matrix of the same workload in element-row strips, one per rank; owned columns complete on their owner.  halo_reduce: "
+                          "interface columns travel to their owner over NCCL, overlapped with the bulk of the strip; halo_compute: every rank also "
+                          "integrates the p element rows of the previous strip that its owned control-point rows reach into, no exchange.  The headline "
+                          "of this record is the faster of the two (`mode`)"}
         del K_full, R_full
 
     # ---- multi-patch (configs[3] as framed): 8 glued patches, patch -> GPU partition with the interface exchange when N > 1
