@@ -826,13 +826,82 @@ __device__ __forceinline__ void sw_point(const PointData& pd, double N1, double 
 #ifndef KL_SW_MINB
 #define KL_SW_MINB 6
 #endif
+// ---- flush through the TMA engine (EXPERIMENT, off by default: -DKL_SW_BULK=1).  A regular matrix column (J,dd) holds, per row
+// component c and row i2 of row functions, the seven row functions I1 = J1-3 .. J1+3 as seven consecutive doubles, and one thread
+// produces all seven during the four elements its column function stays in the window.  The thread stages them in shared memory (NK
+// runs of 8 doubles) and, when the column function leaves, adds the 16-byte aligned 48 bytes of every run with ONE
+// cp.reduce.async.bulk (.add.f64); the odd element and the transposed entries stay RED.F64: 432 RED + 96 bulk operations per element
+// instead of 1008 RED.  Measured (profiles/r3_ablation.txt): the flush alone is twice as fast (tools/micro/red_bulk.cu, 1.87 -> 0.94 ms
+// at 576 x 576) and the LSU stalls of the kernel vanish (mio_throttle 0.17 -> 0.01, short scoreboard 0.64 -> 0.26 per issue), but
+// UBLKRED takes uniform registers, so every bulk operation is issued lane by lane: +27 % warp instructions (1.87 G -> 2.38 G) in a
+// kernel that is bound by its issue rate (47 % issue slots, `wait` stalls): 3.51 -> 4.46 ms.  Parity is green in both modes.
+#ifndef KL_SW_BULK
+#define KL_SW_BULK 0
+#endif
+struct SwRun {
+    double* s;          // this thread's NK runs, 8 doubles each, 16-byte aligned
+    unsigned mask;      // run positions (st1 = 0..6) written for the current column function
+    bool pending;       // a bulk group of this thread may still be reading s
+};
+__device__ __forceinline__ void bulk_red_add_f64(double* gdst, const double* ssrc, unsigned bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+// component pair k -> (c, dd): k = dd (dd + 1) / 2 + c (c <= dd) for the symmetric part, k = 3 c + dd for the pressure tangent
+template <int NK> __device__ __forceinline__ int sw_pair_c(int k) { return NK == 9 ? k / 3 : (k < 1 ? 0 : (k < 3 ? k - 1 : k - 3)); }
+template <int NK> __device__ __forceinline__ int sw_pair_d(int k) { return NK == 9 ? k % 3 : (k < 1 ? 0 : (k < 3 ? 1 : 2)); }
+// direct entries of one slot: position pos of the NK runs (rowoff = 7 (i2 - b2 + 3): start of the run inside the 49-block)
+template <int NK>
+__device__ __forceinline__ void sw_stage_slot(double* __restrict__ val, SwRun& rs, const double (&v)[NK], const int4 cbJ, int rowoff, int pos) {
+    if (rs.pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); rs.pending = false; }
+    const int col[3] = {cbJ.x, cbJ.y, cbJ.z};
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int base = col[sw_pair_d<NK>(k)] + rowoff + 49 * sw_pair_c<NK>(k), par = base & 1;
+        if (pos == (par ? 0 : 6)) atomicAdd(val + (base + pos), v[k]);
+        else rs.s[k * 8 + pos + par] = v[k];
+    }
+    rs.mask |= 1u << pos;
+}
+// the column function leaves the window: zero what was never written (segment ends, irregular neighbours), hand the runs to the TMA engine
+template <int NK>
+__device__ __forceinline__ void sw_drain(double* __restrict__ val, SwRun& rs, const int4 cbJ, int rowoff) {
+    if (!rs.mask) return;
+    const int col[3] = {cbJ.x, cbJ.y, cbJ.z};
+    if (rs.mask != 0x7fu) {
+        for (int p = 0; p < 7; ++p)
+            if (!((rs.mask >> p) & 1u)) {
+#pragma unroll
+                for (int k = 0; k < NK; ++k) {
+                    const int par = (col[sw_pair_d<NK>(k)] + rowoff + 49 * sw_pair_c<NK>(k)) & 1;
+                    rs.s[k * 8 + p + par] = 0.0;
+                }
+            }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        const int base = col[sw_pair_d<NK>(k)] + rowoff + 49 * sw_pair_c<NK>(k), par = base & 1;
+        bulk_red_add_f64(val + (base + par), rs.s + (k * 8 + 2 * par), 48u);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    rs.pending = true;
+    rs.mask = 0;
+}
+
 // flush one window slot: the 3x3 component block (c <= d computed; c < d also written transposed) of node pair (I, J).
 // cbJ / cbI = colbase of the two control points; regular columns are addressed arithmetically.
 __device__ __forceinline__ void sw_flush_slot(const KLDev& d, double* __restrict__ val, const double (&v)[6], const int4 cbJ, const int4 cbI,
-                                              int Ic, int Jc, int st_ij) {
+                                              int Ic, int Jc, int st_ij, SwRun& rs, int rowoff, int pos) {
     constexpr int NST = 49, S3 = 147;
     const int st_ji = NST - 1 - st_ij;
-    if (cbJ.w & cbI.w) {
+    if (KL_SW_BULK && (cbJ.w & cbI.w)) {
+        sw_stage_slot<6>(val, rs, v, cbJ, rowoff, pos);
+        double* pi0 = val + (cbI.x + st_ji);
+        double* pi1 = val + (cbI.y + st_ji);
+        atomicAdd(pi0 + NST, v[1]);                                        // transposes of (0,1), (0,2), (1,2): row (J,dd), col (I,c)
+        atomicAdd(pi0 + 2 * NST, v[3]);
+        atomicAdd(pi1 + 2 * NST, v[4]);
+    } else if (cbJ.w & cbI.w) {
         double* pj0 = val + (cbJ.x + st_ij);
         double* pj1 = val + (cbJ.y + st_ij);
         double* pj2 = val + (cbJ.z + st_ij);
@@ -862,13 +931,67 @@ __device__ __forceinline__ void sw_flush_slot(const KLDev& d, double* __restrict
     }
 }
 
-template <bool HASB>
+// follower-pressure tangent in the same window (PRES instantiation of k_jacobian_sw): K^{c,dd}_{ij} += p wJ R_i n_dd g_j[c],
+// g_j = N_j,1 a^1 + N_j,2 a^2.  Unsymmetric, so all nine component pairs are kept (k = 3 c + dd) and nothing is written transposed.
+// The integrand is cheap (22 FP64 instructions per point), so lane (j, i2) walks the four q2 points of the q1 column itself instead
+// of reduce-scattering over the q2 lanes: the first version with 27 shuffles per point was bound by the shuffle / LSU queue
+// (mio_throttle 2.1 + short scoreboard 1.8 stall cycles per issue, 1.96 ms; profiles/r3_pressure_summary.txt).  The four lanes that
+// share a column function read the same record at the same time (one broadcast wavefront).
+__device__ __forceinline__ void sw_point_pressure(const PointData* pd4, double pressure, double x0, double x1, const double (&yjv)[4],
+                                                  const double (&yjd)[4], const double (&yi)[4], const double (&xa)[3][4], double (&acc)[4][9]) {
+    double V[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) V[k] = 0.0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const PointData& pd = pd4[q];
+        const double N1 = x1 * yjv[q], N2 = x0 * yjd[q];
+        const double pw = (pd.wJ * pressure) * yi[q];
+        const double pn[3] = {pw * pd.n[0], pw * pd.n[1], pw * pd.n[2]};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double g = fma(N1, pd.c1[c], N2 * pd.c2[c]);
+#pragma unroll
+            for (int dd = 0; dd < 3; ++dd) V[3 * c + dd] = fma(pn[dd], g, V[3 * c + dd]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a][k] = fma(xa[0][a], V[k], acc[a][k]);
+}
+__device__ __forceinline__ void sw_flush_slot(const KLDev& d, double* __restrict__ val, const double (&v)[9], const int4 cbJ, const int4 /*cbI*/,
+                                              int /*Ic*/, int Jc, int st_ij, SwRun& rs, int rowoff, int pos) {
+    constexpr int NST = 49, S3 = 147;
+    if (KL_SW_BULK && cbJ.w) {
+        sw_stage_slot<9>(val, rs, v, cbJ, rowoff, pos);
+    } else if (cbJ.w) {
+        const int col[3] = {cbJ.x, cbJ.y, cbJ.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dd = 0; dd < 3; ++dd) atomicAdd(val + (col[dd] + st_ij + c * NST), v[3 * c + dd]);   // row (I,c), column (J,dd)
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int dd = 0; dd < 3; ++dd) {
+                const int p1 = __ldg(&d.pos[(size_t)(Jc * 3 + dd) * S3 + st_ij * 3 + c]);
+                if (p1 >= 0) atomicAdd(&val[p1], v[3 * c + dd]);
+            }
+    }
+}
+
+template <bool HASB, bool PRES = false>
 __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_begin, int e2_end, int seg_len) {
     constexpr int P = 3, NQ2 = 16, NB = 48, W = 7;
     __shared__ __align__(128) PointData s_pd[2][NQ2];
     __shared__ __align__(16) double s_b1[2][NB];        // [q1][m][a] of the element
     __shared__ __align__(16) int4 s_cb[2][4][4];        // colbase of the element's control points [row i2][a]
     __shared__ unsigned long long s_bar[2];
+    constexpr int NK = PRES ? 9 : 6;     // component pairs kept per node pair
+    constexpr int RS = NK * 8 + 2;       // doubles per thread in the run staging area (+2: threads 2-way instead of 16-way bank-aliased)
+    extern __shared__ __align__(16) double s_run[];     // [64][RS] when KL_SW_BULK (dynamic: 54 KB in all for the pressure instantiation)
     const int tid = threadIdx.x;
     const int nrows = e2_end - e2_begin;
     const int row = blockIdx.x % nrows, seg = blockIdx.x / nrows;     // consecutive CTAs take consecutive element rows of one segment column
@@ -904,16 +1027,29 @@ __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_
 #pragma unroll
         for (int s = 0; s < 4; ++s) yk[s][m] = __ldg(&g2[(q2 * 3 + m) * 4 + (q2 ^ s)]);
     }
-    double acc[4][6];
+    // pressure instantiation: values / first derivatives of the column function and values of the row function i2 at all four q2
+    double yjv[4], yjd[4], yi[4];
+    if constexpr (PRES) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            yjv[q] = __ldg(&g2[(q * 3 + 0) * 4 + b2]);
+            yjd[q] = __ldg(&g2[(q * 3 + 1) * 4 + b2]);
+            yi[q] = __ldg(&g2[(q * 3 + 0) * 4 + i2]);
+        }
+    }
+    double acc[4][NK];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int k = 0; k < 6; ++k) acc[a][k] = 0.0;
+        for (int k = 0; k < NK; ++k) acc[a][k] = 0.0;
+    const double pressure = d.mat.pressure;
     int i0 = __ldg(&d.span1[e1_begin]) - P;
     int b = (jcls - i0) & 3;          // local index of this thread's column function in the current element
     bool live = false;                // the accumulators hold contributions of the current column function
     double* __restrict__ val = d.values;
     const int I2 = j0 + i2, J2 = j0 + b2;
+    SwRun rs{s_run + (KL_SW_BULK ? tid * RS : 0), 0u, false};
+    const int rowoff = W * (i2 - b2 + P);
 
     for (int e1 = e1_begin; e1 < e1_end; ++e1) {
         const int le = e1 - e1_begin, s = le & 1;
@@ -933,7 +1069,8 @@ __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_
                 xa[m][0] = u.x; xa[m][1] = u.y; xa[m][2] = v.x; xa[m][3] = v.y;
             }
             const double x0 = xb[b], x1 = xb[4 + b], x2 = xb[8 + b];
-            sw_point<HASB>(s_pd[s][q1 * 4 + q2], x1 * yj[0], x0 * yj[1], x2 * yj[0], x0 * yj[2], x1 * yj[1], yk, xa, acc);
+            if constexpr (PRES) sw_point_pressure(&s_pd[s][q1 * 4], pressure, x0, x1, yjv, yjd, yi, xa, acc);
+            else sw_point<HASB>(s_pd[s][q1 * 4 + q2], x1 * yj[0], x0 * yj[1], x2 * yj[0], x0 * yj[2], x1 * yj[1], yk, xa, acc);
         }
         live = true;
         // scatter addressing of this element: column function J and the four row functions of row i2
@@ -948,20 +1085,25 @@ __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_
         }
         // ---- window step: row functions I1 < i0n and column functions J1 < i0n have received their last contribution of this row
         for (int st = i0; st < i0n; ++st) {
+#ifdef KL_SW_NOFLUSH        // timing ablation only (profiles/r3_ablation.txt): the flush never executes but the accumulators stay live
+            if (live && acc[0][0] == 1.2345e-300) {
+#else
             if (live) {
+#endif
                 const int Jc = (st + b) + d.n1 * J2, Ic0 = st + d.n1 * I2;
                 const int st0 = (P - b) + W * (i2 - b2 + P);
-                sw_flush_slot(d, val, acc[0], cbJ, cbI[0], Ic0, Jc, st0);
+                sw_flush_slot(d, val, acc[0], cbJ, cbI[0], Ic0, Jc, st0, rs, rowoff, P - b);
                 if (b == 0) {        // the column function leaves the support: all its pairs are complete
 #pragma unroll
                     for (int a = 1; a < 4; ++a)
-                        if (st + a <= i0 + P) sw_flush_slot(d, val, acc[a], cbJ, cbI[a], Ic0 + a, Jc, st0 + a);
+                        if (st + a <= i0 + P) sw_flush_slot(d, val, acc[a], cbJ, cbI[a], Ic0 + a, Jc, st0 + a, rs, rowoff, P + a);
+                    if (KL_SW_BULK) sw_drain<NK>(val, rs, cbJ, rowoff);
                 }
             }
             // shift the window by one function
             const bool wrap = (b == 0);
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
+            for (int k = 0; k < NK; ++k) {
                 acc[0][k] = wrap ? 0.0 : acc[1][k];
                 acc[1][k] = wrap ? 0.0 : acc[2][k];
                 acc[2][k] = wrap ? 0.0 : acc[3][k];
@@ -973,6 +1115,7 @@ __global__ void __launch_bounds__(64, KL_SW_MINB) k_jacobian_sw(KLDev d, int e2_
         }
         i0 = i0n;
     }
+    if (KL_SW_BULK) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");    // shared memory must outlive the bulk reads
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1082,6 +1225,7 @@ int kl_launch_points(kl_ctx* ctx, int e2_begin, int e2_end, cudaStream_t s, doub
     return KL_E_ARG;
 }
 
+static size_t sw_run_bytes(int nk) { return KL_SW_BULK ? sizeof(double) * 64 * (nk * 8 + 2) : 0; }
 template <int P>
 static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
     using Cfg = JacCfg<P>;
@@ -1109,14 +1253,26 @@ static int launch_jac(kl_ctx* ctx, int e2b, int e2e, cudaStream_t s) {
             seg = (int)std::min<long long>(24, std::max<long long>(8, ((long long)nel + slots - 1) / slots));
         }
         const int nseg = (ctx->d.nel1 + seg - 1) / seg;
-        if (hasB) k_jacobian_sw<true><<<(e2e - e2b) * nseg, 64, 0, s>>>(ctx->d, e2b, e2e, seg);
-        else k_jacobian_sw<false><<<(e2e - e2b) * nseg, 64, 0, s>>>(ctx->d, e2b, e2e, seg);
+        if (!(ctx->attr_done & 4u)) {
+            KL_CUDA(cudaFuncSetAttribute(k_jacobian_sw<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_run_bytes(6)));
+            KL_CUDA(cudaFuncSetAttribute(k_jacobian_sw<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_run_bytes(6)));
+            KL_CUDA(cudaFuncSetAttribute(k_jacobian_sw<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_run_bytes(9)));
+            ctx->attr_done |= 4u;
+        }
+        if (hasB) k_jacobian_sw<true><<<(e2e - e2b) * nseg, 64, sw_run_bytes(6), s>>>(ctx->d, e2b, e2e, seg);
+        else k_jacobian_sw<false><<<(e2e - e2b) * nseg, 64, sw_run_bytes(6), s>>>(ctx->d, e2b, e2e, seg);
     } else if (hasB) k_jacobian<P, true><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     else k_jacobian<P, false><<<grid, Cfg::NT, smem, s>>>(ctx->d, e2b, e2e);
     KL_CUDA(cudaEventRecord(ctx->ev[5], s));
     ctx->launches++;
     KL_CUDA(cudaGetLastError());
-    if (ctx->d.mat.pressure != 0.0) {
+    if (ctx->d.mat.pressure != 0.0 && P == 3 && !ctx->jac_shared) {
+        // same walk, pressure term only (9 unsymmetric component pairs): 1008 RED per element at arithmetic addresses
+        const int seg = 16, nseg = (ctx->d.nel1 + seg - 1) / seg;
+        k_jacobian_sw<false, true><<<(e2e - e2b) * nseg, 64, sw_run_bytes(9), s>>>(ctx->d, e2b, e2e, seg);
+        ctx->launches++;
+        KL_CUDA(cudaGetLastError());
+    } else if (ctx->d.mat.pressure != 0.0) {
         k_pressure_tangent<P><<<nel, 256, 0, s>>>(ctx->d, e2b, e2e);
         ctx->launches++;
         KL_CUDA(cudaGetLastError());
