@@ -686,6 +686,239 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Tri-cubic Jacobian, sliding window along direction 1 (the production kernel for p = (3,3,3)).
+//
+// Same contraction and task layout as k3_jacobian — U task (q2, column b, cd), W task (i3, column b, cd), 16 accumulators
+// acc[i2][a] per thread — but the CTA is persistent along an element row: it walks the elements e1 of one (e2, e3) row for its
+// block of 8 column functions (4 classes J1 mod 4 x 2 values of j2, one j3) and keeps the accumulators while a node pair stays
+// inside the support.  After each element the row functions that leave the support (a = 0) are flushed, the column function that
+// leaves (local j1 = 0) flushes the rest, and the window shifts by one function: 7 instead of 16 RED per thread and element
+// (the shell kernel's scheme, kl_assemble.cu: k_jacobian_sw).  The slabs of records (16 points x 90 doubles, contiguous in HBM)
+// and the direction-1 table of the element arrive by TMA bulk copies behind two mbarriers, two slabs ahead; the tables of
+// directions 2 and 3 are staged once per CTA.
+namespace sw3 {
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+}  // namespace sw3
+
+struct JacSwSmem {
+    double T[2][16][KS_PD];                    // records of two slabs (fixed q1): TMA destination, 720-byte rows (conflict-free for the 9 cd offsets)
+    double U[4][4][KS_JB][9][3];               // [q2][i3][b][cd][p]
+    double b1[2][4][2][4];                     // direction-1 table of the current / next element [q][value|derivative][a]
+    double b2[4][2][4], b3[4][2][4];           // directions 2 and 3: fixed along the walk
+    unsigned long long bar[2];
+};
+
+#define KS_SW_NT 288
+__global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int seg_len) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    JacSwSmem& S = *reinterpret_cast<JacSwSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int blk = blockIdx.x & 7;                                  // the 8 column blocks of an element row run side by side (records shared in L2)
+    const int rest = blockIdx.x >> 3;
+    const int nrows = d.nel[1] * d.nel[2];
+    const int row = rest % nrows, seg = rest / nrows;
+    const int e2 = row % d.nel[1], e3 = row / d.nel[1];
+    const int e1_begin = seg * seg_len, e1_end = min(d.nel[0], e1_begin + seg_len);
+    const int nstage = (e1_end - e1_begin) * 4;
+    const int cd = tid % 9, bl = (tid / 9) % KS_JB, r = tid / (9 * KS_JB);     // r = q2 of the U task = i3 of the W task
+    const int c = cd / 3, dd = cd - 3 * c;
+    const int jcls = bl & 3, j2 = 2 * (blk & 1) + (bl >> 2), j3 = blk >> 1;    // column function: class of J1 mod 4, local j2, j3
+    const int f2 = __ldg(&d.span[1][e2]) - 3, f3 = __ldg(&d.span[2][e3]) - 3;
+    const bool sym = d.symmetric != 0;
+    const bool hasW = !(sym && r > j3);
+
+    const size_t row_elem0 = (size_t)d.nel[0] * (e2 + (size_t)d.nel[1] * e3);
+    auto issue = [&](int n) {
+        const int e1 = e1_begin + (n >> 2), q1 = n & 3, buf = n & 1;
+        const unsigned bytes = 16u * KS_PD * 8u + (q1 == 0 ? 256u : 0u);
+        sw3::mbar_expect_tx(&S.bar[buf], bytes);
+        sw3::tma_bulk_g2s(&S.T[buf][0][0], d.pd + ((row_elem0 + e1) * 64 + (size_t)q1 * 16) * KS_PD, 16u * KS_PD * 8u, &S.bar[buf]);
+        if (q1 == 0) sw3::tma_bulk_g2s(&S.b1[(n >> 2) & 1][0][0][0], d.bas[0] + (size_t)e1 * 32, 256u, &S.bar[buf]);
+    };
+    if (tid == 0) { sw3::mbar_init(&S.bar[0], 1); sw3::mbar_init(&S.bar[1], 1); }
+    if (tid < 32) {
+        (&S.b2[0][0][0])[tid] = __ldg(d.bas[1] + (size_t)e2 * 32 + tid);
+        (&S.b3[0][0][0])[tid] = __ldg(d.bas[2] + (size_t)e3 * 32 + tid);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(0);
+        if (nstage > 1) issue(1);
+    }
+    double acc[4][4];                                   // [i2][a]
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[k][a] = 0.0;
+    int i0 = __ldg(&d.span[0][e1_begin]) - 3;
+    int b1l = (jcls - i0) & 3;                          // local direction-1 index of this thread's column function
+    bool live = false;
+    const int n0 = d.n[0], n1 = d.n[1];
+    const int J2 = f2 + j2, J3 = f3 + j3, I3 = f3 + r;
+    const int i3max = sym ? j3 : 3;
+
+    for (int e1 = e1_begin; e1 < e1_end; ++e1) {
+        const int le = e1 - e1_begin;
+        const int i0n = (e1 + 1 < e1_end) ? __ldg(&d.span[0][e1 + 1]) - 3 : i0 + 4;
+        const double (*B1)[2][4] = S.b1[le & 1];
+        for (int q1 = 0; q1 < 4; ++q1) {
+            const int n = le * 4 + q1, buf = n & 1;
+            sw3::mbar_wait(&S.bar[buf], (n >> 1) & 1);
+            __syncthreads();                            // the W tasks of the previous slab have read U
+            // ---- U task (q2 = r, b, cd): Z_b = T g_b at the four points of the (q1, q2) line, contracted at once over q3
+            if (!(d.ablate & 4)) {
+                const double x0 = B1[q1][0][b1l], x1 = B1[q1][1][b1l], y0 = S.b2[r][0][j2], y1 = S.b2[r][1][j2];
+                const double gx = x1 * y0, gy = x0 * y1, gz = x0 * y0;
+                double u[4][3];
+#pragma unroll
+                for (int i3 = 0; i3 < 4; ++i3) u[i3][0] = u[i3][1] = u[i3][2] = 0.0;
+#pragma unroll
+                for (int q3 = 0; q3 < 4; ++q3) {
+                    const double z0 = S.b3[q3][0][j3], z1 = S.b3[q3][1][j3];
+                    const double g0 = gx * z0, g1 = gy * z0, g2 = gz * z1;
+                    const double* Tp = S.T[buf][r * 4 + q3] + cd * 9;
+                    const double zz0 = Tp[0] * g0 + Tp[1] * g1 + Tp[2] * g2;
+                    const double zz1 = Tp[3] * g0 + Tp[4] * g1 + Tp[5] * g2;
+                    const double zz2 = Tp[6] * g0 + Tp[7] * g1 + Tp[8] * g2;
+                    const double2* vr = reinterpret_cast<const double2*>(S.b3[q3][0]);
+                    const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];
+                    const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+                    for (int i3 = 0; i3 < 4; ++i3) {
+                        if (i3 > i3max) continue;
+                        u[i3][0] = fma(v[i3], zz0, u[i3][0]);
+                        u[i3][1] = fma(v[i3], zz1, u[i3][1]);
+                        u[i3][2] = fma(dv[i3], zz2, u[i3][2]);
+                    }
+                }
+#pragma unroll
+                for (int i3 = 0; i3 < 4; ++i3) {
+                    double* uo = S.U[r][i3][bl][cd];
+                    uo[0] = u[i3][0]; uo[1] = u[i3][1]; uo[2] = u[i3][2];
+                }
+            }
+            __syncthreads();                            // U complete, T[buf] consumed
+            if (tid == 0 && n + 2 < nstage) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(n + 2);
+            }
+            // ---- W task (i3 = r, b, cd): directions 2 and 1
+            if (hasW && !(d.ablate & 2)) {
+                double w0[4], w12[4];
+#pragma unroll
+                for (int i2 = 0; i2 < 4; ++i2) w0[i2] = w12[i2] = 0.0;
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2) {
+                    const double* u = S.U[q2][r][bl][cd];
+                    const double u0 = u[0], u1 = u[1], u2 = u[2];
+                    const double2* vr = reinterpret_cast<const double2*>(S.b2[q2][0]);
+                    const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];
+                    const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2) {
+                        w0[i2] = fma(v[i2], u0, w0[i2]);
+                        w12[i2] = fma(dv[i2], u1, fma(v[i2], u2, w12[i2]));
+                    }
+                }
+                const double2* xr = reinterpret_cast<const double2*>(B1[q1][0]);
+                const double2 v01 = xr[0], v23 = xr[1], d01 = xr[2], d23 = xr[3];
+                const double xv[4] = {v01.x, v01.y, v23.x, v23.y}, xd[4] = {d01.x, d01.y, d23.x, d23.y};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2) acc[i2][a] = fma(xd[a], w0[i2], fma(xv[a], w12[i2], acc[i2][a]));
+            }
+        }
+        live = true;
+        // ---- window step: row functions I1 < i0n and column functions J1 < i0n have received their last contribution of this row
+        for (int st = i0; st < i0n; ++st) {
+            if (live && hasW && !(d.ablate & 1)) {
+                const int J1 = st + b1l;
+                const int J = J1 + n0 * (J2 + n1 * J3);
+                const int4 cb = __ldg(reinterpret_cast<const int4*>(d.colbase) + J);
+                const int base = dd == 0 ? cb.x : (dd == 1 ? cb.y : cb.z);
+                const int amax = (b1l == 0) ? min(3, i0 + 3 - st) : 0;       // a = 0 always; the rest when the column function leaves
+                if (base >= 0) {
+                    if (cb.w) {
+                        const int lo1 = __ldg(&d.nlo[0][J1]), lo2 = __ldg(&d.nlo[1][J2]), lo3 = __ldg(&d.nlo[2][J3]);
+                        const int w1 = __ldg(&d.nhi[0][J1]) - lo1 + 1, w2 = __ldg(&d.nhi[1][J2]) - lo2 + 1, w3 = __ldg(&d.nhi[2][J3]) - lo3 + 1;
+                        double* col0 = d.values + base + c * (w1 * w2 * w3) + ((I3 - lo3) * w2 - lo2) * w1 + (st - lo1);
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            if (a > amax) continue;
+#pragma unroll
+                            for (int i2 = 0; i2 < 4; ++i2) {
+                                // symmetric mode: node pairs I <= J in node order (I3, I2, I1)
+                                if (sym && r == j3 && (i2 > j2 || (i2 == j2 && a > b1l))) continue;
+                                atomicAdd(col0 + (f2 + i2) * w1 + a, acc[i2][a]);
+                            }
+                        }
+                    } else {
+                        const int col = d.map[dd * d.ncp + J];
+                        const int lo0 = base, hi0 = d.outer[col + 1] - 1;
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            if (a > amax) continue;
+#pragma unroll
+                            for (int i2 = 0; i2 < 4; ++i2) {
+                                if (sym && r == j3 && (i2 > j2 || (i2 == j2 && a > b1l))) continue;
+                                const int I = (st + a) + n0 * ((f2 + i2) + n1 * I3);
+                                const int rowd = d.map[c * d.ncp + I];
+                                if (rowd >= d.nfree) continue;
+                                int lo = lo0, hi = hi0;
+                                while (lo <= hi) {
+                                    const int mid = (lo + hi) >> 1;
+                                    const int rr = d.inner[mid];
+                                    if (rr == rowd) { atomicAdd(d.values + mid, acc[i2][a]); break; }
+                                    if (rr < rowd) lo = mid + 1; else hi = mid - 1;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // shift the window by one function
+            const bool wrap = (b1l == 0);
+#pragma unroll
+            for (int i2 = 0; i2 < 4; ++i2) {
+                acc[i2][0] = wrap ? 0.0 : acc[i2][1];
+                acc[i2][1] = wrap ? 0.0 : acc[i2][2];
+                acc[i2][2] = wrap ? 0.0 : acc[i2][3];
+                acc[i2][3] = 0.0;
+            }
+            if (wrap) live = false;
+            b1l = (b1l - 1) & 3;
+        }
+        i0 = i0n;
+    }
+}
+
 // symmetric mode: values of the node pairs I > J are copies of the transposed entries (row (J,d), col (I,c)) assembled by
 // k3_jacobian.  One warp per column, lanes stride its entries; the transposed position is arithmetic for boxed columns.
 __global__ void __launch_bounds__(256) k3_mirror(KSDev d) {
@@ -1070,6 +1303,8 @@ static int assemble_dev(ks_ctx* ctx, const double* x_dev, int want_matrix, doubl
         KS_ATTR((k3_jacobian<0, 0, 0>)) KS_ATTR((k3_jacobian<3, 3, 3>)) KS_ATTR((k3_jacobian<2, 2, 2>)) KS_ATTR((k3_jacobian<3, 3, 2>))
         KS_ATTR((k3_jacobian<1, 1, 1>))
 #undef KS_ATTR
+        KL_CUDA(cudaFuncSetAttribute(k3_jacobian_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacSwSmem)));
+        KL_CUDA(cudaFuncSetAttribute(k3_jacobian_sw, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         ctx->attr_done = true;
     }
     k3_points<<<nelem, 64, smem_pts, s>>>(d);
@@ -1081,7 +1316,18 @@ static int assemble_dev(ks_ctx* ctx, const double* x_dev, int want_matrix, doubl
         const unsigned grid = nelem * d.nblk;
         const int pk = d.p[0] * 100 + d.p[1] * 10 + d.p[2];
         static const bool generic = getenv("KS_GENERIC") != nullptr;      // testing aid: force the run-time-degree kernel
-        if (pk == 333 && !generic) k3_jacobian<3, 3, 3><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
+        static const bool no_sw = getenv("KS_NO_SW") != nullptr;          // A/B: the element-per-CTA kernel for tri-cubics
+        if (pk == 333 && !generic && !no_sw) {
+            // segments of element rows: about 16 waves of resident CTAs, at least 8 elements long
+            int nsm = 0;
+            KL_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+            const long long rows8 = (long long)d.nel[1] * d.nel[2] * 8, want = 16LL * nsm * KS_MINB;
+            int nseg = (int)std::max<long long>(1, std::min<long long>((want + rows8 - 1) / rows8, std::max(1, d.nel[0] / 8)));
+            if (const char* e = getenv("KS_SW_SEG")) nseg = std::max(1, (d.nel[0] + atoi(e) - 1) / std::max(1, atoi(e)));
+            const int seg_len = (d.nel[0] + nseg - 1) / nseg;
+            nseg = (d.nel[0] + seg_len - 1) / seg_len;
+            k3_jacobian_sw<<<(unsigned)(rows8 * nseg), KS_SW_NT, sizeof(JacSwSmem), s>>>(d, seg_len);
+        } else if (pk == 333 && !generic) k3_jacobian<3, 3, 3><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
         else if (pk == 222 && !generic) k3_jacobian<2, 2, 2><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
         else if (pk == 332 && !generic) k3_jacobian<3, 3, 2><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
         else if (pk == 111 && !generic) k3_jacobian<1, 1, 1><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);

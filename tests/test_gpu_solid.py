@@ -67,6 +67,20 @@ def test_degrees_and_meshes(gpu, degrees, nels):
     _compare(gpu, pr, 5e-3, f"brick-{degrees}-{nels}")
 
 
+@pytest.mark.parametrize("nels,seg,full", [((11, 2, 3), None, False), ((11, 2, 3), "4", False), ((9, 3, 2), "8", True), ((2, 4, 2), "1", False)])
+def test_tricubic_sliding_window(gpu, monkeypatch, nels, seg, full):
+    """k3_jacobian_sw (the tri-cubic production kernel): long element rows, segments of 1 / 4 / 8 elements (partial windows at both
+    ends of a segment), I <= J + mirror and the full assembly, Dirichlet faces on both ends of the walking direction."""
+    if seg:
+        monkeypatch.setenv("KS_SW_SEG", seg)
+    if full:
+        monkeypatch.setenv("KS_FULL", "1")
+    v = S.brick(3.0, 1.0, 0.7, degrees=(3, 3, 3), nels=nels)
+    bc = S.SolidBC().add_condition(S.KS_WEST).add_condition(S.KS_EAST, 1).add_condition(S.KS_FRONT, 2)
+    pr = S.SolidProblem(v, bc, law=S.KS_LAW_NEO_HOOKE_QUAD, E=7.0, nu=0.3, tractions=[(S.KS_NORTH, (0.0, -0.3, 0.1))], body_force=(0.0, 0.0, -0.2))
+    _compare(gpu, pr, 5e-3, f"sw-{nels}-{seg}-{full}")
+
+
 def test_beam_with_prescribed_displacement(gpu):
     """benchmark_Elasticity_Beam_APALM.cpp:226-236 style beam; non-zero fixedDofs on the clamped face."""
     v = S.brick(1.0, 0.01, 0.01, degrees=(3, 2, 2), nels=(8, 1, 1))
