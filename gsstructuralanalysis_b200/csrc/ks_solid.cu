@@ -23,9 +23,11 @@
 
 #define KS_MAXP 3
 static_assert(KS_MAXP == 3, "the vectorised basis-row loads assume rows of 4 doubles");
-#define KS_PD 90            // doubles per quadrature-point record: T[3][3][3][3] + f[3][3]
+#define KS_TC 10            // doubles per (c,d) block of T: 9 + 1 pad, so that every block starts on a 16-byte boundary (LDS.128)
+#define KS_FO 90            // offset of f[3][3] in the record
+#define KS_PD 100           // doubles per quadrature-point record: T[3][3] blocks of KS_TC + f[3][3] + 1 pad (800 B: whole 16-byte chunks)
 #define KS_JB 8             // column functions per CTA
-#define KS_TS 82            // doubles of a record staged per point: T (81) rounded up to whole 16-byte chunks
+#define KS_TS 90            // doubles of a record staged per point by the element-per-CTA kernel: the nine T blocks
 #ifndef KS_MINB
 #define KS_MINB 2           // CTAs per SM the Jacobian kernel is compiled for (measured: 2 -> 145 ms, 3 -> 155 ms with spills)
 #endif
@@ -355,13 +357,16 @@ __global__ void __launch_bounds__(64) k3_points(KSDev d) {
                     for (int q = 0; q < 3; ++q) {
                         double t = c1 * FXG[c][p] * FXG[dd][q] + c2 * (FXF[c][dd] * GXG[p][q] + FXG[c][q] * FXG[dd][p]);
                         if (c == dd && !linear) t += GSG[p][q];
-                        out[((c * 3 + dd) * 3 + p) * 3 + q] = w * t;
+                        out[(c * 3 + dd) * KS_TC + p * 3 + q] = w * t;
                     }
         // f^c[p] = sum_ij Fb[c][i] S_ij G[p][j]
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int p = 0; p < 3; ++p) out[81 + c * 3 + p] = w * (Fb[c][0] * SG[0][p] + Fb[c][1] * SG[1][p] + Fb[c][2] * SG[2][p]);
+            for (int p = 0; p < 3; ++p) out[KS_FO + c * 3 + p] = w * (Fb[c][0] * SG[0][p] + Fb[c][1] * SG[1][p] + Fb[c][2] * SG[2][p]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out[k * KS_TC + 9] = 0.0;
+        out[KS_PD - 1] = 0.0;
         bool bad = false;
         for (int k = 0; k < KS_PD; ++k) bad |= !(fabs(out[k]) <= 1.79e308);
         if (bad) flag |= KLF_NONFINITE;
@@ -490,7 +495,7 @@ __global__ void __launch_bounds__(192) k3_residual(KSDev d, double* __restrict__
     elem_of(d, e, e1, e2, e3);
     stage_tables(d, e1, e2, e3, E, tid, blockDim.x);
     const double* g = d.pd + (size_t)e * d.nqp * KS_PD;
-    for (int k = tid; k < d.nqp * 9; k += blockDim.x) s_f[k / 9][k % 9] = g[(size_t)(k / 9) * KS_PD + 81 + k % 9];
+    for (int k = tid; k < d.nqp * 9; k += blockDim.x) s_f[k / 9][k % 9] = g[(size_t)(k / 9) * KS_PD + KS_FO + k % 9];
     __syncthreads();
     const int np1 = d.p[0] + 1, np2 = d.p[1] + 1;
     for (int t = tid; t < d.nloc * 3; t += blockDim.x) {
@@ -580,7 +585,7 @@ __global__ void __launch_bounds__(KS_NT, KS_MINB) k3_jacobian(KSDev d) {
             for (int q3 = 0; q3 < nq3; ++q3) {
                 const double z0 = S.E.b[2][q3][0][a3], z1 = S.E.b[2][q3][1][a3];
                 const double g0 = gx * z0, g1 = gy * z0, g2 = gz * z1;
-                const double* Tp = S.T[buf][q2 * nq3 + q3] + cd * 9;
+                const double* Tp = S.T[buf][q2 * nq3 + q3] + cd * KS_TC;
                 const double zz0 = Tp[0] * g0 + Tp[1] * g1 + Tp[2] * g2;
                 const double zz1 = Tp[3] * g0 + Tp[4] * g1 + Tp[5] * g2;
                 const double zz2 = Tp[6] * g0 + Tp[7] * g1 + Tp[8] * g2;
@@ -725,9 +730,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 }  // namespace sw3
 
+#define KS_SW_UQ (4 * KS_JB * 9 * 3 + 8)
 struct JacSwSmem {
-    double T[2][16][KS_PD];                    // records of two slabs (fixed q1): TMA destination, 720-byte rows (conflict-free for the 9 cd offsets)
-    double U[4][4][KS_JB][9][3];               // [q2][i3][b][cd][p]
+    double T[2][16][KS_PD];                    // records of two slabs (fixed q1): TMA destination, 800-byte rows
+    double U[4][KS_SW_UQ];                     // [q2]{[i3][b][cd][p], 8 pad}: the pad puts q2 and q2 + 1 on complementary banks for the U-task stores
     double b1[2][4][2][4];                     // direction-1 table of the current / next element [q][value|derivative][a]
     double b2[4][2][4], b3[4][2][4];           // directions 2 and 3: fixed along the walk
     unsigned long long bar[2];
@@ -745,9 +751,15 @@ __global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int
     const int e2 = row % d.nel[1], e3 = row / d.nel[1];
     const int e1_begin = seg * seg_len, e1_end = min(d.nel[0], e1_begin + seg_len);
     const int nstage = (e1_end - e1_begin) * 4;
-    const int cd = tid % 9, bl = (tid / 9) % KS_JB, r = tid / (9 * KS_JB);     // r = q2 of the U task = i3 of the W task
+    // Two task maps.  W task (accumulators, scatter): cd fastest, i3 slowest, so that whole warps drop out in symmetric mode (i3 > j3).
+    // U task (Z = T g, direction 3): one (c,d) block per WARP, lanes = (column b, q2): the eight lanes of a quarter-warp read the same
+    // T block (128-bit loads served in 2 instead of 4 wavefronts), which is what the shared-memory pipe of this kernel is busy with.
+    const int cd = tid % 9, bl = (tid / 9) % KS_JB, r = tid / (9 * KS_JB);     // W task: r = i3
     const int c = cd / 3, dd = cd - 3 * c;
-    const int jcls = bl & 3, j2 = 2 * (blk & 1) + (bl >> 2), j3 = blk >> 1;    // column function: class of J1 mod 4, local j2, j3
+    const int j3 = blk >> 1;
+    const int jcls = bl & 3, j2 = 2 * (blk & 1) + (bl >> 2);                    // W task's column function: class of J1 mod 4, local j2 (j3 per CTA)
+    const int ucd = tid >> 5, ubl = tid & 7, uq2 = (tid >> 3) & 3;              // U task
+    const int ujcls = ubl & 3, uj2 = 2 * (blk & 1) + (ubl >> 2);
     const int f2 = __ldg(&d.span[1][e2]) - 3, f3 = __ldg(&d.span[2][e3]) - 3;
     const bool sym = d.symmetric != 0;
     const bool hasW = !(sym && r > j3);
@@ -776,6 +788,11 @@ __global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int
     for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int a = 0; a < 4; ++a) acc[k][a] = 0.0;
+    // factors of the column function that never change along the walk: direction 2 at the U task's q2, direction 3 at every q3
+    const double y0 = S.b2[uq2][0][uj2], y1 = S.b2[uq2][1][uj2];
+    double zv[4], zd[4];
+#pragma unroll
+    for (int q3 = 0; q3 < 4; ++q3) { zv[q3] = S.b3[q3][0][j3]; zd[q3] = S.b3[q3][1][j3]; }
     int i0 = __ldg(&d.span[0][e1_begin]) - 3;
     int b1l = (jcls - i0) & 3;                          // local direction-1 index of this thread's column function
     bool live = false;
@@ -793,19 +810,21 @@ __global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int
             __syncthreads();                            // the W tasks of the previous slab have read U
             // ---- U task (q2 = r, b, cd): Z_b = T g_b at the four points of the (q1, q2) line, contracted at once over q3
             if (!(d.ablate & 4)) {
-                const double x0 = B1[q1][0][b1l], x1 = B1[q1][1][b1l], y0 = S.b2[r][0][j2], y1 = S.b2[r][1][j2];
+                const int ub1l = (ujcls - i0) & 3;
+                const double x0 = B1[q1][0][ub1l], x1 = B1[q1][1][ub1l];
                 const double gx = x1 * y0, gy = x0 * y1, gz = x0 * y0;
                 double u[4][3];
 #pragma unroll
                 for (int i3 = 0; i3 < 4; ++i3) u[i3][0] = u[i3][1] = u[i3][2] = 0.0;
 #pragma unroll
                 for (int q3 = 0; q3 < 4; ++q3) {
-                    const double z0 = S.b3[q3][0][j3], z1 = S.b3[q3][1][j3];
-                    const double g0 = gx * z0, g1 = gy * z0, g2 = gz * z1;
-                    const double* Tp = S.T[buf][r * 4 + q3] + cd * 9;
-                    const double zz0 = Tp[0] * g0 + Tp[1] * g1 + Tp[2] * g2;
-                    const double zz1 = Tp[3] * g0 + Tp[4] * g1 + Tp[5] * g2;
-                    const double zz2 = Tp[6] * g0 + Tp[7] * g1 + Tp[8] * g2;
+                    const double g0 = gx * zv[q3], g1 = gy * zv[q3], g2 = gz * zd[q3];
+                    // the 3 x 3 block T^{cd} of the point: five 128-bit loads (blocks are padded to 10 doubles)
+                    const double2* Tp = reinterpret_cast<const double2*>(S.T[buf][uq2 * 4 + q3] + ucd * KS_TC);
+                    const double2 t01 = Tp[0], t23 = Tp[1], t45 = Tp[2], t67 = Tp[3], t8 = Tp[4];
+                    const double zz0 = t01.x * g0 + t01.y * g1 + t23.x * g2;
+                    const double zz1 = t23.y * g0 + t45.x * g1 + t45.y * g2;
+                    const double zz2 = t67.x * g0 + t67.y * g1 + t8.x * g2;
                     const double2* vr = reinterpret_cast<const double2*>(S.b3[q3][0]);
                     const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];
                     const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
@@ -819,7 +838,7 @@ __global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int
                 }
 #pragma unroll
                 for (int i3 = 0; i3 < 4; ++i3) {
-                    double* uo = S.U[r][i3][bl][cd];
+                    double* uo = &S.U[uq2][((i3 * KS_JB + ubl) * 9 + ucd) * 3];
                     uo[0] = u[i3][0]; uo[1] = u[i3][1]; uo[2] = u[i3][2];
                 }
             }
@@ -835,7 +854,7 @@ __global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int
                 for (int i2 = 0; i2 < 4; ++i2) w0[i2] = w12[i2] = 0.0;
 #pragma unroll
                 for (int q2 = 0; q2 < 4; ++q2) {
-                    const double* u = S.U[q2][r][bl][cd];
+                    const double* u = &S.U[q2][((r * KS_JB + bl) * 9 + cd) * 3];
                     const double u0 = u[0], u1 = u[1], u2 = u[2];
                     const double2* vr = reinterpret_cast<const double2*>(S.b2[q2][0]);
                     const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];

@@ -39,4 +39,4 @@ flops = 2.0 * fma_per_elem * asm.n_elements
 print(json.dumps({"workload": f"unit cube, tri-cubic, {nel}^3 elements, law {law}", "n_dofs": n, "nnz": asm.nnz, "elements": asm.n_elements,
                   "quad_points": asm.n_qp, "setup_s": setup, "ms_per_assembly": ms, "quad_pts_per_s": asm.n_qp / (ms * 1e-3),
                   "kernels_ms": t, "jacobian_flops": flops, "jacobian_TFLOPs": flops / (t["jacobian_ms"] * 1e-3) / 1e12,
-                  "values_GB": 8 * asm.nnz / 1e9, "records_GB": 8 * 90 * asm.n_qp / 1e9}))
+                  "values_GB": 8 * asm.nnz / 1e9, "records_GB": 8 * 100 * asm.n_qp / 1e9}))
