@@ -306,6 +306,53 @@ def config_records(torch, capi, args, local, hbm_peak, fp64_peak):
     return out
 
 
+def solid_record(torch, args, local, fp64_peak):
+    """SURVEY 8a row a9 / 8f rank 3 (north_star: "and gsElasticity solids"): K and rhs of a tri-cubic neo-Hookean block at ~1M DOF in ONE
+    device-resident pass (the reference's closures run the full assemble twice), per-kernel times, and the parity of a coarse twin."""
+    from gsstructuralanalysis_b200 import solid as S
+    from oracle.binding_solid import SolidOracle
+    nel = args.solid_nel
+
+    def mk(n):
+        v = S.brick(1.0, 1.0, 1.0, degrees=(3, 3, 3), nels=(n, n, n))
+        return S.SolidProblem(v, S.SolidBC().add_condition(S.KS_WEST), law=S.KS_LAW_NEO_HOOKE_LN, E=5.0, nu=0.3, tractions=[(S.KS_EAST, (0.0, 0.0, 0.01))])
+    asm = S.SolidAssembler(mk(nel), device=local)
+    n = asm.n_dofs
+    x = torch.from_numpy(1e-3 / nel * np.random.default_rng(20240607).uniform(-1, 1, n)).cuda()
+    r = torch.empty(n, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        asm.assemble_device(x.data_ptr(), r.data_ptr(), True, stream)
+    for _ in range(3):
+        step()
+    if asm.check(stream) != 0:
+        raise RuntimeError("solid assembly flagged an invalid state")
+    ms = time_device_steps(torch, step, 3)
+    ok, K, rr = asm.assemble(x.cpu().numpy())          # host entry: fills the per-kernel event times
+    t = asm.last_timing()
+    fma_per_elem = 8 * 4 * (128 * 81 + 3456 * 4 + 1152 * 12 + 1152 * 8)      # Z, U, W, acc per (column block, slab), every node pair
+    rec = {"workload": f"gsElasticity solid: unit cube, tri-cubic, {nel}^3 elements, neo_hooke_ln, west face fixed, dead traction on the east face",
+           "n_dofs": n, "nnz": asm.nnz, "elements": asm.n_elements, "quad_points": asm.n_qp,
+           "ms_per_assembly": ms, "quad_pts_per_s": asm.n_qp / (ms * 1e-3), "kernels_ms": t,
+           "jacobian_kernel": "k3_jacobian_sw (sliding window along direction 1) + k3_mirror",
+           "fp64_frac_full_contraction": 2.0 * fma_per_elem * asm.n_elements / (t["jacobian_ms"] * 1e-3) / 1e12 / fp64_peak,
+           "values_GB": 8 * asm.nnz / 1e9, "records_GB": 8 * 100 * asm.n_qp / 1e9,
+           "what": "K and rhs in one pass, device resident (ks_assemble_device); kernels_ms from the library's events through the host entry"}
+    del K, rr
+    asm.close()
+    torch.cuda.empty_cache()
+    p2 = mk(5)
+    a2, o2 = S.SolidAssembler(p2, device=local), SolidOracle(p2)
+    xs = 1e-3 * np.random.default_rng(3).standard_normal(a2.n_dofs)
+    ok, K2, r2 = a2.assemble(xs)
+    Ko, ro = o2.assemble(xs)
+    rec["max_rel_diff_vs_oracle_5x5x5"] = {"K": float(np.abs(K2.values - Ko).max() / np.abs(Ko).max()),
+                                           "R": float(np.abs(r2 - ro).max() / max(np.abs(ro).max(), np.abs(o2.force()).max(), 1e-300))}
+    a2.close()
+    return rec
+
+
 def multipatch_record(torch, dist, args, local, rank, world, barrier, allmax):
     """configs[3] as BASELINE.json frames it ("multipatch row-partitioned assembly at 1/2/4/8 GPUs"): the tension sheet cut into 8 conforming
     patches along the second direction, glued C0 by one DoF mapper (kl_mp_*).  N = 1: all patches on one GPU next to the uncut single
@@ -400,6 +447,8 @@ def main():
     ap.add_argument("--no-strips", action="store_true", help="N>1: skip the strong-scaling strips sub-record")
     ap.add_argument("--no-apalm", action="store_true", help="skip the gsAPALM traversal sub-record")
     ap.add_argument("--no-multipatch", action="store_true", help="skip the multi-patch sub-record")
+    ap.add_argument("--no-solid", action="store_true", help="skip the gsElasticity solid sub-record")
+    ap.add_argument("--solid-nel", type=int, default=67)
     ap.add_argument("--apalm-nel", type=int, default=64)
     ap.add_argument("--apalm-steps", type=int, default=16)
     ap.add_argument("--fused-call", action="store_true", help="device leg: the single-call entry kl_assemble_device instead of the two closure calls")
@@ -724,6 +773,16 @@ def main():
         torch.cuda.empty_cache()
         configs = config_records(torch, capi, args, local, hbm_peak, peak.value)
 
+    solid = None
+    if world == 1 and not args.no_solid:
+        try:
+            asm.close()
+            torch.cuda.empty_cache()
+            solid = solid_record(torch, args, local, peak.value)
+        except Exception as exc:
+            solid = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline on a bounded sample of the SAME workload (oracle port; the checker timed, never shipped)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -769,6 +828,7 @@ def main():
         "multipatch": multipatch,
         "apalm": apalm,
         "configs": configs,
+        "solid": solid,
     }
     emit(out)
     if world > 1:

@@ -4,7 +4,7 @@ TAG=$1; shift
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest "$@" -q -m gpu -x 2>&1 | tail -8
-timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-apalm --no-multipatch > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no-apalm --no-multipatch --no-solid > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 tail -3 gpurun_out/bench_$TAG.err
 python - <<PY
 import json
