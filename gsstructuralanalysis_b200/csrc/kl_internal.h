@@ -130,6 +130,10 @@ struct kl_mp {
                                      // kl_spmv, kl_fetch_values, kl_set_values, kl_pattern_host, kl_sizes
     int64_t n_elements = 0, n_qp = 0;
     std::vector<int> coupled_cols;   // global DoFs shared by more than one patch (interface columns), ascending
+    // the patches of one assembly run side by side (fork / join around the caller's stream): they only meet in the RED scatter
+    std::vector<cudaStream_t> pstream;
+    std::vector<cudaEvent_t> pdone;
+    cudaEvent_t fork = nullptr;
 };
 
 void kl_set_error(const std::string& s);

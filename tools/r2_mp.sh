@@ -3,7 +3,7 @@
 N=$1; TAG=$2
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-FLAGS="--steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-configs --no-apalm"
+FLAGS="--steps 10 --warmup 3 --no-cpu-baseline --no-e2e --no-configs --no-apalm --no-solid"
 if [ "$N" = "1" ]; then
   timeout 900 python bench.py $FLAGS > gpurun_out/bench_${TAG}_n$N.json 2> gpurun_out/bench_${TAG}_n$N.err
 else
