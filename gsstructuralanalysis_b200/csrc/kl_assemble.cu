@@ -54,7 +54,15 @@ __global__ void k_axpby(double* __restrict__ r, const double* __restrict__ f, do
 template <int P>
 struct PointCfg {
     static constexpr int NQ2 = (P + 1) * (P + 1);
-    static constexpr int EPG = (P == 2) ? 14 : (P == 3 ? 8 : 5);   // elements per CTA
+// p = 3: elements per CTA of the point kernels and the CTAs per SM they are compiled for.  Measured (profiles/r3_ablation.txt): 8 / 3 ->
+// 0.782 ms, 6 / 4 -> 0.799, 4 / 6 -> 0.748, 2 / 12 -> 0.745: smaller CTAs stagger their load / compute / store phases better.
+#ifndef KL_PTS_EPG
+#define KL_PTS_EPG 4
+#endif
+#ifndef KL_PTS_MINB
+#define KL_PTS_MINB 6
+#endif
+    static constexpr int EPG = (P == 2) ? 14 : (P == 3 ? KL_PTS_EPG : 5);   // elements per CTA
     static constexpr int NT = EPG * NQ2;
 };
 
@@ -66,7 +74,7 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)_
 // WITH_RES: also integrate the internal force F_int - F_pressure into r from the staged records (RED), which makes the separate
 // k_residual pass unnecessary when Jacobian and residual are wanted at the same state (kl_assemble_device).
 template <int P, bool WITH_RES>
-__global__ void __launch_bounds__(PointCfg<P>::NT, 3) k_points(KLDev d, int e2_begin, int e2_end, double* __restrict__ r, const int* __restrict__ skip) {
+__global__ void __launch_bounds__(PointCfg<P>::NT, KL_PTS_MINB) k_points(KLDev d, int e2_begin, int e2_end, double* __restrict__ r, const int* __restrict__ skip) {
     using Cfg = PointCfg<P>;
     if (skip && *skip) return;     // the records of this state are already in d.pd (same-state fusion)
     constexpr int NQ = P + 1, NQ2 = Cfg::NQ2, EPG = Cfg::EPG;

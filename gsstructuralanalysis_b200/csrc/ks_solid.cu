@@ -17,6 +17,7 @@
 //   k3_residual  one CTA per element: rhs_a^c -= sum_q g_a . f^c
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <cub/cub.cuh>
 #include "kl_internal.h"
 #include "../../include/ks_solid.h"
@@ -74,6 +75,7 @@ struct ks_ctx {
     float ms_points = 0, ms_jac = 0, ms_res = 0;
     int launches = 0;
     bool attr_done = false;
+    std::vector<double> h_bas[3];     // host copies of the 1-D tables (constant-memory upload)
 };
 
 namespace {
@@ -731,6 +733,15 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }  // namespace sw3
 
 #define KS_SW_UQ (4 * KS_JB * 9 * 3 + 8)
+// The 1-D tables of the three directions in constant memory: every read of a whole table row is warp-uniform (the element indices
+// come from blockIdx / the walk counter), so it becomes a constant-cache access instead of a shared-memory wavefront — the pipe this
+// kernel is bound by.  64 KB hold 85 elements per direction; one solid context per device owns the tables at a time (ks_create
+// takes them when they are free and the mesh fits, ks_destroy releases them), everybody else runs the shared-memory instantiation.
+#define KS_CT_MAX 85
+__constant__ double c_tab[3][KS_CT_MAX][32];
+static std::mutex g_ct_mutex;
+static const void* g_ct_owner[64] = {};          // per device: the context whose tables are resident
+
 struct JacSwSmem {
     double T[2][16][KS_PD];                    // records of two slabs (fixed q1): TMA destination, 800-byte rows
     double U[4][KS_SW_UQ];                     // [q2]{[i3][b][cd][p], 8 pad}: the pad puts q2 and q2 + 1 on complementary banks for the U-task stores
@@ -740,6 +751,7 @@ struct JacSwSmem {
 };
 
 #define KS_SW_NT 288
+template <bool CT>
 __global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int seg_len) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     JacSwSmem& S = *reinterpret_cast<JacSwSmem*>(smem_raw);
@@ -825,9 +837,16 @@ __global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int
                     const double zz0 = t01.x * g0 + t01.y * g1 + t23.x * g2;
                     const double zz1 = t23.y * g0 + t45.x * g1 + t45.y * g2;
                     const double zz2 = t67.x * g0 + t67.y * g1 + t8.x * g2;
-                    const double2* vr = reinterpret_cast<const double2*>(S.b3[q3][0]);
-                    const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];
-                    const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
+                    double v[4], dv[4];
+                    if (CT) {
+                        const double* tr = &c_tab[2][e3][q3 * 8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { v[i] = tr[i]; dv[i] = tr[4 + i]; }
+                    } else {
+                        const double2* vr = reinterpret_cast<const double2*>(S.b3[q3][0]);
+                        const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];
+                        v[0] = v01.x; v[1] = v01.y; v[2] = v23.x; v[3] = v23.y; dv[0] = d01.x; dv[1] = d01.y; dv[2] = d23.x; dv[3] = d23.y;
+                    }
 #pragma unroll
                     for (int i3 = 0; i3 < 4; ++i3) {
                         if (i3 > i3max) continue;
@@ -856,18 +875,32 @@ __global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int
                 for (int q2 = 0; q2 < 4; ++q2) {
                     const double* u = &S.U[q2][((r * KS_JB + bl) * 9 + cd) * 3];
                     const double u0 = u[0], u1 = u[1], u2 = u[2];
-                    const double2* vr = reinterpret_cast<const double2*>(S.b2[q2][0]);
-                    const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];
-                    const double v[4] = {v01.x, v01.y, v23.x, v23.y}, dv[4] = {d01.x, d01.y, d23.x, d23.y};
+                    double v[4], dv[4];
+                    if (CT) {
+                        const double* tr = &c_tab[1][e2][q2 * 8];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { v[i] = tr[i]; dv[i] = tr[4 + i]; }
+                    } else {
+                        const double2* vr = reinterpret_cast<const double2*>(S.b2[q2][0]);
+                        const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];
+                        v[0] = v01.x; v[1] = v01.y; v[2] = v23.x; v[3] = v23.y; dv[0] = d01.x; dv[1] = d01.y; dv[2] = d23.x; dv[3] = d23.y;
+                    }
 #pragma unroll
                     for (int i2 = 0; i2 < 4; ++i2) {
                         w0[i2] = fma(v[i2], u0, w0[i2]);
                         w12[i2] = fma(dv[i2], u1, fma(v[i2], u2, w12[i2]));
                     }
                 }
-                const double2* xr = reinterpret_cast<const double2*>(B1[q1][0]);
-                const double2 v01 = xr[0], v23 = xr[1], d01 = xr[2], d23 = xr[3];
-                const double xv[4] = {v01.x, v01.y, v23.x, v23.y}, xd[4] = {d01.x, d01.y, d23.x, d23.y};
+                double xv[4], xd[4];
+                if (CT) {
+                    const double* tr = &c_tab[0][e1][q1 * 8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { xv[i] = tr[i]; xd[i] = tr[4 + i]; }
+                } else {
+                    const double2* xr = reinterpret_cast<const double2*>(B1[q1][0]);
+                    const double2 v01 = xr[0], v23 = xr[1], d01 = xr[2], d23 = xr[3];
+                    xv[0] = v01.x; xv[1] = v01.y; xv[2] = v23.x; xv[3] = v23.y; xd[0] = d01.x; xd[1] = d01.y; xd[2] = d23.x; xd[3] = d23.y;
+                }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -1129,6 +1162,10 @@ extern "C" void ks_destroy(ks_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    {
+        std::lock_guard<std::mutex> lk(g_ct_mutex);
+        if (g_ct_owner[ctx->device & 63] == ctx) g_ct_owner[ctx->device & 63] = nullptr;
+    }
     for (void* p : ctx->owned) cudaFree(p);
     if (ctx->h_x) cudaFreeHost(ctx->h_x);
     if (ctx->h_r) cudaFreeHost(ctx->h_r);
@@ -1195,6 +1232,7 @@ extern "C" int ks_create(const ks_problem* P, int device, ks_ctx** out) {
             }
         }
         if ((rc = dev_upload(ctx, &d.bas[k], bas.data(), bas.size()))) return rc;
+        ctx->h_bas[k] = bas;
         if ((rc = dev_upload(ctx, &d.wq[k], wq.data(), wq.size()))) return rc;
         if ((rc = dev_upload(ctx, &d.span[k], ctx->span[k].data(), ctx->span[k].size()))) return rc;
     }
@@ -1244,6 +1282,15 @@ extern "C" int ks_create(const ks_problem* P, int device, ks_ctx** out) {
         ctx->launches++;
     }
     KL_CUDA(cudaDeviceSynchronize());
+    // constant-memory tables of the tri-cubic window kernel: taken when they are free on this device and the mesh fits
+    if (d.p[0] == 3 && d.p[1] == 3 && d.p[2] == 3 && std::max(d.nel[0], std::max(d.nel[1], d.nel[2])) <= KS_CT_MAX && !getenv("KS_NO_CONST")) {
+        std::lock_guard<std::mutex> lk(g_ct_mutex);
+        if (!g_ct_owner[ctx->device & 63]) {
+            for (int k = 0; k < 3; ++k)
+                KL_CUDA(cudaMemcpyToSymbol(c_tab, ctx->h_bas[k].data(), sizeof(double) * ctx->h_bas[k].size(), sizeof(double) * (size_t)k * KS_CT_MAX * 32));
+            g_ct_owner[ctx->device & 63] = ctx;
+        }
+    }
     guard.ok = true;
     *out = ctx;
     return KL_OK;
@@ -1322,8 +1369,10 @@ static int assemble_dev(ks_ctx* ctx, const double* x_dev, int want_matrix, doubl
         KS_ATTR((k3_jacobian<0, 0, 0>)) KS_ATTR((k3_jacobian<3, 3, 3>)) KS_ATTR((k3_jacobian<2, 2, 2>)) KS_ATTR((k3_jacobian<3, 3, 2>))
         KS_ATTR((k3_jacobian<1, 1, 1>))
 #undef KS_ATTR
-        KL_CUDA(cudaFuncSetAttribute(k3_jacobian_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacSwSmem)));
-        KL_CUDA(cudaFuncSetAttribute(k3_jacobian_sw, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        KL_CUDA(cudaFuncSetAttribute(k3_jacobian_sw<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacSwSmem)));
+        KL_CUDA(cudaFuncSetAttribute(k3_jacobian_sw<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        KL_CUDA(cudaFuncSetAttribute(k3_jacobian_sw<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(JacSwSmem)));
+        KL_CUDA(cudaFuncSetAttribute(k3_jacobian_sw<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         ctx->attr_done = true;
     }
     k3_points<<<nelem, 64, smem_pts, s>>>(d);
@@ -1345,7 +1394,10 @@ static int assemble_dev(ks_ctx* ctx, const double* x_dev, int want_matrix, doubl
             if (const char* e = getenv("KS_SW_SEG")) nseg = std::max(1, (d.nel[0] + atoi(e) - 1) / std::max(1, atoi(e)));
             const int seg_len = (d.nel[0] + nseg - 1) / nseg;
             nseg = (d.nel[0] + seg_len - 1) / seg_len;
-            k3_jacobian_sw<<<(unsigned)(rows8 * nseg), KS_SW_NT, sizeof(JacSwSmem), s>>>(d, seg_len);
+            bool ct;
+            { std::lock_guard<std::mutex> lk(g_ct_mutex); ct = g_ct_owner[ctx->device & 63] == ctx; }
+            if (ct) k3_jacobian_sw<true><<<(unsigned)(rows8 * nseg), KS_SW_NT, sizeof(JacSwSmem), s>>>(d, seg_len);
+            else k3_jacobian_sw<false><<<(unsigned)(rows8 * nseg), KS_SW_NT, sizeof(JacSwSmem), s>>>(d, seg_len);
         } else if (pk == 333 && !generic) k3_jacobian<3, 3, 3><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
         else if (pk == 222 && !generic) k3_jacobian<2, 2, 2><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
         else if (pk == 332 && !generic) k3_jacobian<3, 3, 2><<<grid, KS_NT, sizeof(JacSmem), s>>>(d);
