@@ -744,7 +744,9 @@ static const void* g_ct_owner[64] = {};          // per device: the context whos
 
 struct JacSwSmem {
     double T[2][16][KS_PD];                    // records of two slabs (fixed q1): TMA destination, 800-byte rows
-    double U[4][KS_SW_UQ];                     // [q2]{[i3][b][cd][p], 8 pad}: the pad puts q2 and q2 + 1 on complementary banks for the U-task stores
+    double U[2][4][KS_SW_UQ];                  // two slabs x [q2]{[i3][b][cd][p], 8 pad}: the pad puts q2 and q2 + 1 on complementary banks for the
+                                               // U-task stores; double-buffered so that ONE barrier per slab is enough (W tasks of slab n read U[n & 1]
+                                               // while the U tasks of slab n + 1 already write the other half)
     double b1[2][4][2][4];                     // direction-1 table of the current / next element [q][value|derivative][a]
     double b2[4][2][4], b3[4][2][4];           // directions 2 and 3: fixed along the walk
     unsigned long long bar[2];
@@ -819,46 +821,38 @@ __global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int
         for (int q1 = 0; q1 < 4; ++q1) {
             const int n = le * 4 + q1, buf = n & 1;
             sw3::mbar_wait(&S.bar[buf], (n >> 1) & 1);
-            __syncthreads();                            // the W tasks of the previous slab have read U
             // ---- U task (q2 = r, b, cd): Z_b = T g_b at the four points of the (q1, q2) line, contracted at once over q3
             if (!(d.ablate & 4)) {
                 const int ub1l = (ujcls - i0) & 3;
                 const double x0 = B1[q1][0][ub1l], x1 = B1[q1][1][ub1l];
                 const double gx = x1 * y0, gy = x0 * y1, gz = x0 * y0;
-                double u[4][3];
-#pragma unroll
-                for (int i3 = 0; i3 < 4; ++i3) u[i3][0] = u[i3][1] = u[i3][2] = 0.0;
+                // Z at the four points of the line first (12 numbers), then one row function i3 at a time: rows above j3 are never
+                // used in symmetric mode and the loop leaves through a CTA-uniform branch (a per-row predicate inside the q3 loop
+                // made the compiler compute everything and select: 24 FSEL per point, 17 % of the instructions of this step)
+                double zz[4][3];
 #pragma unroll
                 for (int q3 = 0; q3 < 4; ++q3) {
                     const double g0 = gx * zv[q3], g1 = gy * zv[q3], g2 = gz * zd[q3];
                     // the 3 x 3 block T^{cd} of the point: five 128-bit loads (blocks are padded to 10 doubles)
                     const double2* Tp = reinterpret_cast<const double2*>(S.T[buf][uq2 * 4 + q3] + ucd * KS_TC);
                     const double2 t01 = Tp[0], t23 = Tp[1], t45 = Tp[2], t67 = Tp[3], t8 = Tp[4];
-                    const double zz0 = t01.x * g0 + t01.y * g1 + t23.x * g2;
-                    const double zz1 = t23.y * g0 + t45.x * g1 + t45.y * g2;
-                    const double zz2 = t67.x * g0 + t67.y * g1 + t8.x * g2;
-                    double v[4], dv[4];
-                    if (CT) {
-                        const double* tr = &c_tab[2][e3][q3 * 8];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) { v[i] = tr[i]; dv[i] = tr[4 + i]; }
-                    } else {
-                        const double2* vr = reinterpret_cast<const double2*>(S.b3[q3][0]);
-                        const double2 v01 = vr[0], v23 = vr[1], d01 = vr[2], d23 = vr[3];
-                        v[0] = v01.x; v[1] = v01.y; v[2] = v23.x; v[3] = v23.y; dv[0] = d01.x; dv[1] = d01.y; dv[2] = d23.x; dv[3] = d23.y;
-                    }
-#pragma unroll
-                    for (int i3 = 0; i3 < 4; ++i3) {
-                        if (i3 > i3max) continue;
-                        u[i3][0] = fma(v[i3], zz0, u[i3][0]);
-                        u[i3][1] = fma(v[i3], zz1, u[i3][1]);
-                        u[i3][2] = fma(dv[i3], zz2, u[i3][2]);
-                    }
+                    zz[q3][0] = t01.x * g0 + t01.y * g1 + t23.x * g2;
+                    zz[q3][1] = t23.y * g0 + t45.x * g1 + t45.y * g2;
+                    zz[q3][2] = t67.x * g0 + t67.y * g1 + t8.x * g2;
                 }
+                const double* t3 = CT ? &c_tab[2][e3][0] : &S.b3[0][0][0];       // [q3][value|derivative][i3]
+#pragma unroll 1
+                for (int i3 = 0; i3 <= i3max; ++i3) {
+                    double u0 = 0.0, u1 = 0.0, u2 = 0.0;
 #pragma unroll
-                for (int i3 = 0; i3 < 4; ++i3) {
-                    double* uo = &S.U[uq2][((i3 * KS_JB + ubl) * 9 + ucd) * 3];
-                    uo[0] = u[i3][0]; uo[1] = u[i3][1]; uo[2] = u[i3][2];
+                    for (int q3 = 0; q3 < 4; ++q3) {
+                        const double v = t3[q3 * 8 + i3], dv = t3[q3 * 8 + 4 + i3];
+                        u0 = fma(v, zz[q3][0], u0);
+                        u1 = fma(v, zz[q3][1], u1);
+                        u2 = fma(dv, zz[q3][2], u2);
+                    }
+                    double* uo = &S.U[buf][uq2][((i3 * KS_JB + ubl) * 9 + ucd) * 3];
+                    uo[0] = u0; uo[1] = u1; uo[2] = u2;
                 }
             }
             __syncthreads();                            // U complete, T[buf] consumed
@@ -873,7 +867,7 @@ __global__ void __launch_bounds__(KS_SW_NT, KS_MINB) k3_jacobian_sw(KSDev d, int
                 for (int i2 = 0; i2 < 4; ++i2) w0[i2] = w12[i2] = 0.0;
 #pragma unroll
                 for (int q2 = 0; q2 < 4; ++q2) {
-                    const double* u = &S.U[q2][((r * KS_JB + bl) * 9 + cd) * 3];
+                    const double* u = &S.U[buf][q2][((r * KS_JB + bl) * 9 + cd) * 3];
                     const double u0 = u[0], u1 = u[1], u2 = u[2];
                     double v[4], dv[4];
                     if (CT) {
