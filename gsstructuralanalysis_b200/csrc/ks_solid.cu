@@ -971,32 +971,54 @@ __global__ void __launch_bounds__(256) k3_mirror(KSDev d) {
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarps = gridDim.x * (blockDim.x >> 5);
     const int n1 = d.n[0], n2 = d.n[1];
+    // transposed position of entry (row (I,c), col (J,dd)): row (J,dd) in column (I,c)
+    auto source = [&](int I, int c, int J1, int J2, int J3, int dd, int col) -> int {
+        const int4 cb = __ldg(reinterpret_cast<const int4*>(d.colbase) + I);
+        const int base = c == 0 ? cb.x : (c == 1 ? cb.y : cb.z);
+        if (cb.w) {
+            const int I1 = I % n1, I2 = (I / n1) % n2, I3 = I / (n1 * n2);
+            const int lo1 = __ldg(&d.nlo[0][I1]), lo2 = __ldg(&d.nlo[1][I2]), lo3 = __ldg(&d.nlo[2][I3]);
+            const int w1 = __ldg(&d.nhi[0][I1]) - lo1 + 1, w2 = __ldg(&d.nhi[1][I2]) - lo2 + 1, w3 = __ldg(&d.nhi[2][I3]) - lo3 + 1;
+            return base + dd * (w1 * w2 * w3) + ((J3 - lo3) * w2 + (J2 - lo2)) * w1 + (J1 - lo1);
+        }
+        const int row = d.map[c * d.ncp + I];
+        int lo = base, hi = d.outer[row + 1] - 1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1;
+            const int rr = d.inner[mid];
+            if (rr == col) return mid;
+            if (rr < col) lo = mid + 1; else hi = mid - 1;
+        }
+        return -1;
+    };
     for (int col = warp; col < d.nfree; col += nwarps) {
         const int ncJ = d.dof2node[col], J = ncJ / 3, dd = ncJ - 3 * J;
         const int J1 = J % n1, J2 = (J / n1) % n2, J3 = J / (n1 * n2);
         const int kb = d.outer[col], ke = d.outer[col + 1];
-        for (int k = kb + lane; k < ke; k += 32) {
-            const int row = d.inner[k];
-            const int ncI = d.dof2node[row], I = ncI / 3, c = ncI - 3 * I;
-            if (I <= J) continue;
-            const int4 cb = reinterpret_cast<const int4*>(d.colbase)[I];
-            const int base = c == 0 ? cb.x : (c == 1 ? cb.y : cb.z);
-            int pos = -1;
-            if (cb.w) {
-                const int I1 = I % n1, I2 = (I / n1) % n2, I3 = I / (n1 * n2);
-                const int lo1 = d.nlo[0][I1], lo2 = d.nlo[1][I2], lo3 = d.nlo[2][I3];
-                const int w1 = d.nhi[0][I1] - lo1 + 1, w2 = d.nhi[1][I2] - lo2 + 1, w3 = d.nhi[2][I3] - lo3 + 1;
-                pos = base + dd * (w1 * w2 * w3) + ((J3 - lo3) * w2 + (J2 - lo2)) * w1 + (J1 - lo1);
-            } else {
-                int lo = base, hi = d.outer[row + 1] - 1;
-                while (lo <= hi) {
-                    const int mid = (lo + hi) >> 1;
-                    const int rr = d.inner[mid];
-                    if (rr == col) { pos = mid; break; }
-                    if (rr < col) lo = mid + 1; else hi = mid - 1;
-                }
+        const int4 cbJ = __ldg(reinterpret_cast<const int4*>(d.colbase) + J);
+        if (cbJ.w) {
+            // boxed column: rows = 3 x node box in the order (c, i3, i2, i1), so the nodes I > J are the tail of every c block and the
+            // row node follows from the offset: no look-up of `inner` / `dof2node`, half the trips
+            const int lo1 = d.nlo[0][J1], lo2 = d.nlo[1][J2], lo3 = d.nlo[2][J3];
+            const int w1 = d.nhi[0][J1] - lo1 + 1, w2 = d.nhi[1][J2] - lo2 + 1, w3 = d.nhi[2][J3] - lo3 + 1;
+            const int nb = w1 * w2 * w3, w12 = w1 * w2;
+            const int self = ((J3 - lo3) * w2 + (J2 - lo2)) * w1 + (J1 - lo1);
+            const int ntail = nb - self - 1;
+            for (int t = lane; t < 3 * ntail; t += 32) {
+                const int c = t / ntail, o = self + 1 + (t - c * ntail);
+                const int i3l = o / w12, rem = o - i3l * w12, i2l = rem / w1, i1l = rem - i2l * w1;
+                const int I = (lo1 + i1l) + n1 * ((lo2 + i2l) + n2 * (lo3 + i3l));
+                const int pos = source(I, c, J1, J2, J3, dd, col);
+                if (pos >= 0) d.values[kb + c * nb + o] = d.values[pos];
             }
-            if (pos >= 0) d.values[k] = d.values[pos];
+        } else {
+            for (int k = kb + lane; k < ke; k += 32) {
+                const int row = d.inner[k];
+                const int ncI = d.dof2node[row], I = ncI / 3, c = ncI - 3 * I;
+                if (I <= J) continue;
+                const int pos = source(I, c, J1, J2, J3, dd, col);
+                if (pos >= 0) d.values[k] = d.values[pos];
+            }
         }
     }
 }
