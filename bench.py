@@ -749,7 +749,7 @@ def main():
     achieved_tf = fpq * nqp / (jac_kernel_ms * 1e-3) / 1e12
     traffic = None      # dram__bytes_read+write of the kernel from the committed ncu --set full capture of this workload
     try:
-        tj_ = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        tj_ = json.load(open(os.path.join(ROOT, "profiles", "r3_traffic.json")))
         if args.nel == 576 and args.material == "svk":
             traffic = tj_["traffic"]
     except Exception:
@@ -759,7 +759,7 @@ def main():
                 "share_of_step": jac_kernel_ms / ms_per_step,
                 "note": "FP64 flops are the binding roofline of the fused assembly (11.5 kflop executed vs 224 B per point); flops_per_qp is "
                         "the kernel's own executed count (ncu: dfma/dmul/dadd), so frac equals the share of peak DFMA-equivalent issue; ncu: "
-                        "FP64 pipe 58 % busy, L1/LSU data pipe 69 % (shuffles + per-point record loads) - profiles/r2_sw1_jacobian_summary.txt, DESIGN.md section 5",
+                        "FP64 pipe 58 % busy, L1/LSU data pipe 69 % (shuffles, RED scatter, per-point record loads) - profiles/r3_head_jacobian_summary.txt, DESIGN.md section 5",
                 "hbm": {"algorithmic_bytes": bytes_alg, "bytes_per_qp": bytes_alg / nqp,
                         "achieved": bytes_alg / (jac_kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_alg / (jac_kernel_ms * 1e-3) / 1e9 / hbm_peak},
