@@ -596,9 +596,12 @@ static int cg_run(kl_ctx* ctx, KLSolveWS* w, double tol, int max_iter, int* iter
         KL_CUDA(cudaMemcpyAsync(w->st_host, w->st, sizeof(CGState), cudaMemcpyDeviceToHost, s));
         KL_CUDA(cudaStreamSynchronize(s));
         if (w->st_host->done) break;
-        {   // an indefinite or unassembled matrix makes pAp <= 0 / NaN: the stop test |r|^2 < threshold can then never fire
+        {   // an unassembled (p.Ap = 0 -> alpha = inf) or broken matrix makes the iteration non-finite: the stop test |r|^2 < threshold can
+            // then never fire, so leave at once.  A finite p.Ap <= 0 is NOT an error: Eigen's ConjugateGradient has no such test, and the
+            // arc-length solvers do solve with an indefinite tangent past a limit point (gsALMBase.hpp:249-258) — the iteration goes on
+            // until the tolerance or max_iter, exactly as in the reference.
             const CGState& c = *w->st_host;
-            if (batches > 0 && (!(c.rn2 == c.rn2) || !(c.pAp == c.pAp) || c.pAp <= 0.0 || !std::isfinite(c.rn2))) break;
+            if (batches > 0 && (!std::isfinite(c.rn2) || !std::isfinite(c.pAp))) break;
         }
         if (use_graph) KL_CUDA(cudaGraphLaunch(w->graph, s));
         else
@@ -612,8 +615,8 @@ static int cg_run(kl_ctx* ctx, KLSolveWS* w, double tol, int max_iter, int* iter
     ctx->launches += (int)(batches * CG_BATCH * 5);
     if (iters) *iters = st.iters;
     if (rel_err) *rel_err = st.rhsNorm2 > 0.0 ? std::sqrt(st.rn2 / st.rhsNorm2) : 0.0;
-    if (!(st.rn2 == st.rn2) || !(st.pAp == st.pAp) || !std::isfinite(st.rn2) || (!st.done && st.pAp <= 0.0)) {
-        kl_set_error("kl_cg_solve: non-finite value or p.Ap <= 0 in the iteration (matrix not assembled or not positive definite?)");
+    if (!std::isfinite(st.rn2) || !std::isfinite(st.pAp)) {
+        kl_set_error("kl_cg_solve: non-finite value in the iteration (matrix not assembled?)");
         return KL_E_NONFINITE;
     }
     cudaEventElapsedTime(&w->ms_total, w->e0, w->e1);
