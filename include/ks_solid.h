@@ -60,7 +60,11 @@ typedef struct ks_ctx ks_ctx;
 /* DoF numbering of the component-wise gsDofMappers of gsElasticityAssembler (free DoFs of component 0, 1, 2, then the
  * eliminated ones in the same order) */
 int ks_build_dofmap(int32_t n1, int32_t n2, int32_t n3, const ks_bc* bc, int32_t* dof_map, int32_t* n_free, int32_t* n_fixed);
-/* gsElasticityAssembler ctor: tables, F_ext (body force + tractions), symbolic pattern on the GPU. KL_E_NOGPU without a device. */
+/* gsElasticityAssembler ctor: tables, F_ext (body force + tractions), symbolic pattern on the GPU. KL_E_NOGPU without a device.
+ * Performance note (results are identical either way): the tri-cubic Jacobian kernel keeps its 1-D basis tables in the 64 KB constant
+ * memory of the device when the mesh has at most 85 elements per direction; ONE context per device owns those tables (the first such
+ * ks_create takes them, ks_destroy releases them) and any other context alive at the same time runs the shared-memory instantiation,
+ * about 13 % slower.  KS_NO_CONST=1 in the environment disables the constant tables. */
 int ks_create(const ks_problem* prob, int device, ks_ctx** out);
 void ks_destroy(ks_ctx* ctx);
 int ks_sizes(const ks_ctx* ctx, int32_t* n_dofs, int64_t* nnz, int64_t* n_elements, int64_t* n_qp);   /* numDofs() */
