@@ -81,6 +81,25 @@ def test_tricubic_sliding_window(gpu, monkeypatch, nels, seg, full):
     _compare(gpu, pr, 5e-3, f"sw-{nels}-{seg}-{full}")
 
 
+def test_tricubic_window_with_nonuniform_and_repeated_knots(gpu):
+    """Walking direction with a non-uniform knot vector and interior knots of multiplicity 2 and 3 (C1 / C0 lines): the window shifts by
+    2 or 3 functions at such an element boundary."""
+    from gsstructuralanalysis_b200 import geometry as G
+    degrees = (3, 3, 3)
+    U = (np.array([0, 0, 0, 0, 0.15, 0.4, 0.4, 0.55, 0.8, 0.8, 0.8, 0.9, 1, 1, 1, 1.0]), G.open_uniform_knots(3, 2), G.open_uniform_knots(3, 2))
+    gr = [G.greville(p, u) for p, u in zip(degrees, U)]
+    B = [G.basis_matrix(p, u, g) for p, u, g in zip(degrees, U, gr)]
+    g3, g2, g1 = np.meshgrid(gr[2], gr[1], gr[0], indexing="ij")
+    X = np.stack((2.0 * g1 + 0.1 * g2 * g3, 1.0 * g2 + 0.05 * g1 * g1, 0.5 * g3 + 0.05 * g1 * g2), axis=-1)
+    for axis, Bm in ((0, B[2]), (1, B[1]), (2, B[0])):
+        Xm = np.moveaxis(X, axis, 0)
+        X = np.moveaxis(np.linalg.solve(Bm, Xm.reshape(Bm.shape[0], -1)).reshape(Xm.shape), 0, axis)
+    v = S.Volume(degrees, tuple(U), np.ascontiguousarray(X.reshape(-1, 3)))
+    bc = S.SolidBC().add_condition(S.KS_WEST).add_condition(S.KS_FRONT, 2)
+    pr = S.SolidProblem(v, bc, law=S.KS_LAW_NEO_HOOKE_LN, E=7.0, nu=0.3, tractions=[(S.KS_EAST, (0.1, 0.0, 0.2))])
+    _compare(gpu, pr, 5e-3, "sw-repeated-knots")
+
+
 def test_beam_with_prescribed_displacement(gpu):
     """benchmark_Elasticity_Beam_APALM.cpp:226-236 style beam; non-zero fixedDofs on the clamped face."""
     v = S.brick(1.0, 0.01, 0.01, degrees=(3, 2, 2), nels=(8, 1, 1))
