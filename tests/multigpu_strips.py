@@ -31,12 +31,16 @@ def main():
     from oracle.binding import Oracle
     nel = int(os.environ.get("KL_NEL", "24"))
     case = os.environ.get("KL_CASE", "roof")
-    pr = {"roof": lambda: W.roof(nel), "tension": lambda: W.tension_sheet(nel)}[case]()
+    def roof_pressure():     # follower pressure: the unsymmetric tangent of k_jacobian_sw<false,true> in strips (both phases of the overlap)
+        p = W.roof(nel)
+        p.pressure = 0.3
+        return p
+    pr = {"roof": lambda: W.roof(nel), "tension": lambda: W.tension_sheet(nel), "roof_pressure": roof_pressure}[case]()
     asm = ShellAssembler(pr, device=local)
     n1, n2 = pr.surface.n
     plan = plan_strips(n1, n2, 3, function_supports(pr.surface.U[1], 3)[2], pr.dof_map, pr.n_free, world, rank, knots2=pr.surface.U[1])
     asm.set_strip(plan.e2_begin, plan.e2_end)
-    x = W.displacement_state(asm.n_dofs, 0.05 if case == "roof" else 1e-5)
+    x = W.displacement_state(asm.n_dofs, 0.05 if case.startswith("roof") else 1e-5)
     xd = torch.from_numpy(x).cuda()
     rd = torch.zeros(asm.n_dofs, dtype=torch.float64, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
