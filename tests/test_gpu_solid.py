@@ -67,7 +67,8 @@ def test_degrees_and_meshes(gpu, degrees, nels):
     _compare(gpu, pr, 5e-3, f"brick-{degrees}-{nels}")
 
 
-@pytest.mark.parametrize("nels,seg,full", [((11, 2, 3), None, False), ((11, 2, 3), "4", False), ((9, 3, 2), "8", True), ((2, 4, 2), "1", False)])
+@pytest.mark.parametrize("nels,seg,full", [((11, 2, 3), None, False), ((11, 2, 3), "4", False), ((9, 3, 2), "8", True), ((2, 4, 2), "1", False),
+                                           ((90, 1, 1), None, False)])       # more than 85 elements per direction: tables in shared memory
 def test_tricubic_sliding_window(gpu, monkeypatch, nels, seg, full):
     """k3_jacobian_sw (the tri-cubic production kernel): long element rows, segments of 1 / 4 / 8 elements (partial windows at both
     ends of a segment), I <= J + mirror and the full assembly, Dirichlet faces on both ends of the walking direction."""
